@@ -1,0 +1,179 @@
+/* mgmb200.h -- C ABI of the B200-native MGM stereo hot path.
+ *
+ * Drop-in boundary for the hot path of gfacciol/mgm (cost volume -> multi-direction
+ * MGM aggregation -> WTA + sub-pixel).  Every entry point states the reference
+ * interface it replaces (file:line under the reference tree).  Plain pointers and
+ * sizes only; the library owns nothing but the opaque context (stream, device
+ * scratch).  All functions return 0 on success or a negative MGMB200_E* code;
+ * mgmb200_last_error() gives the message of the last failure on the calling
+ * thread.  There is no CPU fallback: without a CUDA device every compute entry
+ * point fails with MGMB200_ECUDA.
+ *
+ * Host layouts (identical to the reference):
+ *   image    planar float  data[x + y*nx + c*nx*ny]                       img.h:35
+ *   weights  Img(nx,ny,8), planes W,E,S,N,NW,NE,SE,SW                      mgm_weights.h:69
+ *   volume   pixel-major, label-fastest  vol[(x + y*nx)*L + (o - dmin)]    dvec.cc:129,
+ *            i.e. the flat layout of mgm_costvolume.h:276-299; L = dmax-dmin+1
+ * Device layout of a volume ("padded"): [ny*nx][VS] floats with
+ *   VS = mgmb200_padded_labels(L); labels >= L hold +INF.
+ */
+#ifndef MGMB200_H_
+#define MGMB200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGMB200_VERSION 100
+
+enum {
+   MGMB200_OK = 0,
+   MGMB200_EINVAL = -1,       /* bad argument */
+   MGMB200_ECUDA = -2,        /* CUDA runtime failure (incl. no device) */
+   MGMB200_EUNSUPPORTED = -3, /* outside the supported envelope */
+   MGMB200_ENOMEM = -4
+};
+
+/* mgm_costvolume.h:170-190  distance table: ad sd census ncc btad btsd (unknown -> 0) */
+int mgmb200_distance_index(const char *name);
+/* mgm_costvolume.h:194-207  prefilter table: none census sobelx gblur (unknown -> 0) */
+int mgmb200_prefilter_index(const char *name);
+/* mgm_refine.h:14-35        refinement table: none vfit parabola cubic parabolaOCV (unknown -> 0) */
+int mgmb200_refinement_index(const char *name);
+
+typedef struct mgmb200_ctx mgmb200_ctx;
+
+int mgmb200_version(void);
+const char *mgmb200_last_error(void);
+
+/* One context per GPU (one process per GPU in multi-GPU runs).  device < 0: current device. */
+int mgmb200_create(int device, mgmb200_ctx **ctx);
+void mgmb200_destroy(mgmb200_ctx *ctx);
+/* Use a caller-provided CUDA stream (cudaStream_t as void*); NULL restores the context's own. */
+int mgmb200_set_stream(mgmb200_ctx *ctx, void *cuda_stream);
+/* Tuning / test knob: rows per band of the aggregation wavefront (0 = derive from shared memory). */
+int mgmb200_set_rows_per_band(mgmb200_ctx *ctx, int rows);
+/* Block until everything queued on the context's stream is finished. */
+int mgmb200_synchronize(mgmb200_ctx *ctx);
+
+int mgmb200_padded_labels(int L);
+size_t mgmb200_volume_bytes(int nx, int ny, int L);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-pointer entry points: the reference's operator interface, one call per reference
+ * function.  Host<->device copies happen inside the call.
+ * ---------------------------------------------------------------------------------------- */
+
+/* struct Img compute_mgm_weights(struct Img &u, float aP, float aThresh)        mgm_weights.h:63
+ * w_out: 8*nx*ny floats. */
+int mgmb200_compute_mgm_weights(mgmb200_ctx *ctx, const float *u, int nx, int ny, int nch, float aP,
+                                float aThresh, float *w_out);
+
+/* struct costvolume_t allocate_and_fill_sgm_costvolume(Img &in_u, Img &in_v, Img &dminI, Img &dmaxI,
+ *        char *prefilter, char *distance, float truncDist)                      mgm_costvolume.h:337
+ * Uniform disparity range [dmin,dmax]; census_ncc_win is the CENSUS_NCC_WIN environment
+ * parameter (mgm_costvolume.h:61).  cc_out: nx*ny*L floats (host volume layout). */
+int mgmb200_costvolume(mgmb200_ctx *ctx, const float *u, const float *v, int nx, int ny, int nch, int vnx,
+                       int vny, int dmin, int dmax, const char *prefilter, const char *distance,
+                       float truncDist, int census_ncc_win, float *cc_out);
+
+/* struct costvolume_t mgm(struct costvolume_t CC, const Img &in_w, const Img &dminI, const Img &dmaxI,
+ *        Img *out, Img *outcost, float P1, float P2, int NDIR, int MGM,
+ *        int USE_FELZENSZWALB_POTENTIALS, int SGM_FIX_OVERCOUNT)                 mgm_core.cc:408
+ * cc: nx*ny*L floats; w: 8*nx*ny floats or NULL (all ones); out/outcost: nx*ny floats;
+ * S_out: NULL or nx*ny*L floats receiving the returned (over-count corrected) volume. */
+int mgmb200_mgm(mgmb200_ctx *ctx, const float *cc, const float *w, int nx, int ny, int dmin, int dmax,
+                float P1, float P2, int NDIR, int MGM, int use_felzenszwalb_potentials,
+                int sgm_fix_overcount, float *out, float *outcost, float *S_out);
+
+/* Same, cost volume given as label-major planes costs[i + o*nx*ny] -- the input.bin protocol of
+ * the standalone aggregator (matlab/mgm_o.cc:544-595, MGM_wrapper.m:88-94). Labels 0..nlab-1. */
+int mgmb200_mgm_labelmajor(mgmb200_ctx *ctx, const float *costs, const float *w, int ncol, int nrow, int nlab,
+                           float P1, float P2, int NDIR, int MGM, int use_felzenszwalb_potentials,
+                           float *labels_out, float *outcost);
+
+/* void subpixel_refinement_sgm(struct costvolume_t &S, std::vector<float> &out,
+ *        std::vector<float> &outcost, char *refinement)                          mgm_refine.h:40
+ * S: nx*ny*L floats; out/outcost updated in place. */
+int mgmb200_subpixel_refinement_sgm(mgmb200_ctx *ctx, const float *S, int nx, int ny, int dmin, int dmax,
+                                    float *out, float *outcost, const char *refinement);
+
+/* The whole hot path as mgm.cc:356-385 strings it together for one direction of the LR pair:
+ * weights(u) -> cost volume(u,v) -> mgm -> sub-pixel, nothing but the images going in and the two
+ * maps coming out.  P1/P2 are the command-line values: they are multiplied by nch here exactly
+ * like mgm.cc:356-357.  aP is the CLI's -aP2 (mgm.cc:372). */
+typedef struct mgmb200_stereo_params {
+   int dmin, dmax;                /* -r -R */
+   float P1, P2;                  /* -P1 -P2 */
+   int NDIR;                      /* -O */
+   int MGM;                       /* env TSGM */
+   int use_felzenszwalb_potentials; /* env USE_TRUNCATED_LINEAR_POTENTIALS */
+   int sgm_fix_overcount;         /* env TSGM_FIX_OVERCOUNT */
+   float aP, aThresh;             /* -aP2 -aThresh */
+   const char *prefilter;         /* -p */
+   const char *distance;          /* -t */
+   float truncDist;               /* -truncDist */
+   int census_ncc_win;            /* env CENSUS_NCC_WIN */
+   const char *refinement;        /* -s */
+} mgmb200_stereo_params;
+void mgmb200_stereo_params_default(mgmb200_stereo_params *p);   /* defaults of mgm.cc:186-196,303-318 */
+int mgmb200_stereo(mgmb200_ctx *ctx, const float *u, const float *v, int nx, int ny, int nch,
+                   const mgmb200_stereo_params *p, float *out, float *outcost);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-pointer entry points (inputs and outputs resident in HBM, asynchronous on the
+ * context's stream).  d_cc is a padded volume.
+ * ---------------------------------------------------------------------------------------- */
+int mgmb200_weights_dev(mgmb200_ctx *ctx, const float *d_u, int nx, int ny, int nch, float aP, float aThresh,
+                        float *d_w);
+int mgmb200_costvolume_dev(mgmb200_ctx *ctx, const float *d_u, const float *d_v, int nx, int ny, int nch,
+                           int vnx, int vny, int dmin, int dmax, int prefilter_index, int distance_index,
+                           float truncDist, int census_ncc_win, float *d_cc);
+/* weights_mode: 0 = d_w ignored (all ones), 1 = use d_w as image dependent weights,
+ *               2 = decide like mgm_core.cc:420-422 (scans d_w, synchronises the stream).
+ * refinement_index as mgmb200_refinement_index.  d_S: NULL or dense nx*ny*L floats.
+ */
+int mgmb200_aggregate_dev(mgmb200_ctx *ctx, const float *d_cc, const float *d_w, int weights_mode, int nx,
+                          int ny, int dmin, int dmax, float P1, float P2, int NDIR, int MGM,
+                          int use_felzenszwalb_potentials, int sgm_fix_overcount, int refinement_index,
+                          float *d_out, float *d_outcost, float *d_S);
+
+/* Multi-GPU direction sharding: the sweeps are split over ranks; every rank
+ * aggregates its own sweeps into its own per-sweep volumes, then each rank finishes a slab of
+ * image rows reading all NDIR sweep volumes (its own and, through CUDA peer/IPC mappings, the
+ * other ranks') in sweep order. */
+int mgmb200_aggregate_sweeps_dev(mgmb200_ctx *ctx, const float *d_cc, const float *d_w, int weights_mode,
+                                 int nx, int ny, int dmin, int dmax, float P1, float P2, int NDIR, int MGM,
+                                 int use_felzenszwalb_potentials, unsigned sweep_mask);
+/* device pointer of the volume this context holds for sweep p after mgmb200_aggregate_sweeps_dev */
+int mgmb200_sweep_volume(mgmb200_ctx *ctx, int sweep, float **d_ptr, size_t *bytes);
+/* 64-byte CUDA IPC handle of a device allocation / mapping of a peer handle */
+int mgmb200_ipc_export(mgmb200_ctx *ctx, const void *d_ptr, unsigned char handle_out[64]);
+int mgmb200_ipc_open(mgmb200_ctx *ctx, const unsigned char handle[64], void **d_ptr);
+int mgmb200_ipc_close(mgmb200_ctx *ctx, void *d_ptr);
+/* ordered sum + fix + WTA + sub-pixel over rows [row_begin,row_end) with explicit per-sweep
+ * volume pointers (local or peer); d_out/d_outcost are full nx*ny maps, only the slab is written */
+int mgmb200_finish_rows_dev(mgmb200_ctx *ctx, const float *const *d_sweeps, const float *d_cc, int nx, int ny,
+                            int dmin, int dmax, int NDIR, int sgm_fix_overcount, int refinement_index,
+                            int row_begin, int row_end, float *d_out, float *d_outcost);
+
+/* device memory helpers so that non-CUDA hosts (ctypes, cgo, JNI) can drive the dev entry points */
+int mgmb200_malloc(mgmb200_ctx *ctx, size_t bytes, void **d_ptr);
+int mgmb200_free(mgmb200_ctx *ctx, void *d_ptr);
+int mgmb200_memcpy_h2d(mgmb200_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int mgmb200_memcpy_d2h(mgmb200_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+/* dense host-layout volume <-> padded device volume (both device pointers) */
+int mgmb200_pad_volume_dev(mgmb200_ctx *ctx, const float *d_dense, float *d_padded, int nx, int ny, int L,
+                           int label_major);
+int mgmb200_unpad_volume_dev(mgmb200_ctx *ctx, const float *d_padded, float *d_dense, int nx, int ny, int L);
+
+/* counters of the last aggregate call, for benchmarks: kernels launched, rows per band used */
+int mgmb200_last_launch_info(mgmb200_ctx *ctx, int *kernel_launches, int *rows_axis, int *rows_diag,
+                             int *threads_per_cta, size_t *smem_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGMB200_H_ */

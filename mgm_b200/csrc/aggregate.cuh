@@ -1,0 +1,39 @@
+// Parameters and launch plan of the aggregation kernel (aggregate.cu).
+#pragma once
+#include "common.cuh"
+
+#define MGM_AGG_MAX_THREADS 160   // 128 row threads + one boundary-producer warp
+
+namespace mgm {
+
+enum PotKind { POT_SGM = 0, POT_TRUNC = 1 };
+
+struct AggParams {
+   const float *cc;            // matching costs [ny][nx][VS], labels >= L hold +INF
+   const float *w;             // 8 weight planes [8][ny][nx] (weighted kernels only)
+   float *ldir[8];             // per-sweep message volumes [ny][nx][VS], indexed by sweep id
+   float *bnd[8];              // per-sweep boundary lines [nbands][maxii][VS]
+   float *bndm[8];             // per-sweep boundary minima [nbands][maxii]
+   int *progress[8];           // per-sweep [nbands]: finished pixels of each band's last row
+   const int2 *tickets;        // (sweep, band) in claim order
+   unsigned int *ticket_counter;
+   int ntickets;
+   int nx, ny, L, VS;
+   int T[2];                   // rows per band: [0] axis sweeps 0-3, [1] diagonal sweeps 4-7
+   int TS[2];                  // per-row shared-memory stride in floats
+   float P1, P2;
+   // dynamic shared memory carve-up (bytes)
+   unsigned off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
+};
+
+struct AggPlan {
+   int VS, T[2], TS[2], block, num_sms;
+   size_t smem;
+   size_t off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
+};
+
+void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
+              int t_override);
+cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st);
+
+}  // namespace mgm

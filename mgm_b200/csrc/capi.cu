@@ -1,0 +1,648 @@
+// C ABI of the B200 MGM hot path (include/mgmb200.h): context, buffer cache and the
+// orchestration of the kernels in costvolume.cu / aggregate.cu / wta.cu.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+
+#include "../../include/mgmb200.h"
+#include "aggregate.cuh"
+#include "costvolume.cuh"
+#include "wta.cuh"
+
+using namespace mgm;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(g_err, sizeof(g_err), fmt, ap);
+   va_end(ap);
+   return code;
+}
+#define CU(call)                                                                              \
+   do {                                                                                       \
+      cudaError_t e_ = (call);                                                                \
+      if (e_ != cudaSuccess)                                                                  \
+         return fail(MGMB200_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+   } while (0)
+#define RET(call)              \
+   do {                        \
+      int r_ = (call);         \
+      if (r_ != 0) return r_;  \
+   } while (0)
+
+struct DevBuf {
+   void *p = nullptr;
+   size_t cap = 0;
+   int reserve(size_t bytes) {
+      if (bytes <= cap) return 0;
+      if (p) cudaFree(p);
+      p = nullptr; cap = 0;
+      cudaError_t e = cudaMalloc(&p, bytes);
+      if (e != cudaSuccess) {
+         cudaGetLastError();
+         return fail(MGMB200_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+      }
+      cap = bytes;
+      return 0;
+   }
+   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+   template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct mgmb200_ctx {
+   int device = 0, num_sms = 0, max_smem = 0;
+   cudaStream_t own_stream = nullptr, stream = nullptr;
+   int rows_override = 0;
+   // scratch (grow-only, reused across calls)
+   DevBuf u, v, fu, fv, cu, cv, w, cc, dense, out, outcost, flags, tickets, progress, bnd, bndm;
+   DevBuf sweep[8];
+   size_t sweep_bytes = 0;
+   // last launch info
+   int n_launches = 0, rows_axis = 0, rows_diag = 0, block = 0;
+   size_t smem = 0;
+   // ticket table currently resident in `tickets` (avoids a blocking pageable H2D copy per call)
+   long long tk_key[6] = {-1, -1, -1, -1, -1, -1};
+};
+
+// ------------------------------------------------------------------------------------------ tables
+static int lookup(const char *name, const char *const *names, int n) {
+   int r = 0;   // unknown names silently map to entry 0, like the reference
+   if (!name) return 0;
+   for (int i = 0; i < n; i++) if (!strcmp(name, names[i])) r = i;
+   return r;
+}
+extern "C" int mgmb200_distance_index(const char *name) {
+   static const char *const t[] = {"ad", "sd", "census", "ncc", "btad", "btsd"};
+   return lookup(name, t, 6);
+}
+extern "C" int mgmb200_prefilter_index(const char *name) {
+   static const char *const t[] = {"none", "census", "sobelx", "gblur"};
+   return lookup(name, t, 4);
+}
+extern "C" int mgmb200_refinement_index(const char *name) {
+   static const char *const t[] = {"none", "vfit", "parabola", "cubic", "parabolaOCV"};
+   return lookup(name, t, 5);
+}
+
+extern "C" int mgmb200_version(void) { return MGMB200_VERSION; }
+extern "C" const char *mgmb200_last_error(void) { return g_err; }
+extern "C" int mgmb200_padded_labels(int L) { return (L + 3) & ~3; }
+extern "C" size_t mgmb200_volume_bytes(int nx, int ny, int L) {
+   return (size_t)nx * ny * mgmb200_padded_labels(L) * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------ context
+extern "C" int mgmb200_create(int device, mgmb200_ctx **out) {
+   if (!out) return fail(MGMB200_EINVAL, "ctx output pointer is NULL");
+   *out = nullptr;
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount(&ndev);
+   if (e != cudaSuccess || ndev == 0) {
+      cudaGetLastError();
+      return fail(MGMB200_ECUDA, "no CUDA device available (%s); mgmb200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+   }
+   if (device < 0) CU(cudaGetDevice(&device));
+   if (device >= ndev) return fail(MGMB200_EINVAL, "device %d out of range (%d devices)", device, ndev);
+   CU(cudaSetDevice(device));
+   mgmb200_ctx *c = new mgmb200_ctx();
+   c->device = device;
+   cudaDeviceProp prop;
+   CU(cudaGetDeviceProperties(&prop, device));
+   c->num_sms = prop.multiProcessorCount;
+   c->max_smem = (int)prop.sharedMemPerBlockOptin;
+   if (prop.major < 9) {
+      delete c;
+      return fail(MGMB200_EUNSUPPORTED, "compute capability %d.%d: the kernels need TMA bulk copies (sm_100a build)",
+                  prop.major, prop.minor);
+   }
+   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+   c->stream = c->own_stream;
+   const char *env = getenv("MGMB200_ROWS_PER_BAND");
+   if (env) c->rows_override = atoi(env);
+   *out = c;
+   return 0;
+}
+
+extern "C" void mgmb200_destroy(mgmb200_ctx *c) {
+   if (!c) return;
+   cudaSetDevice(c->device);
+   cudaStreamSynchronize(c->stream);
+   DevBuf *bufs[] = {&c->u, &c->v, &c->fu, &c->fv, &c->cu, &c->cv, &c->w, &c->cc, &c->dense, &c->out,
+                     &c->outcost, &c->flags, &c->tickets, &c->progress, &c->bnd, &c->bndm};
+   for (DevBuf *b : bufs) b->release();
+   for (int i = 0; i < 8; i++) c->sweep[i].release();
+   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+   delete c;
+}
+
+extern "C" int mgmb200_set_stream(mgmb200_ctx *c, void *s) {
+   if (!c) return fail(MGMB200_EINVAL, "ctx is NULL");
+   c->stream = s ? (cudaStream_t)s : c->own_stream;
+   return 0;
+}
+extern "C" int mgmb200_set_rows_per_band(mgmb200_ctx *c, int rows) {
+   if (!c) return fail(MGMB200_EINVAL, "ctx is NULL");
+   c->rows_override = rows < 0 ? 0 : rows;
+   return 0;
+}
+extern "C" int mgmb200_synchronize(mgmb200_ctx *c) {
+   if (!c) return fail(MGMB200_EINVAL, "ctx is NULL");
+   CU(cudaSetDevice(c->device));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+
+extern "C" int mgmb200_malloc(mgmb200_ctx *c, size_t bytes, void **p) {
+   if (!c || !p) return fail(MGMB200_EINVAL, "NULL argument");
+   CU(cudaSetDevice(c->device));
+   cudaError_t e = cudaMalloc(p, bytes);
+   if (e != cudaSuccess) { cudaGetLastError(); return fail(MGMB200_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+   return 0;
+}
+extern "C" int mgmb200_free(mgmb200_ctx *c, void *p) {
+   if (!c) return fail(MGMB200_EINVAL, "ctx is NULL");
+   CU(cudaSetDevice(c->device));
+   CU(cudaFree(p));
+   return 0;
+}
+extern "C" int mgmb200_memcpy_h2d(mgmb200_ctx *c, void *d, const void *h, size_t bytes) {
+   if (!c) return fail(MGMB200_EINVAL, "ctx is NULL");
+   CU(cudaSetDevice(c->device));
+   CU(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+extern "C" int mgmb200_memcpy_d2h(mgmb200_ctx *c, void *h, const void *d, size_t bytes) {
+   if (!c) return fail(MGMB200_EINVAL, "ctx is NULL");
+   CU(cudaSetDevice(c->device));
+   CU(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+
+// ------------------------------------------------------------------------------------------ argument checks
+static int check_dims(int nx, int ny, int dmin, int dmax) {
+   if (nx < 1 || ny < 1) return fail(MGMB200_EINVAL, "image size %dx%d", nx, ny);
+   if (dmax <= dmin) return fail(MGMB200_EINVAL, "empty disparity range [%d,%d] (the reference asserts min<max, dvec.cc:57)", dmin, dmax);
+   long long L = (long long)dmax - dmin + 1;
+   if (L > 4096) return fail(MGMB200_EUNSUPPORTED, "%lld labels: at most 4096 are supported", L);
+   return 0;
+}
+
+static int read_flags(mgmb200_ctx *c, int *h) {
+   CU(cudaMemcpyAsync(h, c->flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+static int clear_flags(mgmb200_ctx *c) {
+   RET(c->flags.reserve(64));
+   CU(cudaMemsetAsync(c->flags.p, 0, 64, c->stream));
+   return 0;
+}
+
+// ------------------------------------------------------------------------------------------ device stages
+extern "C" int mgmb200_weights_dev(mgmb200_ctx *c, const float *d_u, int nx, int ny, int nch, float aP,
+                                   float aThresh, float *d_w) {
+   if (!c || !d_u || !d_w) return fail(MGMB200_EINVAL, "NULL argument");
+   if (nx < 1 || ny < 1 || nch < 1) return fail(MGMB200_EINVAL, "image %dx%dx%d", nx, ny, nch);
+   CU(cudaSetDevice(c->device));
+   CU(weights_launch(d_u, nx, ny, nch, aP, aThresh, d_w, nullptr, c->stream));
+   return 0;
+}
+
+extern "C" int mgmb200_costvolume_dev(mgmb200_ctx *c, const float *d_u, const float *d_v, int nx, int ny, int nch,
+                                      int vnx, int vny, int dmin, int dmax, int pf, int dist, float truncDist,
+                                      int win, float *d_cc) {
+   if (!c || !d_u || !d_v || !d_cc) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, dmin, dmax));
+   if (vnx < 1 || vny < 1 || nch < 1) return fail(MGMB200_EINVAL, "image v %dx%dx%d", vnx, vny, nch);
+   if (dist < 0 || dist > 5 || pf < 0 || pf > 3) return fail(MGMB200_EINVAL, "distance/prefilter index");
+   if (win < 1) return fail(MGMB200_EINVAL, "CENSUS_NCC_WIN=%d", win);
+   CU(cudaSetDevice(c->device));
+   const int L = dmax - dmin + 1, VS = mgmb200_padded_labels(L);
+   // the reference picks the cost function before forcing census/census (mgm_costvolume.h:355-362);
+   // "-p census" with another distance would run it on bit patterns reinterpreted as floats.
+   if (pf == PF_CENSUS && dist != DIST_CENSUS)
+      return fail(MGMB200_EUNSUPPORTED, "prefilter census with a non-census distance is not supported");
+   if (pf == PF_GBLUR) return fail(MGMB200_EUNSUPPORTED, "prefilter gblur is not implemented yet");
+   const float *uu = d_u, *vv = d_v;
+   const uint32_t *cu = nullptr, *cv = nullptr;
+   int cnch = nch;
+   if (dist == DIST_CENSUS) {
+      cnch = census_nwords(nch, win);
+      if (cnch < 1 || cnch > 32) return fail(MGMB200_EUNSUPPORTED, "census window %d with %d channels", win, nch);
+      RET(c->cu.reserve((size_t)nx * ny * cnch * 4));
+      RET(c->cv.reserve((size_t)vnx * vny * cnch * 4));
+      CU(census_launch(d_u, nx, ny, nch, win, c->cu.as<uint32_t>(), c->stream));
+      CU(census_launch(d_v, vnx, vny, nch, win, c->cv.as<uint32_t>(), c->stream));
+      cu = c->cu.as<uint32_t>(); cv = c->cv.as<uint32_t>();
+   } else if (pf == PF_SOBELX) {
+      RET(c->fu.reserve((size_t)nx * ny * nch * 4));
+      RET(c->fv.reserve((size_t)vnx * vny * nch * 4));
+      CU(sobelx_launch(d_u, nx, ny, nch, c->fu.as<float>(), c->stream));
+      CU(sobelx_launch(d_v, vnx, vny, nch, c->fv.as<float>(), c->stream));
+      uu = c->fu.as<float>(); vv = c->fv.as<float>();
+   }
+   CU(costvolume_launch(dist, uu, vv, cu, cv, nx, ny, vnx, vny, cnch, win, dmin, L, VS, truncDist, d_cc,
+                        c->num_sms, c->stream));
+   return 0;
+}
+
+extern "C" int mgmb200_pad_volume_dev(mgmb200_ctx *c, const float *d_dense, float *d_padded, int nx, int ny, int L,
+                                      int label_major) {
+   if (!c || !d_dense || !d_padded) return fail(MGMB200_EINVAL, "NULL argument");
+   CU(cudaSetDevice(c->device));
+   CU(pad_volume_launch(d_dense, d_padded, (long long)nx * ny, L, mgmb200_padded_labels(L), label_major, c->stream));
+   return 0;
+}
+extern "C" int mgmb200_unpad_volume_dev(mgmb200_ctx *c, const float *d_padded, float *d_dense, int nx, int ny,
+                                        int L) {
+   if (!c || !d_dense || !d_padded) return fail(MGMB200_EINVAL, "NULL argument");
+   CU(cudaSetDevice(c->device));
+   CU(unpad_volume_launch(d_padded, d_dense, (long long)nx * ny, L, mgmb200_padded_labels(L), c->stream));
+   return 0;
+}
+
+// Runs the sweeps in `mask` into c->sweep[p]; fills `weighted`.  d_cc padded.
+static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int weights_mode, int nx, int ny,
+                      int L, float P1, float P2, int NDIR, int K, int felz, unsigned mask) {
+   if (NDIR < 1 || NDIR > 8)
+      return fail(MGMB200_EUNSUPPORTED, "NDIR=%d: the reference defines 8 sweeps (mgm_core.cc:463-471); "
+                  "-O 16 indexes past its table", NDIR);
+   if (K < 1 || K > 4) return fail(MGMB200_EINVAL, "MGM/TSGM=%d not in 1..4", K);
+   if (!(P1 >= 0.f) || !(P2 >= 0.f)) return fail(MGMB200_EUNSUPPORTED, "P1=%g P2=%g must be >= 0", P1, P2);
+   if (!(P1 < INFINITY)) return fail(MGMB200_EUNSUPPORTED, "P1 must be finite");
+   const int pot = felz > 0 ? POT_TRUNC : POT_SGM;
+   if (pot == POT_SGM && !(P2 < INFINITY)) return fail(MGMB200_EUNSUPPORTED, "P2 must be finite with SGM potentials");
+   const int VS = mgmb200_padded_labels(L);
+   const size_t vol = (size_t)nx * ny * VS * sizeof(float);
+   c->n_launches = 0;
+
+   bool weighted = false;
+   if (weights_mode == 1) weighted = true;
+   if (weights_mode == 2 && d_w) {
+      RET(clear_flags(c));
+      CU(scan_weights_launch(d_w, (long long)nx * ny * 8, c->flags.as<int>(), c->stream));
+      c->n_launches++;
+      int fl = 0;
+      RET(read_flags(c, &fl));
+      weighted = fl & 1;
+      if (fl & 2) return fail(MGMB200_EUNSUPPORTED, "edge weights must be finite and >= 0");
+   }
+   if (weighted && !d_w) return fail(MGMB200_EINVAL, "weighted aggregation without weights");
+
+   for (int p = 0; p < NDIR; p++)
+      if (mask & (1u << p)) RET(c->sweep[p].reserve(vol));
+   c->sweep_bytes = vol;
+
+   if (nx < 3 || ny < 3) {
+      // every pixel has a neighbour outside the image: all messages stay equal to the costs (mgm_core.cc:538-541)
+      for (int p = 0; p < NDIR; p++)
+         if (mask & (1u << p)) CU(cudaMemcpyAsync(c->sweep[p].p, d_cc, vol, cudaMemcpyDeviceToDevice, c->stream));
+      return 0;
+   }
+
+   AggPlan plan;
+   agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, c->rows_override);
+   if (plan.T[0] < 1 || plan.T[1] < 1)
+      return fail(MGMB200_EUNSUPPORTED, "%d labels do not fit the shared-memory wavefront (max_smem=%d)", L, c->max_smem);
+   c->rows_axis = plan.T[0]; c->rows_diag = plan.T[1]; c->block = plan.block; c->smem = plan.smem;
+
+   // tickets in dependency order: band-major over the requested sweeps
+   std::vector<int2> tk;
+   int nb[8] = {0}, maxb = 0;
+   size_t bnd_off[8] = {0}, bndm_off[8] = {0}, prog_off[8] = {0};
+   size_t bnd_total = 0, bndm_total = 0, prog_total = 0;
+   for (int p = 0; p < NDIR; p++) {
+      if (!(mask & (1u << p))) continue;
+      PassGeom g = pass_geometry(p, nx, ny);
+      const int T = plan.T[p < 4 ? 0 : 1];
+      nb[p] = (g.maxjj + T - 1) / T;
+      if (nb[p] > maxb) maxb = nb[p];
+      bnd_off[p] = bnd_total; bnd_total += (size_t)nb[p] * g.maxii * VS;
+      bndm_off[p] = bndm_total; bndm_total += (size_t)nb[p] * g.maxii;
+      prog_off[p] = prog_total; prog_total += nb[p];
+   }
+   for (int b = 0; b < maxb; b++)
+      for (int p = 0; p < NDIR; p++)
+         if ((mask & (1u << p)) && b < nb[p]) tk.push_back(make_int2(p, b));
+   if (tk.empty()) return 0;
+
+   if (tk.size() * sizeof(int2) > c->tickets.cap) c->tk_key[0] = -1;
+   RET(c->tickets.reserve(tk.size() * sizeof(int2)));
+   RET(c->progress.reserve((prog_total + 4) * sizeof(int)));
+   RET(c->bnd.reserve(bnd_total * sizeof(float)));
+   RET(c->bndm.reserve(bndm_total * sizeof(float)));
+   const long long key[6] = {nx, ny, plan.T[0], plan.T[1], (long long)mask, NDIR};
+   if (memcmp(key, c->tk_key, sizeof(key)) != 0) {
+      CU(cudaMemcpyAsync(c->tickets.p, tk.data(), tk.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      memcpy(c->tk_key, key, sizeof(key));
+   }
+   CU(cudaMemsetAsync(c->progress.p, 0, (prog_total + 4) * sizeof(int), c->stream));
+
+   AggParams P;
+   memset(&P, 0, sizeof(P));
+   P.cc = d_cc; P.w = d_w;
+   for (int p = 0; p < 8; p++) {
+      P.ldir[p] = c->sweep[p].as<float>();
+      P.bnd[p] = c->bnd.as<float>() + bnd_off[p];
+      P.bndm[p] = c->bndm.as<float>() + bndm_off[p];
+      P.progress[p] = c->progress.as<int>() + prog_off[p];
+   }
+   P.tickets = c->tickets.as<int2>();
+   P.ticket_counter = reinterpret_cast<unsigned int *>(c->progress.as<int>() + prog_total);
+   P.ntickets = (int)tk.size();
+   P.nx = nx; P.ny = ny; P.L = L; P.VS = VS;
+   P.T[0] = plan.T[0]; P.T[1] = plan.T[1];
+   P.TS[0] = plan.TS[0]; P.TS[1] = plan.TS[1];
+   P.P1 = P1; P.P2 = P2;
+   P.off_phase = (unsigned)plan.off_phase; P.off_cbar = (unsigned)plan.off_cbar; P.off_vbar = (unsigned)plan.off_vbar;
+   P.off_ms = (unsigned)plan.off_ms; P.off_vms = (unsigned)plan.off_vms; P.off_virt = (unsigned)plan.off_virt;
+   P.off_thr = (unsigned)plan.off_thr;
+   CU(agg_launch(P, plan, pot, K, weighted, c->stream));
+   c->n_launches++;
+   return 0;
+}
+
+static int finish_rows(mgmb200_ctx *c, const float *const *d_sweeps, const float *d_cc, int nx, int ny, int dmin,
+                       int L, int NDIR, int fix, int refine, int row_begin, int row_end, float *d_out,
+                       float *d_outcost, float *d_S) {
+   WtaParams W;
+   memset(&W, 0, sizeof(W));
+   for (int p = 0; p < NDIR; p++) W.ldir[p] = d_sweeps[p];
+   W.cc = d_cc; W.out = d_out; W.outcost = d_outcost; W.S_out = d_S;
+   W.pix_begin = (long long)row_begin * nx; W.pix_end = (long long)row_end * nx;
+   W.ndir = NDIR; W.L = L; W.VS = mgmb200_padded_labels(L); W.dmin = dmin;
+   W.fix = (fix == 1); W.refine = refine;
+   CU(wta_launch(W, c->num_sms, c->stream));
+   c->n_launches++;
+   return 0;
+}
+
+extern "C" int mgmb200_aggregate_sweeps_dev(mgmb200_ctx *c, const float *d_cc, const float *d_w, int weights_mode,
+                                            int nx, int ny, int dmin, int dmax, float P1, float P2, int NDIR,
+                                            int K, int felz, unsigned sweep_mask) {
+   if (!c || !d_cc) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, dmin, dmax));
+   CU(cudaSetDevice(c->device));
+   if (NDIR >= 1 && NDIR <= 8) sweep_mask &= (1u << NDIR) - 1u;
+   return run_sweeps(c, d_cc, d_w, weights_mode, nx, ny, dmax - dmin + 1, P1, P2, NDIR, K, felz, sweep_mask);
+}
+
+extern "C" int mgmb200_sweep_volume(mgmb200_ctx *c, int sweep, float **d_ptr, size_t *bytes) {
+   if (!c || sweep < 0 || sweep > 7 || !d_ptr) return fail(MGMB200_EINVAL, "bad argument");
+   *d_ptr = c->sweep[sweep].as<float>();
+   if (bytes) *bytes = c->sweep[sweep].p ? c->sweep_bytes : 0;
+   return 0;
+}
+
+extern "C" int mgmb200_finish_rows_dev(mgmb200_ctx *c, const float *const *d_sweeps, const float *d_cc, int nx,
+                                       int ny, int dmin, int dmax, int NDIR, int fix, int refine, int row_begin,
+                                       int row_end, float *d_out, float *d_outcost) {
+   if (!c || !d_sweeps || !d_cc || !d_out || !d_outcost) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, dmin, dmax));
+   if (NDIR < 1 || NDIR > 8) return fail(MGMB200_EUNSUPPORTED, "NDIR=%d", NDIR);
+   if (row_begin < 0 || row_end > ny || row_begin > row_end) return fail(MGMB200_EINVAL, "rows [%d,%d)", row_begin, row_end);
+   if (refine < 0 || refine > 4) return fail(MGMB200_EINVAL, "refinement index %d", refine);
+   CU(cudaSetDevice(c->device));
+   if (row_begin == row_end) return 0;
+   return finish_rows(c, d_sweeps, d_cc, nx, ny, dmin, dmax - dmin + 1, NDIR, fix, refine, row_begin, row_end,
+                      d_out, d_outcost, nullptr);
+}
+
+extern "C" int mgmb200_aggregate_dev(mgmb200_ctx *c, const float *d_cc, const float *d_w, int weights_mode, int nx,
+                                     int ny, int dmin, int dmax, float P1, float P2, int NDIR, int K, int felz,
+                                     int fix, int refine, float *d_out, float *d_outcost, float *d_S) {
+   if (!c || !d_cc || !d_out || !d_outcost) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, dmin, dmax));
+   if (refine < 0 || refine > 4) return fail(MGMB200_EINVAL, "refinement index %d", refine);
+   CU(cudaSetDevice(c->device));
+   const int L = dmax - dmin + 1;
+   unsigned mask = (NDIR >= 1 && NDIR <= 8) ? ((1u << NDIR) - 1u) : 0u;
+   RET(run_sweeps(c, d_cc, d_w, weights_mode, nx, ny, L, P1, P2, NDIR, K, felz, mask));
+   const float *sw[8];
+   for (int p = 0; p < 8; p++) sw[p] = c->sweep[p].as<float>();
+   return finish_rows(c, sw, d_cc, nx, ny, dmin, L, NDIR, fix, refine, 0, ny, d_out, d_outcost, d_S);
+}
+
+// ------------------------------------------------------------------------------------------ IPC (multi-GPU)
+extern "C" int mgmb200_ipc_export(mgmb200_ctx *c, const void *d_ptr, unsigned char handle_out[64]) {
+   if (!c || !d_ptr || !handle_out) return fail(MGMB200_EINVAL, "NULL argument");
+   CU(cudaSetDevice(c->device));
+   cudaIpcMemHandle_t h;
+   CU(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+   static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+   memcpy(handle_out, &h, 64);
+   return 0;
+}
+extern "C" int mgmb200_ipc_open(mgmb200_ctx *c, const unsigned char handle[64], void **d_ptr) {
+   if (!c || !handle || !d_ptr) return fail(MGMB200_EINVAL, "NULL argument");
+   CU(cudaSetDevice(c->device));
+   cudaIpcMemHandle_t h;
+   memcpy(&h, handle, 64);
+   CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+   return 0;
+}
+extern "C" int mgmb200_ipc_close(mgmb200_ctx *c, void *d_ptr) {
+   if (!c || !d_ptr) return fail(MGMB200_EINVAL, "NULL argument");
+   CU(cudaSetDevice(c->device));
+   CU(cudaIpcCloseMemHandle(d_ptr));
+   return 0;
+}
+
+extern "C" int mgmb200_last_launch_info(mgmb200_ctx *c, int *launches, int *rows_axis, int *rows_diag, int *threads,
+                                        size_t *smem) {
+   if (!c) return fail(MGMB200_EINVAL, "ctx is NULL");
+   if (launches) *launches = c->n_launches;
+   if (rows_axis) *rows_axis = c->rows_axis;
+   if (rows_diag) *rows_diag = c->rows_diag;
+   if (threads) *threads = c->block;
+   if (smem) *smem = c->smem;
+   return 0;
+}
+
+// ------------------------------------------------------------------------------------------ host-pointer API
+static int upload(mgmb200_ctx *c, DevBuf &b, const void *h, size_t bytes) {
+   RET(b.reserve(bytes));
+   CU(cudaMemcpyAsync(b.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
+   return 0;
+}
+static int download(mgmb200_ctx *c, void *h, const void *d, size_t bytes) {
+   CU(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+   return 0;
+}
+
+extern "C" int mgmb200_compute_mgm_weights(mgmb200_ctx *c, const float *u, int nx, int ny, int nch, float aP,
+                                           float aThresh, float *w_out) {
+   if (!c || !u || !w_out) return fail(MGMB200_EINVAL, "NULL argument");
+   if (nx < 1 || ny < 1 || nch < 1) return fail(MGMB200_EINVAL, "image %dx%dx%d", nx, ny, nch);
+   CU(cudaSetDevice(c->device));
+   const size_t np = (size_t)nx * ny;
+   RET(upload(c, c->u, u, np * nch * 4));
+   RET(c->w.reserve(np * 8 * 4));
+   RET(mgmb200_weights_dev(c, c->u.as<float>(), nx, ny, nch, aP, aThresh, c->w.as<float>()));
+   RET(download(c, w_out, c->w.p, np * 8 * 4));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+
+extern "C" int mgmb200_costvolume(mgmb200_ctx *c, const float *u, const float *v, int nx, int ny, int nch, int vnx,
+                                  int vny, int dmin, int dmax, const char *prefilter, const char *distance,
+                                  float truncDist, int win, float *cc_out) {
+   if (!c || !u || !v || !cc_out) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, dmin, dmax));
+   CU(cudaSetDevice(c->device));
+   int pf = mgmb200_prefilter_index(prefilter), di = mgmb200_distance_index(distance);
+   if (di == DIST_CENSUS) pf = PF_CENSUS;   // consistency fix of mgm_costvolume.h:358-362
+   const int L = dmax - dmin + 1, VS = mgmb200_padded_labels(L);
+   const size_t np = (size_t)nx * ny;
+   RET(upload(c, c->u, u, np * nch * 4));
+   RET(upload(c, c->v, v, (size_t)vnx * vny * nch * 4));
+   RET(c->cc.reserve(np * VS * 4));
+   RET(mgmb200_costvolume_dev(c, c->u.as<float>(), c->v.as<float>(), nx, ny, nch, vnx, vny, dmin, dmax, pf, di,
+                              truncDist, win, c->cc.as<float>()));
+   if (VS == L) {
+      RET(download(c, cc_out, c->cc.p, np * L * 4));
+   } else {
+      RET(c->dense.reserve(np * L * 4));
+      CU(unpad_volume_launch(c->cc.as<float>(), c->dense.as<float>(), (long long)np, L, VS, c->stream));
+      RET(download(c, cc_out, c->dense.p, np * L * 4));
+   }
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+
+// uploads a host volume (pixel-major or label-major) into the padded c->cc and validates the
+// fast-path preconditions
+static int upload_volume(mgmb200_ctx *c, const float *cc, int nx, int ny, int L, int label_major) {
+   const int VS = mgmb200_padded_labels(L);
+   const size_t np = (size_t)nx * ny;
+   RET(c->cc.reserve(np * VS * 4));
+   if (VS == L && !label_major) {
+      CU(cudaMemcpyAsync(c->cc.p, cc, np * L * 4, cudaMemcpyHostToDevice, c->stream));
+   } else {
+      RET(upload(c, c->dense, cc, np * L * 4));
+      CU(pad_volume_launch(c->dense.as<float>(), c->cc.as<float>(), (long long)np, L, VS, label_major, c->stream));
+   }
+   RET(clear_flags(c));
+   CU(validate_volume_launch(c->cc.as<float>(), (long long)np, L, VS, c->flags.as<int>(), c->num_sms, c->stream));
+   int fl = 0;
+   RET(read_flags(c, &fl));
+   if (fl)
+      return fail(MGMB200_EUNSUPPORTED, "cost volume outside the supported envelope:%s%s%s",
+                  (fl & 1) ? " a pixel without any finite cost" : "", (fl & 2) ? " NaN cost" : "",
+                  (fl & 4) ? " -INF cost" : "");
+   return 0;
+}
+
+static int mgm_host(mgmb200_ctx *c, const float *cc, const float *w, int nx, int ny, int dmin, int dmax, float P1,
+                    float P2, int NDIR, int K, int felz, int fix, int label_major, float *out, float *outcost,
+                    float *S_out) {
+   if (!c || !cc || !out || !outcost) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, dmin, dmax));
+   CU(cudaSetDevice(c->device));
+   const int L = dmax - dmin + 1;
+   const size_t np = (size_t)nx * ny;
+   RET(upload_volume(c, cc, nx, ny, L, label_major));
+   if (w) RET(upload(c, c->w, w, np * 8 * 4));
+   RET(c->out.reserve(np * 4));
+   RET(c->outcost.reserve(np * 4));
+   float *dS = nullptr;
+   if (S_out) { RET(c->dense.reserve(np * L * 4)); dS = c->dense.as<float>(); }
+   RET(mgmb200_aggregate_dev(c, c->cc.as<float>(), w ? c->w.as<float>() : nullptr, w ? 2 : 0, nx, ny, dmin, dmax, P1,
+                             P2, NDIR, K, felz, fix, 0, c->out.as<float>(), c->outcost.as<float>(), dS));
+   RET(download(c, out, c->out.p, np * 4));
+   RET(download(c, outcost, c->outcost.p, np * 4));
+   if (S_out) RET(download(c, S_out, dS, np * L * 4));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+
+extern "C" int mgmb200_mgm(mgmb200_ctx *c, const float *cc, const float *w, int nx, int ny, int dmin, int dmax,
+                           float P1, float P2, int NDIR, int MGM, int felz, int fix, float *out, float *outcost,
+                           float *S_out) {
+   return mgm_host(c, cc, w, nx, ny, dmin, dmax, P1, P2, NDIR, MGM, felz, fix, 0, out, outcost, S_out);
+}
+
+extern "C" int mgmb200_mgm_labelmajor(mgmb200_ctx *c, const float *costs, const float *w, int ncol, int nrow,
+                                      int nlab, float P1, float P2, int NDIR, int MGM, int felz, float *labels_out,
+                                      float *outcost) {
+   if (!labels_out) return fail(MGMB200_EINVAL, "NULL argument");
+   std::vector<float> tmp;
+   if (!outcost) { tmp.resize((size_t)ncol * nrow); outcost = tmp.data(); }
+   return mgm_host(c, costs, w, ncol, nrow, 0, nlab - 1, P1, P2, NDIR, MGM, felz, 1, 1, labels_out, outcost, nullptr);
+}
+
+extern "C" int mgmb200_subpixel_refinement_sgm(mgmb200_ctx *c, const float *S, int nx, int ny, int dmin, int dmax,
+                                               float *out, float *outcost, const char *refinement) {
+   if (!c || !S || !out || !outcost) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, dmin, dmax));
+   const int m = mgmb200_refinement_index(refinement);
+   if (m == 0) return 0;   // "none": out/outcost untouched (mgm_refine.h:47)
+   // Separate entry point for callers that keep the reference call sequence mgm() -> refine();
+   // the fused path (mgmb200_stereo / mgmb200_aggregate_dev) refines inside the WTA kernel.
+   CU(cudaSetDevice(c->device));
+   const int L = dmax - dmin + 1;
+   const size_t np = (size_t)nx * ny;
+   RET(upload(c, c->dense, S, np * L * 4));
+   RET(upload(c, c->out, out, np * 4));
+   RET(upload(c, c->outcost, outcost, np * 4));
+   CU(refine_launch(c->dense.as<float>(), (long long)np, L, dmin, m, c->out.as<float>(), c->outcost.as<float>(),
+                    c->stream));
+   RET(download(c, out, c->out.p, np * 4));
+   RET(download(c, outcost, c->outcost.p, np * 4));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+
+extern "C" void mgmb200_stereo_params_default(mgmb200_stereo_params *p) {
+   if (!p) return;
+   p->dmin = -30; p->dmax = 30;
+   p->P1 = 8.f; p->P2 = 32.f;
+   p->NDIR = 4; p->MGM = 4;
+   p->use_felzenszwalb_potentials = 0; p->sgm_fix_overcount = 1;
+   p->aP = 1.f; p->aThresh = 5.f;
+   p->prefilter = "none"; p->distance = "ad";
+   p->truncDist = INFINITY; p->census_ncc_win = 3;
+   p->refinement = "none";
+}
+
+extern "C" int mgmb200_stereo(mgmb200_ctx *c, const float *u, const float *v, int nx, int ny, int nch,
+                              const mgmb200_stereo_params *p, float *out, float *outcost) {
+   if (!c || !u || !v || !p || !out || !outcost) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, p->dmin, p->dmax));
+   CU(cudaSetDevice(c->device));
+   const int L = p->dmax - p->dmin + 1, VS = mgmb200_padded_labels(L);
+   const size_t np = (size_t)nx * ny;
+   int pf = mgmb200_prefilter_index(p->prefilter), di = mgmb200_distance_index(p->distance);
+   if (di == DIST_CENSUS) pf = PF_CENSUS;
+   RET(upload(c, c->u, u, np * nch * 4));
+   RET(upload(c, c->v, v, np * nch * 4));
+   RET(c->w.reserve(np * 8 * 4));
+   RET(c->cc.reserve(np * VS * 4));
+   RET(c->out.reserve(np * 4));
+   RET(c->outcost.reserve(np * 4));
+   RET(clear_flags(c));
+   // weights + the "all ones?" scan of mgm_core.cc:420-422 in one kernel
+   CU(weights_launch(c->u.as<float>(), nx, ny, nch, p->aP, p->aThresh, c->w.as<float>(), c->flags.as<int>(), c->stream));
+   RET(mgmb200_costvolume_dev(c, c->u.as<float>(), c->v.as<float>(), nx, ny, nch, nx, ny, p->dmin, p->dmax, pf, di,
+                              p->truncDist, p->census_ncc_win, c->cc.as<float>()));
+   int fl = 0;
+   RET(read_flags(c, &fl));
+   if ((fl & 1) && !(p->aP >= 0.f && p->aP < INFINITY)) return fail(MGMB200_EUNSUPPORTED, "aP must be finite and >= 0");
+   const float P1 = p->P1 * nch, P2 = p->P2 * nch;   // mgm.cc:356-357
+   RET(mgmb200_aggregate_dev(c, c->cc.as<float>(), c->w.as<float>(), (fl & 1) ? 1 : 0, nx, ny, p->dmin, p->dmax, P1, P2,
+                             p->NDIR, p->MGM, p->use_felzenszwalb_potentials, p->sgm_fix_overcount,
+                             mgmb200_refinement_index(p->refinement), c->out.as<float>(), c->outcost.as<float>(),
+                             nullptr));
+   RET(download(c, out, c->out.p, np * 4));
+   RET(download(c, outcost, c->outcost.p, np * 4));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}

@@ -1,0 +1,331 @@
+// K1-K3 -- edge weights, census transform and the W x H x L matching-cost volume.
+//   K3 weights      : compute_mgm_weights            mgm_weights.h:63-85
+//   K1 census       : census_transform               census_tools.cc:127-153
+//   K2 cost volume  : allocate_and_fill_sgm_costvolume mgm_costvolume.h:337-424
+//                     with the cost functions of mgm_costvolume.h:23-165
+// Device layout of a volume: [y][x][VS] floats, VS = L rounded up to a multiple of
+// four; the padding labels hold +INF, which is exactly what Dvec::operator[] returns
+// outside [min,max] (dvec.cc:129), so the aggregation needs no range checks.
+#include "costvolume.cuh"
+
+namespace mgm {
+
+// ------------------------------------------------------------------ K3 weights
+__global__ void mgm_weights_kernel(const float *__restrict__ u, int nx, int ny, int nch, float aP, float aThresh,
+                                   float *__restrict__ w, int *__restrict__ not_all_ones) {
+   const long long np = (long long)nx * ny;
+   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= np * 8) return;
+   const int k = (int)(i / np);
+   const long long p = i - (long long)k * np;
+   const int x = (int)(p % nx), y = (int)(p / nx);
+   // plane order W E S N NW NE SE SW (mgm_weights.h:69)
+   const int ox = (k == 0 || k == 4 || k == 7) ? -1 : ((k == 1 || k == 5 || k == 6) ? 1 : 0);
+   const int oy = (k == 3 || k == 4 || k == 5) ? -1 : ((k == 2 || k == 6 || k == 7) ? 1 : 0);
+   const int qx = x + ox, qy = y + oy;
+   float wv = 1.0f;
+   if (qx >= 0 && qy >= 0 && qx < nx && qy < ny) {
+      float d = 0.f;
+      for (int c = 0; c < nch; ++c) {
+         const float diff = u[p + c * np] - u[qx + (long long)qy * nx + c * np];
+         d += diff * diff;
+      }
+      d = __fdiv_rn(d, (float)nch);
+      if (fabsf(d) < aThresh * aThresh) wv = aP;
+   }
+   w[i] = wv;
+   if (wv != 1.0f && not_all_ones) atomicOr(not_all_ones, 1);   // the scan of mgm_core.cc:420-422
+}
+
+// ------------------------------------------------------------------ K1 census transform
+// Bit b of the reference's MSB-first bit string sits in byte b/8; bytes are memcpy'd into
+// little-endian floats, i.e. byte j of a word occupies bits [8j, 8j+8).
+__global__ void mgm_census_kernel(const float *__restrict__ u, int nx, int ny, int nch, int r, int nwords,
+                                  uint32_t *__restrict__ out) {
+   const long long np = (long long)nx * ny;
+   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (p >= np) return;
+   const int x = (int)(p % nx), y = (int)(p / nx);
+   uint32_t word = 0;
+   int bit = 0, widx = 0;
+   for (int c = 0; c < nch; ++c) {
+      const float a = u[p + c * np];
+      for (int dy = -r; dy <= r; ++dy)
+         for (int dx = -r; dx <= r; ++dx) {
+            if (!dx && !dy) continue;
+            const int qx = x + dx, qy = y + dy;
+            bool b = false;
+            if (qx >= 0 && qx < nx && qy >= 0 && qy < ny) b = a < u[qx + (long long)qy * nx + c * np];
+            if (b) word |= 1u << (8 * ((bit >> 3) & 3) + 7 - (bit & 7));
+            ++bit;
+            if ((bit & 31) == 0) { out[p + (long long)widx * np] = word; word = 0; ++widx; }
+         }
+   }
+   if (widx < nwords) out[p + (long long)widx * np] = word;
+}
+
+// ------------------------------------------------------------------ N3 sobelx prefilter
+__global__ void mgm_sobelx_kernel(const float *__restrict__ u, int nx, int ny, int nch, float *__restrict__ out) {
+   const long long np = (long long)nx * ny;
+   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= np * nch) return;
+   const int c = (int)(i / np);
+   const long long p = i - (long long)c * np;
+   const int x = (int)(p % nx), y = (int)(p / nx);
+   const float kx[3] = {-1.f, 0.f, 1.f};
+   const float ky[3] = {1.f, 2.f, 1.f};
+   float v = 0.f;
+   for (int jj = 0; jj < 3; ++jj)
+      for (int ii = 0; ii < 3; ++ii) {   // img_tools.h:105-124, Neumann borders, accumulate in tap order
+         int xx = x + ii - 1, yy = y + jj - 1;
+         xx = xx < 0 ? 0 : (xx >= nx ? nx - 1 : xx);
+         yy = yy < 0 ? 0 : (yy >= ny ? ny - 1 : yy);
+         v += u[xx + (long long)yy * nx + c * np] * (kx[ii] * ky[jj]);
+      }
+   out[i] = v;
+}
+
+// ------------------------------------------------------------------ per-cell costs
+struct CostArgs {
+   const float *u, *v;          // (prefiltered) images, planar
+   const uint32_t *cu, *cv;     // census words, planar [nwords][ny][nx]
+   int nx, ny, vnx, vny, nch;   // nch: channels of the images the cost reads (census: nwords)
+   int win;                     // CENSUS_NCC_WIN
+};
+
+__device__ __forceinline__ float bt_channel(const float *__restrict__ ur, const float *__restrict__ vr, int nx,
+                                            int vnx, int px, int qx) {   // BTAD mgm_costvolume.h:82-110
+   const float IL = ur[px];
+   float ILp = IL, ILm = IL;
+   if (px < nx - 1) ILp = (IL + ur[px + 1]) * 0.5f;   // (a+b)/2.0 in double then to float == exact halving
+   if (px >= 1) ILm = (IL + ur[px - 1]) * 0.5f;
+   const float IR = vr[qx];
+   float IRp = IR, IRm = IR;
+   if (qx < vnx - 1) IRp = (IR + vr[qx + 1]) * 0.5f;
+   if (qx >= 1) IRm = (IR + vr[qx - 1]) * 0.5f;
+   const float IminR = fminf(fminf(IRm, IRp), IR), ImaxR = fmaxf(fmaxf(IRm, IRp), IR);
+   const float IminL = fminf(fminf(ILm, ILp), IL), ImaxL = fmaxf(fmaxf(ILm, ILp), IL);
+   const float dLR = fmaxf(0.f, fmaxf(IL - ImaxR, IminR - IL));
+   const float dRL = fmaxf(0.f, fmaxf(IR - ImaxL, IminL - IR));
+   return fabsf(fminf(dLR, dRL));
+}
+
+template <int DIST>
+__device__ __forceinline__ float cell_cost(const CostArgs &A, int px, int py, int qx, int qy) {
+   const long long np = (long long)A.nx * A.ny, vnp = (long long)A.vnx * A.vny;
+   const long long pi = px + (long long)py * A.nx, qi = qx + (long long)qy * A.vnx;
+   if (DIST == DIST_AD || DIST == DIST_SD) {   // mgm_costvolume.h:23-44
+      float acc = 0.f;
+      for (int c = 0; c < A.nch; ++c) {
+         float x = __ldg(A.u + pi + c * np) - __ldg(A.v + qi + c * vnp);
+         x = sel_max(x, -x);
+         acc += (DIST == DIST_SD) ? x * x : x;
+      }
+      return acc;
+   } else if (DIST == DIST_CENSUS) {   // mgm_costvolume.h:65-78
+      float r = 0.f;
+      for (int t = 0; t < A.nch; ++t) r += (float)__popc(__ldg(A.cu + pi + t * np) ^ __ldg(A.cv + qi + t * vnp));
+      if (A.nch == 1) return r;
+      return (float)((double)r / (double)A.nch);
+   } else if (DIST == DIST_BTAD || DIST == DIST_BTSD) {   // mgm_costvolume.h:114-133
+      float acc = 0.f;
+      for (int c = 0; c < A.nch; ++c) {
+         const float x = bt_channel(A.u + (long long)py * A.nx + c * np, A.v + (long long)qy * A.vnx + c * vnp,
+                                    A.nx, A.vnx, px, qx);
+         acc += (DIST == DIST_BTSD) ? x * x : x;
+      }
+      return acc;
+   } else {   // clipped NCC, mgm_costvolume.h:137-165
+      const int h = A.win / 2;
+      float NCC = 0.f;
+      for (int c = 0; c < A.nch; ++c) {
+         float mu1 = 0.f, mu2 = 0.f, s1 = 0.f, s2 = 0.f, prod = 0.f;
+         int n = 0;
+         for (int i = -h; i <= h; ++i)
+            for (int j = -h; j <= h; ++j) {   // dx outer, dy inner
+               const int ax = px + i, ay = py + j, bx = qx + i, by = qy + j;
+               if (ax < 0 || ay < 0 || ax >= A.nx || ay >= A.ny) return MGM_INF;
+               if (bx < 0 || by < 0 || bx >= A.vnx || by >= A.vny) return MGM_INF;
+               const float v1 = __ldg(A.u + ax + (long long)ay * A.nx + c * np);
+               const float v2 = __ldg(A.v + bx + (long long)by * A.vnx + c * vnp);
+               if (v1 != v1 || v2 != v2) return MGM_INF;
+               mu1 += v1; mu2 += v2;
+               s1 += v1 * v1; s2 += v2 * v2; prod += v1 * v2;
+               ++n;
+            }
+         const float fn = (float)n;
+         mu1 = __fdiv_rn(mu1, fn); mu2 = __fdiv_rn(mu2, fn);
+         s1 = __fdiv_rn(s1, fn); s2 = __fdiv_rn(s2, fn); prod = __fdiv_rn(prod, fn);
+         const float num = prod - mu1 * mu2;
+         const float var = (s1 - mu1 * mu1) * (s2 - mu2 * mu2);
+         const double den = (0.0000001 > (double)var) ? 0.0000001 : (double)var;
+         NCC = (float)((double)NCC + (double)num / sqrt(den));
+      }
+      const float fnch = (float)A.nch;
+      float t = (NCC < fnch) ? NCC : fnch;
+      t = (0.f > t) ? 0.f : t;
+      return (fnch - t) * 64.f;
+   }
+}
+
+// ------------------------------------------------------------------ K2 cost volume: one warp per pixel
+template <int DIST>
+__global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, int dmin, int L, int VS, float cap,
+                                                             float *__restrict__ cc) {
+   const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const long long np = (long long)A.nx * A.ny;
+   const int nq = VS >> 2;
+   for (long long p = (long long)blockIdx.x * warps + wid; p < np; p += (long long)gridDim.x * warps) {
+      const int x = (int)(p % A.nx), y = (int)(p / A.nx);
+      float4 *dst = reinterpret_cast<float4 *>(cc + (size_t)p * VS);
+      bool anyfinite = false;
+      for (int q = lane; q < nq; q += 32) {
+         float e4[4];
+#pragma unroll
+         for (int j = 0; j < 4; ++j) {
+            const int k = q * 4 + j;
+            float e = MGM_INF;   // padding labels
+            if (k < L) {
+               const int qx = x + dmin + k;
+               e = cap;   // truncDist * nch' when the match falls outside v (mgm_costvolume.h:398-400)
+               if (qx >= 0 && qx < A.vnx && y < A.vny) e = cell_cost<DIST>(A, x, y, qx, y);
+               e = sel_min(e, cap);   // :403 (NaN cost -> cap)
+               anyfinite |= (fabsf(e) < MGM_INF);
+            }
+            e4[j] = e;
+         }
+         dst[q] = make_float4(e4[0], e4[1], e4[2], e4[3]);
+      }
+      if (!__any_sync(0xffffffffu, anyfinite)) {   // no valid hypothesis: all costs become 0 (:414-421)
+         for (int q = lane; q < nq; q += 32) {
+            const int k = q * 4;
+            dst[q] = make_float4(k < L ? 0.f : MGM_INF, k + 1 < L ? 0.f : MGM_INF, k + 2 < L ? 0.f : MGM_INF,
+                                 k + 3 < L ? 0.f : MGM_INF);
+         }
+      }
+   }
+}
+
+// ------------------------------------------------------------------ layout helpers
+// dense [npix][L] (the flat Dvec layout of mgm_costvolume.h:276-299) <-> padded [npix][VS]
+__global__ void mgm_pad_volume_kernel(const float *__restrict__ src, float *__restrict__ dst, long long npix, int L,
+                                      int VS, long long sp, long long sl) {
+   // src element (p,o) at src[p*sp + o*sl]: (sp,sl) = (L,1) pixel-major, (1,npix) label-major planes
+   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= npix * VS) return;
+   const long long p = i / VS;
+   const int o = (int)(i - p * VS);
+   dst[i] = (o < L) ? src[p * sp + (long long)o * sl] : MGM_INF;
+}
+__global__ void mgm_unpad_volume_kernel(const float *__restrict__ src, float *__restrict__ dst, long long npix,
+                                        int L, int VS) {
+   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= npix * L) return;
+   const long long p = i / L;
+   const int o = (int)(i - p * L);
+   dst[i] = src[p * VS + o];
+}
+
+// flags: bit0 a vector without any finite entry, bit1 NaN, bit2 -INF (fast-path preconditions)
+__global__ void mgm_validate_volume_kernel(const float *__restrict__ cc, long long npix, int L, int VS,
+                                           int *__restrict__ flags) {
+   const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   for (long long p = (long long)blockIdx.x * warps + wid; p < npix; p += (long long)gridDim.x * warps) {
+      bool fin = false, bad_nan = false, bad_ninf = false;
+      for (int o = lane; o < L; o += 32) {
+         const float v = cc[(size_t)p * VS + o];
+         fin |= fabsf(v) < MGM_INF;
+         bad_nan |= (v != v);
+         bad_ninf |= (v == -MGM_INF);
+      }
+      const bool f = __any_sync(0xffffffffu, fin);
+      const bool n = __any_sync(0xffffffffu, bad_nan);
+      const bool i = __any_sync(0xffffffffu, bad_ninf);
+      if (lane == 0) {
+         const int fl = (f ? 0 : 1) | (n ? 2 : 0) | (i ? 4 : 0);
+         if (fl) atomicOr(flags, fl);
+      }
+   }
+}
+
+// flags: bit0 some weight != 1, bit1 a weight that is negative / NaN / INF
+__global__ void mgm_scan_weights_kernel(const float *__restrict__ w, long long n, int *__restrict__ flags) {
+   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   int fl = 0;
+   if (i < n) {
+      const float v = w[i];
+      if (v != 1.0f) fl |= 1;
+      if (!(v >= 0.f) || !(fabsf(v) < MGM_INF)) fl |= 2;
+   }
+   fl = __reduce_or_sync(0xffffffffu, fl);
+   if ((threadIdx.x & 31) == 0 && fl) atomicOr(flags, fl);
+}
+
+// ------------------------------------------------------------------ host launchers
+static inline unsigned blocks_for(long long n, int b) { return (unsigned)((n + b - 1) / b); }
+
+cudaError_t weights_launch(const float *d_u, int nx, int ny, int nch, float aP, float aThresh, float *d_w,
+                           int *d_flag, cudaStream_t st) {
+   const long long n = (long long)nx * ny * 8;
+   mgm_weights_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_u, nx, ny, nch, aP, aThresh, d_w, d_flag);
+   return cudaGetLastError();
+}
+
+cudaError_t census_launch(const float *d_u, int nx, int ny, int nch, int win, uint32_t *d_out, cudaStream_t st) {
+   const int r = win / 2;
+   mgm_census_kernel<<<blocks_for((long long)nx * ny, 128), 128, 0, st>>>(d_u, nx, ny, nch, r,
+                                                                          census_nwords(nch, win), d_out);
+   return cudaGetLastError();
+}
+
+cudaError_t sobelx_launch(const float *d_u, int nx, int ny, int nch, float *d_out, cudaStream_t st) {
+   mgm_sobelx_kernel<<<blocks_for((long long)nx * ny * nch, 256), 256, 0, st>>>(d_u, nx, ny, nch, d_out);
+   return cudaGetLastError();
+}
+
+cudaError_t costvolume_launch(int dist, const float *d_u, const float *d_v, const uint32_t *d_cu,
+                              const uint32_t *d_cv, int nx, int ny, int vnx, int vny, int nch, int win, int dmin,
+                              int L, int VS, float truncDist, float *d_cc, int num_sms, cudaStream_t st) {
+   CostArgs A;
+   A.u = d_u; A.v = d_v; A.cu = d_cu; A.cv = d_cv;
+   A.nx = nx; A.ny = ny; A.vnx = vnx; A.vny = vny; A.nch = nch; A.win = win;
+   const float cap = truncDist * (float)nch;   // nch of the image the cost function reads (:398)
+   const long long np = (long long)nx * ny;
+   long long want = (np + 7) / 8;
+   unsigned grid = (unsigned)((want < (long long)num_sms * 16) ? want : (long long)num_sms * 16);
+   if (grid < 1) grid = 1;
+   switch (dist) {
+   case DIST_AD: mgm_costvolume_kernel<DIST_AD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_cc); break;
+   case DIST_SD: mgm_costvolume_kernel<DIST_SD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_cc); break;
+   case DIST_CENSUS: mgm_costvolume_kernel<DIST_CENSUS><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_cc); break;
+   case DIST_NCC: mgm_costvolume_kernel<DIST_NCC><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_cc); break;
+   case DIST_BTAD: mgm_costvolume_kernel<DIST_BTAD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_cc); break;
+   default: mgm_costvolume_kernel<DIST_BTSD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_cc); break;
+   }
+   return cudaGetLastError();
+}
+
+cudaError_t pad_volume_launch(const float *d_src, float *d_dst, long long npix, int L, int VS, int label_major,
+                              cudaStream_t st) {
+   const long long sp = label_major ? 1 : L, sl = label_major ? npix : 1;
+   mgm_pad_volume_kernel<<<blocks_for(npix * VS, 256), 256, 0, st>>>(d_src, d_dst, npix, L, VS, sp, sl);
+   return cudaGetLastError();
+}
+cudaError_t unpad_volume_launch(const float *d_src, float *d_dst, long long npix, int L, int VS, cudaStream_t st) {
+   mgm_unpad_volume_kernel<<<blocks_for(npix * L, 256), 256, 0, st>>>(d_src, d_dst, npix, L, VS);
+   return cudaGetLastError();
+}
+cudaError_t validate_volume_launch(const float *d_cc, long long npix, int L, int VS, int *d_flags, int num_sms,
+                                   cudaStream_t st) {
+   long long want = (npix + 7) / 8;
+   unsigned grid = (unsigned)((want < (long long)num_sms * 16) ? want : (long long)num_sms * 16);
+   if (grid < 1) grid = 1;
+   mgm_validate_volume_kernel<<<grid, 256, 0, st>>>(d_cc, npix, L, VS, d_flags);
+   return cudaGetLastError();
+}
+cudaError_t scan_weights_launch(const float *d_w, long long n, int *d_flags, cudaStream_t st) {
+   mgm_scan_weights_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_w, n, d_flags);
+   return cudaGetLastError();
+}
+
+}  // namespace mgm

@@ -1,0 +1,203 @@
+// K5 -- ordered sweep sum + over-count fix + winner-take-all + sub-pixel refinement.
+// Replaces mgm_core.cc:582-609 (S += Lr in sweep order, S -= (NDIR-1)*C, first
+// finite minimum wins) fused with mgm_refine.h:40-70 / refine.h (vfit, parabola,
+// cubic, parabolaOCV on S[o-1..o+2]).
+//
+// One warp per pixel, lanes over labels with 16-byte accesses.  The per-sweep
+// volumes may live on peer GPUs (multi-GPU direction sharding): the kernel only
+// sees pointers, the additions are always performed in sweep order 0..NDIR-1 so
+// the result does not depend on where a sweep was computed.
+#include "wta.cuh"
+
+namespace mgm {
+
+// ---- refine.h restated; v = {S(o-1), S(o), S(o+1), S(o+2)} -------------------------------
+__device__ void fit_vshape(const float *v, float *vmin, float *xmin) {   // refine.h:70-92
+   if ((v[1] > v[0]) && (v[1] > v[2])) { *vmin = v[1]; *xmin = 0.f; return; }
+   float slope = v[2] - v[1];
+   if ((v[2] - v[1]) < (v[0] - v[1])) slope = v[0] - v[1];
+   const float x = __fdiv_rn(v[0] - v[2], 2.f * slope);
+   *xmin = x;
+   *vmin = v[2] + (x - 1.f) * slope;
+}
+__device__ void fit_parabola(const float *v, float *vmin, float *xmin, bool ocv) {   // refine.h:6-68
+   if (v[1] > v[0] && v[1] > v[2]) { *xmin = 0.f; *vmin = v[1]; return; }
+   const float c = v[1];
+   float b = (v[2] - v[0]) * 0.5f;
+   float a = (v[2] - 2.f * v[1] + v[0]) * 0.5f;
+   float x;
+   if (ocv) {
+      a *= 2.f; b *= 2.f;
+      a = (a > 1.0f) ? a : 1.0f;
+      x = __fdiv_rn(-b + a, 2.f * a);
+   } else {
+      x = __fdiv_rn(-b, 2.f * a);
+   }
+   if (x > 1.f) x = 1.f;
+   if (x < -1.f) x = -1.f;
+   *vmin = (a * x + b) * x + c;
+   *xmin = x;
+}
+__device__ float cubic_at(const float *p, const float x) {   // refine.h:94-98 (double arithmetic, float x)
+   const double xd = (double)x;
+   const double p0 = p[0], p1 = p[1], p2 = p[2], p3 = p[3];
+   const float d12 = p[1] - p[2];            // float subtraction inside 3.0*(p[1]-p[2])
+   const float d20 = p[2] - p[0];            // p[2]-p[0] is a float subtraction too
+   double inner = 3.0 * (double)d12 + p3 - p0;
+   double mid = 2.0 * p0 - 5.0 * p1 + 4.0 * p2 - p3 + xd * inner;
+   double outer = (double)d20 + xd * mid;
+   return (float)(p1 + 0.5 * xd * outer);
+}
+__device__ void fit_cubic(const float *p, float *vmin, float *xmin) {   // refine.h:102-145
+   float pm, xm;
+   if (p[1] < p[2]) { pm = p[1]; xm = 0.f; } else { pm = p[2]; xm = 1.f; }
+   const float d12 = p[1] - p[2];
+   const float d20 = p[2] - p[0];
+   const double a = 1.5 * (3.0 * (double)d12 + (double)p[3] - (double)p[0]);
+   const double b = 2.0 * (double)p[0] - 5.0 * (double)p[1] + 4.0 * (double)p[2] - (double)p[3];
+   const double c = 0.5 * (double)d20;
+   const double discr = b * b - 4.0 * a * c;
+   if (discr >= 0) {
+      const double sq = sqrt(discr);
+      const double z1 = (-b + sq) / (2.0 * a);
+      const double z2 = (-b - sq) / (2.0 * a);
+      if (z1 > 0.0 && z1 < 1.0) {
+         float t = cubic_at(p, (float)z1);
+         if (t < pm) { pm = t; xm = (float)z1; }
+      }
+      if (z2 > 0.0 && z2 < 1.0) {
+         float t = cubic_at(p, (float)z2);
+         if (t < pm) { pm = t; xm = (float)z2; }
+      }
+   }
+   *vmin = pm; *xmin = xm;
+}
+
+__device__ __forceinline__ bool finitef(float v) { return fabsf(v) < MGM_INF; }   // false for NaN and +-INF
+
+__global__ void __launch_bounds__(256) mgm_wta_kernel(const WtaParams P) {
+   extern __shared__ float s_all[];
+   const int warps_per_cta = blockDim.x >> 5;
+   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   float *sS = s_all + (size_t)wid * P.VS;
+   const int nq = P.VS >> 2;
+   const float fixmul = (float)(P.ndir - 1);
+   for (long long pix = (long long)blockIdx.x * warps_per_cta + wid + P.pix_begin; pix < P.pix_end;
+        pix += (long long)gridDim.x * warps_per_cta) {
+      float best = MGM_INF;
+      int besto = -1;
+      const size_t base = (size_t)pix * P.VS;
+      for (int q = lane; q < nq; q += 32) {
+         const size_t off = base + (size_t)q * 4;
+         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+         for (int p = 0; p < P.ndir; ++p) {   // S = ((0 + L0) + L1) + ...   mgm_core.cc:582-587
+            const float4 l = __ldcs(reinterpret_cast<const float4 *>(P.ldir[p] + off));
+            s.x += l.x; s.y += l.y; s.z += l.z; s.w += l.w;
+         }
+         if (P.fix) {   // mgm_core.cc:598-599
+            const float4 c = __ldcs(reinterpret_cast<const float4 *>(P.cc + off));
+            s.x = s.x - fixmul * c.x; s.y = s.y - fixmul * c.y;
+            s.z = s.z - fixmul * c.z; s.w = s.w - fixmul * c.w;
+         }
+         *reinterpret_cast<float4 *>(sS + q * 4) = s;
+         if (P.S_out) {
+            // S_out is dense [pix][L]: element-wise stores (L need not be a multiple of 4)
+            float *dst = P.S_out + (size_t)pix * P.L + (size_t)q * 4;
+            const int o0 = q * 4;
+            if (o0 + 0 < P.L) dst[0] = s.x;
+            if (o0 + 1 < P.L) dst[1] = s.y;
+            if (o0 + 2 < P.L) dst[2] = s.z;
+            if (o0 + 3 < P.L) dst[3] = s.w;
+         }
+         const int o0 = q * 4;   // labels beyond L hold INF-INF=NaN or INF: never finite
+         if (o0 + 0 < P.L && finitef(s.x) && best > s.x) { best = s.x; besto = o0; }
+         if (o0 + 1 < P.L && finitef(s.y) && best > s.y) { best = s.y; besto = o0 + 1; }
+         if (o0 + 2 < P.L && finitef(s.z) && best > s.z) { best = s.z; besto = o0 + 2; }
+         if (o0 + 3 < P.L && finitef(s.w) && best > s.w) { best = s.w; besto = o0 + 3; }
+      }
+      // first minimum wins: smaller value, then smaller label
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+         const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+         const int oo = __shfl_xor_sync(0xffffffffu, besto, d);
+         const bool take = (oo >= 0) && (besto < 0 || ob < best || (ob == best && oo < besto));
+         if (take) { best = ob; besto = oo; }
+      }
+      __syncwarp();
+      if (lane == 0) {
+         float minP, minL = best;
+         if (besto < 0) {
+            minP = __int_as_float(0x7fc00000);   // reference leaves it uninitialised (mgm_core.cc:594)
+         } else {
+            const int o = besto + P.dmin;
+            minP = (float)o;
+            if (P.refine != 0) {
+               const int oi = (int)minP;   // mgm_refine.h:57
+               if (oi - 1 >= P.dmin && oi + 2 <= P.dmin + P.L - 1) {
+                  const float *v = sS + (besto - 1);
+                  float dx = 0.f;
+                  if (P.refine == 1) fit_vshape(v, &minL, &dx);
+                  else if (P.refine == 2) fit_parabola(v, &minL, &dx, false);
+                  else if (P.refine == 3) fit_cubic(v, &minL, &dx);
+                  else fit_parabola(v, &minL, &dx, true);
+                  minP = (float)oi + dx;
+               }
+            }
+         }
+         P.out[pix] = minP;
+         P.outcost[pix] = minL;
+      }
+      __syncwarp();
+   }
+}
+
+// Stand-alone sub-pixel refinement of given labels on a dense volume S [npix][L]
+// (subpixel_refinement_sgm mgm_refine.h:40-70, for callers that keep the reference's
+// two-call sequence mgm() -> refine()).
+__global__ void mgm_refine_kernel(const float *__restrict__ S, long long npix, int L, int dmin, int method,
+                                  float *__restrict__ out, float *__restrict__ outcost) {
+   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= npix) return;
+   float minP = out[i], minL = outcost[i];
+   if (minP != minP) return;   // no finite label (undefined in the reference)
+   const int o = (int)minP;
+   if (o - 1 >= dmin && o + 2 <= dmin + L - 1) {
+      const float *s = S + (size_t)i * L + (o - dmin);
+      const float v[4] = {s[-1], s[0], s[1], s[2]};
+      float dx = 0.f;
+      if (method == 1) fit_vshape(v, &minL, &dx);
+      else if (method == 2) fit_parabola(v, &minL, &dx, false);
+      else if (method == 3) fit_cubic(v, &minL, &dx);
+      else fit_parabola(v, &minL, &dx, true);
+      minP = (float)o + dx;
+   }
+   out[i] = minP;
+   outcost[i] = minL;
+}
+
+cudaError_t refine_launch(const float *d_S, long long npix, int L, int dmin, int method, float *d_out,
+                          float *d_outcost, cudaStream_t st) {
+   mgm_refine_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(d_S, npix, L, dmin, method, d_out, d_outcost);
+   return cudaGetLastError();
+}
+
+cudaError_t wta_launch(const WtaParams &P, int num_sms, cudaStream_t st) {
+   const int block = 256;
+   const size_t smem = (size_t)(block / 32) * P.VS * sizeof(float);
+   cudaError_t e = cudaFuncSetAttribute(mgm_wta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+   if (e != cudaSuccess) return e;
+   int per_sm = 0;
+   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mgm_wta_kernel, block, smem);
+   if (e != cudaSuccess) return e;
+   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+   const long long npix = P.pix_end - P.pix_begin;
+   long long want = (npix + block / 32 - 1) / (block / 32);
+   long long grid = (long long)num_sms * per_sm;
+   if (grid > want) grid = want;
+   if (grid < 1) grid = 1;
+   mgm_wta_kernel<<<(unsigned)grid, block, smem, st>>>(P);
+   return cudaGetLastError();
+}
+
+}  // namespace mgm

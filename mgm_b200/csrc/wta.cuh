@@ -1,0 +1,23 @@
+// Parameters of the fused sum + over-count fix + WTA + sub-pixel kernel (wta.cu).
+#pragma once
+#include "common.cuh"
+
+namespace mgm {
+
+struct WtaParams {
+   const float *ldir[16];   // per-sweep message volumes [npix][VS] in sweep order (local or peer memory)
+   const float *cc;         // matching costs [npix][VS]
+   float *out;              // [npix] disparity (integer WTA label + sub-pixel offset)
+   float *outcost;          // [npix]
+   float *S_out;            // optional dense [npix][L] corrected aggregated volume
+   long long pix_begin, pix_end;
+   int ndir, L, VS, dmin;
+   int fix;                 // SGM_FIX_OVERCOUNT
+   int refine;              // 0 none, 1 vfit, 2 parabola, 3 cubic, 4 parabolaOCV (mgm_refine.h:14-27)
+};
+
+cudaError_t wta_launch(const WtaParams &P, int num_sms, cudaStream_t st);
+cudaError_t refine_launch(const float *d_S, long long npix, int L, int dmin, int method, float *d_out,
+                          float *d_outcost, cudaStream_t st);
+
+}  // namespace mgm
