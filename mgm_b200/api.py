@@ -215,7 +215,7 @@ class Context:
     # ------------------------------------------------------------------ device-pointer interface
     @staticmethod
     def padded_labels(L):
-        return (int(L) + 3) & ~3
+        return (int(L) + 31) & ~31
 
     def weights_dev(self, d_u, nx, ny, nch, aP, aThresh, d_w):
         self._check(self.lib.mgmb200_weights_dev(self._ctx, ctypes.c_void_p(d_u), nx, ny, nch, ctypes.c_float(aP),

@@ -31,6 +31,7 @@ namespace mgm {
 
 static constexpr int RV = 8;   // virtual-row ring (pixels of the previous band's last row)
 static constexpr int PF = 3;   // boundary prefetch distance in pixels
+static constexpr int G = MGM_AGG_GROUP;   // lanes cooperating on one scan row
 
 enum PredType { PRED_SAME = 0, PRED_UP = 1, PRED_UPL = 2, PRED_UPR = 3 };
 
@@ -49,12 +50,67 @@ __device__ __forceinline__ float sgm_x(float l, float c, float r, float p1, floa
    return fminf(fminf(c, fminf(l, r) + p1), cap) - m;
 }
 
+// Truncated-linear min-convolution (minConvTruncatedLinear, mgm_core.cc:152-163) of src into dst by a PAIR
+// of adjacent lanes: lane dir=0 runs the forward recurrence F[o] = min(F[o-1]+c, M[o]) upwards, lane dir=1
+// the same recurrence downwards on the ORIGINAL values (Bp).  Because x -> RN(x+c) is monotone and
+// inflationary (c >= 0) the reference's backward pass over F equals min(F, Bp) bit for bit, so the two
+// sequential chains can run concurrently and meet in the middle: each lane writes its partial values for
+// its first half of the labels, then finishes the other half with the partner's partials.  Every addition
+// is performed in the same order as the reference's sequential loops.  The result written to dst is
+// min(minconv, cap) - sub.  Loads are issued one chunk ahead of the dependent add/min chain.
+__device__ __forceinline__ void minconv_pair(const float4 *src, float4 *dst, int nq, int dir, float c, float cap,
+                                             float sub, unsigned pmask) {
+   const int h = nq >> 1;   // nq is even
+   const int q0 = dir ? (nq - 1) : 0, dq = dir ? -1 : 1;
+   float run = MGM_INF;
+   float4 v = src[q0];
+   int q = q0;
+   for (int i = 0; i < h; ++i, q += dq) {
+      const float4 vn = src[q + dq];   // chunk i+1 always exists (h < nq)
+      float a0 = dir ? v.w : v.x, a1 = dir ? v.z : v.y, a2 = dir ? v.y : v.z, a3 = dir ? v.x : v.w;
+      a0 = run = fminf(run + c, a0);
+      a1 = run = fminf(run + c, a1);
+      a2 = run = fminf(run + c, a2);
+      a3 = run = fminf(run + c, a3);
+      dst[q] = dir ? make_float4(a3, a2, a1, a0) : make_float4(a0, a1, a2, a3);
+      v = vn;
+   }
+   __syncwarp(pmask);
+   float4 o = dst[q];   // partner's partial values
+   for (int i = h; i < nq; ++i, q += dq) {
+      const bool more = (i + 1 < nq);
+      const float4 vn = more ? src[q + dq] : v;
+      const float4 on = more ? dst[q + dq] : o;
+      float a0 = dir ? v.w : v.x, a1 = dir ? v.z : v.y, a2 = dir ? v.y : v.z, a3 = dir ? v.x : v.w;
+      const float b0 = dir ? o.w : o.x, b1 = dir ? o.z : o.y, b2 = dir ? o.y : o.z, b3 = dir ? o.x : o.w;
+      a0 = run = fminf(run + c, a0);
+      a1 = run = fminf(run + c, a1);
+      a2 = run = fminf(run + c, a2);
+      a3 = run = fminf(run + c, a3);
+      a0 = fminf(fminf(a0, b0), cap) - sub;
+      a1 = fminf(fminf(a1, b1), cap) - sub;
+      a2 = fminf(fminf(a2, b2), cap) - sub;
+      a3 = fminf(fminf(a3, b3), cap) - sub;
+      dst[q] = dir ? make_float4(a3, a2, a1, a0) : make_float4(a0, a1, a2, a3);
+      v = vn; o = on;
+   }
+   __syncwarp(pmask);
+}
+
+template <int K>
+__device__ __forceinline__ float4 div4_by_k(const float4 &e) {
+   return make_float4(div_by_k<K>(e.x), div_by_k<K>(e.y), div_by_k<K>(e.z), div_by_k<K>(e.w));
+}
+
 template <int POT, int K, bool WEIGHTED, bool DIAG>
 __device__ void run_band(const AggParams &P, const int pass, const int band, unsigned char *smem) {
    constexpr int SIG = (DIAG || K == 4) ? 2 : 1;
    constexpr int R = SIG + 2;
    constexpr bool NEEDM = WEIGHTED || (POT == POT_TRUNC && K == 2);
+   constexpr bool WTRUNC = WEIGHTED && POT == POT_TRUNC;
+   constexpr bool CHAINS = !WEIGHTED && POT == POT_TRUNC;   // phase-2 transform done by lane pairs
    constexpr int CLS = DIAG ? 1 : 0;
+   constexpr int JB = (K <= 3) ? 4 : 2;   // chunks per lane whose loads are issued together in the gather
 
    const PassGeom g = pass_geometry(pass, P.nx, P.ny);
    const int maxii = g.maxii, maxjj = g.maxjj;
@@ -62,18 +118,30 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    const int TS = P.TS[CLS];
    const int VS = P.VS;
    const int nq = VS >> 2;
+   const int nj = nq / G;   // chunks per lane (VS is a multiple of 4*G)
    const uint32_t vbytes = (uint32_t)VS * 4u;
-   const int t = threadIdx.x;
+   const int tid = threadIdx.x;
    const int ncomp = blockDim.x - 32;
-   const bool is_prod = (t == ncomp);
+   const int plane = tid - ncomp;             // lane of the producer warp (>= 0 there)
+   const bool is_prod = (tid == ncomp);
    const int row0 = band * T;
    const int nrows = min(T, maxjj - row0);
-   const int ys = row0 + t;
-   const bool rowok = (t < nrows);
    const bool has_prev = band > 0;
    const bool has_next = row0 + T < maxjj;
-   const bool last_row = rowok && (t == nrows - 1) && has_next;
    const int nsteps = maxii + SIG * (nrows - 1);
+
+   // group-per-row mapping (gather, label-parallel transforms)
+   const int r = tid / G, gl = tid % G;
+   const unsigned gmask = ((1u << G) - 1u) << ((tid & 31) & ~(G - 1));
+   const bool rowok = (tid < ncomp) && (r < nrows);
+   const int ys = row0 + r;
+   const bool last_row = rowok && (r == nrows - 1) && has_next;
+   // lane-pair mapping for the sequential min-convolution chains: pair p of a warp is lanes (p, p+16); the
+   // forward halves of 8 consecutive rows then sit in one quarter-warp and hit 8 different bank groups
+   // (the row stride is an odd number of 16-byte units), likewise the backward halves
+   const int pair_idx = (tid >> 5) * 16 + (tid & 15);
+   const int pair_dir = (tid >> 4) & 1;
+   const unsigned pmask = 0x00010001u << (tid & 15);
 
    uint64_t *cbar = reinterpret_cast<uint64_t *>(smem + P.off_cbar);
    uint64_t *vbar = reinterpret_cast<uint64_t *>(smem + P.off_vbar);
@@ -83,35 +151,63 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    float *thr = reinterpret_cast<float *>(smem + P.off_thr);
    uint32_t *phase = reinterpret_cast<uint32_t *>(smem + P.off_phase);   // persistent mbarrier parities
 
-   float *mybase = thr + (size_t)t * TS;                    // ring slots [R][VS]
-   float *mycb = mybase + R * VS;                            // cost buffers [2][VS]
-   float *myscr = mycb + 2 * VS;                             // scratch (weighted truncated-linear only)
-   const float *upbase = mybase - TS;                        // row t-1 (t>0)
+   // per-row shared memory: ring slots [R][VS] | cost buffers [2][VS] | scratch [K][VS] (weighted trunc)
+   auto row_base = [&](int rr) -> float * { return thr + (size_t)rr * TS; };
+   auto slot_of = [&](int rr, int px) -> float * {
+      return (rr < 0) ? virt + (px & (RV - 1)) * VS : row_base(rr) + (px % R) * VS;
+   };
+   auto m_of = [&](int rr, int px) -> float { return (rr < 0) ? vms[px & (RV - 1)] : msr[rr * 4 + (px % R)]; };
+   // predecessor k of pixel (xs) of row rr: which row's slot, which pixel
+   auto pred_of = [&](int rr, int xs, int k, int &prow, int &ppx) {
+      const int pt = pred_type<DIAG>(k);
+      ppx = (pt == PRED_UP) ? xs : (pt == PRED_UPR ? xs + 1 : xs - 1);
+      prow = (pt == PRED_SAME) ? rr : rr - 1;   // -1 = virtual row fed from the previous band
+   };
 
    const float *ccv = P.cc;
    float *ldir = P.ldir[pass];
-   float *bnd_out = P.bnd[pass] + (size_t)band * maxii * VS;            // written by this band's last row
+   float *bnd_out = P.bnd[pass] + (size_t)band * maxii * VS;
    float *bndm_out = P.bndm[pass] + (size_t)band * maxii;
    const float *bnd_in = has_prev ? P.bnd[pass] + (size_t)(band - 1) * maxii * VS : nullptr;
    const float *bndm_in = has_prev ? P.bndm[pass] + (size_t)(band - 1) * maxii : nullptr;
    int *prog_out = P.progress[pass] + band;
    const int *prog_in = has_prev ? P.progress[pass] + band - 1 : nullptr;
+   const size_t wplane = (size_t)P.nx * P.ny;
 
-   const long long pix0 = g.base0 + (long long)ys * g.dys;   // pixel of (0, ys)
+   const long long pix0 = g.base0 + (long long)ys * g.dys;   // pixel of (0, ys) for my group's row
 
    uint32_t cph = 0, vph = 0;
-   if (t < ncomp) cph = phase[t];
-   if (t == 0) vph = phase[ncomp];
+   if (tid < ncomp && r < T) cph = phase[r];
+   const int vph_idx = max(P.T[0], P.T[1]);
+   if (tid < G) vph = phase[vph_idx];
    int next_px = 0;   // producer: next boundary pixel to fetch
 
-   // prologue: first cost vector of every row, first boundary pixels
-   if (rowok) {
+   // The producer warp owns every TMA load: lane l feeds the cost buffers of rows l, l+32, ...
+   // Pixel px of a row goes to cost buffer px&1; it may be (re)filled once the step that used the
+   // buffer for pixel px-2 has ended, i.e. from the top of the step in which the row handles px-1.
+   auto issue_cost_loads = [&](int s) {
+      for (int rr = plane; rr < nrows; rr += 32) {
+         const int px = s - SIG * rr + 1;   // the pixel this row handles in the NEXT step
+         if (px >= 0 && px < maxii) {
+            const long long pp = g.base0 + (long long)(row0 + rr) * g.dys + (long long)px * g.dxs;
+            uint64_t *bar = &cbar[2 * rr + (px & 1)];
+            mbar_expect_tx(bar, vbytes);
+            tma_load_1d(row_base(rr) + (R + (px & 1)) * VS, ccv + (size_t)pp * VS, vbytes, bar);
+         }
+      }
+   };
+   if (plane >= 0) {
       fence_proxy_async_smem();
-      mbar_expect_tx(&cbar[2 * t], vbytes);
-      tma_load_1d(mycb, ccv + (size_t)pix0 * VS, vbytes, &cbar[2 * t]);
+      issue_cost_loads(-1);   // pixel 0 of row 0 (the other rows start later)
    }
 
+   long long tA = 0, tW1 = 0, tB = 0, tW2 = 0, tP = 0, tC = 0;
    for (int s = 0; s < nsteps; ++s) {
+      const long long c0 = clock64();
+      if (plane >= 0) {
+         fence_proxy_async_smem();   // the buffers were last touched by generic-proxy accesses (before the barrier)
+         issue_cost_loads(s);
+      }
       if (is_prod && has_prev) {
          const int lim = min(maxii - 1, s + 1 + PF);
          while (next_px <= lim) {
@@ -124,251 +220,232 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
             ++next_px;
          }
       }
-      const int xs = s - SIG * t;
-      if (rowok && xs >= 0 && xs < maxii) {
-         const long long pix = pix0 + (long long)xs * g.dxs;
-         // (a) my earlier bulk stores no longer read shared memory; publish the boundary progress
-         if (last_row) {
+      // virtual row: group 0 waits one step AHEAD for the boundary pixels (xs+2 is first read at step xs+1),
+      // so the end-of-step barrier publishes them to every thread that reads row -1 in the next step
+      if (tid < G && nrows > 0 && has_prev && s < maxii) {
+         if (s == 0) {
+            for (int px = 0; px <= min(2, maxii - 1); ++px) {
+               mbar_wait(&vbar[px & (RV - 1)], (vph >> (px & (RV - 1))) & 1u);
+               vph ^= 1u << (px & (RV - 1));
+            }
+         } else if (s + 2 < maxii) {
+            const int sl = (s + 2) & (RV - 1);
+            mbar_wait(&vbar[sl], (vph >> sl) & 1u);
+            vph ^= 1u << sl;
+         }
+      }
+      const long long c1 = clock64();
+      const int xs = s - SIG * r;
+      const bool act = rowok && xs >= 0 && xs < maxii;
+      const long long pix = pix0 + (long long)xs * g.dxs;
+      const int cbi = xs & 1;
+      float *Cbf = row_base(r) + (R + cbi) * VS;
+      float4 *Cb = reinterpret_cast<float4 *>(Cbf);
+      float4 *cur = reinterpret_cast<float4 *>(row_base(r) + (act ? (xs % R) : 0) * VS);
+      float4 *gout = reinterpret_cast<float4 *>(ldir + (size_t)(act ? pix : 0) * VS);
+      const bool border = (xs == 0) || (ys == 0) || (xs == maxii - 1);
+      float m = MGM_INF;
+
+      // ---------------- phase 0 (weighted truncated-linear only): one lane pair per (row, neighbour)
+      if constexpr (WTRUNC) {
+         const int crow = pair_idx / K, ck = pair_idx % K, cdir = pair_dir;
+         const int cxs = s - SIG * crow;
+         if (tid < ncomp && pair_idx < K * nrows && cxs > 0 && cxs < maxii - 1 && (row0 + crow) != 0) {
+            int prow, ppx;
+            pred_of(crow, cxs, ck, prow, ppx);
+            const long long cpix = g.base0 + (long long)(row0 + crow) * g.dys + (long long)cxs * g.dxs;
+            const float wk = __ldg(P.w + (size_t)pass_weight_plane(pass, ck) * wplane + cpix);
+            const float mk = m_of(prow, ppx);
+            minconv_pair(reinterpret_cast<const float4 *>(slot_of(prow, ppx)),
+                         reinterpret_cast<float4 *>(row_base(crow) + (R + 2 + ck) * VS), nq, cdir, P.P1 * wk,
+                         mk + P.P2 * wk, mk, pmask);
+         }
+         __syncthreads();
+      }
+
+      // ---------------- phase 1: gather the message of pixel (xs,ys), G lanes per row
+      if (act) {
+         if (last_row && gl == 0 && xs > 0) {
+            // the boundary vector of pixel xs-1 was handed to the TMA one step ago: publish it
             tma_wait_all<0>();
-            if (xs > 0) {
-               fence_proxy_async();
-               __threadfence();
-               st_release(prog_out, xs);   // pixels [0,xs) of the boundary row are in global memory
-            }
-         } else {
-            tma_wait_read<0>();
+            fence_proxy_async();
+            __threadfence();
+            st_release(prog_out, xs);   // pixels [0,xs) of the boundary row are in global memory
          }
-         // (b) prefetch the next cost vector of this row
-         if (xs + 1 < maxii) {
-            const int nb = (xs + 1) & 1;
-            fence_proxy_async_smem();
-            mbar_expect_tx(&cbar[2 * t + nb], vbytes);
-            tma_load_1d(mycb + nb * VS, ccv + (size_t)(pix + g.dxs) * VS, vbytes, &cbar[2 * t + nb]);
-         }
-         // (c) this pixel's cost vector
-         const int cbi = xs & 1;
-         mbar_wait(&cbar[2 * t + cbi], (cph >> cbi) & 1u);
+         const long long cw0 = clock64();
+         mbar_wait(&cbar[2 * r + cbi], (cph >> cbi) & 1u);
          cph ^= (1u << cbi);
-         float4 *Cb = reinterpret_cast<float4 *>(mycb + cbi * VS);
-         float4 *cur = reinterpret_cast<float4 *>(mybase + (xs % R) * VS);
-         const bool border = (xs == 0) || (ys == 0) || (xs == maxii - 1);
+         tC += clock64() - cw0;
 
-         // virtual row: make sure the boundary pixels this step reads have landed
-         if (t == 0 && has_prev) {
-            if (xs == 1) {
-               for (int px = 0; px <= min(2, maxii - 1); ++px) {
-                  mbar_wait(&vbar[px & (RV - 1)], (vph >> (px & (RV - 1))) & 1u);
-                  vph ^= 1u << (px & (RV - 1));
-               }
-            } else if (xs >= 2 && xs + 1 < maxii) {
-               const int sl = (xs + 1) & (RV - 1);
-               mbar_wait(&vbar[sl], (vph >> sl) & 1u);
-               vph ^= 1u << sl;
-            }
-         }
-
-         float m = MGM_INF;
          if (border) {
-            for (int q = 0; q < nq; ++q) {
-               float4 c = Cb[q];
+            for (int j = 0; j < nj; ++j) {
+               const int q = gl + G * j;
+               const float4 c = Cb[q];
                m = hmin4(m, c);
-               cur[q] = c;
+               __stcs(gout + q, c);
             }
          } else {
-            // predecessor slots
             const float4 *S[K];
             float mk[K], wk[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-               const int pt = pred_type<DIAG>(k);
-               const int px = (pt == PRED_UP) ? xs : (pt == PRED_UPR ? xs + 1 : xs - 1);
-               const bool own = (pt == PRED_SAME);
-               const float *sp;
-               if (own) sp = mybase + (px % R) * VS;
-               else if (t == 0) sp = virt + (px & (RV - 1)) * VS;
-               else sp = upbase + (px % R) * VS;
-               S[k] = reinterpret_cast<const float4 *>(sp);
+               int prow, ppx;
+               pred_of(r, xs, k, prow, ppx);
+               S[k] = reinterpret_cast<const float4 *>(WTRUNC ? row_base(r) + (R + 2 + k) * VS : slot_of(prow, ppx));
                mk[k] = 0.f; wk[k] = 1.f;
-               if (NEEDM) mk[k] = own ? msr[t * 4 + (px % R)] : (t == 0 ? vms[px & (RV - 1)] : msr[(t - 1) * 4 + (px % R)]);
-               if (WEIGHTED) wk[k] = __ldg(P.w + (size_t)pass_weight_plane(pass, k) * P.nx * P.ny + pix);
+               if (NEEDM) mk[k] = m_of(prow, ppx);
+               if (WEIGHTED && !WTRUNC) wk[k] = __ldg(P.w + (size_t)pass_weight_plane(pass, k) * wplane + pix);
             }
-
-            if constexpr (!WEIGHTED) {
-               // ring slots already hold the producer-side transform
-               for (int q = 0; q < nq; ++q) {
-                  float4 c = Cb[q];
-                  float4 a[K];
+            if constexpr (!WEIGHTED || WTRUNC) {
+               // slots hold the neighbour-side transform already (producer row, or phase 0 scratch)
+               for (int j0 = 0; j0 < nj; j0 += JB) {
+                  float4 c[JB], a[K][JB];
 #pragma unroll
-                  for (int k = 0; k < K; ++k) a[k] = S[k][q];
-                  float4 o;
-                  if constexpr (POT == POT_TRUNC && K == 2) {   // update_cost2_trunclinear association, mgm_core.cc:216
-                     o.x = c.x + (((a[0].x - mk[0]) + a[1 % K].x) - mk[1 % K]) * 0.5f;
-                     o.y = c.y + (((a[0].y - mk[0]) + a[1 % K].y) - mk[1 % K]) * 0.5f;
-                     o.z = c.z + (((a[0].z - mk[0]) + a[1 % K].z) - mk[1 % K]) * 0.5f;
-                     o.w = c.w + (((a[0].w - mk[0]) + a[1 % K].w) - mk[1 % K]) * 0.5f;
-                  } else if constexpr (POT == POT_SGM && K == 2) {   // update_cost2: halves were taken by the producer
-                     o.x = c.x + (a[0].x + a[1 % K].x);
-                     o.y = c.y + (a[0].y + a[1 % K].y);
-                     o.z = c.z + (a[0].z + a[1 % K].z);
-                     o.w = c.w + (a[0].w + a[1 % K].w);
-                  } else {
-                     float4 e = a[0];
+                  for (int jj = 0; jj < JB; ++jj) {
+                     const int q = gl + G * min(j0 + jj, nj - 1);
+                     c[jj] = Cb[q];
 #pragma unroll
-                     for (int k = 1; k < K; ++k) { e.x += a[k].x; e.y += a[k].y; e.z += a[k].z; e.w += a[k].w; }
-                     o.x = c.x + div_by_k<K>(e.x);
-                     o.y = c.y + div_by_k<K>(e.y);
-                     o.z = c.z + div_by_k<K>(e.z);
-                     o.w = c.w + div_by_k<K>(e.w);
+                     for (int k = 0; k < K; ++k) a[k][jj] = S[k][q];
                   }
-                  m = hmin4(m, o);
-                  Cb[q] = o;
-                  cur[q] = o;
-               }
-            } else if constexpr (POT == POT_SGM) {
-               // update_costW with per-edge weights, mgm_core.cc:95-144
-               float pw[K], cap[K], lft[K];
-               float4 cv[K];
 #pragma unroll
-               for (int k = 0; k < K; ++k) {
-                  pw[k] = P.P1 * wk[k];
-                  cap[k] = mk[k] + P.P2 * wk[k];
-                  lft[k] = MGM_INF;
-                  cv[k] = S[k][0];
+                  for (int jj = 0; jj < JB; ++jj) {
+                     if (j0 + jj < nj) {
+                        const int q = gl + G * (j0 + jj);
+                        float4 o;
+                        if constexpr (POT == POT_TRUNC && K == 2 && !WEIGHTED) {   // update_cost2_trunclinear :216
+                           o.x = c[jj].x + (((a[0][jj].x - mk[0]) + a[1 % K][jj].x) - mk[1 % K]) * 0.5f;
+                           o.y = c[jj].y + (((a[0][jj].y - mk[0]) + a[1 % K][jj].y) - mk[1 % K]) * 0.5f;
+                           o.z = c[jj].z + (((a[0][jj].z - mk[0]) + a[1 % K][jj].z) - mk[1 % K]) * 0.5f;
+                           o.w = c[jj].w + (((a[0][jj].w - mk[0]) + a[1 % K][jj].w) - mk[1 % K]) * 0.5f;
+                        } else if constexpr (POT == POT_SGM && K == 2) {   // update_cost2: halves taken by the producer
+                           o.x = c[jj].x + (a[0][jj].x + a[1 % K][jj].x);
+                           o.y = c[jj].y + (a[0][jj].y + a[1 % K][jj].y);
+                           o.z = c[jj].z + (a[0][jj].z + a[1 % K][jj].z);
+                           o.w = c[jj].w + (a[0][jj].w + a[1 % K][jj].w);
+                        } else {
+                           float4 e = a[0][jj];
+#pragma unroll
+                           for (int k = 1; k < K; ++k) {
+                              e.x += a[k][jj].x; e.y += a[k][jj].y; e.z += a[k][jj].z; e.w += a[k][jj].w;
+                           }
+                           const float4 d = div4_by_k<K>(e);
+                           o.x = c[jj].x + d.x; o.y = c[jj].y + d.y; o.z = c[jj].z + d.z; o.w = c[jj].w + d.w;
+                        }
+                        m = hmin4(m, o);
+                        Cb[q] = o;
+                        __stcs(gout + q, o);
+                     }
+                  }
                }
-               for (int q = 0; q < nq; ++q) {
-                  float4 c = Cb[q];
+            } else {
+               // update_costW with per-edge weights (mgm_core.cc:95-144); slots hold the raw messages
+               float pw[K], cap[K];
+#pragma unroll
+               for (int k = 0; k < K; ++k) { pw[k] = P.P1 * wk[k]; cap[k] = mk[k] + P.P2 * wk[k]; }
+               for (int j = 0; j < nj; ++j) {
+                  const int q = gl + G * j;
+                  const float4 c = Cb[q];
                   float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                   for (int k = 0; k < K; ++k) {
-                     float4 v = cv[k];
-                     float4 nx4 = (q + 1 < nq) ? S[k][q + 1] : make_float4(MGM_INF, MGM_INF, MGM_INF, MGM_INF);
-                     e.x += sgm_x(lft[k], v.x, v.y, pw[k], cap[k], mk[k]);
+                     const float *sf = reinterpret_cast<const float *>(S[k]);
+                     const float4 v = S[k][q];
+                     const float lft = (q > 0) ? sf[4 * q - 1] : MGM_INF;
+                     const float rgt = (q + 1 < nq) ? sf[4 * q + 4] : MGM_INF;
+                     e.x += sgm_x(lft, v.x, v.y, pw[k], cap[k], mk[k]);
                      e.y += sgm_x(v.x, v.y, v.z, pw[k], cap[k], mk[k]);
                      e.z += sgm_x(v.y, v.z, v.w, pw[k], cap[k], mk[k]);
-                     e.w += sgm_x(v.z, v.w, nx4.x, pw[k], cap[k], mk[k]);
-                     lft[k] = v.w;
-                     cv[k] = nx4;
+                     e.w += sgm_x(v.z, v.w, rgt, pw[k], cap[k], mk[k]);
                   }
-                  float4 o;
-                  o.x = c.x + div_by_k<K>(e.x);
-                  o.y = c.y + div_by_k<K>(e.y);
-                  o.z = c.z + div_by_k<K>(e.z);
-                  o.w = c.w + div_by_k<K>(e.w);
+                  const float4 d = div4_by_k<K>(e);
+                  const float4 o = make_float4(c.x + d.x, c.y + d.y, c.z + d.z, c.w + d.w);
                   m = hmin4(m, o);
                   Cb[q] = o;
-                  cur[q] = o;
+                  __stcs(gout + q, o);
                }
-            } else {
-               // update_costW_trunclinear with per-edge slopes/caps, mgm_core.cc:229-281
-               float *scr = myscr;
-               float *E = reinterpret_cast<float *>(cur);
+            }
+         }
 #pragma unroll
-               for (int k = 0; k < K; ++k) {
-                  const float pw = P.P1 * wk[k];
-                  const float p2 = P.P2 * wk[k];
-                  const float capv = mk[k] + p2;
-                  const bool trunc = p2 < MGM_INF;
-                  const float *src = reinterpret_cast<const float *>(S[k]);
-                  float run = MGM_INF;
-                  for (int o = 0; o < VS; ++o) {   // forward pass (:154-155)
-                     run = fminf(run + pw, src[o]);
-                     scr[o] = run;
-                  }
-                  run = MGM_INF;
-                  for (int o = VS - 1; o >= 0; --o) {   // backward pass (:157-158) + truncation (:160-162)
-                     run = fminf(run + pw, scr[o]);
-                     float v = trunc ? fminf(run, capv) : run;
-                     v = v - mk[k];
-                     E[o] = (k == 0) ? v : E[o] + v;
-                  }
-               }
-               for (int q = 0; q < nq; ++q) {
-                  float4 c = Cb[q];
-                  float4 e = cur[q];
-                  float4 o;
-                  o.x = c.x + div_by_k<K>(e.x);
-                  o.y = c.y + div_by_k<K>(e.y);
-                  o.z = c.z + div_by_k<K>(e.z);
-                  o.w = c.w + div_by_k<K>(e.w);
-                  m = hmin4(m, o);
-                  Cb[q] = o;
-                  cur[q] = o;
-               }
-            }
-         }
-
-         // (d) the finished message goes to this sweep's volume (smem -> HBM, TMA)
-         fence_proxy_async_smem();
-         tma_store_1d(ldir + (size_t)pix * VS, Cb, vbytes);
-         tma_commit();
-
-         // (e) producer-side transform of the message for its successors (unweighted paths)
-         if (NEEDM) msr[t * 4 + (xs % R)] = m;
-         if constexpr (!WEIGHTED) {
-            if constexpr (POT == POT_SGM) {
-               const float p1 = P.P1;
-               const float cap = m + P.P2;
-               const float sc = (K == 2) ? 0.5f : 1.0f;
-               float lft = MGM_INF;
-               float4 v = cur[0];
-               for (int q = 0; q < nq; ++q) {
-                  float4 nx4 = (q + 1 < nq) ? cur[q + 1] : make_float4(MGM_INF, MGM_INF, MGM_INF, MGM_INF);
-                  float4 a;
-                  a.x = sgm_x(lft, v.x, v.y, p1, cap, m) * sc;
-                  a.y = sgm_x(v.x, v.y, v.z, p1, cap, m) * sc;
-                  a.z = sgm_x(v.y, v.z, v.w, p1, cap, m) * sc;
-                  a.w = sgm_x(v.z, v.w, nx4.x, p1, cap, m) * sc;
-                  lft = v.w;
-                  cur[q] = a;
-                  v = nx4;
-               }
-            } else {
-               // minConvTruncatedLinear (mgm_core.cc:152-163) in place, sequential like the reference
-               const float p1 = P.P1;
-               const float capv = m + P.P2;
-               const bool trunc = P.P2 < MGM_INF;
-               const float sub = (K == 2) ? 0.0f : m;   // A10 subtracts on the consumer side
-               float run = MGM_INF;
-               for (int q = 0; q < nq; ++q) {
-                  float4 v = cur[q];
-                  v.x = run = fminf(run + p1, v.x);
-                  v.y = run = fminf(run + p1, v.y);
-                  v.z = run = fminf(run + p1, v.z);
-                  v.w = run = fminf(run + p1, v.w);
-                  cur[q] = v;
-               }
-               run = MGM_INF;
-               for (int q = nq - 1; q >= 0; --q) {
-                  float4 v = cur[q];
-                  run = fminf(run + p1, v.w); v.w = (trunc ? fminf(run, capv) : run) - sub;
-                  run = fminf(run + p1, v.z); v.z = (trunc ? fminf(run, capv) : run) - sub;
-                  run = fminf(run + p1, v.y); v.y = (trunc ? fminf(run, capv) : run) - sub;
-                  run = fminf(run + p1, v.x); v.x = (trunc ? fminf(run, capv) : run) - sub;
-                  cur[q] = v;
-               }
-            }
-         }
-
-         // (f) hand the boundary row to the next band
-         if (last_row) {
-            if (NEEDM) bndm_out[xs] = m;
-            fence_proxy_async_smem();
-            tma_store_1d(bnd_out + (size_t)xs * VS, cur, vbytes);
-            tma_commit();
-         }
+         for (int d = 1; d < G; d <<= 1) m = fminf(m, __shfl_xor_sync(gmask, m, d));
+         if (gl == 0) msr[r * 4 + (xs % R)] = m;
       }
+      const long long c2 = clock64();
       __syncthreads();
+      const long long c3 = clock64();
+
+      // ---------------- phase 2: build the neighbour-side transform of the message in the ring slot
+      if constexpr (CHAINS) {
+         // minConvTruncatedLinear of the finished message, one lane pair per row
+         const int crow = pair_idx, cdir = pair_dir;
+         const int cxs = s - SIG * crow;
+         if (tid < ncomp && crow < nrows && cxs >= 0 && cxs < maxii) {
+            const float cm = msr[crow * 4 + (cxs % R)];
+            const float *src = row_base(crow) + (R + (cxs & 1)) * VS;
+            float *dst = row_base(crow) + (cxs % R) * VS;
+            minconv_pair(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cdir, P.P1,
+                         cm + P.P2, (K == 2) ? 0.0f : cm, pmask);
+            if (has_next && crow == nrows - 1) fence_proxy_async_smem();   // read by the boundary TMA store
+         }
+      } else if (act) {
+         if constexpr (!WEIGHTED) {
+            // SGM transform, label-parallel: A(o) = min3(L(o), min(L(o-1),L(o+1))+P1, m+P2) - m  [x 1/2 for K=2]
+            const float p1 = P.P1, cap = m + P.P2;
+            const float sc = (K == 2) ? 0.5f : 1.0f;
+            for (int j0 = 0; j0 < nj; j0 += 4) {
+               float4 v[4];
+               float lft[4], rgt[4];
+#pragma unroll
+               for (int jj = 0; jj < 4; ++jj) {
+                  const int q = gl + G * min(j0 + jj, nj - 1);
+                  v[jj] = Cb[q];
+                  lft[jj] = (q > 0) ? Cbf[4 * q - 1] : MGM_INF;
+                  rgt[jj] = (q + 1 < nq) ? Cbf[4 * q + 4] : MGM_INF;
+               }
+#pragma unroll
+               for (int jj = 0; jj < 4; ++jj) {
+                  if (j0 + jj < nj) {
+                     const int q = gl + G * (j0 + jj);
+                     float4 a;
+                     a.x = sgm_x(lft[jj], v[jj].x, v[jj].y, p1, cap, m) * sc;
+                     a.y = sgm_x(v[jj].x, v[jj].y, v[jj].z, p1, cap, m) * sc;
+                     a.z = sgm_x(v[jj].y, v[jj].z, v[jj].w, p1, cap, m) * sc;
+                     a.w = sgm_x(v[jj].z, v[jj].w, rgt[jj], p1, cap, m) * sc;
+                     cur[q] = a;
+                  }
+               }
+            }
+         } else {
+            for (int j = 0; j < nj; ++j) cur[gl + G * j] = Cb[gl + G * j];   // weighted paths keep the raw message
+         }
+         if (last_row) fence_proxy_async_smem();
+      }
+      const long long c4 = clock64();
+      __syncthreads();
+      const long long c5 = clock64();
+      tP += c1 - c0; tA += c2 - c1; tW1 += c3 - c2; tB += c4 - c3; tW2 += c5 - c4;
+
+      // ---------------- hand the boundary row to the next band
+      if (act && last_row && gl == 0) {
+         if (NEEDM) bndm_out[xs] = m;
+         tma_store_1d(bnd_out + (size_t)xs * VS, cur, vbytes);
+         tma_commit();
+      }
    }
 
-   // epilogue: drain stores, publish the full boundary row, save mbarrier parities
-   tma_wait_all<0>();
-   if (last_row) {
+   if (P.dbg && (tid == 0 || tid == ncomp || tid == 8 * (nrows - 1))) {
+      unsigned long long *d = P.dbg + (tid == 0 ? 0 : (tid == ncomp ? 8 : 16));
+      atomicAdd(d + 0, (unsigned long long)tP); atomicAdd(d + 1, (unsigned long long)tA); atomicAdd(d + 2, (unsigned long long)tW1);
+      atomicAdd(d + 3, (unsigned long long)tB); atomicAdd(d + 4, (unsigned long long)tW2); atomicAdd(d + 5, (unsigned long long)nsteps); atomicAdd(d + 6, (unsigned long long)tC);
+   }
+   // epilogue: drain the boundary stores, publish the full boundary row, save mbarrier parities
+   if (last_row && gl == 0) {
+      tma_wait_all<0>();
       fence_proxy_async();
       __threadfence();
       st_release(prog_out, maxii);
    }
-   if (t < ncomp) phase[t] = cph;
-   if (t == 0) phase[ncomp] = vph;
+   if (tid < ncomp && r < T && gl == 0) phase[r] = cph;
+   if (tid == 0) phase[vph_idx] = vph;
    __syncthreads();
 }
 
@@ -379,13 +456,15 @@ __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(c
    const int t = threadIdx.x;
    const int ncomp = blockDim.x - 32;
 
-   // one-time barrier setup: two cost barriers per row thread, RV boundary barriers
+   // one-time barrier setup: two cost barriers per row, RV boundary barriers
    {
       uint64_t *cbar = reinterpret_cast<uint64_t *>(smem + P.off_cbar);
       uint64_t *vbar = reinterpret_cast<uint64_t *>(smem + P.off_vbar);
       uint32_t *phase = reinterpret_cast<uint32_t *>(smem + P.off_phase);
-      if (t < ncomp) { mbar_init(&cbar[2 * t], 1); mbar_init(&cbar[2 * t + 1], 1); phase[t] = 0; }
-      if (t == ncomp) { for (int i = 0; i < RV; ++i) mbar_init(&vbar[i], 1); phase[ncomp] = 0; }
+      const int tmax = max(P.T[0], P.T[1]);
+      if (t < tmax) { mbar_init(&cbar[2 * t], 1); mbar_init(&cbar[2 * t + 1], 1); phase[t] = 0; }
+      if (t == ncomp) { for (int i = 0; i < RV; ++i) mbar_init(&vbar[i], 1); }
+      if (t == 0) phase[tmax] = 0;
       mbar_fence_init();
       __syncthreads();
    }
@@ -432,39 +511,31 @@ static cudaError_t launch_k(int K, const AggParams &P, const AggPlan &plan, cuda
 
 void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
               int t_override) {
-   const int VS = (L + 3) & ~3;
+   const int VS = (L + 31) & ~31;   // 8 lanes x 16 bytes per row and step
    plan->VS = VS;
-   const int xtra = (weighted && pot == POT_TRUNC) ? 1 : 0;
-   // shared memory budget -> rows per band, per sweep class
-   int tmax = MGM_AGG_MAX_THREADS - 32;
-   for (int iter = 0; iter < 2; ++iter) {
-      int T[2];
-      for (int cls = 0; cls < 2; ++cls) {
-         int nbuf = ring_slots(cls, K) + 2 + xtra;
-         int TS = nbuf * VS;
-         if (((TS >> 2) & 1) == 0) TS += 4;   // odd number of 16-byte units: conflict-free LDS.128 across rows
-         plan->TS[cls] = TS;
-         size_t fixed = 1024 + (size_t)RV * VS * 4 + (size_t)tmax * (16 + 16 + 4) + RV * 16;
-         long avail = (long)max_smem - (long)fixed;
-         int Tc = (int)(avail / ((long)TS * 4));
-         if (Tc > tmax) Tc = tmax;
-         if (Tc < 1) Tc = 0;
-         T[cls] = Tc;
-      }
-      plan->T[0] = T[0];
-      plan->T[1] = T[1];
-      if (t_override > 0) { plan->T[0] = min(plan->T[0], t_override); plan->T[1] = min(plan->T[1], t_override); }
-      int tm = max(plan->T[0], plan->T[1]);
-      int ncomp = (tm + 31) & ~31;
-      if (ncomp == tmax || iter == 1) { plan->block = ncomp + 32; break; }
-      tmax = ncomp;   // recompute the fixed part with the real thread count
+   const int xtra = (weighted && pot == POT_TRUNC) ? K : 0;
+   const int tcap = (MGM_AGG_MAX_THREADS - 32) / MGM_AGG_GROUP;   // rows per CTA allowed by the thread budget
+   for (int cls = 0; cls < 2; ++cls) {
+      int nbuf = ring_slots(cls, K) + 2 + xtra;
+      int TS = nbuf * VS;
+      if (((TS >> 2) & 1) == 0) TS += 4;   // odd number of 16-byte units: rows start in different bank groups
+      plan->TS[cls] = TS;
+      size_t fixed = 1024 + (size_t)RV * VS * 4 + (size_t)tcap * (16 + 16 + 4) + RV * 16;
+      long avail = (long)max_smem - (long)fixed;
+      int Tc = (int)(avail / ((long)TS * 4));
+      if (Tc > tcap) Tc = tcap;
+      if (t_override > 0 && Tc > t_override) Tc = t_override;
+      if (Tc < 1) Tc = 0;
+      plan->T[cls] = Tc;
    }
-   const int ncomp = plan->block - 32;
+   const int tm = max(plan->T[0], plan->T[1]);
+   const int ncomp = (tm * MGM_AGG_GROUP + 31) & ~31;
+   plan->block = ncomp + 32;
    size_t off = 0;
-   plan->off_phase = off; off += (size_t)(ncomp + 1) * 4; off = (off + 15) & ~(size_t)15;
-   plan->off_cbar = off; off += (size_t)ncomp * 16;
+   plan->off_phase = off; off += (size_t)(tm + 1) * 4; off = (off + 15) & ~(size_t)15;
+   plan->off_cbar = off; off += (size_t)tm * 16;
    plan->off_vbar = off; off += RV * 8;
-   plan->off_ms = off; off += (size_t)ncomp * 16;
+   plan->off_ms = off; off += (size_t)tm * 16;
    plan->off_vms = off; off += RV * 4; off = (off + 127) & ~(size_t)127;
    plan->off_virt = off; off += (size_t)RV * VS * 4; off = (off + 127) & ~(size_t)127;
    plan->off_thr = off;

@@ -2,7 +2,8 @@
 #pragma once
 #include "common.cuh"
 
-#define MGM_AGG_MAX_THREADS 160   // 128 row threads + one boundary-producer warp
+#define MGM_AGG_GROUP 8           // lanes cooperating on one scan row
+#define MGM_AGG_MAX_THREADS 512   // 60 rows x 8 lanes + one boundary-producer warp
 
 namespace mgm {
 
@@ -22,6 +23,7 @@ struct AggParams {
    int T[2];                   // rows per band: [0] axis sweeps 0-3, [1] diagonal sweeps 4-7
    int TS[2];                  // per-row shared-memory stride in floats
    float P1, P2;
+   unsigned long long *dbg;    // optional 24-word phase-timing accumulator (profiling aid), or nullptr
    // dynamic shared memory carve-up (bytes)
    unsigned off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };

@@ -60,6 +60,7 @@ struct mgmb200_ctx {
    // scratch (grow-only, reused across calls)
    DevBuf u, v, fu, fv, cu, cv, w, cc, dense, out, outcost, flags, tickets, progress, bnd, bndm;
    DevBuf sweep[8];
+   DevBuf dbgbuf;
    size_t sweep_bytes = 0;
    // last launch info
    int n_launches = 0, rows_axis = 0, rows_diag = 0, block = 0;
@@ -90,7 +91,7 @@ extern "C" int mgmb200_refinement_index(const char *name) {
 
 extern "C" int mgmb200_version(void) { return MGMB200_VERSION; }
 extern "C" const char *mgmb200_last_error(void) { return g_err; }
-extern "C" int mgmb200_padded_labels(int L) { return (L + 3) & ~3; }
+extern "C" int mgmb200_padded_labels(int L) { return (L + 31) & ~31; }
 extern "C" size_t mgmb200_volume_bytes(int nx, int ny, int L) {
    return (size_t)nx * ny * mgmb200_padded_labels(L) * sizeof(float);
 }
@@ -362,11 +363,28 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
    P.T[0] = plan.T[0]; P.T[1] = plan.T[1];
    P.TS[0] = plan.TS[0]; P.TS[1] = plan.TS[1];
    P.P1 = P1; P.P2 = P2;
+   P.dbg = nullptr;
+   if (getenv("MGMB200_PHASE_TIMING")) {
+      RET(c->dbgbuf.reserve(24 * 8));
+      CU(cudaMemsetAsync(c->dbgbuf.p, 0, 24 * 8, c->stream));
+      P.dbg = c->dbgbuf.as<unsigned long long>();
+   }
    P.off_phase = (unsigned)plan.off_phase; P.off_cbar = (unsigned)plan.off_cbar; P.off_vbar = (unsigned)plan.off_vbar;
    P.off_ms = (unsigned)plan.off_ms; P.off_vms = (unsigned)plan.off_vms; P.off_virt = (unsigned)plan.off_virt;
    P.off_thr = (unsigned)plan.off_thr;
    CU(agg_launch(P, plan, pot, K, weighted, c->stream));
    c->n_launches++;
+   if (P.dbg) {
+      unsigned long long h[24];
+      CU(cudaMemcpyAsync(h, P.dbg, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      const char *who[3] = {"thread0", "producer", "lastrow"};
+      for (int i = 0; i < 3; i++) {
+         double n = (double)(h[8 * i + 5] ? h[8 * i + 5] : 1);
+         fprintf(stderr, "[mgmb200 phase timing] %s: steps=%llu cycles/step: top=%.0f gather=%.0f (cost wait %.0f) bar1=%.0f transform=%.0f bar2=%.0f\n", who[i],
+                 h[8 * i + 5], h[8 * i + 0] / n, h[8 * i + 1] / n, h[8 * i + 6] / n, h[8 * i + 2] / n, h[8 * i + 3] / n, h[8 * i + 4] / n);
+      }
+   }
    return 0;
 }
 

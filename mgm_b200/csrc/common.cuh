@@ -27,18 +27,17 @@ __device__ __forceinline__ float min3_gt(float a, float b, float c) {
    return m;
 }
 
-// Correctly rounded x/3 without the generic division sequence: q0 = x*RN(1/3),
-// one exact residual (fma) and one correction.  Checked exhaustively on the host
-// against x/3.0f for every finite float with 2^-100 <= |x| <= 2^100 and for 0
-// (tests/test_host_math.py); everything else takes the IEEE division.
+// Correctly rounded x/3 without the generic division sequence: q0 = x*RN(1/3), one exact
+// residual (fma) and one correction.  Checked exhaustively on the host against x/3.0f for
+// every finite float, denormals included (tests/test_host_math.py): the only difference in
+// 2^32 inputs is the sign of the zero returned for x = -0.  Non-finite x is returned as is
+// (INF/3 = INF, NaN/3 = NaN).  Branch-free on purpose: it sits in the gather inner loop.
 __device__ __forceinline__ float div3_exact(float x) {
    const float c3 = 0x1.555556p-2f;
-   float q = __fmul_rn(x, c3);
-   float r = __fmaf_rn(-3.0f, q, x);
-   float q2 = __fmaf_rn(r, c3, q);
-   float ax = fabsf(x);
-   if (!((ax >= 0x1p-100f && ax <= 0x1p100f) || ax == 0.0f)) q2 = __fdiv_rn(x, 3.0f);
-   return q2;
+   const float q = __fmul_rn(x, c3);
+   const float r = __fmaf_rn(-3.0f, q, x);
+   const float q2 = __fmaf_rn(r, c3, q);
+   return (fabsf(x) < MGM_INF) ? q2 : x;
 }
 
 // edge_potentials / howmany  (mgm_core.cc:141,278): float divided by an int

@@ -4,7 +4,7 @@
 //   K2 cost volume  : allocate_and_fill_sgm_costvolume mgm_costvolume.h:337-424
 //                     with the cost functions of mgm_costvolume.h:23-165
 // Device layout of a volume: [y][x][VS] floats, VS = L rounded up to a multiple of
-// four; the padding labels hold +INF, which is exactly what Dvec::operator[] returns
+// 32; the padding labels hold +INF, which is exactly what Dvec::operator[] returns
 // outside [min,max] (dvec.cc:129), so the aggregation needs no range checks.
 #include "costvolume.cuh"
 

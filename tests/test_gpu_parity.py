@@ -1,0 +1,213 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI (mgm_b200.Context -> libmgmb200.so), against
+ * the oracle port on seeded inputs at sizes it finishes in seconds          (bit-exact, see below)
+ * the golden vectors generated from the unmodified reference               (bit-exact)
+ * size-independent properties at BASELINE.json's full sizes.
+Tolerances: WTA disparity indices, aggregated costs S, output costs and sub-pixel offsets are all compared
+BIT-EXACT here (the kernels perform the reference's IEEE operations in the reference's order; this is
+stricter than north_star's 1e-4 relative).  NaN patterns must coincide (equal_nan)."""
+import itertools
+
+import numpy as np
+import pytest
+
+import oracle as O
+from tests.conftest import synth_pair, synth_volume, synth_weights
+from tests.golden_util import golden_files, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def same(a, b):
+    return np.array_equal(a, b, equal_nan=True)
+
+
+def mism(a, b):
+    return float(np.mean(~((a == b) | (np.isnan(a) & np.isnan(b)))))
+
+
+# ------------------------------------------------------------------------------------------ stages
+@pytest.mark.parametrize("nch", [1, 3])
+def test_weights(ctx, nch):
+    u, _ = synth_pair(53, 31, 12, seed=3, nch=nch)
+    for aP, aT in [(4.0, 12.0), (0.5, 40.0), (1.0, 5.0)]:
+        assert same(ctx.compute_mgm_weights(u, aP, aT), O.orc_weights(u, aP, aT))
+
+
+@pytest.mark.parametrize("dist,win", [("ad", 3), ("sd", 3), ("census", 3), ("census", 5), ("census", 7), ("ncc", 3),
+                                      ("ncc", 5), ("btad", 3), ("btsd", 3)])
+@pytest.mark.parametrize("nch", [1, 3])
+def test_costvolume(ctx, dist, win, nch):
+    u, v = synth_pair(45, 29, 14, seed=win + nch, nch=nch)
+    u = u + np.float32(0.37)
+    for trunc in [np.inf, 17.5]:
+        a = ctx.allocate_and_fill_sgm_costvolume(u, v, -13, 3, "none", dist, trunc, win)
+        assert same(a, O.orc_costvolume(u, v, -13, 3, "none", dist, trunc, win)), (dist, win, nch, trunc)
+    a = ctx.allocate_and_fill_sgm_costvolume(u, v[:, :, :33], -13, 3, "none", dist, np.inf, win)   # ragged sizes
+    assert same(a, O.orc_costvolume(u, v[:, :, :33], -13, 3, "none", dist, np.inf, win))
+
+
+def test_costvolume_edge_cases(ctx):
+    u, v = synth_pair(40, 9, 60, seed=1)
+    # range entirely outside the right image for most pixels -> the all-invalid rule (mgm_costvolume.h:414-421)
+    a = ctx.allocate_and_fill_sgm_costvolume(u, v, 30, 75, "none", "ad", np.inf, 3)
+    b = O.orc_costvolume(u, v, 30, 75, "none", "ad", np.inf, 3)
+    assert same(a, b) and (b[:, -5:, :] == 0).all()
+    # sobelx prefilter + truncation, unknown names fall back to entry 0
+    assert same(ctx.allocate_and_fill_sgm_costvolume(u, v, -20, 3, "sobelx", "sd", 90.0, 3),
+                O.orc_costvolume(u, v, -20, 3, "sobelx", "sd", 90.0, 3))
+    assert same(ctx.allocate_and_fill_sgm_costvolume(u, v, -20, 3, "sobel_x", "l1", np.inf, 3),
+                O.orc_costvolume(u, v, -20, 3, "none", "ad", np.inf, 3))
+
+
+MGM_SHAPES = [(23, 17, 9), (67, 41, 19), (131, 37, 40)]
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 4])
+@pytest.mark.parametrize("felz", [0, 1])
+@pytest.mark.parametrize("weighted", [0, 1])
+def test_mgm_matches_oracle(ctx, K, felz, weighted):
+    """all message-update variants (mgm_core.cc:66-281) x sweep counts x band layouts, S/out/outcost bit-exact"""
+    for (nx, ny, L), real, rows in itertools.product(MGM_SHAPES, [0, 1], [0, 5]):
+        cc = synth_volume(nx, ny, L, seed=nx + K, real=bool(real))
+        w = synth_weights(nx, ny, seed=nx) if weighted else None
+        ctx.set_rows_per_band(rows)   # 5 rows per band forces many chained bands on these small images
+        for NDIR in ([8] if rows == 0 else [1, 4, 8]):
+            P1, P2 = ((8, 32) if K % 2 else (3.5, 21.25)) if not felz else ((2, 20000) if K != 4 else (1.5, 11))
+            r = ctx.mgm(cc, w, -(L - 1), P1, P2, NDIR, K, felz, 1)
+            o = O.orc_mgm(cc, w, -(L - 1), P1, P2, NDIR, K, felz, 1)
+            tag = (nx, ny, L, real, rows, NDIR, mism(r["S"], o["S"]), mism(r["out"], o["out"]))
+            assert same(r["out"], o["out"]), tag
+            assert same(r["S"], o["S"]), tag
+            assert same(r["outcost"], o["outcost"]), tag
+    ctx.set_rows_per_band(0)
+
+
+def test_mgm_overcount_flag_and_small_images(ctx):
+    cc = synth_volume(31, 22, 12, seed=8, real=True)
+    for fix in [0, 1]:
+        r = ctx.mgm(cc, None, -11, 8, 32, 8, 2, 0, fix)
+        o = O.orc_mgm(cc, None, -11, 8, 32, 8, 2, 0, fix)
+        assert same(r["S"], o["S"]) and same(r["out"], o["out"])
+    for nx, ny in [(2, 9), (9, 2), (1, 1), (3, 3), (4, 3)]:   # images without interior pixels and the smallest with one
+        cc = synth_volume(nx, ny, 7, seed=nx, inf_border=False)
+        r = ctx.mgm(cc, None, 0, 8, 32, 8, 4, 0, 1)
+        o = O.orc_mgm(cc, None, 0, 8, 32, 8, 4, 0, 1)
+        assert same(r["S"], o["S"]) and same(r["out"], o["out"]), (nx, ny)
+
+
+def test_mgm_label_counts(ctx):
+    """label counts around the padding granularity, two labels (minimum), a few hundred"""
+    for L in [2, 3, 31, 32, 33, 64, 65, 300]:
+        cc = synth_volume(37, 11, L, seed=L, real=True, inf_border=(L < 37))
+        for K, felz in [(2, 0), (3, 1)]:
+            r = ctx.mgm(cc, None, -5, 8, 32, 4, K, felz, 1)
+            o = O.orc_mgm(cc, None, -5, 8, 32, 4, K, felz, 1)
+            assert same(r["S"], o["S"]) and same(r["out"], o["out"]), (L, K, felz)
+
+
+def test_mgm_labelmajor_protocol(ctx):
+    """matlab/mgm_o.cc input.bin layout: costs[i + o*ncol*nrow], labels 0..nlab-1"""
+    cc = synth_volume(41, 23, 16, seed=3, inf_border=False)
+    w = synth_weights(41, 23, seed=3)
+    lab, _ = ctx.mgm_labelmajor(np.ascontiguousarray(np.transpose(cc, (2, 0, 1))), w, 8, 32, 8, 2, 0)
+    o = O.orc_mgm(cc, w, 0, 8, 32, 8, 2, 0, 1)
+    assert same(lab, o["out"])
+
+
+def test_unsupported_inputs_fail_loudly(ctx):
+    import mgm_b200
+    cc = synth_volume(9, 9, 5, seed=1, inf_border=False)
+    bad = cc.copy(); bad[4, 4, :] = np.inf          # a pixel without any finite cost
+    with pytest.raises(mgm_b200.MgmError):
+        ctx.mgm(bad, None, 0, 8, 32, 4, 2)
+    bad = cc.copy(); bad[2, 3, 1] = np.nan
+    with pytest.raises(mgm_b200.MgmError):
+        ctx.mgm(bad, None, 0, 8, 32, 4, 2)
+    with pytest.raises(mgm_b200.MgmError):
+        ctx.mgm(cc, None, 0, 8, 32, 16, 2)             # -O 16 indexes past the reference's table
+    with pytest.raises(mgm_b200.MgmError):
+        ctx.mgm(cc, None, 0, 8, 32, 4, 5)
+
+
+@pytest.mark.parametrize("method", ["none", "vfit", "parabola", "cubic", "parabolaOCV", "bogus"])
+def test_refinement(ctx, method):
+    cc = synth_volume(67, 41, 19, seed=5, real=True)
+    o = O.orc_mgm(cc, None, -18, 8, 32, 8, 2, 0, 1)
+    a = ctx.subpixel_refinement_sgm(o["S"], -18, o["out"], o["outcost"], method)
+    b = O.orc_refine(o["S"], -18, o["out"], o["outcost"], method)
+    assert same(a[0], b[0]) and same(a[1], b[1])
+
+
+# ------------------------------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("path", golden_files("pipeline"))
+def test_golden_pipeline(ctx, path):
+    g = load_golden(path)
+    p = dict(g["params"])
+    kw = dict(dmin=p.pop("dmin"), dmax=p.pop("dmax"), MGM=p.pop("K"), use_felzenszwalb_potentials=p.pop("felz", 0),
+              census_ncc_win=p.pop("win", 3))
+    kw.update(p)
+    out, cost = ctx.stereo(g["u"], g["v"], **kw)
+    assert same(out, g["out"]), (g["name"], mism(out, g["out"]))
+    assert same(cost, g["outcost"]), g["name"]
+
+
+@pytest.mark.parametrize("path", golden_files("volume"))
+def test_golden_volume(ctx, path):
+    g = load_golden(path)
+    p = g["params"]
+    r = ctx.mgm(g["cc"], g["w"], p["dmin"], p["P1"], p["P2"], p["NDIR"], p["K"], p["felz"], p["fix"])
+    assert same(r["out"], g["out"]) and same(r["outcost"], g["outcost"])
+    assert same(r["S"][r["S"].shape[0] // 2], g["S_row"])
+
+
+# ------------------------------------------------------------------------------------------ whole hot path
+@pytest.mark.parametrize("kw", [
+    dict(distance="census", census_ncc_win=5, NDIR=8, MGM=2, refinement="vfit"),                       # BASELINE cfg 2 shape of flags
+    dict(distance="census", census_ncc_win=3, NDIR=8, MGM=3, use_felzenszwalb_potentials=1, P1=2, P2=20000,
+         refinement="vfit"),                                                                          # cfg 3 / Makefile:17
+    dict(distance="ad", NDIR=4, MGM=4, aP=4.0, aThresh=6.0, refinement="cubic"),                       # weights on
+    dict(distance="ncc", census_ncc_win=5, NDIR=8, MGM=4, refinement="parabola"),                      # cfg 5 flags (8 sweeps)
+])
+def test_stereo_matches_oracle(ctx, kw):
+    u, v = synth_pair(197, 75, 48, seed=1, nch=1)
+    out, cost = ctx.stereo(u, v, dmin=-47, dmax=0, **kw)
+    kk = dict(kw)
+    kk["win"] = kk.pop("census_ncc_win", 3); kk["K"] = kk.pop("MGM"); kk["felz"] = kk.pop("use_felzenszwalb_potentials", 0)
+    b = O.orc_pipeline(u, v, -47, 0, **kk)
+    assert same(out, b["out"]), mism(out, b["out"])
+    assert same(cost, b["outcost"])
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+@pytest.mark.parametrize("cfg", [dict(W=2048, H=1536, L=256, win=3, K=3, felz=1, P1=2.0, P2=20000.0),
+                                 dict(W=1920, H=1080, L=128, win=5, K=2, felz=0, P1=8.0, P2=32.0)])
+def test_full_size_properties(ctx, cfg):
+    """BASELINE.json configs 3 and 2 at full size.  Size-independent properties of the exact algorithm:
+    (1) the result does not depend on how the image is cut into bands (rows per band = default vs 17),
+        which exercises the boundary hand-off between thread blocks tens of thousands of times;
+    (2) a crop of rows/columns that starts at the scan origin of sweep 0 reproduces exactly, for NDIR=1,
+        the corresponding part of the full-size result (messages only flow along the sweep);
+    (3) WTA labels are integers inside the disparity range."""
+    from bench import synth_pair as bench_pair
+    W, H, L = cfg["W"], cfg["H"], cfg["L"]
+    u, v = bench_pair(W, H, L, 0)
+    base = dict(dmin=-(L - 1), dmax=0, P1=cfg["P1"], P2=cfg["P2"], MGM=cfg["K"],
+                use_felzenszwalb_potentials=cfg["felz"], distance="census", census_ncc_win=cfg["win"])
+    ctx.set_rows_per_band(0)
+    out_a, cost_a = ctx.stereo(u, v, NDIR=8, refinement="none", **base)
+    ctx.set_rows_per_band(17)
+    out_b, cost_b = ctx.stereo(u, v, NDIR=8, refinement="none", **base)
+    ctx.set_rows_per_band(0)
+    assert same(out_a, out_b) and same(cost_a, cost_b)
+    assert out_a.min() >= -(L - 1) and out_a.max() <= 0 and np.all(out_a == np.round(out_a))
+    # (2) sweep 0 only: crop invariance, checked against the ORACLE on the crop (small enough for the CPU)
+    out1, cost1 = ctx.stereo(u, v, NDIR=1, refinement="none", **base)
+    cw, ch = 200, 40
+    kk = dict(P1=cfg["P1"], P2=cfg["P2"], NDIR=1, K=cfg["K"], felz=cfg["felz"], distance="census", win=cfg["win"])
+    # the census transform and the matching range need the right image to extend L-1 pixels to the left:
+    # crop at the left border so the INF wedge is identical; rows/cols beyond the crop only influence
+    # later scan positions of sweep 0 (it runs left->right, top->bottom), except the census window at the
+    # crop's last row/column and the border rule there -> compare the interior of the crop.
+    o = O.orc_pipeline(u[:ch, :cw], v[:ch, :cw], -(L - 1), 0, **kk)
+    assert same(out1[:ch - 2, :cw - 2], o["out"][:ch - 2, :cw - 2])
+    assert same(cost1[:ch - 2, :cw - 2], o["outcost"][:ch - 2, :cw - 2])

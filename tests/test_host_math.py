@@ -1,0 +1,63 @@
+"""CPU suite, part 3: host-side checks of the arithmetic identities the kernels rely on."""
+import ctypes
+import ctypes.util
+
+import numpy as np
+
+libm = ctypes.CDLL(ctypes.util.find_library("m"))
+libm.fmaf.restype = ctypes.c_float
+libm.fmaf.argtypes = [ctypes.c_float] * 3
+
+
+def div3_fast(x):
+    """common.cuh div3_exact(): q = x*RN(1/3); r = fma(-3,q,x); q' = fma(r,RN(1/3),q)"""
+    c3 = np.float32(float.fromhex("0x1.555556p-2"))
+    q = np.float32(x) * c3
+    r = libm.fmaf(-3.0, q, x)
+    return np.float32(libm.fmaf(r, c3, q))
+
+
+def test_div3_fast_path_is_correctly_rounded_on_samples():
+    # the exhaustive 2^32 sweep is done once in C; this samples every binade + random mantissas
+    rng = np.random.default_rng(0)
+    bits = np.concatenate([
+        (np.arange(1, 255, dtype=np.uint32)[:, None] << 23 | rng.integers(0, 1 << 23, (254, 40), dtype=np.uint32)).ravel(),
+        rng.integers(1, 1 << 23, 2000, dtype=np.uint32),                      # denormals
+        np.array([0, 1, 0x007FFFFF, 0x00800000, 0x7F7FFFFF], dtype=np.uint32)])
+    xs = bits.view(np.float32)
+    for x in np.concatenate([xs, -xs[:2000]]):
+        ref = np.float32(x) / np.float32(3.0)
+        got = div3_fast(float(x))
+        assert got == ref or (got == 0 and ref == 0), (float(x).hex(), float(ref).hex(), float(got).hex())
+
+
+def test_minconv_backward_pass_identity():
+    """aggregate.cu minconv_pair: with c >= 0 the reference's backward pass over the forward result F equals
+    min(F, Bp), Bp = the same recurrence run downwards on the original values -- bit for bit in fp32."""
+    rng = np.random.default_rng(1)
+    for trial in range(200):
+        n = int(rng.integers(2, 70))
+        M = (rng.random(n) * rng.choice([1, 30, 1000])).astype(np.float32)
+        if trial % 3 == 0:
+            M[rng.random(n) < 0.3] = np.inf
+        c = np.float32(rng.choice([0.0, 2.0, 8.0, 1.3, 0.1]))
+        F = M.copy()
+        for o in range(1, n):
+            F[o] = min(np.float32(F[o - 1] + c), F[o])
+        ref = F.copy()
+        for o in range(n - 2, -1, -1):
+            ref[o] = min(np.float32(ref[o + 1] + c), ref[o])
+        Bp = M.copy()
+        for o in range(n - 2, -1, -1):
+            Bp[o] = min(np.float32(Bp[o + 1] + c), Bp[o])
+        assert np.array_equal(np.minimum(F, Bp), ref)
+
+
+def test_monotone_rounded_add_distributes_over_min():
+    """RN(min(a,b)+c) == min(RN(a+c), RN(b+c)): why the neighbour-side transform can be computed once by the
+    producer pixel and why padded +INF labels never leak into real labels."""
+    rng = np.random.default_rng(2)
+    a = (rng.random(100000) * 100).astype(np.float32)
+    b = (rng.random(100000) * 100).astype(np.float32)
+    c = np.float32(2.0)
+    assert np.array_equal(np.minimum(a, b) + c, np.minimum(a + c, b + c))

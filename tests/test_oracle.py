@@ -1,0 +1,128 @@
+"""CPU suite, part 1: the oracle port (oracle/mgm_oracle.c) against
+ (a) the golden vectors generated from the unmodified reference (tests/golden/, always), and
+ (b) the reference itself, live, when oracle/_ref/libmgmref.so is present (build container, GPU box).
+Bit-exact everywhere: the port restates the same IEEE operations in the same order."""
+import itertools
+
+import numpy as np
+import pytest
+
+import oracle as O
+from tests.conftest import synth_pair, synth_volume, synth_weights
+from tests.golden_util import golden_files, load_golden
+
+needs_ref = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+def same(a, b):
+    return np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("path", golden_files("pipeline"))
+def test_port_matches_golden_pipeline(path):
+    g = load_golden(path)
+    r = O.orc_pipeline(g["u"], g["v"], **g["params"])
+    assert same(r["out"], g["out"]), g["name"]
+    assert same(r["outcost"], g["outcost"]), g["name"]
+    cc = r["cc"]
+    assert int(np.isinf(cc).sum()) == int(g["cc_ninf"][0])
+    assert np.nansum(np.where(np.isfinite(cc), cc, 0), dtype=np.float64) == g["cc_sum"][0]
+    assert int((r["w"] != 1).sum()) == int(g["w_not_one"][0])
+
+
+@pytest.mark.parametrize("path", golden_files("volume"))
+def test_port_matches_golden_volume(path):
+    g = load_golden(path)
+    p = g["params"]
+    r = O.orc_mgm(g["cc"], g["w"], p["dmin"], p["P1"], p["P2"], p["NDIR"], p["K"], p["felz"], p["fix"])
+    assert same(r["out"], g["out"]) and same(r["outcost"], g["outcost"])
+    assert same(r["S"][r["S"].shape[0] // 2], g["S_row"])
+    assert np.sum(np.where(np.isfinite(r["S"]), r["S"], 0), dtype=np.float64) == g["S_sum"][0]
+
+
+def test_scan_space_predecessors():
+    """every sweep reads the same four scan-space predecessors; sweeps 0-3 and 4-7 differ
+    only in the order."""
+    axis = [(-1, 0), (0, -1), (-1, -1), (1, -1)]
+    diag = [(1, -1), (-1, -1), (0, -1), (-1, 0)]
+    for p in range(8):
+        assert O.orc_scan_preds(p) == (axis if p < 4 else diag)
+
+
+def test_name_tables_fall_back_to_zero():
+    lib = O.orc_lib()
+    assert lib.orc_distance_index(b"census") == 2 and lib.orc_distance_index(b"nonsense") == 0
+    assert lib.orc_prefilter_index(b"sobelx") == 2 and lib.orc_prefilter_index(b"sobel_x") == 0   # Makefile:18
+    assert lib.orc_refinement_index(b"parabolaOCV") == 4 and lib.orc_refinement_index(b"") == 0
+
+
+@needs_ref
+def test_ref_flavours_agree():
+    """serial, OpenMP and DVEC_ALLOCATION_HACK builds of the reference are bit-identical"""
+    cc = synth_volume(33, 21, 11, seed=4, real=True)
+    w = synth_weights(33, 21, seed=4)
+    base = O.ref_mgm(cc, w, -10, 8, 32, 8, 4)
+    for fl in ["_serial", "_flat"]:
+        r = O.ref_mgm(cc, w, -10, 8, 32, 8, 4, flavour=fl)
+        assert same(r["S"], base["S"]) and same(r["out"], base["out"])
+
+
+@needs_ref
+@pytest.mark.parametrize("dist,win", [("ad", 3), ("sd", 3), ("census", 3), ("census", 5), ("census", 7), ("ncc", 3),
+                                      ("ncc", 5), ("btad", 3), ("btsd", 3)])
+@pytest.mark.parametrize("nch", [1, 3])
+def test_port_costvolume_vs_ref(dist, win, nch):
+    u, v = synth_pair(41, 27, 14, seed=win + nch, nch=nch)
+    u = u + np.float32(0.37)   # non-integer values exercise the float paths (NCC, BT halves)
+    for trunc in [np.inf, 17.5]:
+        a = O.orc_costvolume(u, v, -13, 3, "none", dist, trunc, win)
+        b = O.ref_costvolume(u, v, -13, 3, "none", dist, trunc, win)
+        assert same(a, b), (dist, win, nch, trunc)
+    # different image sizes for u and v (the R->L run of the CLI uses the same sizes, the API allows any)
+    a = O.orc_costvolume(u, v[:, :, :30], -13, 3, "none", dist, np.inf, win)
+    b = O.ref_costvolume(u, v[:, :, :30], -13, 3, "none", dist, np.inf, win)
+    assert same(a, b)
+
+
+@needs_ref
+def test_port_sobelx_and_weights_vs_ref():
+    u, v = synth_pair(37, 23, 12, seed=9, nch=3)
+    assert same(O.orc_costvolume(u, v, -11, 2, "sobelx", "ad", 50.0, 3), O.ref_costvolume(u, v, -11, 2, "sobelx", "ad", 50.0, 3))
+    for aP, aT in [(4.0, 5.0), (0.5, 30.0), (1.0, 5.0)]:
+        assert same(O.orc_weights(u, aP, aT), O.ref_weights(u, aP, aT))
+
+
+@needs_ref
+@pytest.mark.parametrize("K", [1, 2, 3, 4])
+@pytest.mark.parametrize("felz", [0, 1])
+@pytest.mark.parametrize("weighted", [0, 1])
+def test_port_mgm_vs_ref(K, felz, weighted):
+    nx, ny, L = 29, 19, 10
+    for real, NDIR, fix, (P1, P2) in itertools.product([0, 1], [1, 3, 8], [0, 1], [(8, 32), (2, 20000), (1.3, 7.7)]):
+        cc = synth_volume(nx, ny, L, seed=NDIR, real=bool(real))
+        w = synth_weights(nx, ny, seed=K) if weighted else None
+        a = O.orc_mgm(cc, w, -(L - 1), P1, P2, NDIR, K, felz, fix)
+        b = O.ref_mgm(cc, w, -(L - 1), P1, P2, NDIR, K, felz, fix)
+        assert same(a["S"], b["S"]) and same(a["out"], b["out"]) and same(a["outcost"], b["outcost"]), \
+            (real, NDIR, fix, P1, P2)
+
+
+@needs_ref
+@pytest.mark.parametrize("method", O.REFINEMENTS + ["bogus"])
+def test_port_refine_vs_ref(method):
+    cc = synth_volume(41, 25, 13, seed=2, real=True)
+    r = O.ref_mgm(cc, None, -12, 8, 32, 8, 2)
+    a = O.orc_refine(r["S"], -12, r["out"], r["outcost"], method)
+    b = O.ref_refine(r["S"], -12, r["out"], r["outcost"], method)
+    assert same(a[0], b[0]) and same(a[1], b[1])
+
+
+@needs_ref
+def test_port_pipeline_vs_ref():
+    u, v = synth_pair(61, 37, 20, seed=5)
+    for kw in [dict(distance="census", win=5, NDIR=8, K=2, refinement="vfit"),
+               dict(distance="census", win=3, NDIR=8, K=3, felz=1, P1=2.0, P2=20000.0, refinement="vfit"),
+               dict(distance="ad", NDIR=4, K=4, aP=4.0, aThresh=6.0, refinement="cubic")]:
+        a = O.orc_pipeline(u, v, -19, 0, **kw)
+        b = O.ref_pipeline(u, v, -19, 0, **kw)
+        assert same(a["out"], b["out"]) and same(a["outcost"], b["outcost"]), kw
