@@ -301,13 +301,6 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
       if (mask & (1u << p)) RET(c->sweep[p].reserve(vol));
    c->sweep_bytes = vol;
 
-   if (nx < 3 || ny < 3) {
-      // every pixel has a neighbour outside the image: all messages stay equal to the costs (mgm_core.cc:538-541)
-      for (int p = 0; p < NDIR; p++)
-         if (mask & (1u << p)) CU(cudaMemcpyAsync(c->sweep[p].p, d_cc, vol, cudaMemcpyDeviceToDevice, c->stream));
-      return 0;
-   }
-
    AggPlan plan;
    agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, c->rows_override);
    if (plan.T[0] < 1 || plan.T[1] < 1)

@@ -88,7 +88,7 @@ def test_mgm_overcount_flag_and_small_images(ctx):
         r = ctx.mgm(cc, None, -11, 8, 32, 8, 2, 0, fix)
         o = O.orc_mgm(cc, None, -11, 8, 32, 8, 2, 0, fix)
         assert same(r["S"], o["S"]) and same(r["out"], o["out"])
-    for nx, ny in [(2, 9), (9, 2), (1, 1), (3, 3), (4, 3)]:   # images without interior pixels and the smallest with one
+    for nx, ny in [(2, 9), (9, 2), (1, 1), (1, 6), (6, 1), (2, 2), (3, 3), (4, 3), (3, 2)]:   # degenerate sizes: few or no interior pixels
         cc = synth_volume(nx, ny, 7, seed=nx, inf_border=False)
         r = ctx.mgm(cc, None, 0, 8, 32, 8, 4, 0, 1)
         o = O.orc_mgm(cc, None, 0, 8, 32, 8, 4, 0, 1)
