@@ -225,26 +225,16 @@ def main():
                            wl["win"], dcc.data_ptr())
     stream.synchronize()
 
-    my_mask = 0
-    for p in range(NDIR):
-        if p % world == rank:
-            my_mask |= 1 << p
+    from mgm_b200 import sharding
+    my_mask = sharding.sweep_mask(NDIR, world, rank)
     peer_ptrs = None
-    rows = [(H * r) // world for r in range(world + 1)]
+    slabs = sharding.row_slabs(H, world)
+    rows = [a for a, _ in slabs] + [H]
     if world > 1:
         # one un-timed run so that the sweep volumes exist, then exchange their IPC handles once
         ctx.aggregate_sweeps_dev(dcc.data_ptr(), 0, 0, W, H, dmin, dmax, wl["P1"], wl["P2"], NDIR, K, wl["felz"], my_mask)
         ctx.synchronize()
-        handles = [None] * NDIR
-        for p in range(NDIR):
-            if (my_mask >> p) & 1:
-                handles[p] = ctx.ipc_export(ctx.sweep_volume(p)[0])
-        allh = [None] * world
-        dist.all_gather_object(allh, handles)
-        peer_ptrs = []
-        for p in range(NDIR):
-            owner = p % world
-            peer_ptrs.append(ctx.sweep_volume(p)[0] if owner == rank else ctx.ipc_open(allh[owner][p]))
+        peer_ptrs = sharding.exchange_sweep_handles(ctx, dist, NDIR, world, rank)
         gout = [torch.empty((rows[r + 1] - rows[r], W), dtype=torch.float32, device="cuda") for r in range(world)]
         gcost = [torch.empty((rows[r + 1] - rows[r], W), dtype=torch.float32, device="cuda") for r in range(world)]
 

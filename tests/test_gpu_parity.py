@@ -138,6 +138,29 @@ def test_refinement(ctx, method):
     assert same(a[0], b[0]) and same(a[1], b[1])
 
 
+def test_sweep_sharding_api_single_gpu(ctx):
+    """The multi-GPU protocol on one device: aggregate the sweeps in two separate calls (as two ranks would),
+    finish two row slabs with explicit sweep pointers -> identical to the one-call path and to the oracle."""
+    import torch
+    nx, ny, L = 83, 47, 24
+    cc = synth_volume(nx, ny, L, seed=21, real=True)
+    VS = ctx.padded_labels(L)
+    dense = torch.from_numpy(cc).cuda()
+    dcc = torch.empty((ny, nx, VS), device="cuda")
+    dout = torch.full((ny, nx), -777.0, device="cuda")
+    dcost = torch.empty((ny, nx), device="cuda")
+    ctx.pad_volume_dev(dense.data_ptr(), dcc.data_ptr(), nx, ny, L)
+    for mask in (0x55, 0xAA):
+        ctx.aggregate_sweeps_dev(dcc.data_ptr(), 0, 0, nx, ny, -(L - 1), 0, 2.0, 20000.0, 8, 3, 1, mask)
+    ptrs = [ctx.sweep_volume(p)[0] for p in range(8)]
+    for r0, r1 in ((0, 20), (20, ny)):
+        ctx.finish_rows_dev(ptrs, dcc.data_ptr(), nx, ny, -(L - 1), 0, 8, 1, "vfit", r0, r1, dout.data_ptr(), dcost.data_ptr())
+    ctx.synchronize()
+    o = O.orc_mgm(cc, None, -(L - 1), 2.0, 20000.0, 8, 3, 1, 1)
+    ro, rc = O.orc_refine(o["S"], -(L - 1), o["out"], o["outcost"], "vfit")
+    assert same(dout.cpu().numpy(), ro) and same(dcost.cpu().numpy(), rc)
+
+
 # ------------------------------------------------------------------------------------------ golden vectors
 @pytest.mark.parametrize("path", golden_files("pipeline"))
 def test_golden_pipeline(ctx, path):
