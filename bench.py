@@ -158,6 +158,9 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rows-per-band", type=int, default=0)
+    ap.add_argument("--shard", default="batch", choices=["batch", "sweeps"],
+                    help="N>1: 'batch' = one stereo pair per GPU, no data-path collective (weak scaling); "
+                         "'sweeps' = one pair, sweeps sharded over the GPUs + ordered peer-memory finish (strong)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     W, H, L, NDIR, K = wl["W"], wl["H"], wl["L"], wl["NDIR"], wl["K"]
@@ -173,6 +176,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        if world > 1 or os.environ.get("OMP_NUM_THREADS") == "1":
+            os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)   # torchrun pins it to 1; use all host threads
         t0 = time.perf_counter()
         rates = []
         info = None
@@ -209,7 +214,8 @@ def main():
 
     dmin, dmax = -(L - 1), 0
     VS = ctx.padded_labels(L)
-    u, v = synth_pair(W, H, L, seed=0)
+    batch_mode = world > 1 and args.shard == "batch"
+    u, v = synth_pair(W, H, L, seed=rank if batch_mode else 0)
     hu = torch.from_numpy(u).pin_memory()
     hv = torch.from_numpy(v).pin_memory()
     hout = torch.empty((H, W), dtype=torch.float32).pin_memory()
@@ -231,7 +237,7 @@ def main():
     slabs = sharding.row_slabs(H, world)
     rows = [a for a, _ in slabs] + [H]
     if world > 1:
-        # one un-timed run so that the sweep volumes exist, then exchange their IPC handles once
+        # (sweeps mode) one un-timed run so that the sweep volumes exist, then exchange their IPC handles once
         ctx.aggregate_sweeps_dev(dcc.data_ptr(), 0, 0, W, H, dmin, dmax, wl["P1"], wl["P2"], NDIR, K, wl["felz"], my_mask)
         ctx.synchronize()
         peer_ptrs = sharding.exchange_sweep_handles(ctx, dist, NDIR, world, rank)
@@ -240,7 +246,7 @@ def main():
 
     def step_device():
         """cost volume resident -> maps resident (the metric's timed region)"""
-        if world == 1:
+        if world == 1 or batch_mode:
             ctx.aggregate_dev(dcc.data_ptr(), 0, 0, W, H, dmin, dmax, wl["P1"], wl["P2"], NDIR, K, wl["felz"], 1,
                               wl["refine"], dout.data_ptr(), dcost.data_ptr())
         else:
@@ -282,6 +288,11 @@ def main():
         sampler.start()
     ms_dev = timed(step_device, args.steps, args.warmup)
     info = ctx.last_launch_info()
+    ms_sweeps = None
+    if batch_mode:   # also measure the north_star layout (sweeps sharded, ordered exchange) in the same run
+        batch_mode = False
+        ms_sweeps = timed(step_device, max(2, args.steps // 2), 2)
+        batch_mode = True
 
     # per-kernel split on rank 0 / single GPU: aggregation kernel vs finish kernel (roofline of the dominant one)
     ms_agg = ms_fin = None
@@ -307,7 +318,7 @@ def main():
 
     # end-to-end through the reference-facing C-ABI call with host buffers
     ms_e2e = None
-    if world == 1:
+    if world == 1 or batch_mode:
         def step_e2e():
             o, c = ctx.stereo(u, v, dmin=dmin, dmax=dmax, P1=wl["P1"], P2=wl["P2"], NDIR=NDIR, MGM=K,
                               use_felzenszwalb_potentials=wl["felz"], distance="census", census_ncc_win=wl["win"],
@@ -315,12 +326,16 @@ def main():
             return o
         for _ in range(max(1, args.warmup - 1)):
             step_e2e()
-        torch.cuda.synchronize()
+        barrier_sync()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             step_e2e()
         torch.cuda.synchronize()
         ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+        if dist is not None:
+            t = torch.tensor([ms_e2e], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
     clocks = sampler.finish() if rank == 0 else None
 
     if rank != 0:
@@ -330,17 +345,24 @@ def main():
         return
 
     peak, peak_src = measured_peaks()
-    value = updates / (ms_dev * 1e-3) / 1e9
+    nunits = world if batch_mode else 1          # stereo pairs processed per step by the whole job
+    value = nunits * updates / (ms_dev * 1e-3) / 1e9
     line = {"metric": "Gdisp-updates/s (W*H*L*Ndirs)", "value": round(value, 3), "unit": "Gdisp-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev, 4),
-            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak" if (world == 1 or batch_mode) else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
-            "gpu_launches": info["kernel_launches"] * args.steps if world == 1 else 2 * args.steps,
+            "gpu_launches": 2 * args.steps * world,
             "launch_info": info, "clocks": clocks,
-            "mpix_per_s_device": round(W * H / (ms_dev * 1e-3) / 1e6, 2)}
-    if world > 1:
-        config["parallelism"] = "sweeps sharded %d per GPU, ordered peer-memory finish + NCCL all_gather of the maps" % (
-            (NDIR + world - 1) // world)
+            "mpix_per_s_device": round(nunits * W * H / (ms_dev * 1e-3) / 1e6, 2)}
+    sweeps_desc = "sweeps sharded %d per GPU, ordered peer-memory finish over NVLink + NCCL all_gather of the maps" % (
+        (NDIR + world - 1) // world)
+    if world > 1 and batch_mode:
+        config["parallelism"] = "batch: one stereo pair per GPU (%d pairs per step), no data-path collective" % world
+        line["sweep_sharded"] = {"value": round(updates / (ms_sweeps * 1e-3) / 1e9, 3), "unit": "Gdisp-updates/s",
+                                 "ms_per_step": round(ms_sweeps, 4), "scaling": "strong", "parallelism": sweeps_desc,
+                                 "note": "one pair, north_star layout; bit-identical to 1 GPU"}
+    elif world > 1:
+        config["parallelism"] = sweeps_desc
     if ms_agg is not None:
         agg_bytes = 8.0 * updates   # read C + write the sweep's message, fp32, per label update
         fin_bytes = 4.0 * W * H * L * (NDIR + 1)
@@ -355,9 +377,9 @@ def main():
                             "whole_step": {"bytes": 12.0 * updates + 4.0 * W * H * L,
                                            "frac": round((12.0 * updates + 4.0 * W * H * L) / (ms_dev * 1e-3) / 1e9 / peak, 4)}}
     if ms_e2e is not None:
-        line["e2e"] = {"value": round(updates / (ms_e2e * 1e-3) / 1e9, 3), "unit": "Gdisp-updates/s",
-                       "h2d_bytes_per_step": 2 * W * H * 4, "d2h_bytes_per_step": 2 * W * H * 4,
-                       "ms_per_step": round(ms_e2e, 3), "mpix_per_s": round(W * H / (ms_e2e * 1e-3) / 1e6, 2),
+        line["e2e"] = {"value": round(nunits * updates / (ms_e2e * 1e-3) / 1e9, 3), "unit": "Gdisp-updates/s",
+                       "h2d_bytes_per_step": nunits * 2 * W * H * 4, "d2h_bytes_per_step": nunits * 2 * W * H * 4,
+                       "ms_per_step": round(ms_e2e, 3), "mpix_per_s": round(nunits * W * H / (ms_e2e * 1e-3) / 1e6, 2),
                        "call": "mgmb200_stereo (host images in, host maps out)"}
     if not args.no_cpu_baseline and world == 1:
         try:

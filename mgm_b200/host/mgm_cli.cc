@@ -1,0 +1,197 @@
+// `mgm` command line on the B200 hot path: same options, environment variables, console output and file
+// outputs as the reference CLI (mgm.cc:266-450), with the hot path (weights, cost volume, aggregation, WTA,
+// sub-pixel: mgm.cc:372-385 and :405-414) executed by libmgmb200 on the GPU.  The O(W*H) post-processing
+// around it (left-right test mgm.cc:68-91, median img_tools.h:203-238, back-projection mgm.cc:432-443) is
+// host code here.  Not supported yet (exit code 2 with a message, never a silent fallback): -m/-M range
+// images, TSGM_ITER > 1, WITH_MGM2, -O 16.
+#include <algorithm>
+#include <cmath>
+
+#include "imgio.hpp"
+
+using namespace mgmb200;
+
+// pick_option (mgm.cc:165-179): "-name value" anywhere on the line, removed in place; with d == NULL a flag
+static char *pick_option(int *c, char ***v, const char *o, const char *d) {
+   int argc = *c;
+   char **argv = *v;
+   const int id = d ? 1 : 0;
+   for (int i = 0; i < argc - id; i++)
+      if (argv[i][0] == '-' && 0 == strcmp(argv[i] + 1, o)) {
+         char *r = argv[i + id] + 1 - id;
+         *c -= id + 1;
+         for (int j = i; j < argc - id; j++) (*v)[j] = (*v)[j + id + 1];
+         return r;
+      }
+   return const_cast<char *>(d);
+}
+
+MGMB200_SMART_PARAMETER(TSGM, 4)
+MGMB200_SMART_PARAMETER(TSGM_FIX_OVERCOUNT, 1)
+MGMB200_SMART_PARAMETER(USE_TRUNCATED_LINEAR_POTENTIALS, 0)
+MGMB200_SMART_PARAMETER(WITH_MGM2, 0)
+MGMB200_SMART_PARAMETER(TSGM_ITER, 1)
+MGMB200_SMART_PARAMETER(TESTLRRL, 1)
+MGMB200_SMART_PARAMETER(TESTLRRL_TAU, 1.0)
+MGMB200_SMART_PARAMETER(MEDIAN, 0)
+
+static void remove_nonfinite_values_Img(Img &u, float newval) {
+   for (float &f : u.data) if (!std::isfinite(f)) f = newval;
+}
+
+// leftright_test, mgm.cc:68-91
+static void leftright_test(Img &dx, const Img &Rdx, float threshold) {
+   const int nc = dx.nx, nr = dx.ny, Rnc = Rdx.nx;
+   for (int y = 0; y < nr; y++)
+      for (int x = 0; x < nc; x++) {
+         const int i = x + y * nc;
+         const int Lx = (int)round(x + dx[i]);
+         if (Lx < Rnc && Lx >= 0) {
+            const float Rx = Lx + Rdx[Lx + y * Rnc];
+            if (fabs(Rx - x) > threshold) dx[i] = NAN;
+         } else
+            dx[i] = NAN;
+      }
+}
+
+// median_filter, img_tools.h:203-238 (NaN-aware, upper median)
+static Img median_filter(const Img &u, int radius) {
+   Img M = u;
+   std::vector<float> v;
+   for (int k = 0; k < u.nch; k++)
+      for (int y = 0; y < u.ny; y++)
+         for (int x = 0; x < u.nx; x++) {
+            v.clear();
+            for (int j = -radius; j <= radius; j++)
+               for (int i = -radius; i <= radius; i++) {
+                  const int xx = x + i, yy = y + j;
+                  if (xx < 0 || yy < 0 || xx >= u.nx || yy >= u.ny) continue;
+                  const float t = u.val(xx, yy, k);
+                  if (!std::isnan(t)) v.push_back(t);
+               }
+            if (!v.empty()) {
+               std::nth_element(v.begin(), v.begin() + v.size() / 2, v.end());
+               M.val(x, y, k) = v[v.size() / 2];
+            }
+         }
+   return M;
+}
+
+static const char *help_usage = "usage:\n\tmgm [-options] u v out [cost [backflow]]";
+
+int main(int argc, char *argv[]) {
+   if (argc < 2 || !strcmp(argv[1], "-h")) return 0 * puts(help_usage);
+   if (!strcmp(argv[1], "-?")) return 0 * puts("Compute stereo disparities by the MGM algorithm.");
+   if (!strcmp(argv[1], "--version")) return 0 * puts("mgm 2.0 (mgm_b200)");
+   if (!strcmp(argv[1], "--help")) {
+      puts("mgm [options] in_u in_v out_disp [out_cost [out_backflow]]\n"
+           " -r {-30} -R {30} -O {4} -P1 {8} -P2 {32} -p {none|census|sobelx|gblur} -t {ad|sd|census|ncc|btad|btsd}\n"
+           " -truncDist {inf} -s {none|vfit|parabola|cubic|parabolaOCV} -aP1 {1} -aP2 {1} -aThresh {5}\n"
+           " -m FILE -M FILE -l FILE\n"
+           "Environment: CENSUS_NCC_WIN=3 TESTLRRL=1 TESTLRRL_TAU=1.0 MEDIAN=0 TSGM=4 TSGM_ITER=1\n"
+           "             TSGM_FIX_OVERCOUNT=1 USE_TRUNCATED_LINEAR_POTENTIALS=0 MGMB200_DEVICE=<gpu>\n"
+           "Same surface as gfacciol/mgm; the hot path runs on the GPU (libmgmb200).");
+      return 0;
+   }
+   if (argc < 4) {
+      fprintf(stderr, "too few parameters\n   %s\n", help_usage);
+      return 1;
+   }
+   try {
+      char *in_min_disp_file = pick_option(&argc, &argv, "m", "");
+      char *in_max_disp_file = pick_option(&argc, &argv, "M", "");
+      int dmin = atoi(pick_option(&argc, &argv, "r", "-30"));
+      int dmax = atoi(pick_option(&argc, &argv, "R", "30"));
+      int NDIR = atoi(pick_option(&argc, &argv, "O", "4"));
+      float P1 = atof(pick_option(&argc, &argv, "P1", "8"));
+      float P2 = atof(pick_option(&argc, &argv, "P2", "32"));
+      float aP1 = atof(pick_option(&argc, &argv, "aP1", "1"));
+      float aP2 = atof(pick_option(&argc, &argv, "aP2", "1"));
+      float aThresh = atof(pick_option(&argc, &argv, "aThresh", "5"));
+      char *distance = pick_option(&argc, &argv, "t", "ad");
+      char *prefilter = pick_option(&argc, &argv, "p", "none");
+      char *refine = pick_option(&argc, &argv, "s", "none");
+      float truncDist = atof(pick_option(&argc, &argv, "truncDist", "inf"));
+      char *nolr_disp_file = pick_option(&argc, &argv, "l", "");
+      (void)aP1;   // parsed but unused by the reference as well (mgm.cc:372)
+
+      int i = 1;
+      char *filename_u = (argc > i) ? argv[i] : NULL; i++;
+      char *filename_v = (argc > i) ? argv[i] : NULL; i++;
+      char *filename_out = (argc > i) ? argv[i] : NULL; i++;
+      char *filename_cost = (argc > i) ? argv[i] : NULL; i++;
+      char *filename_back = (argc > i) ? argv[i] : NULL; i++;
+      if (!filename_u || !filename_v || !filename_out) { fprintf(stderr, "too few parameters\n"); return 1; }
+
+      printf("%d %d\n", dmin, dmax);
+
+      if (strcmp(in_min_disp_file, "") != 0 || strcmp(in_max_disp_file, "") != 0) {
+         fprintf(stderr, "mgm_b200: per-pixel disparity range files (-m/-M) are not supported yet\n");
+         return 2;
+      }
+      if ((int)TSGM_ITER() != 1) { fprintf(stderr, "mgm_b200: TSGM_ITER != 1 is not supported yet\n"); return 2; }
+      if (WITH_MGM2()) fprintf(stderr, "mgm_b200: WITH_MGM2 ignored (the sweeps always run concurrently, summed in order)\n");
+
+      Img u = io::read_image(filename_u);
+      Img v = io::read_image(filename_v);
+      remove_nonfinite_values_Img(u, 0);
+      remove_nonfinite_values_Img(v, 0);
+      if (u.nx != v.nx || u.ny != v.ny || u.nch != v.nch) {
+         fprintf(stderr, "mgm_b200: u and v must have the same size and channels\n");
+         return 2;
+      }
+
+      mgmb200_stereo_params p;
+      mgmb200_stereo_params_default(&p);
+      p.P1 = P1; p.P2 = P2;   // scaled by nch inside mgmb200_stereo exactly like mgm.cc:356-357
+      p.NDIR = NDIR;
+      p.MGM = (int)TSGM();   // double -> int truncation like mgm.cc:380
+      p.use_felzenszwalb_potentials = (int)USE_TRUNCATED_LINEAR_POTENTIALS();
+      p.sgm_fix_overcount = (int)TSGM_FIX_OVERCOUNT();
+      p.aP = aP2; p.aThresh = aThresh;
+      p.prefilter = prefilter; p.distance = distance; p.truncDist = truncDist;
+      p.census_ncc_win = (int)CENSUS_NCC_WIN();
+      p.refinement = refine;
+
+      Img outoff(u.nx, u.ny), outcost(u.nx, u.ny), outoffR(v.nx, v.ny), outcostR(v.nx, v.ny);
+      auto run = [&](Img &a, Img &b, int lo, int hi, Img &off, Img &cost) {
+         p.dmin = lo; p.dmax = hi;
+         check(mgmb200_stereo(context(), a.data.data(), b.data.data(), a.nx, a.ny, a.nch, &p, off.data.data(), cost.data.data()));
+         for (int pass = 0; pass < NDIR; pass++) printf("%d", pass);   // mgm_core.cc:491
+         printf("\n");                                                  // print_solution_energy, mgm_print_energy.h:110
+      };
+      run(u, v, dmin, dmax, outoff, outcost);
+      if (MEDIAN()) outoff = median_filter(outoff, (int)MEDIAN());
+      if (0 != strcmp(nolr_disp_file, "")) io::write_image(nolr_disp_file, outoff);
+
+      if (TESTLRRL()) {
+         run(v, u, -dmax, -dmin, outoffR, outcostR);
+         if (MEDIAN()) outoffR = median_filter(outoffR, (int)MEDIAN());
+         Img tmpL(outoff), tmpR(outoffR);
+         leftright_test(outoffR, tmpL, (float)TESTLRRL_TAU());
+         leftright_test(outoff, tmpR, (float)TESTLRRL_TAU());
+      }
+
+      // back-projected image, mgm.cc:432-443
+      Img syn(u.nx, u.ny, u.nch);
+      for (int x = 0; x < u.nx; x++)
+         for (int y = 0; y < u.ny; y++) {
+            const float qx = outoff[x + u.nx * y];
+            const float px = x + qx;
+            for (int c = 0; c < u.nch; c++) {
+               if (px >= 0 && px < v.nx)   // check_inside_image(p+q, v) on float coordinates (NaN -> outside)
+                  syn.data[x + y * u.nx + (size_t)c * u.npix] = v.data[(int)px + y * v.nx + (size_t)c * v.npix];
+               else
+                  syn.data[x + y * u.nx + (size_t)c * u.npix] = u.data[x + y * u.nx + (size_t)c * u.npix];
+            }
+         }
+
+      io::write_image(filename_out, outoff);
+      if (filename_cost) io::write_image(filename_cost, outcost);
+      if (filename_back) io::write_image(filename_back, syn);
+      return 0;
+   } catch (const std::exception &e) {
+      fprintf(stderr, "%s\n", e.what());
+      return 3;
+   }
+}

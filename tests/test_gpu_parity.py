@@ -234,3 +234,69 @@ def test_full_size_properties(ctx, cfg):
     o = O.orc_pipeline(u[:ch, :cw], v[:ch, :cw], -(L - 1), 0, **kk)
     assert same(out1[:ch - 2, :cw - 2], o["out"][:ch - 2, :cw - 2])
     assert same(cost1[:ch - 2, :cw - 2], o["outcost"][:ch - 2, :cw - 2])
+
+
+# ------------------------------------------------------------------------------------------ command lines
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_MGM = os.path.join(ROOT, "oracle", "_ref", "mgm")
+REF_MGM_O = os.path.join(ROOT, "oracle", "_ref", "mgm_o")
+OUR_MGM = os.path.join(ROOT, "mgm_b200", "bin", "mgm")
+OUR_MGM_O = os.path.join(ROOT, "mgm_b200", "bin", "mgm_o")
+
+
+def _pnm(path, a):
+    a = np.clip(a, 0, 255).astype(np.uint8)
+    if a.shape[0] == 1:
+        open(path, "wb").write(b"P5\n%d %d\n255\n" % (a.shape[2], a.shape[1]) + a[0].tobytes())
+    else:
+        open(path, "wb").write(b"P6\n%d %d\n255\n" % (a.shape[2], a.shape[1]) + np.transpose(a, (1, 2, 0)).tobytes())
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_MGM) and os.path.exists(OUR_MGM)), reason="CLI binaries not built")
+@pytest.mark.parametrize("case", [
+    (dict(TSGM="2"), ["-r", "-23", "-R", "4", "-t", "ad", "-O", "4"], 1),                                   # BASELINE cfg 1 flags
+    (dict(MEDIAN="1", CENSUS_NCC_WIN="3", USE_TRUNCATED_LINEAR_POTENTIALS="1", TSGM="3"),
+     ["-P2", "20000", "-P1", "2", "-r", "-23", "-R", "4", "-t", "census", "-s", "vfit", "-O", "8"], 3),     # Makefile:17
+    (dict(MEDIAN="1", USE_TRUNCATED_LINEAR_POTENTIALS="1", TSGM="3"),
+     ["-P2", "20000", "-P1", "4", "-r", "-23", "-R", "4", "-p", "sobel_x", "-truncDist", "63", "-s", "vfit", "-O", "8"], 3),  # Makefile:18
+    (dict(TESTLRRL="0"), ["-r", "-23", "-R", "4", "-aP2", "4", "-aThresh", "9", "-s", "cubic", "-O", "8"], 1),  # CLI defaults, weights
+])
+def test_cli_matches_reference_cli(tmp_path, case):
+    """the whole `mgm` command (both LR directions, median, LR test, back-projection, console output)"""
+    env_extra, args, nch = case
+    u, v = synth_pair(120, 64, 24, seed=4, nch=nch)
+    _pnm(str(tmp_path / "u.pnm"), u)
+    _pnm(str(tmp_path / "v.pnm"), v)
+    outs = {}
+    for tag, exe in (("ref", REF_MGM), ("our", OUR_MGM)):
+        names = [str(tmp_path / ("%s_%s.npy" % (tag, k))) for k in ("disp", "cost", "back")]
+        env = dict(os.environ, **env_extra)
+        r = subprocess.run([exe] + args + [str(tmp_path / "u.pnm"), str(tmp_path / "v.pnm")] + names + ["-l", str(tmp_path / (tag + "_nolr.npy"))],
+                           env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs[tag] = (r.stdout, [np.squeeze(np.load(n)) for n in names + [str(tmp_path / (tag + "_nolr.npy"))]])
+    assert outs["our"][0].replace(" USING IMAGE DEPENDENT WEIGHTS\n", "") == outs["ref"][0].replace(" USING IMAGE DEPENDENT WEIGHTS\n", "")
+    for a, b, what in zip(outs["our"][1], outs["ref"][1], ("disp", "cost", "back", "nolr")):
+        assert a.shape == b.shape and same(a, b), (what, mism(a, b))
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_MGM_O) and os.path.exists(OUR_MGM_O)), reason="mgm_o binaries not built")
+@pytest.mark.parametrize("argv", [["8", "32", "2", "0"], ["2", "20000", "4", "1"], ["8", "32", "1", "0"]])
+def test_mgm_o_file_protocol(tmp_path, argv):
+    """matlab/mgm_o.cc: input.bin -> output.bin"""
+    ncol, nrow, nlab, NDIR = 47, 31, 12, 8
+    rng = np.random.default_rng(5)
+    costs = rng.integers(0, 64, (nlab, nrow, ncol)).astype(np.float32)
+    w = np.where(rng.random((8, nrow, ncol)) < 0.25, 3.0, 1.0).astype(np.float32)
+    with open(tmp_path / "input.bin", "wb") as f:
+        f.write(np.array([ncol, nrow, nlab, NDIR], np.int32).tobytes() + costs.tobytes() + w.tobytes())
+    res = {}
+    for tag, exe in (("ref", REF_MGM_O), ("our", OUR_MGM_O)):
+        out = tmp_path / (tag + ".bin")
+        r = subprocess.run([exe, str(tmp_path / "input.bin"), str(out)] + argv, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        res[tag] = np.fromfile(out, np.float32)
+    assert same(res["our"], res["ref"])
