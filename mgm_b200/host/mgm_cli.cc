@@ -176,12 +176,14 @@ int main(int argc, char *argv[]) {
       Img syn(u.nx, u.ny, u.nch);
       for (int x = 0; x < u.nx; x++)
          for (int y = 0; y < u.ny; y++) {
-            const float qx = outoff[x + u.nx * y];
+            const float qx = outoff[x + u.nx * y], qy = 0.f;
             const float px = x + qx;
             for (int c = 0; c < u.nch; c++) {
-               if (px >= 0 && px < v.nx)   // check_inside_image(p+q, v) on float coordinates (NaN -> outside)
-                  syn.data[x + y * u.nx + (size_t)c * u.npix] = v.data[(int)px + y * v.nx + (size_t)c * v.npix];
-               else
+               if (px >= 0 && px < v.nx) {   // check_inside_image(p+q, v) on float coordinates (NaN -> outside)
+                  // the reference indexes v.data with a FLOAT expression (mgm.cc:439): same arithmetic here
+                  const float fidx = x + qx + (y + qy) * v.nx + c * v.npix;
+                  syn.data[x + y * u.nx + (size_t)c * u.npix] = v.data[(size_t)fidx];
+               } else
                   syn.data[x + y * u.nx + (size_t)c * u.npix] = u.data[x + y * u.nx + (size_t)c * u.npix];
             }
          }
