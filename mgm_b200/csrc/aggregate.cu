@@ -58,43 +58,65 @@ __device__ __forceinline__ float sgm_x(float l, float c, float r, float p1, floa
 // its first half of the labels, then finishes the other half with the partner's partials.  Every addition
 // is performed in the same order as the reference's sequential loops.  The result written to dst is
 // min(minconv, cap) - sub.  Loads are issued one chunk ahead of the dependent add/min chain.
-__device__ __forceinline__ void minconv_pair(const float4 *src, float4 *dst, int nq, int dir, float c, float cap,
-                                             float sub, unsigned pmask) {
+// One chunk of four labels of the recurrence F[o] = min(F[o-1]+c, a[o]), two labels per dependent step.  By
+// monotonicity of x -> RN(x+c):  F1 = min(r+c, a0),  F2 = min((r+c)+c, a0+c, a1)  with every "+c" a separately
+// rounded addition -- bit-identical to the step-by-step form.  The loop-carried dependency per pair is two
+// additions and one 3-input minimum (~13 cycles) instead of two add->min pairs (~20) for five instructions
+// instead of four; the kernel is issue-bound in this phase, so the cheaper two-label form beats deeper unrolling.
+__device__ __forceinline__ void chain4(float &run, float &a0, float &a1, float &a2, float &a3, const float c) {
+   {
+      const float u1 = run + c, u2 = u1 + c, a0p = a0 + c;
+      a0 = fminf(u1, a0);
+      a1 = fminf(fminf(u2, a0p), a1);
+   }
+   {
+      const float u1 = a1 + c, u2 = u1 + c, a2p = a2 + c;
+      a2 = fminf(u1, a2);
+      a3 = fminf(fminf(u2, a2p), a3);
+   }
+   run = a3;
+}
+
+// named barrier shared by one forward warp and its backward partner warp (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// Half of the meet-in-the-middle min-convolution of `src` into `dst`, executed by a whole WARP whose lanes
+// hold the same direction (DIR=0 upwards, DIR=1 downwards) of 32 different vectors; the partner warp runs
+// the other direction of the same vectors.  Warp-uniform direction: no divergence, no lane swizzles.
+// `on` = this lane has a vector to process (the barrier is executed by every lane regardless).
+template <int DIR>
+__device__ __forceinline__ void minconv_half(bool on, const float4 *src, float4 *dst, int nq, float c, float cap,
+                                             float sub, int bar_id) {
    const int h = nq >> 1;   // nq is even
-   const int q0 = dir ? (nq - 1) : 0, dq = dir ? -1 : 1;
+   const int dq = DIR ? -1 : 1;
+   int q = DIR ? (nq - 1) : 0;
    float run = MGM_INF;
-   float4 v = src[q0];
-   int q = q0;
-   for (int i = 0; i < h; ++i, q += dq) {
-      const float4 vn = src[q + dq];   // chunk i+1 always exists (h < nq)
-      float a0 = dir ? v.w : v.x, a1 = dir ? v.z : v.y, a2 = dir ? v.y : v.z, a3 = dir ? v.x : v.w;
-      a0 = run = fminf(run + c, a0);
-      a1 = run = fminf(run + c, a1);
-      a2 = run = fminf(run + c, a2);
-      a3 = run = fminf(run + c, a3);
-      dst[q] = dir ? make_float4(a3, a2, a1, a0) : make_float4(a0, a1, a2, a3);
-      v = vn;
+   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+   if (on) {
+      v = src[q];
+      for (int i = 0; i < h; ++i, q += dq) {
+         const float4 vn = src[q + dq];   // chunk i+1 always exists (h < nq)
+         if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
+         dst[q] = v;
+         v = vn;
+      }
    }
-   __syncwarp(pmask);
-   float4 o = dst[q];   // partner's partial values
-   for (int i = h; i < nq; ++i, q += dq) {
-      const bool more = (i + 1 < nq);
-      const float4 vn = more ? src[q + dq] : v;
-      const float4 on = more ? dst[q + dq] : o;
-      float a0 = dir ? v.w : v.x, a1 = dir ? v.z : v.y, a2 = dir ? v.y : v.z, a3 = dir ? v.x : v.w;
-      const float b0 = dir ? o.w : o.x, b1 = dir ? o.z : o.y, b2 = dir ? o.y : o.z, b3 = dir ? o.x : o.w;
-      a0 = run = fminf(run + c, a0);
-      a1 = run = fminf(run + c, a1);
-      a2 = run = fminf(run + c, a2);
-      a3 = run = fminf(run + c, a3);
-      a0 = fminf(fminf(a0, b0), cap) - sub;
-      a1 = fminf(fminf(a1, b1), cap) - sub;
-      a2 = fminf(fminf(a2, b2), cap) - sub;
-      a3 = fminf(fminf(a3, b3), cap) - sub;
-      dst[q] = dir ? make_float4(a3, a2, a1, a0) : make_float4(a0, a1, a2, a3);
-      v = vn; o = on;
+   pair_barrier(bar_id);   // partner's partial values are now in dst
+   if (on) {
+      float4 o = dst[q];
+      for (int i = h; i < nq; ++i, q += dq) {
+         const bool more = (i + 1 < nq);
+         const float4 vn = more ? src[q + dq] : v;
+         const float4 on4 = more ? dst[q + dq] : o;
+         if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
+         v.x = fminf(fminf(v.x, o.x), cap) - sub;
+         v.y = fminf(fminf(v.y, o.y), cap) - sub;
+         v.z = fminf(fminf(v.z, o.z), cap) - sub;
+         v.w = fminf(fminf(v.w, o.w), cap) - sub;
+         dst[q] = v;
+         v = vn; o = on4;
+      }
    }
-   __syncwarp(pmask);
 }
 
 template <int K>
@@ -139,9 +161,10 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    // lane-pair mapping for the sequential min-convolution chains: pair p of a warp is lanes (p, p+16); the
    // forward halves of 8 consecutive rows then sit in one quarter-warp and hit 8 different bank groups
    // (the row stride is an odd number of 16-byte units), likewise the backward halves
-   const int pair_idx = (tid >> 5) * 16 + (tid & 15);
-   const int pair_dir = (tid >> 4) & 1;
-   const unsigned pmask = 0x00010001u << (tid & 15);
+   // (superseded mapping kept simple) chain work is distributed per WARP: warps [0,NCW) run the upward halves of
+   // vectors 32w..32w+31, warps [NCW,2NCW) the downward halves of the same vectors; 8 consecutive rows in a
+   // quarter-warp hit 8 different bank groups because the row stride is an odd number of 16-byte units
+   const int warp_id = tid >> 5, lane_id = tid & 31;
 
    uint64_t *cbar = reinterpret_cast<uint64_t *>(smem + P.off_cbar);
    uint64_t *vbar = reinterpret_cast<uint64_t *>(smem + P.off_vbar);
@@ -248,17 +271,28 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 
       // ---------------- phase 0 (weighted truncated-linear only): one lane pair per (row, neighbour)
       if constexpr (WTRUNC) {
-         const int crow = pair_idx / K, ck = pair_idx % K, cdir = pair_dir;
-         const int cxs = s - SIG * crow;
-         if (tid < ncomp && pair_idx < K * nrows && cxs > 0 && cxs < maxii - 1 && (row0 + crow) != 0) {
-            int prow, ppx;
-            pred_of(crow, cxs, ck, prow, ppx);
-            const long long cpix = g.base0 + (long long)(row0 + crow) * g.dys + (long long)cxs * g.dxs;
-            const float wk = __ldg(P.w + (size_t)pass_weight_plane(pass, ck) * wplane + cpix);
-            const float mk = m_of(prow, ppx);
-            minconv_pair(reinterpret_cast<const float4 *>(slot_of(prow, ppx)),
-                         reinterpret_cast<float4 *>(row_base(crow) + (R + 2 + ck) * VS), nq, cdir, P.P1 * wk,
-                         mk + P.P2 * wk, mk, pmask);
+         const int ncw = (K * nrows + 31) >> 5;   // warps per direction
+         if (warp_id < 2 * ncw) {
+            const int cw = warp_id % ncw, cdir = warp_id / ncw;
+            const int pidx = cw * 32 + lane_id;
+            const int crow = pidx / K, ck = pidx % K;
+            const int cxs = s - SIG * crow;
+            const bool on = pidx < K * nrows && cxs > 0 && cxs < maxii - 1 && (row0 + crow) != 0;
+            const float *src = thr;
+            float *dst = thr;
+            float cw1 = 0.f, capv = 0.f, mk = 0.f;
+            if (on) {
+               int prow, ppx;
+               pred_of(crow, cxs, ck, prow, ppx);
+               const long long cpix = g.base0 + (long long)(row0 + crow) * g.dys + (long long)cxs * g.dxs;
+               const float wk = __ldg(P.w + (size_t)pass_weight_plane(pass, ck) * wplane + cpix);
+               mk = m_of(prow, ppx);
+               cw1 = P.P1 * wk; capv = mk + P.P2 * wk;
+               src = slot_of(prow, ppx);
+               dst = row_base(crow) + (R + 2 + ck) * VS;
+            }
+            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 1 + cw);
+            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 1 + cw);
          }
          __syncthreads();
       }
@@ -376,15 +410,18 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
       // ---------------- phase 2: build the neighbour-side transform of the message in the ring slot
       if constexpr (CHAINS) {
          // minConvTruncatedLinear of the finished message, one lane pair per row
-         const int crow = pair_idx, cdir = pair_dir;
-         const int cxs = s - SIG * crow;
-         if (tid < ncomp && crow < nrows && cxs >= 0 && cxs < maxii) {
-            const float cm = msr[crow * 4 + (cxs % R)];
-            const float *src = row_base(crow) + (R + (cxs & 1)) * VS;
-            float *dst = row_base(crow) + (cxs % R) * VS;
-            minconv_pair(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cdir, P.P1,
-                         cm + P.P2, (K == 2) ? 0.0f : cm, pmask);
-            if (has_next && crow == nrows - 1) fence_proxy_async_smem();   // read by the boundary TMA store
+         const int ncw = (nrows + 31) >> 5;   // warps per direction
+         if (warp_id < 2 * ncw) {
+            const int cw = warp_id % ncw, cdir = warp_id / ncw;
+            const int crow = cw * 32 + lane_id;
+            const int cxs = s - SIG * crow;
+            const bool on = crow < nrows && cxs >= 0 && cxs < maxii;
+            const float cm = on ? msr[crow * 4 + (cxs % R)] : 0.f;
+            const float *src = on ? row_base(crow) + (R + (cxs & 1)) * VS : thr;
+            float *dst = on ? row_base(crow) + (cxs % R) * VS : thr;
+            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, 1 + cw);
+            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, 1 + cw);
+            if (on && has_next && crow == nrows - 1) fence_proxy_async_smem();   // read by the boundary TMA store
          }
       } else if (act) {
          if constexpr (!WEIGHTED) {
