@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/mgmb200.h"
@@ -322,9 +323,24 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
       bndm_off[p] = bndm_total; bndm_total += (size_t)nb[p] * g.maxii;
       prog_off[p] = prog_total; prog_total += nb[p];
    }
-   for (int b = 0; b < maxb; b++)
-      for (int p = 0; p < NDIR; p++)
-         if ((mask & (1u << p)) && b < nb[p]) tk.push_back(make_int2(p, b));
+   // Claim order = longest remaining dependency chain first (list scheduling): band b of sweep p still has
+   // (nb-b) band hand-offs of ~sigma*T+6 steps plus maxii steps ahead of it.  Within a sweep the key decreases
+   // with b, so a band is always claimed after its predecessor (required for deadlock freedom).
+   {
+      struct Item { long long key; int p, b; };
+      std::vector<Item> items;
+      for (int p = 0; p < NDIR; p++) {
+         if (!(mask & (1u << p))) continue;
+         PassGeom g = pass_geometry(p, nx, ny);
+         const int cls = p < 4 ? 0 : 1;
+         const int sig = (cls == 1 || K == 4) ? 2 : 1;
+         const long long lag = (long long)sig * plan.T[cls] + 6;
+         for (int b = 0; b < nb[p]; b++) items.push_back({(long long)(nb[p] - b) * lag + g.maxii, p, b});
+      }
+      std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.key > b.key; });
+      for (const Item &it : items) tk.push_back(make_int2(it.p, it.b));
+   }
+   (void)maxb;
    if (tk.empty()) return 0;
 
    if (tk.size() * sizeof(int2) > c->tickets.cap) c->tk_key[0] = -1;
