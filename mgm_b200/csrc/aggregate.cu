@@ -25,6 +25,8 @@
 // Precondition of this fast path (enforced by the host): every cost
 // vector holds a finite value, no NaN / -INF, P1,P2 >= 0 and weights >= 0; then the
 // hardware min is bit-identical to the reference's compare-select forms.
+#include <type_traits>
+
 #include "aggregate.cuh"
 
 namespace mgm {
@@ -143,9 +145,9 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    const int nj = nq / G;   // chunks per lane (VS is a multiple of 4*G)
    const uint32_t vbytes = (uint32_t)VS * 4u;
    const int tid = threadIdx.x;
-   const int ncomp = blockDim.x - 32;
-   const int plane = tid - ncomp;             // lane of the producer warp (>= 0 there)
-   const bool is_prod = (tid == ncomp);
+   const int ncomp = blockDim.x - 64;   // two service warps follow the row threads
+   const bool is_prod = (tid == ncomp);        // fetches the previous band's boundary row
+   const bool is_pub = (tid == ncomp + 32);    // stores and publishes this band's boundary row
    const int row0 = band * T;
    const int nrows = min(T, maxjj - row0);
    const bool has_prev = band > 0;
@@ -166,7 +168,6 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    // quarter-warp hit 8 different bank groups because the row stride is an odd number of 16-byte units
    const int warp_id = tid >> 5, lane_id = tid & 31;
 
-   uint64_t *cbar = reinterpret_cast<uint64_t *>(smem + P.off_cbar);
    uint64_t *vbar = reinterpret_cast<uint64_t *>(smem + P.off_vbar);
    float *msr = reinterpret_cast<float *>(smem + P.off_ms);
    float *vms = reinterpret_cast<float *>(smem + P.off_vms);
@@ -199,42 +200,50 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 
    const long long pix0 = g.base0 + (long long)ys * g.dys;   // pixel of (0, ys) for my group's row
 
-   uint32_t cph = 0, vph = 0;
-   if (tid < ncomp && r < T) cph = phase[r];
+   uint32_t vph = 0;
    const int vph_idx = max(P.T[0], P.T[1]);
    if (tid < G) vph = phase[vph_idx];
    int next_px = 0;   // producer: next boundary pixel to fetch
 
-   // The producer warp owns every TMA load: lane l feeds the cost buffers of rows l, l+32, ...
-   // Pixel px of a row goes to cost buffer px&1; it may be (re)filled once the step that used the
-   // buffer for pixel px-2 has ended, i.e. from the top of the step in which the row handles px-1.
-   auto issue_cost_loads = [&](int s) {
-      for (int rr = plane; rr < nrows; rr += 32) {
-         const int px = s - SIG * rr + 1;   // the pixel this row handles in the NEXT step
-         if (px >= 0 && px < maxii) {
-            const long long pp = g.base0 + (long long)(row0 + rr) * g.dys + (long long)px * g.dxs;
-            uint64_t *bar = &cbar[2 * rr + (px & 1)];
-            mbar_expect_tx(bar, vbytes);
-            tma_load_1d(row_base(rr) + (R + (px & 1)) * VS, ccv + (size_t)pp * VS, vbytes, bar);
-         }
+   // Cost vectors: every lane prefetches, one pixel ahead, exactly the 16-byte chunks it will read itself
+   // (cp.async, LDGSTS: no registers, no cross-thread hand-off, 128-byte coalesced per row); pixel px of a row
+   // lands in cost buffer px&1, free again once the step that used it for pixel px-2 has ended.
+   auto prefetch_cost = [&](int s) {
+      const int px = s - SIG * r + 1;   // the pixel my row handles in the NEXT step
+      if (rowok && px >= 0 && px < maxii) {
+         const float4 *src = reinterpret_cast<const float4 *>(ccv + (size_t)(pix0 + (long long)px * g.dxs) * VS);
+         float4 *dst = reinterpret_cast<float4 *>(row_base(r) + (R + (px & 1)) * VS);
+         for (int j = 0; j < nj; ++j) cp_async16(dst + gl + G * j, src + gl + G * j);
       }
+      cp_async_commit();   // one (possibly empty) group per step keeps the wait count uniform
    };
-   if (plane >= 0) {
-      fence_proxy_async_smem();
-      issue_cost_loads(-1);   // pixel 0 of row 0 (the other rows start later)
-   }
+   prefetch_cost(-1);   // pixel 0 of row 0 (the other rows start later)
 
    long long tA = 0, tW1 = 0, tB = 0, tW2 = 0, tP = 0, tC = 0;
    for (int s = 0; s < nsteps; ++s) {
       const long long c0 = clock64();
-      if (plane >= 0) {
-         fence_proxy_async_smem();   // the buffers were last touched by generic-proxy accesses (before the barrier)
-         issue_cost_loads(s);
+      prefetch_cost(s);
+      if (is_pub && has_next) {
+         // boundary stores are issued by this thread (end of each step, below); all but the most recent one
+         // are complete -> publish them.  Runs on the otherwise idle producer warp, off the rows' critical path.
+         const int pl = (s - 1) - SIG * (nrows - 1);   // pixel stored at the end of the previous step
+         if (pl >= 1 && pl < maxii) {
+            tma_wait_all<1>();
+            fence_proxy_async();
+            st_release(prog_out, pl);   // pixels [0,pl) of the boundary row are in global memory
+         }
       }
       if (is_prod && has_prev) {
+         // boundary pixels up to s+2 are needed before the next step (blocking); up to s+1+PF are fetched
+         // ahead of time when the previous band has already published them (non-blocking)
+         const int need = min(maxii - 1, s + 2);
          const int lim = min(maxii - 1, s + 1 + PF);
+         int avail = ld_acquire(prog_in);
          while (next_px <= lim) {
-            while (ld_acquire(prog_in) < next_px + 1) __nanosleep(40);
+            if (avail < next_px + 1) {
+               if (next_px > need) break;
+               do { __nanosleep(20); avail = ld_acquire(prog_in); } while (avail < next_px + 1);
+            }
             fence_proxy_async();
             const int slot = next_px & (RV - 1);
             if (NEEDM) vms[slot] = __ldcg(bndm_in + next_px);
@@ -299,16 +308,8 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 
       // ---------------- phase 1: gather the message of pixel (xs,ys), G lanes per row
       if (act) {
-         if (last_row && gl == 0 && xs > 0) {
-            // the boundary vector of pixel xs-1 was handed to the TMA one step ago: publish it
-            tma_wait_all<0>();
-            fence_proxy_async();
-            __threadfence();
-            st_release(prog_out, xs);   // pixels [0,xs) of the boundary row are in global memory
-         }
          const long long cw0 = clock64();
-         mbar_wait(&cbar[2 * r + cbi], (cph >> cbi) & 1u);
-         cph ^= (1u << cbi);
+         cp_async_wait<1>();   // everything but the prefetch issued at the top of this step has landed
          tC += clock64() - cw0;
 
          if (border) {
@@ -331,46 +332,50 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                if (WEIGHTED && !WTRUNC) wk[k] = __ldg(P.w + (size_t)pass_weight_plane(pass, k) * wplane + pix);
             }
             if constexpr (!WEIGHTED || WTRUNC) {
-               // slots hold the neighbour-side transform already (producer row, or phase 0 scratch)
-               for (int j0 = 0; j0 < nj; j0 += JB) {
-                  float4 c[JB], a[K][JB];
+               // slots hold the neighbour-side transform already (producer row, or phase 0 scratch).
+               // Straight-line batches: all loads of a batch are issued before the first use.
+               auto batch = [&](auto jbc, int j0) {
+                  constexpr int B = decltype(jbc)::value;
+                  float4 c[B], a[K][B];
 #pragma unroll
-                  for (int jj = 0; jj < JB; ++jj) {
-                     const int q = gl + G * min(j0 + jj, nj - 1);
+                  for (int jj = 0; jj < B; ++jj) {
+                     const int q = gl + G * (j0 + jj);
                      c[jj] = Cb[q];
 #pragma unroll
                      for (int k = 0; k < K; ++k) a[k][jj] = S[k][q];
                   }
 #pragma unroll
-                  for (int jj = 0; jj < JB; ++jj) {
-                     if (j0 + jj < nj) {
-                        const int q = gl + G * (j0 + jj);
-                        float4 o;
-                        if constexpr (POT == POT_TRUNC && K == 2 && !WEIGHTED) {   // update_cost2_trunclinear :216
-                           o.x = c[jj].x + (((a[0][jj].x - mk[0]) + a[1 % K][jj].x) - mk[1 % K]) * 0.5f;
-                           o.y = c[jj].y + (((a[0][jj].y - mk[0]) + a[1 % K][jj].y) - mk[1 % K]) * 0.5f;
-                           o.z = c[jj].z + (((a[0][jj].z - mk[0]) + a[1 % K][jj].z) - mk[1 % K]) * 0.5f;
-                           o.w = c[jj].w + (((a[0][jj].w - mk[0]) + a[1 % K][jj].w) - mk[1 % K]) * 0.5f;
-                        } else if constexpr (POT == POT_SGM && K == 2) {   // update_cost2: halves taken by the producer
-                           o.x = c[jj].x + (a[0][jj].x + a[1 % K][jj].x);
-                           o.y = c[jj].y + (a[0][jj].y + a[1 % K][jj].y);
-                           o.z = c[jj].z + (a[0][jj].z + a[1 % K][jj].z);
-                           o.w = c[jj].w + (a[0][jj].w + a[1 % K][jj].w);
-                        } else {
-                           float4 e = a[0][jj];
+                  for (int jj = 0; jj < B; ++jj) {
+                     const int q = gl + G * (j0 + jj);
+                     float4 o;
+                     if constexpr (POT == POT_TRUNC && K == 2 && !WEIGHTED) {   // update_cost2_trunclinear :216
+                        o.x = c[jj].x + (((a[0][jj].x - mk[0]) + a[1 % K][jj].x) - mk[1 % K]) * 0.5f;
+                        o.y = c[jj].y + (((a[0][jj].y - mk[0]) + a[1 % K][jj].y) - mk[1 % K]) * 0.5f;
+                        o.z = c[jj].z + (((a[0][jj].z - mk[0]) + a[1 % K][jj].z) - mk[1 % K]) * 0.5f;
+                        o.w = c[jj].w + (((a[0][jj].w - mk[0]) + a[1 % K][jj].w) - mk[1 % K]) * 0.5f;
+                     } else if constexpr (POT == POT_SGM && K == 2) {   // update_cost2: halves taken by the producer
+                        o.x = c[jj].x + (a[0][jj].x + a[1 % K][jj].x);
+                        o.y = c[jj].y + (a[0][jj].y + a[1 % K][jj].y);
+                        o.z = c[jj].z + (a[0][jj].z + a[1 % K][jj].z);
+                        o.w = c[jj].w + (a[0][jj].w + a[1 % K][jj].w);
+                     } else {
+                        float4 e = a[0][jj];
 #pragma unroll
-                           for (int k = 1; k < K; ++k) {
-                              e.x += a[k][jj].x; e.y += a[k][jj].y; e.z += a[k][jj].z; e.w += a[k][jj].w;
-                           }
-                           const float4 d = div4_by_k<K>(e);
-                           o.x = c[jj].x + d.x; o.y = c[jj].y + d.y; o.z = c[jj].z + d.z; o.w = c[jj].w + d.w;
+                        for (int k = 1; k < K; ++k) {
+                           e.x += a[k][jj].x; e.y += a[k][jj].y; e.z += a[k][jj].z; e.w += a[k][jj].w;
                         }
-                        m = hmin4(m, o);
-                        Cb[q] = o;
-                        __stcs(gout + q, o);
+                        const float4 d = div4_by_k<K>(e);
+                        o.x = c[jj].x + d.x; o.y = c[jj].y + d.y; o.z = c[jj].z + d.z; o.w = c[jj].w + d.w;
                      }
+                     m = hmin4(m, o);
+                     Cb[q] = o;
+                     __stcs(gout + q, o);
                   }
-               }
+               };
+               int j0 = 0;
+               for (; j0 + JB <= nj; j0 += JB) batch(std::integral_constant<int, JB>{}, j0);
+               for (; j0 + 2 <= nj; j0 += 2) batch(std::integral_constant<int, 2>{}, j0);
+               for (; j0 < nj; ++j0) batch(std::integral_constant<int, 1>{}, j0);
             } else {
                // update_costW with per-edge weights (mgm_core.cc:95-144); slots hold the raw messages
                float pw[K], cap[K];
@@ -428,29 +433,31 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
             // SGM transform, label-parallel: A(o) = min3(L(o), min(L(o-1),L(o+1))+P1, m+P2) - m  [x 1/2 for K=2]
             const float p1 = P.P1, cap = m + P.P2;
             const float sc = (K == 2) ? 0.5f : 1.0f;
-            for (int j0 = 0; j0 < nj; j0 += 4) {
-               float4 v[4];
-               float lft[4], rgt[4];
+            auto tbatch = [&](auto jbc, int j0) {
+               constexpr int B = decltype(jbc)::value;
+               float4 v[B];
+               float lft[B], rgt[B];
 #pragma unroll
-               for (int jj = 0; jj < 4; ++jj) {
-                  const int q = gl + G * min(j0 + jj, nj - 1);
+               for (int jj = 0; jj < B; ++jj) {
+                  const int q = gl + G * (j0 + jj);
                   v[jj] = Cb[q];
                   lft[jj] = (q > 0) ? Cbf[4 * q - 1] : MGM_INF;
                   rgt[jj] = (q + 1 < nq) ? Cbf[4 * q + 4] : MGM_INF;
                }
 #pragma unroll
-               for (int jj = 0; jj < 4; ++jj) {
-                  if (j0 + jj < nj) {
-                     const int q = gl + G * (j0 + jj);
-                     float4 a;
-                     a.x = sgm_x(lft[jj], v[jj].x, v[jj].y, p1, cap, m) * sc;
-                     a.y = sgm_x(v[jj].x, v[jj].y, v[jj].z, p1, cap, m) * sc;
-                     a.z = sgm_x(v[jj].y, v[jj].z, v[jj].w, p1, cap, m) * sc;
-                     a.w = sgm_x(v[jj].z, v[jj].w, rgt[jj], p1, cap, m) * sc;
-                     cur[q] = a;
-                  }
+               for (int jj = 0; jj < B; ++jj) {
+                  const int q = gl + G * (j0 + jj);
+                  float4 a;
+                  a.x = sgm_x(lft[jj], v[jj].x, v[jj].y, p1, cap, m) * sc;
+                  a.y = sgm_x(v[jj].x, v[jj].y, v[jj].z, p1, cap, m) * sc;
+                  a.z = sgm_x(v[jj].y, v[jj].z, v[jj].w, p1, cap, m) * sc;
+                  a.w = sgm_x(v[jj].z, v[jj].w, rgt[jj], p1, cap, m) * sc;
+                  cur[q] = a;
                }
-            }
+            };
+            int j0 = 0;
+            for (; j0 + 4 <= nj; j0 += 4) tbatch(std::integral_constant<int, 4>{}, j0);
+            for (; j0 < nj; ++j0) tbatch(std::integral_constant<int, 1>{}, j0);
          } else {
             for (int j = 0; j < nj; ++j) cur[gl + G * j] = Cb[gl + G * j];   // weighted paths keep the raw message
          }
@@ -461,11 +468,14 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
       const long long c5 = clock64();
       tP += c1 - c0; tA += c2 - c1; tW1 += c3 - c2; tB += c4 - c3; tW2 += c5 - c4;
 
-      // ---------------- hand the boundary row to the next band
-      if (act && last_row && gl == 0) {
-         if (NEEDM) bndm_out[xs] = m;
-         tma_store_1d(bnd_out + (size_t)xs * VS, cur, vbytes);
-         tma_commit();
+      // ---------------- hand the boundary row to the next band (producer thread, TMA bulk store)
+      if (is_pub && has_next) {
+         const int xl = s - SIG * (nrows - 1);
+         if (xl >= 0 && xl < maxii) {
+            if (NEEDM) bndm_out[xl] = msr[(nrows - 1) * 4 + (xl % R)];
+            tma_store_1d(bnd_out + (size_t)xl * VS, slot_of(nrows - 1, xl), vbytes);
+            tma_commit();
+         }
       }
    }
 
@@ -475,13 +485,12 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
       atomicAdd(d + 3, (unsigned long long)tB); atomicAdd(d + 4, (unsigned long long)tW2); atomicAdd(d + 5, (unsigned long long)nsteps); atomicAdd(d + 6, (unsigned long long)tC);
    }
    // epilogue: drain the boundary stores, publish the full boundary row, save mbarrier parities
-   if (last_row && gl == 0) {
+   if (is_pub && has_next) {
       tma_wait_all<0>();
       fence_proxy_async();
-      __threadfence();
       st_release(prog_out, maxii);
    }
-   if (tid < ncomp && r < T && gl == 0) phase[r] = cph;
+   cp_async_wait<0>();
    if (tid == 0) phase[vph_idx] = vph;
    __syncthreads();
 }
@@ -491,15 +500,13 @@ __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(c
    extern __shared__ __align__(128) unsigned char smem[];
    __shared__ int s_ticket;
    const int t = threadIdx.x;
-   const int ncomp = blockDim.x - 32;
+   const int ncomp = blockDim.x - 64;   // two service warps follow the row threads
 
-   // one-time barrier setup: two cost barriers per row, RV boundary barriers
+   // one-time barrier setup: RV boundary barriers
    {
-      uint64_t *cbar = reinterpret_cast<uint64_t *>(smem + P.off_cbar);
       uint64_t *vbar = reinterpret_cast<uint64_t *>(smem + P.off_vbar);
       uint32_t *phase = reinterpret_cast<uint32_t *>(smem + P.off_phase);
       const int tmax = max(P.T[0], P.T[1]);
-      if (t < tmax) { mbar_init(&cbar[2 * t], 1); mbar_init(&cbar[2 * t + 1], 1); phase[t] = 0; }
       if (t == ncomp) { for (int i = 0; i < RV; ++i) mbar_init(&vbar[i], 1); }
       if (t == 0) phase[tmax] = 0;
       mbar_fence_init();
@@ -551,7 +558,7 @@ void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighte
    const int VS = (L + 31) & ~31;   // 8 lanes x 16 bytes per row and step
    plan->VS = VS;
    const int xtra = (weighted && pot == POT_TRUNC) ? K : 0;
-   const int tcap = (MGM_AGG_MAX_THREADS - 32) / MGM_AGG_GROUP;   // rows per CTA allowed by the thread budget
+   const int tcap = (MGM_AGG_MAX_THREADS - 64) / MGM_AGG_GROUP;   // rows per CTA allowed by the thread budget
    for (int cls = 0; cls < 2; ++cls) {
       int nbuf = ring_slots(cls, K) + 2 + xtra;
       int TS = nbuf * VS;
@@ -567,7 +574,7 @@ void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighte
    }
    const int tm = max(plan->T[0], plan->T[1]);
    const int ncomp = (tm * MGM_AGG_GROUP + 31) & ~31;
-   plan->block = ncomp + 32;
+   plan->block = ncomp + 64;   // + boundary-consumer warp + boundary-publisher warp
    size_t off = 0;
    plan->off_phase = off; off += (size_t)(tm + 1) * 4; off = (off + 15) & ~(size_t)15;
    plan->off_cbar = off; off += (size_t)tm * 16;

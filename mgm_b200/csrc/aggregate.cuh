@@ -3,7 +3,7 @@
 #include "common.cuh"
 
 #define MGM_AGG_GROUP 8           // lanes cooperating on one scan row
-#define MGM_AGG_MAX_THREADS 512   // 60 rows x 8 lanes + one boundary-producer warp
+#define MGM_AGG_MAX_THREADS 512   // 56 rows x 8 lanes + two service warps (boundary consumer / publisher)
 
 namespace mgm {
 

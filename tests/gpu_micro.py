@@ -28,7 +28,10 @@ def run(W, H, L, K, felz, mask, NDIR=8, reps=3, rows=0):
     ms = min(ts[1:])
     return ms, info
 
-CASES = [
+if __name__ != '__main__':
+    CASES = []
+else:
+  CASES = [
     (2048, 43, 256, 3, 1, 0x01, "1 band sweep0 trunc K3"),
     (2048, 35, 256, 3, 1, 0x10, "1 band sweep4 trunc K3"),
     (2048, 43, 256, 3, 0, 0x01, "1 band sweep0 sgm K3"),
@@ -40,7 +43,7 @@ CASES = [
     (2048, 1536, 256, 3, 0, 0xFF, "full all sgm K3"),
     (1920, 1080, 128, 2, 0, 0xFF, "cfg2 all sgm K2"),
 ]
-if len(sys.argv) > 1:
+if __name__ == '__main__' and len(sys.argv) > 1:
     CASES = [c for c in CASES if sys.argv[1] in c[6]]
 for (W, H, L, K, felz, mask, label) in CASES:
     ms, info = run(W, H, L, K, felz, mask, reps=int(sys.argv[2]) if len(sys.argv) > 2 else 3)
