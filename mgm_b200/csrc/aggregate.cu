@@ -25,6 +25,8 @@
 // Precondition of this fast path (enforced by the host): every cost
 // vector holds a finite value, no NaN / -INF, P1,P2 >= 0 and weights >= 0; then the
 // hardware min is bit-identical to the reference's compare-select forms.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "aggregate.cuh"
@@ -106,18 +108,22 @@ __device__ __forceinline__ void minconv_half(bool on, const float4 *src, float4 
    pair_barrier(bar_id);   // partner's partial values are now in dst
    if (on) {
       float4 o = dst[q];
-      for (int i = h; i < nq; ++i, q += dq) {
-         const bool more = (i + 1 < nq);
-         const float4 vn = more ? src[q + dq] : v;
-         const float4 on4 = more ? dst[q + dq] : o;
-         if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
-         v.x = fminf(fminf(v.x, o.x), cap) - sub;
-         v.y = fminf(fminf(v.y, o.y), cap) - sub;
-         v.z = fminf(fminf(v.z, o.z), cap) - sub;
-         v.w = fminf(fminf(v.w, o.w), cap) - sub;
+      auto finish = [&](float4 &vv, const float4 &oo) {
+         if (DIR) { chain4(run, vv.w, vv.z, vv.y, vv.x, c); } else { chain4(run, vv.x, vv.y, vv.z, vv.w, c); }
+         vv.x = fminf(fminf(vv.x, oo.x), cap) - sub;
+         vv.y = fminf(fminf(vv.y, oo.y), cap) - sub;
+         vv.z = fminf(fminf(vv.z, oo.z), cap) - sub;
+         vv.w = fminf(fminf(vv.w, oo.w), cap) - sub;
+      };
+      for (int i = h; i + 1 < nq; ++i, q += dq) {   // all but the last chunk: unconditional prefetch
+         const float4 vn = src[q + dq];
+         const float4 on4 = dst[q + dq];
+         finish(v, o);
          dst[q] = v;
          v = vn; o = on4;
       }
+      finish(v, o);
+      dst[q] = v;
    }
 }
 
@@ -218,11 +224,14 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
       cp_async_commit();   // one (possibly empty) group per step keeps the wait count uniform
    };
    prefetch_cost(-1);   // pixel 0 of row 0 (the other rows start later)
+   // Lanes of warps that run min-convolution chains in phase 2 issue their prefetch at the top of the step;
+   // all other warps are idle in phase 2 and issue it there (the LSU is less busy then).
+   const bool late_prefetch = CHAINS && (warp_id >= 2 * ((nrows + 31) >> 5));
 
    long long tA = 0, tW1 = 0, tB = 0, tW2 = 0, tP = 0, tC = 0;
    for (int s = 0; s < nsteps; ++s) {
       const long long c0 = clock64();
-      prefetch_cost(s);
+      if (!late_prefetch) prefetch_cost(s);
       if (is_pub && has_next) {
          // boundary stores are issued by this thread (end of each step, below); all but the most recent one
          // are complete -> publish them.  Runs on the otherwise idle producer warp, off the rows' critical path.
@@ -309,7 +318,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
       // ---------------- phase 1: gather the message of pixel (xs,ys), G lanes per row
       if (act) {
          const long long cw0 = clock64();
-         cp_async_wait<1>();   // everything but the prefetch issued at the top of this step has landed
+         if (late_prefetch) cp_async_wait<0>(); else cp_async_wait<1>();   // all but a prefetch issued this step
          tC += clock64() - cw0;
 
          if (border) {
@@ -413,6 +422,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
       const long long c3 = clock64();
 
       // ---------------- phase 2: build the neighbour-side transform of the message in the ring slot
+      if (late_prefetch) prefetch_cost(s);
       if constexpr (CHAINS) {
          // minConvTruncatedLinear of the finished message, one lane pair per row
          const int ncw = (nrows + 31) >> 5;   // warps per direction
@@ -568,7 +578,11 @@ void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighte
       long avail = (long)max_smem - (long)fixed;
       int Tc = (int)(avail / ((long)TS * 4));
       if (Tc > tcap) Tc = tcap;
-      if (t_override > 0 && Tc > t_override) Tc = t_override;
+      {
+         const char *e = getenv(cls == 0 ? "MGMB200_ROWS_AXIS" : "MGMB200_ROWS_DIAG");   // tuning knobs
+         const int ov = e ? atoi(e) : t_override;
+         if (ov > 0 && Tc > ov) Tc = ov;
+      }
       if (Tc < 1) Tc = 0;
       plan->T[cls] = Tc;
    }
