@@ -49,6 +49,36 @@ __device__ __forceinline__ float hmin4(float m, const float4 &v) {
    return fminf(fminf(fminf(m, v.x), fminf(v.y, v.z)), v.w);
 }
 
+// Packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): each lane is an independently rounded IEEE operation, so
+// the results are bit-identical to the scalar forms; one issue slot per two labels in the ALU-bound gather.
+__device__ __forceinline__ float4 add4(const float4 &a, const float4 &b) {
+   const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+   const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+   return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 add4s(const float4 &a, const float s) {   // a + s per label (s = -m: a - m exactly)
+   const float2 ss = make_float2(s, s);
+   const float2 lo = __fadd2_rn(make_float2(a.x, a.y), ss);
+   const float2 hi = __fadd2_rn(make_float2(a.z, a.w), ss);
+   return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 mul4s(const float4 &a, const float s) {
+   const float2 ss = make_float2(s, s);
+   const float2 lo = __fmul2_rn(make_float2(a.x, a.y), ss);
+   const float2 hi = __fmul2_rn(make_float2(a.z, a.w), ss);
+   return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// e/3 for FINITE e (div3_exact without its non-finite guard; common.cuh).  The sums of neighbour terms are finite
+// under the fast-path preconditions (finite caps m+P2*w or a finite entry in every vector, P1 finite).
+__device__ __forceinline__ float4 div3_4(const float4 &e) {
+   const float2 c3 = make_float2(0x1.555556p-2f, 0x1.555556p-2f), m3 = make_float2(-3.0f, -3.0f);
+   const float2 elo = make_float2(e.x, e.y), ehi = make_float2(e.z, e.w);
+   const float2 qlo = __fmul2_rn(elo, c3), qhi = __fmul2_rn(ehi, c3);
+   const float2 rlo = __ffma2_rn(m3, qlo, elo), rhi = __ffma2_rn(m3, qhi, ehi);
+   const float2 lo = __ffma2_rn(rlo, c3, qlo), hi = __ffma2_rn(rhi, c3, qhi);
+   return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 // SGM neighbour transform of one label: min3(L(o), min(L(o-1),L(o+1))+P1, m+P2) - m   (mgm_core.cc:113-116)
 __device__ __forceinline__ float sgm_x(float l, float c, float r, float p1, float cap, float m) {
    return fminf(fminf(c, fminf(l, r) + p1), cap) - m;
@@ -88,6 +118,13 @@ __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0
 // hold the same direction (DIR=0 upwards, DIR=1 downwards) of 32 different vectors; the partner warp runs
 // the other direction of the same vectors.  Warp-uniform direction: no divergence, no lane swizzles.
 // `on` = this lane has a vector to process (the barrier is executed by every lane regardless).
+//
+// Second half without re-reading the source: with F the upward recurrence and B the downward one, both on the
+// original values M, the result is Q[o] = min(F[o], B[o]).  Since F[o] <= M[o] and x -> RN(x+c) is monotone,
+//    min(F[o], B[o]) = min(F[o], min(B[o+1]+c, M[o])) = min(F[o], B[o+1]+c)   and   F[o+1]+c >= min(F[o], B[o+1]+c),
+// hence Q[o] = min(Q[o+1]+c, F[o]) (and symmetrically Q[o] = min(Q[o-1]+c, B[o])): each lane continues ITS
+// recurrence over the partner's partial values only -- same additions in the same order as the reference,
+// one shared-memory read per label less (checked bit for bit in tests/micro/chain_bench.cu, form 6).
 template <int DIR>
 __device__ __forceinline__ void minconv_half(bool on, const float4 *src, float4 *dst, int nq, float c, float cap,
                                              float sub, int bar_id) {
@@ -107,29 +144,23 @@ __device__ __forceinline__ void minconv_half(bool on, const float4 *src, float4 
    }
    pair_barrier(bar_id);   // partner's partial values are now in dst
    if (on) {
-      float4 o = dst[q];
-      auto finish = [&](float4 &vv, const float4 &oo) {
-         if (DIR) { chain4(run, vv.w, vv.z, vv.y, vv.x, c); } else { chain4(run, vv.x, vv.y, vv.z, vv.w, c); }
-         vv.x = fminf(fminf(vv.x, oo.x), cap) - sub;
-         vv.y = fminf(fminf(vv.y, oo.y), cap) - sub;
-         vv.z = fminf(fminf(vv.z, oo.z), cap) - sub;
-         vv.w = fminf(fminf(vv.w, oo.w), cap) - sub;
-      };
-      for (int i = h; i + 1 < nq; ++i, q += dq) {   // all but the last chunk: unconditional prefetch
-         const float4 vn = src[q + dq];
-         const float4 on4 = dst[q + dq];
-         finish(v, o);
+      v = dst[q];
+      for (int i = h; i < nq; ++i, q += dq) {
+         const float4 vn = dst[(i + 1 < nq) ? q + dq : q];
+         if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
+         v = add4s(make_float4(fminf(v.x, cap), fminf(v.y, cap), fminf(v.z, cap), fminf(v.w, cap)), -sub);
          dst[q] = v;
-         v = vn; o = on4;
+         v = vn;
       }
-      finish(v, o);
-      dst[q] = v;
    }
 }
 
 template <int K>
-__device__ __forceinline__ float4 div4_by_k(const float4 &e) {
-   return make_float4(div_by_k<K>(e.x), div_by_k<K>(e.y), div_by_k<K>(e.z), div_by_k<K>(e.w));
+__device__ __forceinline__ float4 div4_by_k(const float4 &e) {   // e finite (see div3_4)
+   if (K == 1) return e;
+   if (K == 2) return mul4s(e, 0.5f);    // exact: same real quotient, same rounding
+   if (K == 4) return mul4s(e, 0.25f);
+   return div3_4(e);
 }
 
 template <int POT, int K, bool WEIGHTED, bool DIAG>
@@ -141,6 +172,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    constexpr bool CHAINS = !WEIGHTED && POT == POT_TRUNC;   // phase-2 transform done by lane pairs
    constexpr int CLS = DIAG ? 1 : 0;
    constexpr int JB = (K <= 3) ? 4 : 2;   // chunks per lane whose loads are issued together in the gather
+   constexpr int NJR = MGM_AGG_CREG;      // cost chunks per lane that can be prefetched into registers
 
    const PassGeom g = pass_geometry(pass, P.nx, P.ny);
    const int maxii = g.maxii, maxjj = g.maxjj;
@@ -149,6 +181,8 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    const int VS = P.VS;
    const int nq = VS >> 2;
    const int nj = nq / G;   // chunks per lane (VS is a multiple of 4*G)
+   const int ncb = P.ncb;   // cost buffers per row: 1 = costs prefetched into registers (nj <= NJR), 2 = cp.async ring
+   const bool creg_mode = (ncb == 1);
    const uint32_t vbytes = (uint32_t)VS * 4u;
    const int tid = threadIdx.x;
    const int ncomp = blockDim.x - 64;   // two service warps follow the row threads
@@ -181,7 +215,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    float *thr = reinterpret_cast<float *>(smem + P.off_thr);
    uint32_t *phase = reinterpret_cast<uint32_t *>(smem + P.off_phase);   // persistent mbarrier parities
 
-   // per-row shared memory: ring slots [R][VS] | cost buffers [2][VS] | scratch [K][VS] (weighted trunc)
+   // per-row shared memory: ring slots [R][VS] | cost buffers [ncb][VS] | scratch [K][VS] (weighted trunc)
    auto row_base = [&](int rr) -> float * { return thr + (size_t)rr * TS; };
    auto slot_of = [&](int rr, int px) -> float * {
       return (rr < 0) ? virt + (px & (RV - 1)) * VS : row_base(rr) + (px % R) * VS;
@@ -211,27 +245,44 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    if (tid < G) vph = phase[vph_idx];
    int next_px = 0;   // producer: next boundary pixel to fetch
 
-   // Cost vectors: every lane prefetches, one pixel ahead, exactly the 16-byte chunks it will read itself
-   // (cp.async, LDGSTS: no registers, no cross-thread hand-off, 128-byte coalesced per row); pixel px of a row
-   // lands in cost buffer px&1, free again once the step that used it for pixel px-2 has ended.
+   // Cost vectors: every lane prefetches, one pixel ahead, exactly the 16-byte chunks it will read itself (128-byte
+   // coalesced per row).  Up to NJR chunks per lane (256 labels) they go straight into REGISTERS with streaming
+   // loads issued at the end of the gather and in flight during phase 2: no shared-memory write + read-back, no
+   // cp.async issue cost, one cost buffer per row instead of two (more rows per band).  Longer label vectors use
+   // cp.async (LDGSTS) into a two-deep ring: pixel px lands in buffer px&1.
+   float4 creg[NJR];
+#pragma unroll
+   for (int j = 0; j < NJR; ++j) creg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+   auto cbuf_of = [&](int rr, int px) -> float * { return row_base(rr) + (R + (ncb == 2 ? (px & 1) : 0)) * VS; };
    auto prefetch_cost = [&](int s) {
       const int px = s - SIG * r + 1;   // the pixel my row handles in the NEXT step
-      if (rowok && px >= 0 && px < maxii) {
+      const bool go = rowok && px >= 0 && px < maxii;
+      if (creg_mode) {
+         if (go) {
+            const float4 *src = reinterpret_cast<const float4 *>(ccv + (size_t)(pix0 + (long long)px * g.dxs) * VS);
+#pragma unroll
+            for (int j = 0; j < NJR; ++j)
+               if (j < nj) creg[j] = __ldcs(src + gl + G * j);
+         }
+         return;
+      }
+      if (go) {
          const float4 *src = reinterpret_cast<const float4 *>(ccv + (size_t)(pix0 + (long long)px * g.dxs) * VS);
-         float4 *dst = reinterpret_cast<float4 *>(row_base(r) + (R + (px & 1)) * VS);
+         float4 *dst = reinterpret_cast<float4 *>(cbuf_of(r, px));
          for (int j = 0; j < nj; ++j) cp_async16(dst + gl + G * j, src + gl + G * j);
       }
       cp_async_commit();   // one (possibly empty) group per step keeps the wait count uniform
    };
    prefetch_cost(-1);   // pixel 0 of row 0 (the other rows start later)
-   // Lanes of warps that run min-convolution chains in phase 2 issue their prefetch at the top of the step;
-   // all other warps are idle in phase 2 and issue it there (the LSU is less busy then).
-   const bool late_prefetch = CHAINS && (warp_id >= 2 * ((nrows + 31) >> 5));
+   // cp.async mode: lanes of warps that run min-convolution chains in phase 2 issue their prefetch at the top of
+   // the step; all other warps are idle in phase 2 and issue it there (the LSU is less busy then).
+   // Register mode: every lane issues its loads right after its gather (they complete during phase 2).
+   const bool late_prefetch = !creg_mode && CHAINS && (warp_id >= 2 * ((nrows + 31) >> 5));
 
    long long tA = 0, tW1 = 0, tB = 0, tW2 = 0, tP = 0, tC = 0;
    for (int s = 0; s < nsteps; ++s) {
       const long long c0 = clock64();
-      if (!late_prefetch) prefetch_cost(s);
+      if (!late_prefetch && !creg_mode) prefetch_cost(s);
       if (is_pub && has_next) {
          // boundary stores are issued by this thread (end of each step, below); all but the most recent one
          // are complete -> publish them.  Runs on the otherwise idle producer warp, off the rows' critical path.
@@ -279,8 +330,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
       const int xs = s - SIG * r;
       const bool act = rowok && xs >= 0 && xs < maxii;
       const long long pix = pix0 + (long long)xs * g.dxs;
-      const int cbi = xs & 1;
-      float *Cbf = row_base(r) + (R + cbi) * VS;
+      float *Cbf = cbuf_of(r, xs);
       float4 *Cb = reinterpret_cast<float4 *>(Cbf);
       float4 *cur = reinterpret_cast<float4 *>(row_base(r) + (act ? (xs % R) : 0) * VS);
       float4 *gout = reinterpret_cast<float4 *>(ldir + (size_t)(act ? pix : 0) * VS);
@@ -307,7 +357,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                mk = m_of(prow, ppx);
                cw1 = P.P1 * wk; capv = mk + P.P2 * wk;
                src = slot_of(prow, ppx);
-               dst = row_base(crow) + (R + 2 + ck) * VS;
+               dst = row_base(crow) + (R + ncb + ck) * VS;
             }
             if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 1 + cw);
             else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 1 + cw);
@@ -318,15 +368,27 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
       // ---------------- phase 1: gather the message of pixel (xs,ys), G lanes per row
       if (act) {
          const long long cw0 = clock64();
-         if (late_prefetch) cp_async_wait<0>(); else cp_async_wait<1>();   // all but a prefetch issued this step
+         if (!creg_mode) { if (late_prefetch) cp_async_wait<0>(); else cp_async_wait<1>(); }   // all but a prefetch issued this step
          tC += clock64() - cw0;
 
          if (border) {
-            for (int j = 0; j < nj; ++j) {
-               const int q = gl + G * j;
-               const float4 c = Cb[q];
-               m = hmin4(m, c);
-               __stcs(gout + q, c);
+            if (creg_mode) {
+#pragma unroll
+               for (int j = 0; j < NJR; ++j) {
+                  if (j < nj) {
+                     const int q = gl + G * j;
+                     m = hmin4(m, creg[j]);
+                     Cb[q] = creg[j];
+                     __stcs(gout + q, creg[j]);
+                  }
+               }
+            } else {
+               for (int j = 0; j < nj; ++j) {
+                  const int q = gl + G * j;
+                  const float4 c = Cb[q];
+                  m = hmin4(m, c);
+                  __stcs(gout + q, c);
+               }
             }
          } else {
             const float4 *S[K];
@@ -335,7 +397,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
             for (int k = 0; k < K; ++k) {
                int prow, ppx;
                pred_of(r, xs, k, prow, ppx);
-               S[k] = reinterpret_cast<const float4 *>(WTRUNC ? row_base(r) + (R + 2 + k) * VS : slot_of(prow, ppx));
+               S[k] = reinterpret_cast<const float4 *>(WTRUNC ? row_base(r) + (R + ncb + k) * VS : slot_of(prow, ppx));
                mk[k] = 0.f; wk[k] = 1.f;
                if (NEEDM) mk[k] = m_of(prow, ppx);
                if (WEIGHTED && !WTRUNC) wk[k] = __ldg(P.w + (size_t)pass_weight_plane(pass, k) * wplane + pix);
@@ -343,53 +405,69 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
             if constexpr (!WEIGHTED || WTRUNC) {
                // slots hold the neighbour-side transform already (producer row, or phase 0 scratch).
                // Straight-line batches: all loads of a batch are issued before the first use.
-               auto batch = [&](auto jbc, int j0) {
+               auto batch = [&](auto jbc, int j0, auto regc) {
                   constexpr int B = decltype(jbc)::value;
+                  constexpr bool REGC = decltype(regc)::value;   // costs come from creg[j0 .. j0+B) (j0 compile-time)
                   float4 c[B], a[K][B];
 #pragma unroll
                   for (int jj = 0; jj < B; ++jj) {
                      const int q = gl + G * (j0 + jj);
-                     c[jj] = Cb[q];
+                     if constexpr (!REGC) c[jj] = Cb[q];
 #pragma unroll
                      for (int k = 0; k < K; ++k) a[k][jj] = S[k][q];
+                  }
+                  if constexpr (REGC) {
+#pragma unroll
+                     for (int jj = 0; jj < B; ++jj) c[jj] = creg[(j0 + jj) < NJR ? (j0 + jj) : 0];
                   }
 #pragma unroll
                   for (int jj = 0; jj < B; ++jj) {
                      const int q = gl + G * (j0 + jj);
                      float4 o;
                      if constexpr (POT == POT_TRUNC && K == 2 && !WEIGHTED) {   // update_cost2_trunclinear :216
-                        o.x = c[jj].x + (((a[0][jj].x - mk[0]) + a[1 % K][jj].x) - mk[1 % K]) * 0.5f;
-                        o.y = c[jj].y + (((a[0][jj].y - mk[0]) + a[1 % K][jj].y) - mk[1 % K]) * 0.5f;
-                        o.z = c[jj].z + (((a[0][jj].z - mk[0]) + a[1 % K][jj].z) - mk[1 % K]) * 0.5f;
-                        o.w = c[jj].w + (((a[0][jj].w - mk[0]) + a[1 % K][jj].w) - mk[1 % K]) * 0.5f;
+                        // c + (((a0 - m0) + a1) - m1) / 2
+                        o = add4(c[jj], mul4s(add4s(add4(add4s(a[0][jj], -mk[0]), a[1 % K][jj]), -mk[1 % K]), 0.5f));
                      } else if constexpr (POT == POT_SGM && K == 2) {   // update_cost2: halves taken by the producer
-                        o.x = c[jj].x + (a[0][jj].x + a[1 % K][jj].x);
-                        o.y = c[jj].y + (a[0][jj].y + a[1 % K][jj].y);
-                        o.z = c[jj].z + (a[0][jj].z + a[1 % K][jj].z);
-                        o.w = c[jj].w + (a[0][jj].w + a[1 % K][jj].w);
+                        o = add4(c[jj], add4(a[0][jj], a[1 % K][jj]));
                      } else {
                         float4 e = a[0][jj];
 #pragma unroll
-                        for (int k = 1; k < K; ++k) {
-                           e.x += a[k][jj].x; e.y += a[k][jj].y; e.z += a[k][jj].z; e.w += a[k][jj].w;
-                        }
-                        const float4 d = div4_by_k<K>(e);
-                        o.x = c[jj].x + d.x; o.y = c[jj].y + d.y; o.z = c[jj].z + d.z; o.w = c[jj].w + d.w;
+                        for (int k = 1; k < K; ++k) e = add4(e, a[k][jj]);
+                        o = add4(c[jj], div4_by_k<K>(e));
                      }
                      m = hmin4(m, o);
                      Cb[q] = o;
                      __stcs(gout + q, o);
                   }
                };
-               int j0 = 0;
-               for (; j0 + JB <= nj; j0 += JB) batch(std::integral_constant<int, JB>{}, j0);
-               for (; j0 + 2 <= nj; j0 += 2) batch(std::integral_constant<int, 2>{}, j0);
-               for (; j0 < nj; ++j0) batch(std::integral_constant<int, 1>{}, j0);
+               if (creg_mode) {
+                  // register-resident costs: batch offsets are compile-time so creg[] stays in registers
+                  constexpr int JR = (JB < NJR) ? JB : NJR;
+#pragma unroll
+                  for (int jb = 0; jb < NJR; jb += JR) {
+                     if (jb + JR <= nj) batch(std::integral_constant<int, JR>{}, jb, std::true_type{});
+                     else {
+#pragma unroll
+                        for (int jr = 0; jr < JR; ++jr)
+                           if (jb + jr < nj) batch(std::integral_constant<int, 1>{}, jb + jr, std::true_type{});
+                     }
+                  }
+               } else {
+                  int j0 = 0;
+                  for (; j0 + JB <= nj; j0 += JB) batch(std::integral_constant<int, JB>{}, j0, std::false_type{});
+                  for (; j0 + 2 <= nj; j0 += 2) batch(std::integral_constant<int, 2>{}, j0, std::false_type{});
+                  for (; j0 < nj; ++j0) batch(std::integral_constant<int, 1>{}, j0, std::false_type{});
+               }
             } else {
                // update_costW with per-edge weights (mgm_core.cc:95-144); slots hold the raw messages
                float pw[K], cap[K];
 #pragma unroll
                for (int k = 0; k < K; ++k) { pw[k] = P.P1 * wk[k]; cap[k] = mk[k] + P.P2 * wk[k]; }
+               if (creg_mode) {   // this path reads the costs from the buffer: park the registers there first
+#pragma unroll
+                  for (int j = 0; j < NJR; ++j)
+                     if (j < nj) Cb[gl + G * j] = creg[j];
+               }
                for (int j = 0; j < nj; ++j) {
                   const int q = gl + G * j;
                   const float4 c = Cb[q];
@@ -405,8 +483,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                      e.z += sgm_x(v.y, v.z, v.w, pw[k], cap[k], mk[k]);
                      e.w += sgm_x(v.z, v.w, rgt, pw[k], cap[k], mk[k]);
                   }
-                  const float4 d = div4_by_k<K>(e);
-                  const float4 o = make_float4(c.x + d.x, c.y + d.y, c.z + d.z, c.w + d.w);
+                  const float4 o = add4(c, div4_by_k<K>(e));
                   m = hmin4(m, o);
                   Cb[q] = o;
                   __stcs(gout + q, o);
@@ -417,6 +494,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
          for (int d = 1; d < G; d <<= 1) m = fminf(m, __shfl_xor_sync(gmask, m, d));
          if (gl == 0) msr[r * 4 + (xs % R)] = m;
       }
+      if (creg_mode) prefetch_cost(s);   // costs of the next pixel -> registers, in flight during phase 2
       const long long c2 = clock64();
       __syncthreads();
       const long long c3 = clock64();
@@ -432,7 +510,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
             const int cxs = s - SIG * crow;
             const bool on = crow < nrows && cxs >= 0 && cxs < maxii;
             const float cm = on ? msr[crow * 4 + (cxs % R)] : 0.f;
-            const float *src = on ? row_base(crow) + (R + (cxs & 1)) * VS : thr;
+            const float *src = on ? cbuf_of(crow, cxs) : thr;
             float *dst = on ? row_base(crow) + (cxs % R) * VS : thr;
             if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, 1 + cw);
             else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, 1 + cw);
@@ -505,6 +583,317 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Diagonal sweeps 4-7 with TSGM <= 3 and no image-dependent weights: SHEARED wavefront.
+//
+// Such a pixel (xs,ys) only reads the scan row above: (xs+1,ys-1), (xs-1,ys-1), (xs,ys-1) in that order.  With
+// u = xs+ys (anti-diagonal) and v = ys these are (u,v-1), (u-2,v-1), (u-1,v-1): every predecessor sits at v-1 and
+// at u, u-1 or u-2.  A band therefore holds T consecutive anti-diagonals ("workers"), one per 8-lane group, ALL
+// at the same v in a step -- no lag between the workers of a band, a ring of two slots per worker -- and depends
+// on the previous band only through its last two workers.  The dependency depth of the sweep drops from
+// maxii + 2*maxjj steps (row-per-worker, lag 2) to maxjj + (band hand-off) * #bands.
+// Everything else (register-resident cost prefetch, gather, exact min-convolution chains / SGM transform,
+// boundary lines through TMA stores + release/acquire counters + TMA loads) is as in run_band.
+template <int POT, int K>
+__device__ void run_band_shear(const AggParams &P, const int pass, const int band, unsigned char *smem) {
+   static_assert(K <= 3, "the sheared wavefront needs predecessors in the row above only");
+   constexpr bool NEEDM = (POT == POT_TRUNC && K == 2);
+   constexpr bool CHAINS = (POT == POT_TRUNC);
+   constexpr int JB = 4;
+   constexpr int NJR = MGM_AGG_CREG;
+
+   const PassGeom g = pass_geometry(pass, P.nx, P.ny);
+   const int maxii = g.maxii, maxjj = g.maxjj;
+   const int nu = maxii + maxjj - 1;   // anti-diagonals
+   const int T = P.T[1];
+   const int TS = P.TS[1];
+   const int VS = P.VS;
+   const int nq = VS >> 2;
+   const int nj = nq / G;
+   const int ncb = P.ncb;
+   const bool creg_mode = (ncb == 1);
+   const uint32_t vbytes = (uint32_t)VS * 4u;
+   const int tid = threadIdx.x;
+   const int ncomp = blockDim.x - 64;
+   const bool is_prod = (tid == ncomp);
+   const bool is_pub = (tid == ncomp + 32);
+   const int u0 = band * T;
+   const int nrows = min(T, nu - u0);
+   const bool has_prev = band > 0;
+   const bool has_next = u0 + T < nu;
+   auto vlo = [&](int u) { return max(0, u - (maxii - 1)); };
+   auto vhi = [&](int u) { return min(maxjj - 1, u); };
+   const int sb = vlo(u0), se = vhi(u0 + nrows - 1);   // step window of the band (v = step)
+   // boundary positions this band ever reads from the previous band's last two workers
+   const int pf_lo = max(sb - 1, 0), pf_hi = has_prev ? min(se - 1, vhi(u0 - 1)) : -1;
+
+   const int r = tid / G, gl = tid % G;
+   const unsigned gmask = ((1u << G) - 1u) << ((tid & 31) & ~(G - 1));
+   const bool rowok = (tid < ncomp) && (r < nrows);
+   const int u = u0 + r;
+   const int my_lo = vlo(u), my_hi = vhi(u);
+   const int warp_id = tid >> 5, lane_id = tid & 31;
+
+   uint64_t *vbar = reinterpret_cast<uint64_t *>(smem + P.off_vbar);
+   float *msr = reinterpret_cast<float *>(smem + P.off_ms);
+   float *vms = reinterpret_cast<float *>(smem + P.off_vms);     // [2][RV]
+   float *virt = reinterpret_cast<float *>(smem + P.off_virt);   // [2][RV][VS]: worker -1, worker -2
+   float *thr = reinterpret_cast<float *>(smem + P.off_thr);
+   uint32_t *phase = reinterpret_cast<uint32_t *>(smem + P.off_phase);
+
+   // per-worker shared memory: ring slots [2][VS] (position v&1) | cost buffers [ncb][VS]
+   auto row_base = [&](int rr) -> float * { return thr + (size_t)rr * TS; };
+   auto slot_of = [&](int rr, int v) -> float * {
+      return (rr < 0) ? virt + ((-rr - 1) * RV + (v & (RV - 1))) * VS : row_base(rr) + (v & 1) * VS;
+   };
+   auto m_of = [&](int rr, int v) -> float { return (rr < 0) ? vms[(-rr - 1) * RV + (v & (RV - 1))] : msr[rr * 4 + (v & 1)]; };
+   auto cbuf_of = [&](int rr, int v) -> float * { return row_base(rr) + (2 + (ncb == 2 ? (v & 1) : 0)) * VS; };
+
+   const float *ccv = P.cc;
+   float *ldir = P.ldir[pass];
+   // boundary lines: [band][line][maxjj][VS], line 0 = last worker of the band, line 1 = the one before
+   float *bnd_out = P.bnd[pass] + (size_t)band * 2 * maxjj * VS;
+   float *bndm_out = P.bndm[pass] + (size_t)band * 2 * maxjj;
+   const float *bnd_in = has_prev ? P.bnd[pass] + (size_t)(band - 1) * 2 * maxjj * VS : nullptr;
+   const float *bndm_in = has_prev ? P.bndm[pass] + (size_t)(band - 1) * 2 * maxjj : nullptr;
+   int *prog_out = P.progress[pass] + band;
+   const int *prog_in = has_prev ? P.progress[pass] + band - 1 : nullptr;
+
+   // pixel of (u, v): xs = u - v, ys = v
+   const long long pix_u = g.base0 + (long long)u * g.dxs;
+   const long long dv = g.dys - g.dxs;
+
+   uint32_t vph = 0;
+   const int vph_idx = max(P.T[0], P.T[1]);
+   if (tid < G) vph = phase[vph_idx];
+   int next_p = pf_lo;   // producer: next boundary position to fetch
+
+   float4 creg[NJR];
+#pragma unroll
+   for (int j = 0; j < NJR; ++j) creg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+   auto prefetch_cost = [&](int v) {   // costs of position v+1
+      const int vn = v + 1;
+      const bool go = rowok && vn >= my_lo && vn <= my_hi;
+      if (creg_mode) {
+         if (go) {
+            const float4 *src = reinterpret_cast<const float4 *>(ccv + (size_t)(pix_u + (long long)vn * dv) * VS);
+#pragma unroll
+            for (int j = 0; j < NJR; ++j)
+               if (j < nj) creg[j] = __ldcs(src + gl + G * j);
+         }
+         return;
+      }
+      if (go) {
+         const float4 *src = reinterpret_cast<const float4 *>(ccv + (size_t)(pix_u + (long long)vn * dv) * VS);
+         float4 *dst = reinterpret_cast<float4 *>(cbuf_of(r, vn));
+         for (int j = 0; j < nj; ++j) cp_async16(dst + gl + G * j, src + gl + G * j);
+      }
+      cp_async_commit();
+   };
+   prefetch_cost(sb - 1);
+   const bool late_prefetch = !creg_mode && CHAINS && (warp_id >= 2 * ((nrows + 31) >> 5));
+
+   for (int v = sb; v <= se; ++v) {
+      if (!late_prefetch && !creg_mode) prefetch_cost(v);
+      if (is_pub && has_next && v > sb) {
+         // the stores of position v-1 were issued at the end of the previous step; everything before is complete
+         tma_wait_all<1>();
+         fence_proxy_async();
+         st_release(prog_out, v - 1);   // positions < v-1 of both boundary workers are in global memory
+      }
+      if (is_prod && pf_hi >= pf_lo) {
+         // position v is read in the NEXT step (blocking); up to v+PF are fetched ahead when already published
+         const int need = min(pf_hi, v);
+         const int lim = min(pf_hi, v + PF);
+         int avail = ld_acquire(prog_in);
+         while (next_p <= lim) {
+            if (avail < next_p + 1) {
+               if (next_p > need) break;
+               do { __nanosleep(20); avail = ld_acquire(prog_in); } while (avail < next_p + 1);
+            }
+            fence_proxy_async();
+            const int slot = next_p & (RV - 1);
+            if (NEEDM) {
+               vms[slot] = __ldcg(bndm_in + next_p);
+               vms[RV + slot] = __ldcg(bndm_in + maxjj + next_p);
+            }
+            mbar_expect_tx(&vbar[slot], 2 * vbytes);
+            tma_load_1d(virt + slot * VS, bnd_in + (size_t)next_p * VS, vbytes, &vbar[slot]);
+            tma_load_1d(virt + (RV + slot) * VS, bnd_in + ((size_t)maxjj + next_p) * VS, vbytes, &vbar[slot]);
+            ++next_p;
+         }
+      }
+      // group 0 waits one step AHEAD for the boundary positions; the end-of-step barriers publish them to all
+      if (tid < G && pf_hi >= pf_lo) {
+         auto wait_pos = [&](int p) {
+            if (p >= pf_lo && p <= pf_hi) {
+               const int sl = p & (RV - 1);
+               mbar_wait(&vbar[sl], (vph >> sl) & 1u);
+               vph ^= 1u << sl;
+            }
+         };
+         if (v == sb) { wait_pos(sb - 1); wait_pos(sb); } else wait_pos(v);
+      }
+
+      const bool act = rowok && v >= my_lo && v <= my_hi;
+      const int xs = u - v;
+      const long long pix = pix_u + (long long)v * dv;
+      float *Cbf = cbuf_of(r, v);
+      float4 *Cb = reinterpret_cast<float4 *>(Cbf);
+      float4 *cur = reinterpret_cast<float4 *>(row_base(r) + (v & 1) * VS);
+      float4 *gout = reinterpret_cast<float4 *>(ldir + (size_t)(act ? pix : 0) * VS);
+      const bool border = (xs == 0) || (v == 0) || (xs == maxii - 1);
+      float m = MGM_INF;
+
+      // ---------------- phase 1: gather
+      if (act) {
+         if (!creg_mode) { if (late_prefetch) cp_async_wait<0>(); else cp_async_wait<1>(); }
+         if (border) {
+            if (creg_mode) {
+#pragma unroll
+               for (int j = 0; j < NJR; ++j) {
+                  if (j < nj) {
+                     const int q = gl + G * j;
+                     m = hmin4(m, creg[j]);
+                     Cb[q] = creg[j];
+                     __stcs(gout + q, creg[j]);
+                  }
+               }
+            } else {
+               for (int j = 0; j < nj; ++j) {
+                  const int q = gl + G * j;
+                  const float4 c = Cb[q];
+                  m = hmin4(m, c);
+                  __stcs(gout + q, c);
+               }
+            }
+         } else {
+            const float4 *S[K];
+            float mk[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+               const int prow = (k == 0) ? r : (k == 1 ? r - 2 : r - 1);   // (+1,-1), (-1,-1), (0,-1)
+               S[k] = reinterpret_cast<const float4 *>(slot_of(prow, v - 1));
+               mk[k] = NEEDM ? m_of(prow, v - 1) : 0.f;
+            }
+            auto batch = [&](auto jbc, int j0, auto regc) {
+               constexpr int B = decltype(jbc)::value;
+               constexpr bool REGC = decltype(regc)::value;
+               float4 c[B], a[K][B];
+#pragma unroll
+               for (int jj = 0; jj < B; ++jj) {
+                  const int q = gl + G * (j0 + jj);
+                  if constexpr (!REGC) c[jj] = Cb[q];
+#pragma unroll
+                  for (int k = 0; k < K; ++k) a[k][jj] = S[k][q];
+               }
+               if constexpr (REGC) {
+#pragma unroll
+                  for (int jj = 0; jj < B; ++jj) c[jj] = creg[(j0 + jj) < NJR ? (j0 + jj) : 0];
+               }
+#pragma unroll
+               for (int jj = 0; jj < B; ++jj) {
+                  const int q = gl + G * (j0 + jj);
+                  float4 o;
+                  if constexpr (POT == POT_TRUNC && K == 2) {   // update_cost2_trunclinear :216
+                     o = add4(c[jj], mul4s(add4s(add4(add4s(a[0][jj], -mk[0]), a[1 % K][jj]), -mk[1 % K]), 0.5f));
+                  } else if constexpr (POT == POT_SGM && K == 2) {   // update_cost2: halves taken by the producer
+                     o = add4(c[jj], add4(a[0][jj], a[1 % K][jj]));
+                  } else {
+                     float4 e = a[0][jj];
+#pragma unroll
+                     for (int k = 1; k < K; ++k) e = add4(e, a[k][jj]);
+                     o = add4(c[jj], div4_by_k<K>(e));
+                  }
+                  m = hmin4(m, o);
+                  Cb[q] = o;
+                  __stcs(gout + q, o);
+               }
+            };
+            if (creg_mode) {
+               constexpr int JR = (JB < NJR) ? JB : NJR;
+#pragma unroll
+               for (int jb = 0; jb < NJR; jb += JR) {
+                  if (jb + JR <= nj) batch(std::integral_constant<int, JR>{}, jb, std::true_type{});
+                  else {
+#pragma unroll
+                     for (int jr = 0; jr < JR; ++jr)
+                        if (jb + jr < nj) batch(std::integral_constant<int, 1>{}, jb + jr, std::true_type{});
+                  }
+               }
+            } else {
+               int j0 = 0;
+               for (; j0 + JB <= nj; j0 += JB) batch(std::integral_constant<int, JB>{}, j0, std::false_type{});
+               for (; j0 + 2 <= nj; j0 += 2) batch(std::integral_constant<int, 2>{}, j0, std::false_type{});
+               for (; j0 < nj; ++j0) batch(std::integral_constant<int, 1>{}, j0, std::false_type{});
+            }
+         }
+#pragma unroll
+         for (int d = 1; d < G; d <<= 1) m = fminf(m, __shfl_xor_sync(gmask, m, d));
+         if (gl == 0) msr[r * 4 + (v & 1)] = m;
+      }
+      if (creg_mode) prefetch_cost(v);
+      __syncthreads();
+
+      // ---------------- phase 2: neighbour-side transform of the message into ring slot v&1
+      if (late_prefetch) prefetch_cost(v);
+      if constexpr (CHAINS) {
+         const int ncw = (nrows + 31) >> 5;
+         if (warp_id < 2 * ncw) {
+            const int cw = warp_id % ncw, cdir = warp_id / ncw;
+            const int crow = cw * 32 + lane_id;
+            const bool on = crow < nrows && v >= vlo(u0 + crow) && v <= vhi(u0 + crow);
+            const float cm = on ? msr[crow * 4 + (v & 1)] : 0.f;
+            const float *src = on ? cbuf_of(crow, v) : thr;
+            float *dst = on ? row_base(crow) + (v & 1) * VS : thr;
+            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, 1 + cw);
+            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, 1 + cw);
+            if (on && has_next && crow >= nrows - 2) fence_proxy_async_smem();   // read by the boundary TMA stores
+         }
+      } else if (act) {
+         // SGM transform, label-parallel: A(o) = min3(L(o), min(L(o-1),L(o+1))+P1, m+P2) - m  [x 1/2 for K=2]
+         const float p1 = P.P1, cap = m + P.P2;
+         const float sc = (K == 2) ? 0.5f : 1.0f;
+         for (int j = 0; j < nj; ++j) {
+            const int q = gl + G * j;
+            const float4 x = Cb[q];
+            const float lft = (q > 0) ? Cbf[4 * q - 1] : MGM_INF;
+            const float rgt = (q + 1 < nq) ? Cbf[4 * q + 4] : MGM_INF;
+            float4 a;
+            a.x = sgm_x(lft, x.x, x.y, p1, cap, m) * sc;
+            a.y = sgm_x(x.x, x.y, x.z, p1, cap, m) * sc;
+            a.z = sgm_x(x.y, x.z, x.w, p1, cap, m) * sc;
+            a.w = sgm_x(x.z, x.w, rgt, p1, cap, m) * sc;
+            cur[q] = a;
+         }
+         if (has_next && r >= nrows - 2) fence_proxy_async_smem();
+      }
+      __syncthreads();
+
+      // ---------------- hand the two boundary workers to the next band
+      if (is_pub && has_next) {
+#pragma unroll
+         for (int line = 0; line < 2; ++line) {
+            const int br = nrows - 1 - line;
+            if (v >= vlo(u0 + br) && v <= vhi(u0 + br)) {
+               if (NEEDM) bndm_out[(size_t)line * maxjj + v] = msr[br * 4 + (v & 1)];
+               tma_store_1d(bnd_out + ((size_t)line * maxjj + v) * VS, slot_of(br, v), vbytes);
+            }
+         }
+         tma_commit();   // one (possibly empty) group per step
+      }
+   }
+
+   if (is_pub && has_next) {
+      tma_wait_all<0>();
+      fence_proxy_async();
+      st_release(prog_out, 0x7fffffff);
+   }
+   cp_async_wait<0>();
+   if (tid == 0) phase[vph_idx] = vph;
+   __syncthreads();
+}
+
 template <int POT, int K, bool WEIGHTED>
 __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(const AggParams P) {
    extern __shared__ __align__(128) unsigned char smem[];
@@ -531,7 +920,10 @@ __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(c
       if (tk >= P.ntickets) break;
       const int2 pb = P.tickets[tk];
       if (pb.x < 4) run_band<POT, K, WEIGHTED, false>(P, pb.x, pb.y, smem);
-      else run_band<POT, K, WEIGHTED, true>(P, pb.x, pb.y, smem);
+      else if constexpr (!WEIGHTED && K <= 3) {
+         if (P.shear) run_band_shear<POT, K>(P, pb.x, pb.y, smem);
+         else run_band<POT, K, WEIGHTED, true>(P, pb.x, pb.y, smem);
+      } else run_band<POT, K, WEIGHTED, true>(P, pb.x, pb.y, smem);
    }
 }
 
@@ -563,25 +955,29 @@ static cudaError_t launch_k(int K, const AggParams &P, const AggPlan &plan, cuda
    }
 }
 
-void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
-              int t_override) {
+static void agg_plan_try(AggPlan *plan, int L, int K, int pot, bool weighted, int max_smem, int num_sms, int t_override,
+                         int shear) {
    const int VS = (L + 31) & ~31;   // 8 lanes x 16 bytes per row and step
    plan->VS = VS;
    const int xtra = (weighted && pot == POT_TRUNC) ? K : 0;
    const int tcap = (MGM_AGG_MAX_THREADS - 64) / MGM_AGG_GROUP;   // rows per CTA allowed by the thread budget
+   // costs prefetched into registers when a lane's share fits (one cost buffer per row), else a cp.async ring of two
+   plan->ncb = (VS / (4 * MGM_AGG_GROUP) <= MGM_AGG_CREG && !getenv("MGMB200_NO_CREG")) ? 1 : 2;
+   plan->shear = shear;
+   const int nvirt = shear ? 2 : 1;   // boundary workers kept per position
    for (int cls = 0; cls < 2; ++cls) {
-      int nbuf = ring_slots(cls, K) + 2 + xtra;
+      int nbuf = ((cls == 1 && shear) ? 2 : ring_slots(cls, K)) + plan->ncb + xtra;
       int TS = nbuf * VS;
       if (((TS >> 2) & 1) == 0) TS += 4;   // odd number of 16-byte units: rows start in different bank groups
       plan->TS[cls] = TS;
-      size_t fixed = 1024 + (size_t)RV * VS * 4 + (size_t)tcap * (16 + 16 + 4) + RV * 16;
+      size_t fixed = 1024 + (size_t)nvirt * RV * VS * 4 + (size_t)tcap * (16 + 16 + 4) + RV * 16;
       long avail = (long)max_smem - (long)fixed;
-      int Tc = (int)(avail / ((long)TS * 4));
+      int Tc = avail > 0 ? (int)(avail / ((long)TS * 4)) : 0;
       if (Tc > tcap) Tc = tcap;
       {
          const char *e = getenv(cls == 0 ? "MGMB200_ROWS_AXIS" : "MGMB200_ROWS_DIAG");   // tuning knobs
          const int ov = e ? atoi(e) : t_override;
-         if (ov > 0 && Tc > ov) Tc = ov;
+         if (ov > 0 && Tc > ov) Tc = (cls == 1 && shear && ov < 2) ? 2 : ov;
       }
       if (Tc < 1) Tc = 0;
       plan->T[cls] = Tc;
@@ -594,12 +990,25 @@ void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighte
    plan->off_cbar = off; off += (size_t)tm * 16;
    plan->off_vbar = off; off += RV * 8;
    plan->off_ms = off; off += (size_t)tm * 16;
-   plan->off_vms = off; off += RV * 4; off = (off + 127) & ~(size_t)127;
-   plan->off_virt = off; off += (size_t)RV * VS * 4; off = (off + 127) & ~(size_t)127;
+   plan->off_vms = off; off += (size_t)nvirt * RV * 4; off = (off + 127) & ~(size_t)127;
+   plan->off_virt = off; off += (size_t)nvirt * RV * VS * 4; off = (off + 127) & ~(size_t)127;
    plan->off_thr = off;
    size_t per_thr = (size_t)max(plan->TS[0] * plan->T[0], plan->TS[1] * plan->T[1]) * 4;
    plan->smem = off + per_thr;
    plan->num_sms = num_sms;
+}
+
+void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
+              int t_override) {
+   (void)nx; (void)ny;
+   // diagonal sweeps as sheared wavefronts (run_band_shear): predecessors in the row above only, no image-dependent
+   // weights, and room for at least two workers per band (the hand-off carries the last two)
+   const bool want_shear = (K <= 3 && !weighted && !getenv("MGMB200_NO_SHEAR"));
+   if (want_shear) {
+      agg_plan_try(plan, L, K, pot, weighted, max_smem, num_sms, t_override, 1);
+      if (plan->T[0] >= 1 && plan->T[1] >= 2) return;
+   }
+   agg_plan_try(plan, L, K, pot, weighted, max_smem, num_sms, t_override, 0);
 }
 
 cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st) {

@@ -3,7 +3,8 @@
 #include "common.cuh"
 
 #define MGM_AGG_GROUP 8           // lanes cooperating on one scan row
-#define MGM_AGG_MAX_THREADS 512   // 56 rows x 8 lanes + two service warps (boundary consumer / publisher)
+#define MGM_AGG_MAX_THREADS 480   // 52 rows x 8 lanes + two service warps (boundary consumer / publisher); 136 registers per thread
+#define MGM_AGG_CREG 8            // 16-byte cost chunks per lane prefetched into registers (covers 256 labels)
 
 namespace mgm {
 
@@ -22,6 +23,8 @@ struct AggParams {
    int nx, ny, L, VS;
    int T[2];                   // rows per band: [0] axis sweeps 0-3, [1] diagonal sweeps 4-7
    int TS[2];                  // per-row shared-memory stride in floats
+   int ncb;                    // cost buffers per row (1: costs prefetched into registers, 2: cp.async ring)
+   int shear;                  // 1: sweeps 4-7 run as sheared wavefronts (bands of anti-diagonals, run_band_shear)
    float P1, P2;
    unsigned long long *dbg;    // optional 24-word phase-timing accumulator (profiling aid), or nullptr
    // dynamic shared memory carve-up (bytes)
@@ -29,7 +32,7 @@ struct AggParams {
 };
 
 struct AggPlan {
-   int VS, T[2], TS[2], block, num_sms;
+   int VS, T[2], TS[2], ncb, shear, block, num_sms;
    size_t smem;
    size_t off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };

@@ -317,10 +317,17 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
       if (!(mask & (1u << p))) continue;
       PassGeom g = pass_geometry(p, nx, ny);
       const int T = plan.T[p < 4 ? 0 : 1];
-      nb[p] = (g.maxjj + T - 1) / T;
+      if (p >= 4 && plan.shear) {
+         // sheared wavefront: bands of T anti-diagonals, two boundary lines of maxjj positions per band
+         nb[p] = (g.maxii + g.maxjj - 1 + T - 1) / T;
+         bnd_off[p] = bnd_total; bnd_total += (size_t)nb[p] * 2 * g.maxjj * VS;
+         bndm_off[p] = bndm_total; bndm_total += (size_t)nb[p] * 2 * g.maxjj;
+      } else {
+         nb[p] = (g.maxjj + T - 1) / T;
+         bnd_off[p] = bnd_total; bnd_total += (size_t)nb[p] * g.maxii * VS;
+         bndm_off[p] = bndm_total; bndm_total += (size_t)nb[p] * g.maxii;
+      }
       if (nb[p] > maxb) maxb = nb[p];
-      bnd_off[p] = bnd_total; bnd_total += (size_t)nb[p] * g.maxii * VS;
-      bndm_off[p] = bndm_total; bndm_total += (size_t)nb[p] * g.maxii;
       prog_off[p] = prog_total; prog_total += nb[p];
    }
    // Claim order = longest remaining dependency chain first (list scheduling): band b of sweep p still has
@@ -334,8 +341,10 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
          PassGeom g = pass_geometry(p, nx, ny);
          const int cls = p < 4 ? 0 : 1;
          const int sig = (cls == 1 || K == 4) ? 2 : 1;
-         const long long lag = (long long)sig * plan.T[cls] + 6;
-         for (int b = 0; b < nb[p]; b++) items.push_back({(long long)(nb[p] - b) * lag + g.maxii, p, b});
+         const bool sh = (cls == 1 && plan.shear);
+         const long long lag = sh ? 8 : (long long)sig * plan.T[cls] + 6;
+         const long long len = sh ? (g.maxii < g.maxjj ? g.maxii : g.maxjj) : g.maxii;
+         for (int b = 0; b < nb[p]; b++) items.push_back({(long long)(nb[p] - b) * lag + len, p, b});
       }
       std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.key > b.key; });
       for (const Item &it : items) tk.push_back(make_int2(it.p, it.b));
@@ -348,7 +357,7 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
    RET(c->progress.reserve((prog_total + 4) * sizeof(int)));
    RET(c->bnd.reserve(bnd_total * sizeof(float)));
    RET(c->bndm.reserve(bndm_total * sizeof(float)));
-   const long long key[6] = {nx, ny, plan.T[0], plan.T[1], (long long)mask, NDIR};
+   const long long key[6] = {nx, ny, plan.T[0], plan.T[1] * 2 + plan.shear, (long long)mask, NDIR + 64LL * K};
    if (memcmp(key, c->tk_key, sizeof(key)) != 0) {
       CU(cudaMemcpyAsync(c->tickets.p, tk.data(), tk.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
       CU(cudaStreamSynchronize(c->stream));
@@ -371,6 +380,7 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
    P.nx = nx; P.ny = ny; P.L = L; P.VS = VS;
    P.T[0] = plan.T[0]; P.T[1] = plan.T[1];
    P.TS[0] = plan.TS[0]; P.TS[1] = plan.TS[1];
+   P.ncb = plan.ncb; P.shear = plan.shear;
    P.P1 = P1; P.P2 = P2;
    P.dbg = nullptr;
    if (getenv("MGMB200_PHASE_TIMING")) {
