@@ -25,6 +25,7 @@
 // Precondition of this fast path (enforced by the host): every cost
 // vector holds a finite value, no NaN / -INF, P1,P2 >= 0 and weights >= 0; then the
 // hardware min is bit-identical to the reference's compare-select forms.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -113,6 +114,19 @@ __device__ __forceinline__ void chain4(float &run, float &a0, float &a1, float &
 
 // named barrier shared by one forward warp and its backward partner warp (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// Row groups.  The rows of a band are split into NG groups of TG rows that run the two phases of a step on their
+// OWN named barrier, out of phase with each other: while one group gathers (LSU-bound) the others run their
+// min-convolution chains (latency-bound).  Groups are ordered by two shared-memory step counters:
+//   token: group g starts the gather of step s after group g-1 has finished ITS gather of step s (this also
+//          covers the read-after-write on the rows of group g-1 and serialises the gathers on the LSU);
+//   reuse: group g starts the gather of step s after group g+1 has finished the gather of step s-1 (the ring slot
+//          it is about to overwrite was last read there).
+struct RowGroup {
+   int gi, bar_id, cnt, first_tid;
+   volatile int *flags;   // flags[g] = last step whose gather group g has completed
+   __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(cnt) : "memory"); }
+};
 
 // Half of the meet-in-the-middle min-convolution of `src` into `dst`, executed by a whole WARP whose lanes
 // hold the same direction (DIR=0 upwards, DIR=1 downwards) of 32 different vectors; the partner warp runs
@@ -215,7 +229,21 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    float *thr = reinterpret_cast<float *>(smem + P.off_thr);
    uint32_t *phase = reinterpret_cast<uint32_t *>(smem + P.off_phase);   // persistent mbarrier parities
 
-   // per-row shared memory: ring slots [R][VS] | cost buffers [ncb][VS] | scratch [K][VS] (weighted trunc)
+   // row groups (RowGroup above); the boundary consumer warp belongs to group 0, the publisher warp to the last
+   const int NG = P.ng[CLS], TG = T / NG;
+   RowGroup grp;
+   grp.gi = (tid < ncomp) ? min(r / TG, NG - 1) : (is_prod || (tid > ncomp && tid < ncomp + 32) ? 0 : NG - 1);
+   grp.bar_id = 1 + grp.gi;
+   grp.cnt = (grp.gi < NG - 1 ? TG * G : ncomp - (NG - 1) * TG * G) + (grp.gi == 0 ? 32 : 0) + (grp.gi == NG - 1 ? 32 : 0);
+   grp.first_tid = grp.gi * TG * G;
+   grp.flags = reinterpret_cast<volatile int *>(smem + P.off_cbar);
+   const int gw0 = grp.first_tid >> 5;          // first warp of my group
+   const int ncw = (TG + 31) >> 5;              // chain warps per direction and group
+   const int pair_id0 = 1 + NG + grp.gi * 2;    // named barriers of my group's chain pairs
+   if (tid == 0) { for (int i = 0; i < NG; ++i) grp.flags[i] = -1; }
+   __syncthreads();
+
+   // per-row shared memory: ring slots [R][VS] | cost buffers [ncbuf][VS] | scratch [K][VS] (weighted trunc)
    auto row_base = [&](int rr) -> float * { return thr + (size_t)rr * TS; };
    auto slot_of = [&](int rr, int px) -> float * {
       return (rr < 0) ? virt + (px & (RV - 1)) * VS : row_base(rr) + (px % R) * VS;
@@ -253,6 +281,9 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    float4 creg[NJR];
 #pragma unroll
    for (int j = 0; j < NJR; ++j) creg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+   // CHAINS with register-resident costs: the message is written straight into its ring slot and the
+   // min-convolution runs IN PLACE there (its second half no longer reads the source) -> no cost buffer at all
+   const int ncbuf = (CHAINS && creg_mode) ? 0 : ncb;
    auto cbuf_of = [&](int rr, int px) -> float * { return row_base(rr) + (R + (ncb == 2 ? (px & 1) : 0)) * VS; };
    auto prefetch_cost = [&](int s) {
       const int px = s - SIG * r + 1;   // the pixel my row handles in the NEXT step
@@ -277,11 +308,9 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    // cp.async mode: lanes of warps that run min-convolution chains in phase 2 issue their prefetch at the top of
    // the step; all other warps are idle in phase 2 and issue it there (the LSU is less busy then).
    // Register mode: every lane issues its loads right after its gather (they complete during phase 2).
-   const bool late_prefetch = !creg_mode && CHAINS && (warp_id >= 2 * ((nrows + 31) >> 5));
+   const bool late_prefetch = !creg_mode && CHAINS && (warp_id - gw0 >= 2 * ncw);
 
-   long long tA = 0, tW1 = 0, tB = 0, tW2 = 0, tP = 0, tC = 0;
    for (int s = 0; s < nsteps; ++s) {
-      const long long c0 = clock64();
       if (!late_prefetch && !creg_mode) prefetch_cost(s);
       if (is_pub && has_next) {
          // boundary stores are issued by this thread (end of each step, below); all but the most recent one
@@ -326,22 +355,28 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
             vph ^= 1u << sl;
          }
       }
-      const long long c1 = clock64();
+      if (NG > 1 && tid < ncomp) {   // group ordering (RowGroup): token from the group above, slot reuse below
+         if (lane_id == 0) {
+            if (grp.gi > 0) { while (grp.flags[grp.gi - 1] < s) {} }
+            if (grp.gi < NG - 1) { while (grp.flags[grp.gi + 1] < s - 1) {} }
+         }
+         __syncwarp();
+      }
       const int xs = s - SIG * r;
       const bool act = rowok && xs >= 0 && xs < maxii;
       const long long pix = pix0 + (long long)xs * g.dxs;
-      float *Cbf = cbuf_of(r, xs);
-      float4 *Cb = reinterpret_cast<float4 *>(Cbf);
       float4 *cur = reinterpret_cast<float4 *>(row_base(r) + (act ? (xs % R) : 0) * VS);
+      float *Cbf = (CHAINS && creg_mode) ? reinterpret_cast<float *>(cur) : cbuf_of(r, xs);   // where the message is built
+      float4 *Cb = reinterpret_cast<float4 *>(Cbf);
       float4 *gout = reinterpret_cast<float4 *>(ldir + (size_t)(act ? pix : 0) * VS);
       const bool border = (xs == 0) || (ys == 0) || (xs == maxii - 1);
       float m = MGM_INF;
 
       // ---------------- phase 0 (weighted truncated-linear only): one lane pair per (row, neighbour)
       if constexpr (WTRUNC) {
-         const int ncw = (K * nrows + 31) >> 5;   // warps per direction
-         if (warp_id < 2 * ncw) {
-            const int cw = warp_id % ncw, cdir = warp_id / ncw;
+         const int ncw0 = (K * nrows + 31) >> 5;   // warps per direction (weighted kernels run as one group)
+         if (warp_id < 2 * ncw0) {
+            const int cw = warp_id % ncw0, cdir = warp_id / ncw0;
             const int pidx = cw * 32 + lane_id;
             const int crow = pidx / K, ck = pidx % K;
             const int cxs = s - SIG * crow;
@@ -357,19 +392,17 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                mk = m_of(prow, ppx);
                cw1 = P.P1 * wk; capv = mk + P.P2 * wk;
                src = slot_of(prow, ppx);
-               dst = row_base(crow) + (R + ncb + ck) * VS;
+               dst = row_base(crow) + (R + ncbuf + ck) * VS;
             }
-            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 1 + cw);
-            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 1 + cw);
+            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 1 + NG + cw);
+            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 1 + NG + cw);
          }
-         __syncthreads();
+         grp.sync();
       }
 
       // ---------------- phase 1: gather the message of pixel (xs,ys), G lanes per row
       if (act) {
-         const long long cw0 = clock64();
          if (!creg_mode) { if (late_prefetch) cp_async_wait<0>(); else cp_async_wait<1>(); }   // all but a prefetch issued this step
-         tC += clock64() - cw0;
 
          if (border) {
             if (creg_mode) {
@@ -383,21 +416,24 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                   }
                }
             } else {
+               const float4 *Cin = reinterpret_cast<const float4 *>(cbuf_of(r, xs));
                for (int j = 0; j < nj; ++j) {
                   const int q = gl + G * j;
-                  const float4 c = Cb[q];
+                  const float4 c = Cin[q];
                   m = hmin4(m, c);
+                  if (CHAINS) Cb[q] = c;
                   __stcs(gout + q, c);
                }
             }
          } else {
+            const float4 *Cin = reinterpret_cast<const float4 *>(cbuf_of(r, xs));   // costs (cp.async mode)
             const float4 *S[K];
             float mk[K], wk[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                int prow, ppx;
                pred_of(r, xs, k, prow, ppx);
-               S[k] = reinterpret_cast<const float4 *>(WTRUNC ? row_base(r) + (R + ncb + k) * VS : slot_of(prow, ppx));
+               S[k] = reinterpret_cast<const float4 *>(WTRUNC ? row_base(r) + (R + ncbuf + k) * VS : slot_of(prow, ppx));
                mk[k] = 0.f; wk[k] = 1.f;
                if (NEEDM) mk[k] = m_of(prow, ppx);
                if (WEIGHTED && !WTRUNC) wk[k] = __ldg(P.w + (size_t)pass_weight_plane(pass, k) * wplane + pix);
@@ -412,7 +448,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 #pragma unroll
                   for (int jj = 0; jj < B; ++jj) {
                      const int q = gl + G * (j0 + jj);
-                     if constexpr (!REGC) c[jj] = Cb[q];
+                     if constexpr (!REGC) c[jj] = Cin[q];
 #pragma unroll
                      for (int k = 0; k < K; ++k) a[k][jj] = S[k][q];
                   }
@@ -495,25 +531,24 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
          if (gl == 0) msr[r * 4 + (xs % R)] = m;
       }
       if (creg_mode) prefetch_cost(s);   // costs of the next pixel -> registers, in flight during phase 2
-      const long long c2 = clock64();
-      __syncthreads();
-      const long long c3 = clock64();
+      grp.sync();
+      if (NG > 1 && tid == grp.first_tid) { __threadfence_block(); grp.flags[grp.gi] = s; }
 
       // ---------------- phase 2: build the neighbour-side transform of the message in the ring slot
       if (late_prefetch) prefetch_cost(s);
       if constexpr (CHAINS) {
-         // minConvTruncatedLinear of the finished message, one lane pair per row
-         const int ncw = (nrows + 31) >> 5;   // warps per direction
-         if (warp_id < 2 * ncw) {
-            const int cw = warp_id % ncw, cdir = warp_id / ncw;
-            const int crow = cw * 32 + lane_id;
+         // minConvTruncatedLinear of the finished message, one lane pair per row (the first 2*ncw warps of the group)
+         const int wg = warp_id - gw0;
+         if (tid < ncomp + 64 && wg >= 0 && wg < 2 * ncw) {
+            const int cw = wg % ncw, cdir = wg / ncw;
+            const int crow = grp.gi * TG + cw * 32 + lane_id;
             const int cxs = s - SIG * crow;
-            const bool on = crow < nrows && cxs >= 0 && cxs < maxii;
+            const bool on = cw * 32 + lane_id < TG && crow < nrows && cxs >= 0 && cxs < maxii;
             const float cm = on ? msr[crow * 4 + (cxs % R)] : 0.f;
-            const float *src = on ? cbuf_of(crow, cxs) : thr;
             float *dst = on ? row_base(crow) + (cxs % R) * VS : thr;
-            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, 1 + cw);
-            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, 1 + cw);
+            const float *src = on ? (creg_mode ? dst : cbuf_of(crow, cxs)) : thr;
+            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
+            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
             if (on && has_next && crow == nrows - 1) fence_proxy_async_smem();   // read by the boundary TMA store
          }
       } else if (act) {
@@ -551,10 +586,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
          }
          if (last_row) fence_proxy_async_smem();
       }
-      const long long c4 = clock64();
-      __syncthreads();
-      const long long c5 = clock64();
-      tP += c1 - c0; tA += c2 - c1; tW1 += c3 - c2; tB += c4 - c3; tW2 += c5 - c4;
+      grp.sync();
 
       // ---------------- hand the boundary row to the next band (producer thread, TMA bulk store)
       if (is_pub && has_next) {
@@ -567,11 +599,6 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
       }
    }
 
-   if (P.dbg && (tid == 0 || tid == ncomp || tid == 8 * (nrows - 1))) {
-      unsigned long long *d = P.dbg + (tid == 0 ? 0 : (tid == ncomp ? 8 : 16));
-      atomicAdd(d + 0, (unsigned long long)tP); atomicAdd(d + 1, (unsigned long long)tA); atomicAdd(d + 2, (unsigned long long)tW1);
-      atomicAdd(d + 3, (unsigned long long)tB); atomicAdd(d + 4, (unsigned long long)tW2); atomicAdd(d + 5, (unsigned long long)nsteps); atomicAdd(d + 6, (unsigned long long)tC);
-   }
    // epilogue: drain the boundary stores, publish the full boundary row, save mbarrier parities
    if (is_pub && has_next) {
       tma_wait_all<0>();
@@ -641,7 +668,22 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
    float *thr = reinterpret_cast<float *>(smem + P.off_thr);
    uint32_t *phase = reinterpret_cast<uint32_t *>(smem + P.off_phase);
 
-   // per-worker shared memory: ring slots [2][VS] (position v&1) | cost buffers [ncb][VS]
+   // row groups (RowGroup): the boundary consumer warp belongs to group 0, the publisher warp to the last
+   const int NG = P.ng[1], TG = T / NG;
+   RowGroup grp;
+   grp.gi = (tid < ncomp) ? min(r / TG, NG - 1) : (tid < ncomp + 32 ? 0 : NG - 1);
+   grp.bar_id = 1 + grp.gi;
+   grp.cnt = (grp.gi < NG - 1 ? TG * G : ncomp - (NG - 1) * TG * G) + (grp.gi == 0 ? 32 : 0) + (grp.gi == NG - 1 ? 32 : 0);
+   grp.first_tid = grp.gi * TG * G;
+   grp.flags = reinterpret_cast<volatile int *>(smem + P.off_cbar);
+   const int gw0 = grp.first_tid >> 5;
+   const int ncw = (TG + 31) >> 5;
+   const int pair_id0 = 1 + NG + grp.gi * 2;
+   if (tid == 0) { for (int i = 0; i < NG; ++i) grp.flags[i] = sb - 1; }
+   __syncthreads();
+   const bool inplace = CHAINS && creg_mode;   // message built in its ring slot, min-convolution in place
+
+   // per-worker shared memory: ring slots [2][VS] (position v&1) | cost buffers [ncb][VS] (none when in place)
    auto row_base = [&](int rr) -> float * { return thr + (size_t)rr * TS; };
    auto slot_of = [&](int rr, int v) -> float * {
       return (rr < 0) ? virt + ((-rr - 1) * RV + (v & (RV - 1))) * VS : row_base(rr) + (v & 1) * VS;
@@ -691,7 +733,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
       cp_async_commit();
    };
    prefetch_cost(sb - 1);
-   const bool late_prefetch = !creg_mode && CHAINS && (warp_id >= 2 * ((nrows + 31) >> 5));
+   const bool late_prefetch = !creg_mode && CHAINS && (warp_id - gw0 >= 2 * ncw);
 
    for (int v = sb; v <= se; ++v) {
       if (!late_prefetch && !creg_mode) prefetch_cost(v);
@@ -735,12 +777,19 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
          if (v == sb) { wait_pos(sb - 1); wait_pos(sb); } else wait_pos(v);
       }
 
+      if (NG > 1 && tid < ncomp) {   // group ordering (RowGroup): token from the group above, slot reuse below
+         if (lane_id == 0) {
+            if (grp.gi > 0) { while (grp.flags[grp.gi - 1] < v) {} }
+            if (grp.gi < NG - 1) { while (grp.flags[grp.gi + 1] < v - 1) {} }
+         }
+         __syncwarp();
+      }
       const bool act = rowok && v >= my_lo && v <= my_hi;
       const int xs = u - v;
       const long long pix = pix_u + (long long)v * dv;
-      float *Cbf = cbuf_of(r, v);
-      float4 *Cb = reinterpret_cast<float4 *>(Cbf);
       float4 *cur = reinterpret_cast<float4 *>(row_base(r) + (v & 1) * VS);
+      float *Cbf = inplace ? reinterpret_cast<float *>(cur) : cbuf_of(r, v);   // where the message is built
+      float4 *Cb = reinterpret_cast<float4 *>(Cbf);
       float4 *gout = reinterpret_cast<float4 *>(ldir + (size_t)(act ? pix : 0) * VS);
       const bool border = (xs == 0) || (v == 0) || (xs == maxii - 1);
       float m = MGM_INF;
@@ -760,14 +809,16 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
                   }
                }
             } else {
+               const float4 *Cin = reinterpret_cast<const float4 *>(cbuf_of(r, v));
                for (int j = 0; j < nj; ++j) {
                   const int q = gl + G * j;
-                  const float4 c = Cb[q];
+                  const float4 c = Cin[q];
                   m = hmin4(m, c);
                   __stcs(gout + q, c);
                }
             }
          } else {
+            const float4 *Cin = reinterpret_cast<const float4 *>(cbuf_of(r, v));   // costs (cp.async mode)
             const float4 *S[K];
             float mk[K];
 #pragma unroll
@@ -783,7 +834,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
 #pragma unroll
                for (int jj = 0; jj < B; ++jj) {
                   const int q = gl + G * (j0 + jj);
-                  if constexpr (!REGC) c[jj] = Cb[q];
+                  if constexpr (!REGC) c[jj] = Cin[q];
 #pragma unroll
                   for (int k = 0; k < K; ++k) a[k][jj] = S[k][q];
                }
@@ -833,21 +884,22 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
          if (gl == 0) msr[r * 4 + (v & 1)] = m;
       }
       if (creg_mode) prefetch_cost(v);
-      __syncthreads();
+      grp.sync();
+      if (NG > 1 && tid == grp.first_tid) { __threadfence_block(); grp.flags[grp.gi] = v; }
 
       // ---------------- phase 2: neighbour-side transform of the message into ring slot v&1
       if (late_prefetch) prefetch_cost(v);
       if constexpr (CHAINS) {
-         const int ncw = (nrows + 31) >> 5;
-         if (warp_id < 2 * ncw) {
-            const int cw = warp_id % ncw, cdir = warp_id / ncw;
-            const int crow = cw * 32 + lane_id;
-            const bool on = crow < nrows && v >= vlo(u0 + crow) && v <= vhi(u0 + crow);
+         const int wg = warp_id - gw0;
+         if (wg >= 0 && wg < 2 * ncw) {
+            const int cw = wg % ncw, cdir = wg / ncw;
+            const int crow = grp.gi * TG + cw * 32 + lane_id;
+            const bool on = cw * 32 + lane_id < TG && crow < nrows && v >= vlo(u0 + crow) && v <= vhi(u0 + crow);
             const float cm = on ? msr[crow * 4 + (v & 1)] : 0.f;
-            const float *src = on ? cbuf_of(crow, v) : thr;
             float *dst = on ? row_base(crow) + (v & 1) * VS : thr;
-            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, 1 + cw);
-            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, 1 + cw);
+            const float *src = on ? (inplace ? dst : cbuf_of(crow, v)) : thr;
+            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
+            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
             if (on && has_next && crow >= nrows - 2) fence_proxy_async_smem();   // read by the boundary TMA stores
          }
       } else if (act) {
@@ -868,7 +920,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
          }
          if (has_next && r >= nrows - 2) fence_proxy_async_smem();
       }
-      __syncthreads();
+      grp.sync();
 
       // ---------------- hand the two boundary workers to the next band
       if (is_pub && has_next) {
@@ -894,10 +946,51 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
    __syncthreads();
 }
 
+// Dynamic band scheduling (one thread per CTA).  Bands of a sweep are claimed strictly in order through a
+// per-sweep counter, so a claimed band's predecessor is always running or finished: any grid size is deadlock
+// free.  An axis band (sweeps 0-3) trails its predecessor by a whole band of steps; claiming it before the
+// predecessor has published anything would park an SM for milliseconds.  Hence:
+//   1. an axis band whose predecessor has started publishing its boundary row (or a first band), longest
+//      remaining chain first -- the axis sweeps are the critical path;
+//   2. else the next band of the diagonal sweep that is least advanced (short hand-off: the filler work);
+//   3. else any remaining axis band (it waits inside run_band).
+__device__ int2 claim_band(const AggParams &P) {
+   for (;;) {
+      int best = -1, bb = 0, bestrem = 0;
+      for (int p = 0; p < 4; ++p) {
+         const int nbp = P.nb[p];
+         if (!nbp) continue;
+         const int b = *reinterpret_cast<volatile int *>(P.next_band + p);
+         if (b >= nbp) continue;
+         const bool ready = P.static_order || b == 0 || ld_acquire(P.progress[p] + b - 1) >= 1;
+         if (ready && nbp - b > bestrem) { best = p; bb = b; bestrem = nbp - b; }
+      }
+      if (best < 0) {
+         int bmin = 0x7fffffff;
+         for (int p = 4; p < 8; ++p) {
+            const int nbp = P.nb[p];
+            if (!nbp) continue;
+            const int b = *reinterpret_cast<volatile int *>(P.next_band + p);
+            if (b < nbp && b < bmin) { best = p; bb = b; bmin = b; }
+         }
+      }
+      if (best < 0) {
+         for (int p = 0; p < 4; ++p) {
+            const int nbp = P.nb[p];
+            if (!nbp) continue;
+            const int b = *reinterpret_cast<volatile int *>(P.next_band + p);
+            if (b < nbp && nbp - b > bestrem) { best = p; bb = b; bestrem = nbp - b; }
+         }
+      }
+      if (best < 0) return make_int2(-1, 0);
+      if (atomicCAS(P.next_band + best, bb, bb + 1) == bb) return make_int2(best, bb);
+   }
+}
+
 template <int POT, int K, bool WEIGHTED>
 __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(const AggParams P) {
    extern __shared__ __align__(128) unsigned char smem[];
-   __shared__ int s_ticket;
+   __shared__ int2 s_ticket;
    const int t = threadIdx.x;
    const int ncomp = blockDim.x - 64;   // two service warps follow the row threads
 
@@ -913,12 +1006,11 @@ __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(c
    }
 
    for (;;) {
-      if (t == 0) s_ticket = (int)atomicAdd(P.ticket_counter, 1u);
+      if (t == 0) s_ticket = claim_band(P);
       __syncthreads();
-      const int tk = s_ticket;
+      const int2 pb = s_ticket;
       __syncthreads();
-      if (tk >= P.ntickets) break;
-      const int2 pb = P.tickets[tk];
+      if (pb.x < 0) break;
       if (pb.x < 4) run_band<POT, K, WEIGHTED, false>(P, pb.x, pb.y, smem);
       else if constexpr (!WEIGHTED && K <= 3) {
          if (P.shear) run_band_shear<POT, K>(P, pb.x, pb.y, smem);
@@ -939,8 +1031,11 @@ static cudaError_t launch_t(const AggParams &P, const AggPlan &plan, cudaStream_
    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, plan.block, plan.smem);
    if (e != cudaSuccess) return e;
    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-   int grid = min(P.ntickets, plan.num_sms * per_sm);
+   int grid = min(P.nbands, plan.num_sms * per_sm);
    if (grid < 1) grid = 1;
+   if (getenv("MGMB200_VERBOSE"))
+      fprintf(stderr, "[mgmb200] aggregate: grid=%d block=%d smem=%zu CTAs/SM=%d bands=%d rows=%d/%d groups=%d/%d shear=%d\n", grid,
+              plan.block, plan.smem, per_sm, P.nbands, plan.T[0], plan.T[1], plan.ng[0], plan.ng[1], plan.shear);
    kern<<<grid, plan.block, plan.smem, st>>>(P);
    return cudaGetLastError();
 }
@@ -965,8 +1060,13 @@ static void agg_plan_try(AggPlan *plan, int L, int K, int pot, bool weighted, in
    plan->ncb = (VS / (4 * MGM_AGG_GROUP) <= MGM_AGG_CREG && !getenv("MGMB200_NO_CREG")) ? 1 : 2;
    plan->shear = shear;
    const int nvirt = shear ? 2 : 1;   // boundary workers kept per position
+   // unweighted truncated-linear kernels with register-resident costs build the message in its ring slot and run
+   // the min-convolution in place: no cost buffer
+   const int ncbuf = (pot == POT_TRUNC && !weighted && plan->ncb == 1) ? 0 : plan->ncb;
+   int want_groups = 1;   // row groups per band (RowGroup in the kernel); measured: no gain, the LSU is the shared limit
+   if (const char *e = getenv("MGMB200_GROUPS")) { const int v = atoi(e); if (!weighted && (v == 1 || v == 2 || v == 4)) want_groups = v; }
    for (int cls = 0; cls < 2; ++cls) {
-      int nbuf = ((cls == 1 && shear) ? 2 : ring_slots(cls, K)) + plan->ncb + xtra;
+      int nbuf = ((cls == 1 && shear) ? 2 : ring_slots(cls, K)) + ncbuf + xtra;
       int TS = nbuf * VS;
       if (((TS >> 2) & 1) == 0) TS += 4;   // odd number of 16-byte units: rows start in different bank groups
       plan->TS[cls] = TS;
@@ -980,6 +1080,11 @@ static void agg_plan_try(AggPlan *plan, int L, int K, int pot, bool weighted, in
          if (ov > 0 && Tc > ov) Tc = (cls == 1 && shear && ov < 2) ? 2 : ov;
       }
       if (Tc < 1) Tc = 0;
+      // groups need whole warps (4 rows) and at least two warps each for their chain pair
+      int ng = want_groups;
+      while (ng > 1 && Tc / (4 * ng) * 4 < 8) ng >>= 1;
+      if (ng > 1) Tc = Tc / (4 * ng) * (4 * ng);
+      plan->ng[cls] = ng;
       plan->T[cls] = Tc;
    }
    const int tm = max(plan->T[0], plan->T[1]);

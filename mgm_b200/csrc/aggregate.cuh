@@ -3,7 +3,7 @@
 #include "common.cuh"
 
 #define MGM_AGG_GROUP 8           // lanes cooperating on one scan row
-#define MGM_AGG_MAX_THREADS 480   // 52 rows x 8 lanes + two service warps (boundary consumer / publisher); 136 registers per thread
+#define MGM_AGG_MAX_THREADS 512   // 56 rows x 8 lanes + two service warps (boundary consumer / publisher); 128 registers per thread
 #define MGM_AGG_CREG 8            // 16-byte cost chunks per lane prefetched into registers (covers 256 labels)
 
 namespace mgm {
@@ -17,14 +17,16 @@ struct AggParams {
    float *bnd[8];              // per-sweep boundary lines [nbands][maxii][VS]
    float *bndm[8];             // per-sweep boundary minima [nbands][maxii]
    int *progress[8];           // per-sweep [nbands]: finished pixels of each band's last row
-   const int2 *tickets;        // (sweep, band) in claim order
-   unsigned int *ticket_counter;
-   int ntickets;
+   int *next_band;             // per-sweep claim counters [8]: bands of a sweep are claimed in order
+   int nb[8];                  // bands per sweep (0 = sweep not requested)
+   int nbands;                 // total
+   int static_order;           // debugging knob: claim without the readiness test
    int nx, ny, L, VS;
    int T[2];                   // rows per band: [0] axis sweeps 0-3, [1] diagonal sweeps 4-7
    int TS[2];                  // per-row shared-memory stride in floats
    int ncb;                    // cost buffers per row (1: costs prefetched into registers, 2: cp.async ring)
    int shear;                  // 1: sweeps 4-7 run as sheared wavefronts (bands of anti-diagonals, run_band_shear)
+   int ng[2];                  // row groups per band (axis / diagonal class), each on its own named barrier
    float P1, P2;
    unsigned long long *dbg;    // optional 24-word phase-timing accumulator (profiling aid), or nullptr
    // dynamic shared memory carve-up (bytes)
@@ -32,7 +34,7 @@ struct AggParams {
 };
 
 struct AggPlan {
-   int VS, T[2], TS[2], ncb, shear, block, num_sms;
+   int VS, T[2], TS[2], ncb, shear, ng[2], block, num_sms;
    size_t smem;
    size_t off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };

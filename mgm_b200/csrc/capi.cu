@@ -308,9 +308,8 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
       return fail(MGMB200_EUNSUPPORTED, "%d labels do not fit the shared-memory wavefront (max_smem=%d)", L, c->max_smem);
    c->rows_axis = plan.T[0]; c->rows_diag = plan.T[1]; c->block = plan.block; c->smem = plan.smem;
 
-   // tickets in dependency order: band-major over the requested sweeps
-   std::vector<int2> tk;
-   int nb[8] = {0}, maxb = 0;
+   // bands per sweep; the kernel claims them dynamically, in order within a sweep (aggregate.cu claim_band)
+   int nb[8] = {0}, nbands = 0;
    size_t bnd_off[8] = {0}, bndm_off[8] = {0}, prog_off[8] = {0};
    size_t bnd_total = 0, bndm_total = 0, prog_total = 0;
    for (int p = 0; p < NDIR; p++) {
@@ -327,43 +326,15 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
          bnd_off[p] = bnd_total; bnd_total += (size_t)nb[p] * g.maxii * VS;
          bndm_off[p] = bndm_total; bndm_total += (size_t)nb[p] * g.maxii;
       }
-      if (nb[p] > maxb) maxb = nb[p];
+      nbands += nb[p];
       prog_off[p] = prog_total; prog_total += nb[p];
    }
-   // Claim order = longest remaining dependency chain first (list scheduling): band b of sweep p still has
-   // (nb-b) band hand-offs of ~sigma*T+6 steps plus maxii steps ahead of it.  Within a sweep the key decreases
-   // with b, so a band is always claimed after its predecessor (required for deadlock freedom).
-   {
-      struct Item { long long key; int p, b; };
-      std::vector<Item> items;
-      for (int p = 0; p < NDIR; p++) {
-         if (!(mask & (1u << p))) continue;
-         PassGeom g = pass_geometry(p, nx, ny);
-         const int cls = p < 4 ? 0 : 1;
-         const int sig = (cls == 1 || K == 4) ? 2 : 1;
-         const bool sh = (cls == 1 && plan.shear);
-         const long long lag = sh ? 8 : (long long)sig * plan.T[cls] + 6;
-         const long long len = sh ? (g.maxii < g.maxjj ? g.maxii : g.maxjj) : g.maxii;
-         for (int b = 0; b < nb[p]; b++) items.push_back({(long long)(nb[p] - b) * lag + len, p, b});
-      }
-      std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.key > b.key; });
-      for (const Item &it : items) tk.push_back(make_int2(it.p, it.b));
-   }
-   (void)maxb;
-   if (tk.empty()) return 0;
+   if (nbands == 0) return 0;
 
-   if (tk.size() * sizeof(int2) > c->tickets.cap) c->tk_key[0] = -1;
-   RET(c->tickets.reserve(tk.size() * sizeof(int2)));
-   RET(c->progress.reserve((prog_total + 4) * sizeof(int)));
+   RET(c->progress.reserve((prog_total + 16) * sizeof(int)));
    RET(c->bnd.reserve(bnd_total * sizeof(float)));
    RET(c->bndm.reserve(bndm_total * sizeof(float)));
-   const long long key[6] = {nx, ny, plan.T[0], plan.T[1] * 2 + plan.shear, (long long)mask, NDIR + 64LL * K};
-   if (memcmp(key, c->tk_key, sizeof(key)) != 0) {
-      CU(cudaMemcpyAsync(c->tickets.p, tk.data(), tk.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
-      memcpy(c->tk_key, key, sizeof(key));
-   }
-   CU(cudaMemsetAsync(c->progress.p, 0, (prog_total + 4) * sizeof(int), c->stream));
+   CU(cudaMemsetAsync(c->progress.p, 0, (prog_total + 16) * sizeof(int), c->stream));
 
    AggParams P;
    memset(&P, 0, sizeof(P));
@@ -374,36 +345,21 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
       P.bndm[p] = c->bndm.as<float>() + bndm_off[p];
       P.progress[p] = c->progress.as<int>() + prog_off[p];
    }
-   P.tickets = c->tickets.as<int2>();
-   P.ticket_counter = reinterpret_cast<unsigned int *>(c->progress.as<int>() + prog_total);
-   P.ntickets = (int)tk.size();
+   P.next_band = c->progress.as<int>() + prog_total;   // 8 per-sweep claim counters (zeroed above)
+   for (int p = 0; p < 8; p++) P.nb[p] = nb[p];
+   P.nbands = nbands;
+   P.static_order = getenv("MGMB200_STATIC_ORDER") ? 1 : 0;
    P.nx = nx; P.ny = ny; P.L = L; P.VS = VS;
    P.T[0] = plan.T[0]; P.T[1] = plan.T[1];
    P.TS[0] = plan.TS[0]; P.TS[1] = plan.TS[1];
-   P.ncb = plan.ncb; P.shear = plan.shear;
+   P.ncb = plan.ncb; P.shear = plan.shear; P.ng[0] = plan.ng[0]; P.ng[1] = plan.ng[1];
    P.P1 = P1; P.P2 = P2;
    P.dbg = nullptr;
-   if (getenv("MGMB200_PHASE_TIMING")) {
-      RET(c->dbgbuf.reserve(24 * 8));
-      CU(cudaMemsetAsync(c->dbgbuf.p, 0, 24 * 8, c->stream));
-      P.dbg = c->dbgbuf.as<unsigned long long>();
-   }
    P.off_phase = (unsigned)plan.off_phase; P.off_cbar = (unsigned)plan.off_cbar; P.off_vbar = (unsigned)plan.off_vbar;
    P.off_ms = (unsigned)plan.off_ms; P.off_vms = (unsigned)plan.off_vms; P.off_virt = (unsigned)plan.off_virt;
    P.off_thr = (unsigned)plan.off_thr;
    CU(agg_launch(P, plan, pot, K, weighted, c->stream));
    c->n_launches++;
-   if (P.dbg) {
-      unsigned long long h[24];
-      CU(cudaMemcpyAsync(h, P.dbg, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
-      const char *who[3] = {"thread0", "producer", "lastrow"};
-      for (int i = 0; i < 3; i++) {
-         double n = (double)(h[8 * i + 5] ? h[8 * i + 5] : 1);
-         fprintf(stderr, "[mgmb200 phase timing] %s: steps=%llu cycles/step: top=%.0f gather=%.0f (cost wait %.0f) bar1=%.0f transform=%.0f bar2=%.0f\n", who[i],
-                 h[8 * i + 5], h[8 * i + 0] / n, h[8 * i + 1] / n, h[8 * i + 6] / n, h[8 * i + 2] / n, h[8 * i + 3] / n, h[8 * i + 4] / n);
-      }
-   }
    return 0;
 }
 

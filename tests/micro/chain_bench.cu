@@ -94,6 +94,50 @@ __device__ __forceinline__ void minconv_half_pf(bool on, const float4 *src, floa
    }
 }
 
+template <int D, int DIR>
+__device__ __forceinline__ void minconv_half_pf6(bool on, const float4 *src, float4 *dst, int nq, float c, float cap,
+                                                 float sub, int bar_id) {
+   const int h = nq >> 1;   // multiple of 4
+   const int dq = DIR ? -1 : 1;
+   int q = DIR ? (nq - 1) : 0;
+   const int qend = DIR ? 0 : (nq - 1);
+   float run = INF;
+   float4 sb[D];
+   if (on) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) sb[d] = src[q + d * dq];
+      for (int i = 0; i < h; i += D) {
+#pragma unroll
+         for (int d = 0; d < D; ++d) {
+            float4 v = sb[d];
+            if (i + d + D < h) sb[d] = src[q + D * dq];
+            if (DIR) chain4(run, v.w, v.z, v.y, v.x, c); else chain4(run, v.x, v.y, v.z, v.w, c);
+            dst[q] = v;
+            q += dq;
+         }
+      }
+   }
+   pair_barrier(bar_id);
+   if (on) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) sb[d] = dst[q + d * dq];
+      for (int i = h; i < nq; i += D) {
+#pragma unroll
+         for (int d = 0; d < D; ++d) {
+            float4 v = sb[d];
+            int qn = q + D * dq;
+            qn = DIR ? max(qn, qend) : min(qn, qend);
+            sb[d] = dst[qn];   // never a chunk this lane has already finalised within the last D steps? see note
+            if (DIR) chain4(run, v.w, v.z, v.y, v.x, c); else chain4(run, v.x, v.y, v.z, v.w, c);
+            v.x = fminf(v.x, cap) - sub; v.y = fminf(v.y, cap) - sub;
+            v.z = fminf(v.z, cap) - sub; v.w = fminf(v.w, cap) - sub;
+            dst[q] = v;
+            q += dq;
+         }
+      }
+   }
+}
+
 template <int FORM, int DIR>
 __device__ __forceinline__ void minconv_half(bool on, const float4 *src, float4 *dst, int nq, float c, float cap,
                                              float sub, int bar_id) {
@@ -151,6 +195,8 @@ __device__ __forceinline__ void minconv_half(bool on, const float4 *src, float4 
       }
       return;
    }
+   if (FORM == 7) { minconv_half_pf6<2, DIR>(on, src, dst, nq, c, cap, sub, bar_id); return; }
+   if (FORM == 8) { minconv_half_pf6<4, DIR>(on, src, dst, nq, c, cap, sub, bar_id); return; }
    if (FORM == 3) { minconv_half_pf<2, DIR>(on, src, dst, nq, c, cap, sub, bar_id); return; }
    if (FORM == 4) { minconv_half_pf<4, DIR>(on, src, dst, nq, c, cap, sub, bar_id); return; }
    if (FORM < 2) {
@@ -227,9 +273,11 @@ __device__ __forceinline__ void minconv_half(bool on, const float4 *src, float4 
 // nrows vectors per CTA, chain warps: [0,ncw) upwards, [ncw,2ncw) downwards, as in the kernel
 template <int FORM>
 __global__ void __launch_bounds__(512, 1) chain_kernel(const float *in, float *out, int nrows, int iters, float c, float cap,
-                                                        long long *cycles, int noise) {
+                                                        long long *cycles, int noise, int hi) {
    extern __shared__ __align__(128) float sm[];
-   const int tid = threadIdx.x, warp_id = tid >> 5, lane_id = tid & 31;
+   const int tid = threadIdx.x, lane_id = tid & 31;
+   const int nwarps = blockDim.x >> 5;
+   const int warp_id = hi ? (nwarps - 1 - (tid >> 5)) : (tid >> 5);   // role index: 0..3 = chain warps
    for (int i = tid; i < nrows * VS; i += blockDim.x) {
       const int r = i / VS, o = i % VS;
       sm[r * TS + 3 * VS + o] = in[(size_t)blockIdx.x * nrows * VS + i];   // "cost buffer" = chain source
@@ -262,10 +310,11 @@ __global__ void __launch_bounds__(512, 1) chain_kernel(const float *in, float *o
 #pragma unroll
          for (int k = 0; k < 8; ++k) { float4 x = q0[(tid + k * 37) % 448]; acc.x += x.x; acc.y += x.y; }
          p[0] = acc;
+         if (noise > 1) { const long long tw = clock64(); while (clock64() - tw < noise) {} }
       }
    }
    __syncthreads();
-   if (tid == 0) cycles[blockIdx.x] = (t1 - t0) / iters;
+   if (warp_id == 0 && lane_id == 0) cycles[blockIdx.x] = (t1 - t0) / iters;
    for (int i = tid; i < nrows * VS; i += blockDim.x) {
       const int r = i / VS, o = i % VS;
       out[(size_t)blockIdx.x * nrows * VS + i] = sm[r * TS + o];
@@ -296,30 +345,31 @@ __global__ void lat_kernel(float *out, float c, int n, long long *cycles) {
 
 int main(int argc, char **argv) {
    const int nrows = argc > 1 ? atoi(argv[1]) : 43;
-   const int iters = 200, grid = 148;
+   const int iters = 200;
+   const int grid = argc > 2 ? atoi(argv[2]) : 148;
    const size_t n = (size_t)grid * nrows * VS;
    std::vector<float> h(n);
    srand(1);
    for (size_t i = 0; i < n; ++i) h[i] = (float)(rand() % 4096) / 7.0f;
-   float *din, *dout[7];
+   float *din, *dout[9];
    long long *dcyc;
    cudaMalloc(&din, n * 4);
    cudaMemcpy(din, h.data(), n * 4, cudaMemcpyHostToDevice);
-   for (int f = 0; f < 7; ++f) cudaMalloc(&dout[f], n * 4);
+   for (int f = 0; f < 9; ++f) cudaMalloc(&dout[f], n * 4);
    cudaMalloc(&dcyc, grid * 8);
    const size_t smem = (size_t)nrows * TS * 4 + 1024 + 448 * 16 + 16;
-   std::vector<std::vector<float>> res(7, std::vector<float>(n));
+   std::vector<std::vector<float>> res(9, std::vector<float>(n));
    for (int threads : {128, 448, -448}) {
-      const int noise = threads < 0;
+      const int noise = threads < 0 ? (argc > 3 ? atoi(argv[3]) : 1) : 0;
       if (noise) threads = -threads;
-      for (int f = 0; f < 7; ++f) {
-         auto k = f == 6 ? chain_kernel<6> : f == 5 ? chain_kernel<5> : f == 0 ? chain_kernel<0> : f == 1 ? chain_kernel<1> : f == 2 ? chain_kernel<2> : f == 3 ? chain_kernel<3> : chain_kernel<4>;
+      for (int f = 0; f < 9; ++f) {
+         auto k = f == 8 ? chain_kernel<8> : f == 7 ? chain_kernel<7> : f == 6 ? chain_kernel<6> : f == 5 ? chain_kernel<5> : f == 0 ? chain_kernel<0> : f == 1 ? chain_kernel<1> : f == 2 ? chain_kernel<2> : f == 3 ? chain_kernel<3> : chain_kernel<4>;
          cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-         for (int rep = 0; rep < 2; ++rep) k<<<grid, threads, smem>>>(din, dout[f], nrows, iters, 2.0f, 1e9f, dcyc, noise);
+         for (int rep = 0; rep < 2; ++rep) k<<<grid, threads, smem>>>(din, dout[f], nrows, iters, 2.0f, 1e9f, dcyc, noise, argc > 4 ? atoi(argv[4]) : 0);
          cudaError_t e = cudaDeviceSynchronize();
          if (e != cudaSuccess) { printf("form %d: %s\n", f, cudaGetErrorString(e)); return 1; }
-         long long cyc[148];
-         cudaMemcpy(cyc, dcyc, sizeof(cyc), cudaMemcpyDeviceToHost);
+         std::vector<long long> cyc(grid);
+         cudaMemcpy(cyc.data(), dcyc, grid * 8, cudaMemcpyDeviceToHost);
          cudaMemcpy(res[f].data(), dout[f], n * 4, cudaMemcpyDeviceToHost);
          long long mn = cyc[0], mx = cyc[0];
          for (int i = 1; i < grid; ++i) { mn = cyc[i] < mn ? cyc[i] : mn; mx = cyc[i] > mx ? cyc[i] : mx; }
