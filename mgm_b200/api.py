@@ -24,7 +24,7 @@ class MgmError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libmgmb200.so")
+    return os.environ.get("MGMB200_LIBRARY") or os.path.join(_HERE, "libmgmb200.so")   # override: development builds
 
 
 def build_library(verbose=False):
@@ -197,8 +197,9 @@ class Context:
 
     def stereo(self, u, v, dmin=-30, dmax=30, P1=8.0, P2=32.0, NDIR=4, MGM=4, use_felzenszwalb_potentials=0,
                sgm_fix_overcount=1, aP=1.0, aThresh=5.0, prefilter="none", distance="ad", truncDist=np.inf,
-               census_ncc_win=3, refinement="none"):
-        """The hot path of mgm.cc:356-385 (one direction): images in, (disparity, cost) out."""
+               census_ncc_win=3, refinement="none", out=None, outcost=None):
+        """The hot path of mgm.cc:356-385 (one direction): images in, (disparity, cost) out.
+        `out` / `outcost`: optional caller-owned float32 (ny, nx) arrays to receive the maps (e.g. pinned memory)."""
         u, nx, ny, nch = _img(u)
         v, vnx, vny, vnch = _img(v)
         if (vnx, vny, vnch) != (nx, ny, nch):
@@ -206,8 +207,12 @@ class Context:
         p = StereoParams(int(dmin), int(dmax), P1, P2, int(NDIR), int(MGM), int(use_felzenszwalb_potentials),
                          int(sgm_fix_overcount), aP, aThresh, prefilter.encode(), distance.encode(), truncDist,
                          int(census_ncc_win), refinement.encode())
-        out = np.empty((ny, nx), np.float32)
-        outcost = np.empty((ny, nx), np.float32)
+        for name, a in (("out", out), ("outcost", outcost)):
+            if a is not None and not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.shape == (ny, nx)
+                                      and a.flags["C_CONTIGUOUS"]):
+                raise ValueError("%s must be a C-contiguous float32 array of shape (%d, %d)" % (name, ny, nx))
+        out = np.empty((ny, nx), np.float32) if out is None else out
+        outcost = np.empty((ny, nx), np.float32) if outcost is None else outcost
         self._check(self.lib.mgmb200_stereo(self._ctx, _fp(u), _fp(v), nx, ny, nch, ctypes.byref(p), _fp(out),
                                             _fp(outcost)))
         return out, outcost

@@ -32,6 +32,13 @@
 
 #include "aggregate.cuh"
 
+#ifndef MGM_JB
+#define MGM_JB 2   // chunks per lane whose loads are issued together in the gather (measured: 2 < 4 < 8)
+#endif
+#ifndef MGM_EXP
+#define MGM_EXP 0   // timing experiments only (tests/micro): 1 no message store, 2 no cost load, 3 no gather arithmetic, 4 no min-convolution
+#endif
+
 namespace mgm {
 
 static constexpr int RV = 8;   // virtual-row ring (pixels of the previous band's last row)
@@ -115,18 +122,49 @@ __device__ __forceinline__ void chain4(float &run, float &a0, float &a1, float &
 // named barrier shared by one forward warp and its backward partner warp (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
-// Row groups.  The rows of a band are split into NG groups of TG rows that run the two phases of a step on their
-// OWN named barrier, out of phase with each other: while one group gathers (LSU-bound) the others run their
-// min-convolution chains (latency-bound).  Groups are ordered by two shared-memory step counters:
+// Row groups.  The rows of a band are split into NG <= 3 groups of TG rows that run the two phases of a step on
+// their OWN named barrier, out of phase with each other: while one group gathers (LSU-bound) the others run their
+// min-convolution chains (latency-bound).  Adjacent groups are ordered by two producer/consumer named barriers
+// (bar.arrive by the producer group, bar.sync by the consumer group -- no polling):
 //   token: group g starts the gather of step s after group g-1 has finished ITS gather of step s (this also
 //          covers the read-after-write on the rows of group g-1 and serialises the gathers on the LSU);
 //   reuse: group g starts the gather of step s after group g+1 has finished the gather of step s-1 (the ring slot
 //          it is about to overwrite was last read there).
+// Each barrier sees exactly one arrival and one sync per step in alternation (the token of step s+1 can only be
+// sent after the reuse barrier of step s+1 was passed, which needs the receiver's gather of step s, hence its
+// token sync of step s), so phases never mix.  Barrier ids: 0 CTA, 1..3 groups, 4..9 chain pairs, 10..11 token,
+// 12..13 reuse.
 struct RowGroup {
-   int gi, bar_id, cnt, first_tid;
-   volatile int *flags;   // flags[g] = last step whose gather group g has completed
+   int gi, ng, bar_id, cnt, cnt_prev, cnt_next, first_tid;
    __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(cnt) : "memory"); }
+   // top of step: wait for the token of the group above and for the reuse signal of the group below
+   __device__ __forceinline__ void begin_step(bool first) const {
+      if (ng > 1) {
+         if (gi > 0) asm volatile("bar.sync %0, %1;" ::"r"(10 + gi - 1), "r"(cnt_prev + cnt) : "memory");
+         if (gi < ng - 1 && !first) asm volatile("bar.sync %0, %1;" ::"r"(12 + gi), "r"(cnt + cnt_next) : "memory");
+      }
+   }
+   // my part of the gather of this step is finished
+   __device__ __forceinline__ void gather_done(bool last) const {
+      if (ng > 1) {
+         __threadfence_block();
+         if (gi < ng - 1) asm volatile("bar.arrive %0, %1;" ::"r"(10 + gi), "r"(cnt + cnt_next) : "memory");
+         if (gi > 0 && !last) asm volatile("bar.arrive %0, %1;" ::"r"(12 + gi - 1), "r"(cnt_prev + cnt) : "memory");
+      }
+   }
 };
+__device__ __forceinline__ RowGroup make_row_group(int tid, int ncomp, int r, int NG, int TG) {
+   RowGroup g;
+   g.ng = NG;
+   g.gi = (tid < ncomp) ? min(r / TG, NG - 1) : (tid < ncomp + 32 ? 0 : NG - 1);   // consumer warp -> 0, publisher -> last
+   auto count = [&](int i) { return (i < NG - 1 ? TG * G : ncomp - (NG - 1) * TG * G) + (i == 0 ? 32 : 0) + (i == NG - 1 ? 32 : 0); };
+   g.bar_id = 1 + g.gi;
+   g.cnt = count(g.gi);
+   g.cnt_prev = g.gi > 0 ? count(g.gi - 1) : 0;
+   g.cnt_next = g.gi < NG - 1 ? count(g.gi + 1) : 0;
+   g.first_tid = g.gi * TG * G;
+   return g;
+}
 
 // Half of the meet-in-the-middle min-convolution of `src` into `dst`, executed by a whole WARP whose lanes
 // hold the same direction (DIR=0 upwards, DIR=1 downwards) of 32 different vectors; the partner warp runs
@@ -185,7 +223,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    constexpr bool WTRUNC = WEIGHTED && POT == POT_TRUNC;
    constexpr bool CHAINS = !WEIGHTED && POT == POT_TRUNC;   // phase-2 transform done by lane pairs
    constexpr int CLS = DIAG ? 1 : 0;
-   constexpr int JB = (K <= 3) ? 4 : 2;   // chunks per lane whose loads are issued together in the gather
+   constexpr int JB = (K <= 3) ? MGM_JB : 2;   // chunks per lane whose loads are issued together in the gather
    constexpr int NJR = MGM_AGG_CREG;      // cost chunks per lane that can be prefetched into registers
 
    const PassGeom g = pass_geometry(pass, P.nx, P.ny);
@@ -231,17 +269,10 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 
    // row groups (RowGroup above); the boundary consumer warp belongs to group 0, the publisher warp to the last
    const int NG = P.ng[CLS], TG = T / NG;
-   RowGroup grp;
-   grp.gi = (tid < ncomp) ? min(r / TG, NG - 1) : (is_prod || (tid > ncomp && tid < ncomp + 32) ? 0 : NG - 1);
-   grp.bar_id = 1 + grp.gi;
-   grp.cnt = (grp.gi < NG - 1 ? TG * G : ncomp - (NG - 1) * TG * G) + (grp.gi == 0 ? 32 : 0) + (grp.gi == NG - 1 ? 32 : 0);
-   grp.first_tid = grp.gi * TG * G;
-   grp.flags = reinterpret_cast<volatile int *>(smem + P.off_cbar);
+   const RowGroup grp = make_row_group(tid, ncomp, r, NG, TG);
    const int gw0 = grp.first_tid >> 5;          // first warp of my group
-   const int ncw = (TG + 31) >> 5;              // chain warps per direction and group
-   const int pair_id0 = 1 + NG + grp.gi * 2;    // named barriers of my group's chain pairs
-   if (tid == 0) { for (int i = 0; i < NG; ++i) grp.flags[i] = -1; }
-   __syncthreads();
+   const int ncw = (TG + 31) >> 5;              // chain warps per direction and group (2 only when NG == 1)
+   const int pair_id0 = 4 + grp.gi * 2;         // named barriers of my group's chain pairs
 
    // per-row shared memory: ring slots [R][VS] | cost buffers [ncbuf][VS] | scratch [K][VS] (weighted trunc)
    auto row_base = [&](int rr) -> float * { return thr + (size_t)rr * TS; };
@@ -293,7 +324,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
             const float4 *src = reinterpret_cast<const float4 *>(ccv + (size_t)(pix0 + (long long)px * g.dxs) * VS);
 #pragma unroll
             for (int j = 0; j < NJR; ++j)
-               if (j < nj) creg[j] = __ldcs(src + gl + G * j);
+               if (j < nj) creg[j] = (MGM_EXP == 2) ? make_float4((float)j, 1.f, 2.f, 3.f) : __ldcs(src + gl + G * j);
          }
          return;
       }
@@ -355,13 +386,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
             vph ^= 1u << sl;
          }
       }
-      if (NG > 1 && tid < ncomp) {   // group ordering (RowGroup): token from the group above, slot reuse below
-         if (lane_id == 0) {
-            if (grp.gi > 0) { while (grp.flags[grp.gi - 1] < s) {} }
-            if (grp.gi < NG - 1) { while (grp.flags[grp.gi + 1] < s - 1) {} }
-         }
-         __syncwarp();
-      }
+      grp.begin_step(s == 0);   // group ordering (RowGroup): token from the group above, slot reuse below
       const int xs = s - SIG * r;
       const bool act = rowok && xs >= 0 && xs < maxii;
       const long long pix = pix0 + (long long)xs * g.dxs;
@@ -394,8 +419,8 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                src = slot_of(prow, ppx);
                dst = row_base(crow) + (R + ncbuf + ck) * VS;
             }
-            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 1 + NG + cw);
-            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 1 + NG + cw);
+            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 4 + cw);
+            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 4 + cw);
          }
          grp.sync();
       }
@@ -465,6 +490,8 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                         o = add4(c[jj], mul4s(add4s(add4(add4s(a[0][jj], -mk[0]), a[1 % K][jj]), -mk[1 % K]), 0.5f));
                      } else if constexpr (POT == POT_SGM && K == 2) {   // update_cost2: halves taken by the producer
                         o = add4(c[jj], add4(a[0][jj], a[1 % K][jj]));
+                     } else if (MGM_EXP == 3) {
+                        o = c[jj]; o.x += a[0][jj].x; o.y += a[1 % K][jj].y; o.z += a[2 % K][jj].z;
                      } else {
                         float4 e = a[0][jj];
 #pragma unroll
@@ -473,7 +500,9 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                      }
                      m = hmin4(m, o);
                      Cb[q] = o;
+#if MGM_EXP != 1
                      __stcs(gout + q, o);
+#endif
                   }
                };
                if (creg_mode) {
@@ -531,8 +560,8 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
          if (gl == 0) msr[r * 4 + (xs % R)] = m;
       }
       if (creg_mode) prefetch_cost(s);   // costs of the next pixel -> registers, in flight during phase 2
+      grp.gather_done(s == nsteps - 1);
       grp.sync();
-      if (NG > 1 && tid == grp.first_tid) { __threadfence_block(); grp.flags[grp.gi] = s; }
 
       // ---------------- phase 2: build the neighbour-side transform of the message in the ring slot
       if (late_prefetch) prefetch_cost(s);
@@ -547,7 +576,8 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
             const float cm = on ? msr[crow * 4 + (cxs % R)] : 0.f;
             float *dst = on ? row_base(crow) + (cxs % R) * VS : thr;
             const float *src = on ? (creg_mode ? dst : cbuf_of(crow, cxs)) : thr;
-            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
+            if (MGM_EXP == 4) {}
+            else if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
             else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
             if (on && has_next && crow == nrows - 1) fence_proxy_async_smem();   // read by the boundary TMA store
          }
@@ -626,7 +656,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
    static_assert(K <= 3, "the sheared wavefront needs predecessors in the row above only");
    constexpr bool NEEDM = (POT == POT_TRUNC && K == 2);
    constexpr bool CHAINS = (POT == POT_TRUNC);
-   constexpr int JB = 4;
+   constexpr int JB = MGM_JB;
    constexpr int NJR = MGM_AGG_CREG;
 
    const PassGeom g = pass_geometry(pass, P.nx, P.ny);
@@ -670,17 +700,10 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
 
    // row groups (RowGroup): the boundary consumer warp belongs to group 0, the publisher warp to the last
    const int NG = P.ng[1], TG = T / NG;
-   RowGroup grp;
-   grp.gi = (tid < ncomp) ? min(r / TG, NG - 1) : (tid < ncomp + 32 ? 0 : NG - 1);
-   grp.bar_id = 1 + grp.gi;
-   grp.cnt = (grp.gi < NG - 1 ? TG * G : ncomp - (NG - 1) * TG * G) + (grp.gi == 0 ? 32 : 0) + (grp.gi == NG - 1 ? 32 : 0);
-   grp.first_tid = grp.gi * TG * G;
-   grp.flags = reinterpret_cast<volatile int *>(smem + P.off_cbar);
+   const RowGroup grp = make_row_group(tid, ncomp, r, NG, TG);
    const int gw0 = grp.first_tid >> 5;
    const int ncw = (TG + 31) >> 5;
-   const int pair_id0 = 1 + NG + grp.gi * 2;
-   if (tid == 0) { for (int i = 0; i < NG; ++i) grp.flags[i] = sb - 1; }
-   __syncthreads();
+   const int pair_id0 = 4 + grp.gi * 2;
    const bool inplace = CHAINS && creg_mode;   // message built in its ring slot, min-convolution in place
 
    // per-worker shared memory: ring slots [2][VS] (position v&1) | cost buffers [ncb][VS] (none when in place)
@@ -777,13 +800,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
          if (v == sb) { wait_pos(sb - 1); wait_pos(sb); } else wait_pos(v);
       }
 
-      if (NG > 1 && tid < ncomp) {   // group ordering (RowGroup): token from the group above, slot reuse below
-         if (lane_id == 0) {
-            if (grp.gi > 0) { while (grp.flags[grp.gi - 1] < v) {} }
-            if (grp.gi < NG - 1) { while (grp.flags[grp.gi + 1] < v - 1) {} }
-         }
-         __syncwarp();
-      }
+      grp.begin_step(v == sb);   // group ordering (RowGroup): token from the group above, slot reuse below
       const bool act = rowok && v >= my_lo && v <= my_hi;
       const int xs = u - v;
       const long long pix = pix_u + (long long)v * dv;
@@ -884,8 +901,8 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
          if (gl == 0) msr[r * 4 + (v & 1)] = m;
       }
       if (creg_mode) prefetch_cost(v);
+      grp.gather_done(v == se);
       grp.sync();
-      if (NG > 1 && tid == grp.first_tid) { __threadfence_block(); grp.flags[grp.gi] = v; }
 
       // ---------------- phase 2: neighbour-side transform of the message into ring slot v&1
       if (late_prefetch) prefetch_cost(v);
@@ -1064,7 +1081,7 @@ static void agg_plan_try(AggPlan *plan, int L, int K, int pot, bool weighted, in
    // the min-convolution in place: no cost buffer
    const int ncbuf = (pot == POT_TRUNC && !weighted && plan->ncb == 1) ? 0 : plan->ncb;
    int want_groups = 1;   // row groups per band (RowGroup in the kernel); measured: no gain, the LSU is the shared limit
-   if (const char *e = getenv("MGMB200_GROUPS")) { const int v = atoi(e); if (!weighted && (v == 1 || v == 2 || v == 4)) want_groups = v; }
+   if (const char *e = getenv("MGMB200_GROUPS")) { const int v = atoi(e); if (!weighted && (v == 1 || v == 2 || v == 3)) want_groups = v; }
    for (int cls = 0; cls < 2; ++cls) {
       int nbuf = ((cls == 1 && shear) ? 2 : ring_slots(cls, K)) + ncbuf + xtra;
       int TS = nbuf * VS;
@@ -1082,7 +1099,7 @@ static void agg_plan_try(AggPlan *plan, int L, int K, int pot, bool weighted, in
       if (Tc < 1) Tc = 0;
       // groups need whole warps (4 rows) and at least two warps each for their chain pair
       int ng = want_groups;
-      while (ng > 1 && Tc / (4 * ng) * 4 < 8) ng >>= 1;
+      while (ng > 1 && Tc / (4 * ng) * 4 < 8) --ng;
       if (ng > 1) Tc = Tc / (4 * ng) * (4 * ng);
       plan->ng[cls] = ng;
       plan->T[cls] = Tc;

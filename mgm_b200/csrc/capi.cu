@@ -59,15 +59,13 @@ struct mgmb200_ctx {
    cudaStream_t own_stream = nullptr, stream = nullptr;
    int rows_override = 0;
    // scratch (grow-only, reused across calls)
-   DevBuf u, v, fu, fv, cu, cv, w, cc, dense, out, outcost, flags, tickets, progress, bnd, bndm;
+   DevBuf u, v, fu, fv, ftmp, cu, cv, w, cc, dense, out, outcost, flags, progress, bnd, bndm;
    DevBuf sweep[8];
    DevBuf dbgbuf;
    size_t sweep_bytes = 0;
    // last launch info
    int n_launches = 0, rows_axis = 0, rows_diag = 0, block = 0;
    size_t smem = 0;
-   // ticket table currently resident in `tickets` (avoids a blocking pageable H2D copy per call)
-   long long tk_key[6] = {-1, -1, -1, -1, -1, -1};
 };
 
 // ------------------------------------------------------------------------------------------ tables
@@ -135,7 +133,7 @@ extern "C" void mgmb200_destroy(mgmb200_ctx *c) {
    cudaSetDevice(c->device);
    cudaStreamSynchronize(c->stream);
    DevBuf *bufs[] = {&c->u, &c->v, &c->fu, &c->fv, &c->cu, &c->cv, &c->w, &c->cc, &c->dense, &c->out,
-                     &c->outcost, &c->flags, &c->tickets, &c->progress, &c->bnd, &c->bndm};
+                     &c->outcost, &c->flags, &c->ftmp, &c->progress, &c->bnd, &c->bndm};
    for (DevBuf *b : bufs) b->release();
    for (int i = 0; i < 8; i++) c->sweep[i].release();
    if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -231,7 +229,6 @@ extern "C" int mgmb200_costvolume_dev(mgmb200_ctx *c, const float *d_u, const fl
    // "-p census" with another distance would run it on bit patterns reinterpreted as floats.
    if (pf == PF_CENSUS && dist != DIST_CENSUS)
       return fail(MGMB200_EUNSUPPORTED, "prefilter census with a non-census distance is not supported");
-   if (pf == PF_GBLUR) return fail(MGMB200_EUNSUPPORTED, "prefilter gblur is not implemented yet");
    const float *uu = d_u, *vv = d_v;
    const uint32_t *cu = nullptr, *cv = nullptr;
    int cnch = nch;
@@ -248,6 +245,14 @@ extern "C" int mgmb200_costvolume_dev(mgmb200_ctx *c, const float *d_u, const fl
       RET(c->fv.reserve((size_t)vnx * vny * nch * 4));
       CU(sobelx_launch(d_u, nx, ny, nch, c->fu.as<float>(), c->stream));
       CU(sobelx_launch(d_v, vnx, vny, nch, c->fv.as<float>(), c->stream));
+      uu = c->fu.as<float>(); vv = c->fv.as<float>();
+   } else if (pf == PF_GBLUR) {   // gblur_truncated(., 1.0), mgm_costvolume.h:380-384
+      const size_t nmax = std::max((size_t)nx * ny, (size_t)vnx * vny) * nch * 4;
+      RET(c->fu.reserve((size_t)nx * ny * nch * 4));
+      RET(c->fv.reserve((size_t)vnx * vny * nch * 4));
+      RET(c->ftmp.reserve(nmax));
+      CU(gblur_launch(d_u, nx, ny, nch, 1.0f, c->ftmp.as<float>(), c->fu.as<float>(), c->stream));
+      CU(gblur_launch(d_v, vnx, vny, nch, 1.0f, c->ftmp.as<float>(), c->fv.as<float>(), c->stream));
       uu = c->fu.as<float>(); vv = c->fv.as<float>();
    }
    CU(costvolume_launch(dist, uu, vv, cu, cv, nx, ny, vnx, vny, cnch, win, dmin, L, VS, truncDist, d_cc,

@@ -85,6 +85,31 @@ __global__ void mgm_sobelx_kernel(const float *__restrict__ u, int nx, int ny, i
    out[i] = v;
 }
 
+// ------------------------------------------------------------------ N3 gblur prefilter
+// apply_filter (img_tools.h:105-127) with a 1-D kernel of up to 39 taps along x or y, Neumann borders, taps
+// accumulated in order.  gblur_truncated (:169-180) = the horizontal pass followed by the vertical one; the taps
+// are computed on the host exactly as fill_gaussian_kernel does (:151-167).
+struct FilterTaps { float k[39]; int n; };
+__global__ void mgm_filter1d_kernel(const float *__restrict__ u, int nx, int ny, int nch, const FilterTaps taps,
+                                    int vertical, float *__restrict__ out) {
+   const long long np = (long long)nx * ny;
+   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= np * nch) return;
+   const int c = (int)(i / np);
+   const long long p = i - (long long)c * np;
+   const int x = (int)(p % nx), y = (int)(p / nx);
+   const int h = taps.n / 2;
+   const float *uc = u + c * np;
+   float v = 0.f;
+   for (int t = 0; t < taps.n; ++t) {
+      int xx = vertical ? x : x + t - h, yy = vertical ? y + t - h : y;
+      xx = xx < 0 ? 0 : (xx >= nx ? nx - 1 : xx);
+      yy = yy < 0 ? 0 : (yy >= ny ? ny - 1 : yy);
+      v += uc[xx + (long long)yy * nx] * taps.k[t];
+   }
+   out[i] = v;
+}
+
 // ------------------------------------------------------------------ per-cell costs
 struct CostArgs {
    const float *u, *v;          // (prefiltered) images, planar
@@ -175,10 +200,66 @@ __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, i
    const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const long long np = (long long)A.nx * A.ny;
    const int nq = VS >> 2;
+   // Fast path (AD, SD, census with up to four channels / census words): everything that depends on the pixel
+   // only -- the left pixel's values, the row pointers of the right image -- is hoisted out of the label loop and
+   // the loop indexes with 32-bit offsets; same operations in the same order as cell_cost.
+   constexpr bool FASTDIST = (DIST == DIST_AD || DIST == DIST_SD || DIST == DIST_CENSUS);
+   const bool fast = FASTDIST && A.nch <= 4;
+   const long long vnp = (long long)A.vnx * A.vny;
    for (long long p = (long long)blockIdx.x * warps + wid; p < np; p += (long long)gridDim.x * warps) {
       const int x = (int)(p % A.nx), y = (int)(p / A.nx);
       float4 *dst = reinterpret_cast<float4 *>(cc + (size_t)p * VS);
       bool anyfinite = false;
+      if (fast) {
+         uint32_t lw[4] = {0u, 0u, 0u, 0u};     // left census words, or the bits of the left channel values
+         const uint32_t *rrow[4] = {nullptr, nullptr, nullptr, nullptr};   // right image row, per channel / word
+         const bool vy_ok = y < A.vny;
+#pragma unroll
+         for (int t = 0; t < 4; ++t) {
+            if (t < A.nch) {
+               if (DIST == DIST_CENSUS) {
+                  lw[t] = __ldg(A.cu + p + t * np);
+                  rrow[t] = A.cv + (long long)y * A.vnx + t * vnp;
+               } else {
+                  lw[t] = __float_as_uint(__ldg(A.u + p + t * np));
+                  rrow[t] = reinterpret_cast<const uint32_t *>(A.v + (long long)y * A.vnx + t * vnp);
+               }
+            }
+         }
+         const int qx0 = x + dmin;
+         for (int q = lane; q < nq; q += 32) {
+            float e4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+               const int k = q * 4 + j;
+               float e = MGM_INF;   // padding labels
+               if (k < L) {
+                  const int qx = qx0 + k;
+                  e = cap;
+                  if (vy_ok && (unsigned)qx < (unsigned)A.vnx) {
+                     float acc = 0.f;
+#pragma unroll
+                     for (int t = 0; t < 4; ++t) {
+                        if (t < A.nch) {
+                           const uint32_t rv = __ldg(rrow[t] + qx);
+                           if (DIST == DIST_CENSUS) acc += (float)__popc(lw[t] ^ rv);
+                           else {
+                              float d = __uint_as_float(lw[t]) - __uint_as_float(rv);
+                              d = sel_max(d, -d);
+                              acc += (DIST == DIST_SD) ? d * d : d;
+                           }
+                        }
+                     }
+                     e = (DIST == DIST_CENSUS && A.nch != 1) ? (float)((double)acc / (double)A.nch) : acc;
+                  }
+                  e = sel_min(e, cap);
+                  anyfinite |= (fabsf(e) < MGM_INF);
+               }
+               e4[j] = e;
+            }
+            dst[q] = make_float4(e4[0], e4[1], e4[2], e4[3]);
+         }
+      } else
       for (int q = lane; q < nq; q += 32) {
          float e4[4];
 #pragma unroll
@@ -280,6 +361,31 @@ cudaError_t census_launch(const float *d_u, int nx, int ny, int nch, int win, ui
 
 cudaError_t sobelx_launch(const float *d_u, int nx, int ny, int nch, float *d_out, cudaStream_t st) {
    mgm_sobelx_kernel<<<blocks_for((long long)nx * ny * nch, 256), 256, 0, st>>>(d_u, nx, ny, nch, d_out);
+   return cudaGetLastError();
+}
+
+cudaError_t gblur_launch(const float *d_u, int nx, int ny, int nch, float sigma, float *d_tmp, float *d_out,
+                         cudaStream_t st) {
+   // gaussian_kernel_width / fill_gaussian_kernel, img_tools.h:143-167 (float arithmetic, exp(float))
+   FilterTaps taps;
+   const float radius = 3 * fabsf(sigma);
+   int w = (int)ceilf(1 + 2 * radius);
+   if (w < 1) w = 1;
+   if (w > 39) w = 39;
+   const int cw = (w - 1) / 2;
+   float m = 0;
+   for (int i = 0; i < w; i++) {
+      const float x = (float)hypot((double)(i - cw), 0.0);
+      const float v = expf(-x * x / (2 * sigma * sigma));
+      taps.k[i] = v;
+      m += v;
+   }
+   for (int i = 0; i < w; i++) taps.k[i] /= m;
+   for (int i = w; i < 39; i++) taps.k[i] = 0.f;
+   taps.n = w;
+   const long long n = (long long)nx * ny * nch;
+   mgm_filter1d_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_u, nx, ny, nch, taps, 0, d_tmp);
+   mgm_filter1d_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_tmp, nx, ny, nch, taps, 1, d_out);
    return cudaGetLastError();
 }
 

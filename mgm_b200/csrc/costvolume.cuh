@@ -19,6 +19,8 @@ cudaError_t weights_launch(const float *d_u, int nx, int ny, int nch, float aP, 
                            int *d_flag, cudaStream_t st);
 cudaError_t census_launch(const float *d_u, int nx, int ny, int nch, int win, uint32_t *d_out, cudaStream_t st);
 cudaError_t sobelx_launch(const float *d_u, int nx, int ny, int nch, float *d_out, cudaStream_t st);
+cudaError_t gblur_launch(const float *d_u, int nx, int ny, int nch, float sigma, float *d_tmp, float *d_out,
+                         cudaStream_t st);
 cudaError_t costvolume_launch(int dist, const float *d_u, const float *d_v, const uint32_t *d_cu,
                               const uint32_t *d_cv, int nx, int ny, int vnx, int vny, int nch, int win, int dmin,
                               int L, int VS, float truncDist, float *d_cc, int num_sms, cudaStream_t st);

@@ -1,8 +1,8 @@
 mkdir -p gpurun_out
 (timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5) > gpurun_out/pytest.log 2>&1
 cat gpurun_out/pytest.log
-for g in 1 2 4; do
+for g in 1 2 3; do
   echo "== MGMB200_GROUPS=$g"
   MGMB200_GROUPS=$g timeout 300 python tests/micro/rows_sweep.py 56,56 2>&1 | tail -3
-  MGMB200_GROUPS=$g timeout 300 python tests/gpu_micro.py "1 band" 2>&1 | grep -v "phase timing" | head -4
+  MGMB200_GROUPS=$g timeout 300 python tests/gpu_micro4.py 56 2>&1 | grep "bands=1:"
 done

@@ -138,6 +138,57 @@ __device__ __forceinline__ void minconv_half_pf6(bool on, const float4 *src, flo
    }
 }
 
+// form 9: four labels per carried step.  The local chain b (independent of the carry) of chunk i+1 is computed
+// while the carry runs through chunk i:  F_k = min(g^(k+1)(r), b_k),  b_k = min(b_(k-1)+c, a_k).
+struct Loc4 { float b0, b1, b2, b3; };
+template <int DIR>
+__device__ __forceinline__ Loc4 local4(const float4 &v, float c) {
+   Loc4 l;
+   const float a0 = DIR ? v.w : v.x, a1 = DIR ? v.z : v.y, a2 = DIR ? v.y : v.z, a3 = DIR ? v.x : v.w;
+   l.b0 = a0; l.b1 = fminf(l.b0 + c, a1); l.b2 = fminf(l.b1 + c, a2); l.b3 = fminf(l.b2 + c, a3);
+   return l;
+}
+template <int DIR>
+__device__ __forceinline__ float4 carry4(float &run, const Loc4 &l, float c) {
+   const float u1 = run + c, u2 = u1 + c, u3 = u2 + c, u4 = u3 + c;
+   const float f0 = fminf(u1, l.b0), f1 = fminf(u2, l.b1), f2 = fminf(u3, l.b2), f3 = fminf(u4, l.b3);
+   run = f3;
+   return DIR ? make_float4(f3, f2, f1, f0) : make_float4(f0, f1, f2, f3);
+}
+template <int DIR>
+__device__ __forceinline__ void minconv_half_c4(bool on, const float4 *src, float4 *dst, int nq, float c, float cap,
+                                                float sub, int bar_id) {
+   const int h = nq >> 1;
+   const int dq = DIR ? -1 : 1;
+   int q = DIR ? (nq - 1) : 0;
+   float run = INF;
+   Loc4 ln;
+   if (on) {
+      ln = local4<DIR>(src[q], c);
+      float4 vn = src[q + dq];
+      for (int i = 0; i < h; ++i, q += dq) {
+         const Loc4 l = ln;
+         ln = local4<DIR>(vn, c);
+         vn = src[(i + 2 < nq) ? q + 2 * dq : q];
+         dst[q] = carry4<DIR>(run, l, c);
+      }
+   }
+   pair_barrier(bar_id);
+   if (on) {
+      ln = local4<DIR>(dst[q], c);
+      float4 vn = dst[(h + 1 < nq) ? q + dq : q];
+      for (int i = h; i < nq; ++i, q += dq) {
+         const Loc4 l = ln;
+         ln = local4<DIR>(vn, c);
+         vn = dst[(i + 2 < nq) ? q + 2 * dq : q];
+         float4 v = carry4<DIR>(run, l, c);
+         v.x = fminf(v.x, cap) - sub; v.y = fminf(v.y, cap) - sub;
+         v.z = fminf(v.z, cap) - sub; v.w = fminf(v.w, cap) - sub;
+         dst[q] = v;
+      }
+   }
+}
+
 template <int FORM, int DIR>
 __device__ __forceinline__ void minconv_half(bool on, const float4 *src, float4 *dst, int nq, float c, float cap,
                                              float sub, int bar_id) {
@@ -195,6 +246,7 @@ __device__ __forceinline__ void minconv_half(bool on, const float4 *src, float4 
       }
       return;
    }
+   if (FORM == 9) { minconv_half_c4<DIR>(on, src, dst, nq, c, cap, sub, bar_id); return; }
    if (FORM == 7) { minconv_half_pf6<2, DIR>(on, src, dst, nq, c, cap, sub, bar_id); return; }
    if (FORM == 8) { minconv_half_pf6<4, DIR>(on, src, dst, nq, c, cap, sub, bar_id); return; }
    if (FORM == 3) { minconv_half_pf<2, DIR>(on, src, dst, nq, c, cap, sub, bar_id); return; }
@@ -351,19 +403,19 @@ int main(int argc, char **argv) {
    std::vector<float> h(n);
    srand(1);
    for (size_t i = 0; i < n; ++i) h[i] = (float)(rand() % 4096) / 7.0f;
-   float *din, *dout[9];
+   float *din, *dout[10];
    long long *dcyc;
    cudaMalloc(&din, n * 4);
    cudaMemcpy(din, h.data(), n * 4, cudaMemcpyHostToDevice);
-   for (int f = 0; f < 9; ++f) cudaMalloc(&dout[f], n * 4);
+   for (int f = 0; f < 10; ++f) cudaMalloc(&dout[f], n * 4);
    cudaMalloc(&dcyc, grid * 8);
    const size_t smem = (size_t)nrows * TS * 4 + 1024 + 448 * 16 + 16;
-   std::vector<std::vector<float>> res(9, std::vector<float>(n));
+   std::vector<std::vector<float>> res(10, std::vector<float>(n));
    for (int threads : {128, 448, -448}) {
       const int noise = threads < 0 ? (argc > 3 ? atoi(argv[3]) : 1) : 0;
       if (noise) threads = -threads;
-      for (int f = 0; f < 9; ++f) {
-         auto k = f == 8 ? chain_kernel<8> : f == 7 ? chain_kernel<7> : f == 6 ? chain_kernel<6> : f == 5 ? chain_kernel<5> : f == 0 ? chain_kernel<0> : f == 1 ? chain_kernel<1> : f == 2 ? chain_kernel<2> : f == 3 ? chain_kernel<3> : chain_kernel<4>;
+      for (int f = 0; f < 10; ++f) {
+         auto k = f == 9 ? chain_kernel<9> : f == 8 ? chain_kernel<8> : f == 7 ? chain_kernel<7> : f == 6 ? chain_kernel<6> : f == 5 ? chain_kernel<5> : f == 0 ? chain_kernel<0> : f == 1 ? chain_kernel<1> : f == 2 ? chain_kernel<2> : f == 3 ? chain_kernel<3> : chain_kernel<4>;
          cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
          for (int rep = 0; rep < 2; ++rep) k<<<grid, threads, smem>>>(din, dout[f], nrows, iters, 2.0f, 1e9f, dcyc, noise, argc > 4 ? atoi(argv[4]) : 0);
          cudaError_t e = cudaDeviceSynchronize();

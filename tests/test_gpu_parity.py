@@ -59,6 +59,18 @@ def test_costvolume_edge_cases(ctx):
                 O.orc_costvolume(u, v, -20, 3, "none", "ad", np.inf, 3))
 
 
+@pytest.mark.parametrize("nch", [1, 3])
+def test_costvolume_gblur_prefilter(ctx, nch):
+    """-p gblur (truncated Gaussian, sigma 1, Neumann borders) before AD / SD / BT / NCC; ignored by census"""
+    u, v = synth_pair(57, 33, 14, seed=20 + nch, nch=nch)
+    u = u + np.float32(0.41)
+    for dist, trunc in [("ad", np.inf), ("sd", 400.0), ("btsd", np.inf), ("ncc", np.inf), ("census", np.inf)]:
+        a = ctx.allocate_and_fill_sgm_costvolume(u, v, -13, 3, "gblur", dist, trunc, 3)
+        assert same(a, O.orc_costvolume(u, v, -13, 3, "gblur", dist, trunc, 3)), (dist, nch)
+    a = ctx.allocate_and_fill_sgm_costvolume(u[:, :3, :2], v[:, :3, :2], -1, 1, "gblur", "ad", np.inf, 3)   # image smaller than the kernel
+    assert same(a, O.orc_costvolume(u[:, :3, :2], v[:, :3, :2], -1, 1, "gblur", "ad", np.inf, 3))
+
+
 MGM_SHAPES = [(23, 17, 9), (67, 41, 19), (131, 37, 40)]
 
 
@@ -79,6 +91,25 @@ def test_mgm_matches_oracle(ctx, K, felz, weighted):
             assert same(r["out"], o["out"]), tag
             assert same(r["S"], o["S"]), tag
             assert same(r["outcost"], o["outcost"]), tag
+    ctx.set_rows_per_band(0)
+
+
+@pytest.mark.parametrize("knob", ["MGMB200_GROUPS=2", "MGMB200_GROUPS=3", "MGMB200_NO_SHEAR=1", "MGMB200_NO_CREG=1",
+                                  "MGMB200_STATIC_ORDER=1"])
+def test_mgm_alternative_kernel_layouts(ctx, knob, monkeypatch):
+    """The aggregation kernel's alternative layouts (row groups on their own named barriers, row-per-worker diagonal
+    sweeps, cp.async cost ring, static band order) are selected by environment knobs read at every call: each must
+    give the same bits as the default layout, i.e. as the oracle."""
+    name, val = knob.split("=")
+    monkeypatch.setenv(name, val)
+    for (nx, ny, L), (K, felz, P1, P2) in itertools.product([(131, 37, 40), (90, 150, 24)],
+                                                            [(3, 1, 2, 20000), (2, 1, 2, 20000), (2, 0, 8, 32), (3, 0, 8, 32)]):
+        cc = synth_volume(nx, ny, L, seed=nx + K, real=True)
+        for rows in (0, 16):
+            ctx.set_rows_per_band(rows)
+            r = ctx.mgm(cc, None, -(L - 1), P1, P2, 8, K, felz, 1)
+            o = O.orc_mgm(cc, None, -(L - 1), P1, P2, 8, K, felz, 1)
+            assert same(r["S"], o["S"]) and same(r["out"], o["out"]), (knob, nx, ny, L, K, felz, rows, mism(r["S"], o["S"]))
     ctx.set_rows_per_band(0)
 
 

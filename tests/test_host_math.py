@@ -61,3 +61,35 @@ def test_monotone_rounded_add_distributes_over_min():
     b = (rng.random(100000) * 100).astype(np.float32)
     c = np.float32(2.0)
     assert np.array_equal(np.minimum(a, b) + c, np.minimum(a + c, b + c))
+
+
+def test_minconv_second_half_runs_on_the_partner_partials_only():
+    """aggregate.cu minconv_half: Q = min(F, B) satisfies Q[o] = min(Q[o+1]+c, F[o]) below the meeting point and
+    Q[o] = min(Q[o-1]+c, B[o]) above it, so the second half of each lane never re-reads the source vector."""
+    rng = np.random.default_rng(3)
+    for trial in range(300):
+        n = 2 * int(rng.integers(1, 40))
+        M = (rng.random(n) * rng.choice([1, 30, 1000])).astype(np.float32)
+        if trial % 3 == 0:
+            M[rng.random(n) < 0.3] = np.inf
+        if trial % 7 == 0:
+            M = np.round(M)
+        c = np.float32(rng.choice([0.0, 2.0, 8.0, 1.3, 0.1]))
+        F = M.copy()
+        for o in range(1, n):
+            F[o] = min(np.float32(F[o - 1] + c), F[o])
+        B = M.copy()
+        for o in range(n - 2, -1, -1):
+            B[o] = min(np.float32(B[o + 1] + c), B[o])
+        ref = np.minimum(F, B)
+        h = n // 2
+        Q = np.empty(n, np.float32)
+        run = F[h - 1]                      # upward lane: carry of its first half, then over the partner's B[h:]
+        for o in range(h, n):
+            run = min(np.float32(run + c), B[o])
+            Q[o] = run
+        run = B[h]                          # downward lane: carry of its first half, then over the partner's F[:h]
+        for o in range(h - 1, -1, -1):
+            run = min(np.float32(run + c), F[o])
+            Q[o] = run
+        assert np.array_equal(Q, ref), (trial, n, float(c))

@@ -93,6 +93,18 @@ def test_port_sobelx_and_weights_vs_ref():
 
 
 @needs_ref
+@pytest.mark.parametrize("nch", [1, 3])
+def test_port_gblur_vs_ref(nch):
+    """-p gblur: gblur_truncated(sigma=1) of both images (img_tools.h:143-180), then any non-census distance"""
+    u, v = synth_pair(43, 21, 12, seed=11 + nch, nch=nch)
+    u = u + np.float32(0.41)
+    for dist, trunc in [("ad", np.inf), ("sd", 400.0), ("btad", np.inf), ("ncc", np.inf)]:
+        assert same(O.orc_costvolume(u, v, -11, 2, "gblur", dist, trunc, 3), O.ref_costvolume(u, v, -11, 2, "gblur", dist, trunc, 3)), dist
+    # census forces the census prefilter whatever -p says (mgm_costvolume.h:358-362)
+    assert same(O.orc_costvolume(u, v, -11, 2, "gblur", "census", np.inf, 3), O.ref_costvolume(u, v, -11, 2, "gblur", "census", np.inf, 3))
+
+
+@needs_ref
 @pytest.mark.parametrize("K", [1, 2, 3, 4])
 @pytest.mark.parametrize("felz", [0, 1])
 @pytest.mark.parametrize("weighted", [0, 1])
