@@ -87,6 +87,36 @@ __device__ __forceinline__ float4 div3_4(const float4 &e) {
    return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
+// Shared-memory vectors are moved as 8-byte halves.  Measured on B200 (tests/micro/smem_bw.cu, smem_pat.cu):
+// LDS.128 delivers 64 B/clk per SM, LDS.64 / STS.64 the full 128 B/clk when the 16 lanes of a half-warp hit 16
+// different 8-byte banks.  With a row stride of 8 bytes modulo 128 (register-cost mode, agg_plan) two adjacent
+// rows read by 8 lanes each -- and 16 consecutive rows read by one lane each (the chains) -- do exactly that;
+// the kernel is bound by the LSU, so this layout is worth 2x on the gather loads and 1.3x on the chain loads.
+// Rows are then only 8-byte aligned: chunk q of a vector is the pair of float2 elements 2q, 2q+1 and no float4
+// pointer is ever formed on row memory.
+__device__ __forceinline__ float4 ld16(const float2 *p, int q) {
+   const float2 a = p[2 * q], b = p[2 * q + 1];
+   return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st16(float2 *p, int q, const float4 &v) {
+   p[2 * q] = make_float2(v.x, v.y);
+   p[2 * q + 1] = make_float2(v.z, v.w);
+}
+
+// The publisher warp copies a boundary vector from its ring slot to the global boundary line (rows may be only
+// 8-byte aligned, so no bulk copy here; the consuming band TMA-loads the line into its 128-byte aligned ring).
+__device__ __forceinline__ void warp_copy_vector(float *gdst, const float *ssrc, int VS, int lane) {
+   const float2 *s2 = reinterpret_cast<const float2 *>(ssrc);
+   float2 *d2 = reinterpret_cast<float2 *>(gdst);
+   for (int i = lane; i < (VS >> 1); i += 32) d2[i] = s2[i];
+}
+// all lanes' stores -> gpu-scope fence -> warp barrier -> release by lane 0
+__device__ __forceinline__ void warp_publish(int *prog, int value, int lane) {
+   __threadfence();
+   __syncwarp();
+   if (lane == 0) st_release(prog, value);
+}
+
 // SGM neighbour transform of one label: min3(L(o), min(L(o-1),L(o+1))+P1, m+P2) - m   (mgm_core.cc:113-116)
 __device__ __forceinline__ float sgm_x(float l, float c, float r, float p1, float cap, float m) {
    return fminf(fminf(c, fminf(l, r) + p1), cap) - m;
@@ -178,7 +208,7 @@ __device__ __forceinline__ RowGroup make_row_group(int tid, int ncomp, int r, in
 // recurrence over the partner's partial values only -- same additions in the same order as the reference,
 // one shared-memory read per label less (checked bit for bit in tests/micro/chain_bench.cu, form 6).
 template <int DIR>
-__device__ __forceinline__ void minconv_half(bool on, const float4 *src, float4 *dst, int nq, float c, float cap,
+__device__ __forceinline__ void minconv_half(bool on, const float2 *src, float2 *dst, int nq, float c, float cap,
                                              float sub, int bar_id) {
    const int h = nq >> 1;   // nq is even
    const int dq = DIR ? -1 : 1;
@@ -186,22 +216,22 @@ __device__ __forceinline__ void minconv_half(bool on, const float4 *src, float4 
    float run = MGM_INF;
    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
    if (on) {
-      v = src[q];
+      v = ld16(src, q);
       for (int i = 0; i < h; ++i, q += dq) {
-         const float4 vn = src[q + dq];   // chunk i+1 always exists (h < nq)
+         const float4 vn = ld16(src, q + dq);   // chunk i+1 always exists (h < nq)
          if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
-         dst[q] = v;
+         st16(dst, q, v);
          v = vn;
       }
    }
    pair_barrier(bar_id);   // partner's partial values are now in dst
    if (on) {
-      v = dst[q];
+      v = ld16(dst, q);
       for (int i = h; i < nq; ++i, q += dq) {
-         const float4 vn = dst[(i + 1 < nq) ? q + dq : q];
+         const float4 vn = ld16(dst, (i + 1 < nq) ? q + dq : q);
          if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
          v = add4s(make_float4(fminf(v.x, cap), fminf(v.y, cap), fminf(v.z, cap), fminf(v.w, cap)), -sub);
-         dst[q] = v;
+         st16(dst, q, v);
          v = vn;
       }
    }
@@ -239,7 +269,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    const int tid = threadIdx.x;
    const int ncomp = blockDim.x - 64;   // two service warps follow the row threads
    const bool is_prod = (tid == ncomp);        // fetches the previous band's boundary row
-   const bool is_pub = (tid == ncomp + 32);    // stores and publishes this band's boundary row
+   const bool pub_warp = (tid >= ncomp + 32);  // this warp stores and publishes the band's boundary row
    const int row0 = band * T;
    const int nrows = min(T, maxjj - row0);
    const bool has_prev = band > 0;
@@ -251,7 +281,6 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    const unsigned gmask = ((1u << G) - 1u) << ((tid & 31) & ~(G - 1));
    const bool rowok = (tid < ncomp) && (r < nrows);
    const int ys = row0 + r;
-   const bool last_row = rowok && (r == nrows - 1) && has_next;
    // lane-pair mapping for the sequential min-convolution chains: pair p of a warp is lanes (p, p+16); the
    // forward halves of 8 consecutive rows then sit in one quarter-warp and hit 8 different bank groups
    // (the row stride is an odd number of 16-byte units), likewise the backward halves
@@ -330,8 +359,8 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
       }
       if (go) {
          const float4 *src = reinterpret_cast<const float4 *>(ccv + (size_t)(pix0 + (long long)px * g.dxs) * VS);
-         float4 *dst = reinterpret_cast<float4 *>(cbuf_of(r, px));
-         for (int j = 0; j < nj; ++j) cp_async16(dst + gl + G * j, src + gl + G * j);
+         float *dst = cbuf_of(r, px);   // 16-byte aligned in this mode (agg_plan)
+         for (int j = 0; j < nj; ++j) cp_async16(dst + 4 * (gl + G * j), src + gl + G * j);
       }
       cp_async_commit();   // one (possibly empty) group per step keeps the wait count uniform
    };
@@ -343,16 +372,6 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 
    for (int s = 0; s < nsteps; ++s) {
       if (!late_prefetch && !creg_mode) prefetch_cost(s);
-      if (is_pub && has_next) {
-         // boundary stores are issued by this thread (end of each step, below); all but the most recent one
-         // are complete -> publish them.  Runs on the otherwise idle producer warp, off the rows' critical path.
-         const int pl = (s - 1) - SIG * (nrows - 1);   // pixel stored at the end of the previous step
-         if (pl >= 1 && pl < maxii) {
-            tma_wait_all<1>();
-            fence_proxy_async();
-            st_release(prog_out, pl);   // pixels [0,pl) of the boundary row are in global memory
-         }
-      }
       if (is_prod && has_prev) {
          // boundary pixels up to s+2 are needed before the next step (blocking); up to s+1+PF are fetched
          // ahead of time when the previous band has already published them (non-blocking)
@@ -390,9 +409,9 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
       const int xs = s - SIG * r;
       const bool act = rowok && xs >= 0 && xs < maxii;
       const long long pix = pix0 + (long long)xs * g.dxs;
-      float4 *cur = reinterpret_cast<float4 *>(row_base(r) + (act ? (xs % R) : 0) * VS);
+      float2 *cur = reinterpret_cast<float2 *>(row_base(r) + (act ? (xs % R) : 0) * VS);
       float *Cbf = (CHAINS && creg_mode) ? reinterpret_cast<float *>(cur) : cbuf_of(r, xs);   // where the message is built
-      float4 *Cb = reinterpret_cast<float4 *>(Cbf);
+      float2 *Cb = reinterpret_cast<float2 *>(Cbf);
       float4 *gout = reinterpret_cast<float4 *>(ldir + (size_t)(act ? pix : 0) * VS);
       const bool border = (xs == 0) || (ys == 0) || (xs == maxii - 1);
       float m = MGM_INF;
@@ -419,8 +438,8 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                src = slot_of(prow, ppx);
                dst = row_base(crow) + (R + ncbuf + ck) * VS;
             }
-            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 4 + cw);
-            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, cw1, capv, mk, 4 + cw);
+            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, cw1, capv, mk, 4 + cw);
+            else minconv_half<1>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, cw1, capv, mk, 4 + cw);
          }
          grp.sync();
       }
@@ -436,29 +455,29 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                   if (j < nj) {
                      const int q = gl + G * j;
                      m = hmin4(m, creg[j]);
-                     Cb[q] = creg[j];
+                     st16(Cb, q, creg[j]);
                      __stcs(gout + q, creg[j]);
                   }
                }
             } else {
-               const float4 *Cin = reinterpret_cast<const float4 *>(cbuf_of(r, xs));
+               const float2 *Cin = reinterpret_cast<const float2 *>(cbuf_of(r, xs));
                for (int j = 0; j < nj; ++j) {
                   const int q = gl + G * j;
-                  const float4 c = Cin[q];
+                  const float4 c = ld16(Cin, q);
                   m = hmin4(m, c);
-                  if (CHAINS) Cb[q] = c;
+                  if (CHAINS) st16(Cb, q, c);
                   __stcs(gout + q, c);
                }
             }
          } else {
-            const float4 *Cin = reinterpret_cast<const float4 *>(cbuf_of(r, xs));   // costs (cp.async mode)
-            const float4 *S[K];
+            const float2 *Cin = reinterpret_cast<const float2 *>(cbuf_of(r, xs));   // costs (cp.async mode)
+            const float2 *S[K];
             float mk[K], wk[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                int prow, ppx;
                pred_of(r, xs, k, prow, ppx);
-               S[k] = reinterpret_cast<const float4 *>(WTRUNC ? row_base(r) + (R + ncbuf + k) * VS : slot_of(prow, ppx));
+               S[k] = reinterpret_cast<const float2 *>(WTRUNC ? row_base(r) + (R + ncbuf + k) * VS : slot_of(prow, ppx));
                mk[k] = 0.f; wk[k] = 1.f;
                if (NEEDM) mk[k] = m_of(prow, ppx);
                if (WEIGHTED && !WTRUNC) wk[k] = __ldg(P.w + (size_t)pass_weight_plane(pass, k) * wplane + pix);
@@ -473,9 +492,9 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 #pragma unroll
                   for (int jj = 0; jj < B; ++jj) {
                      const int q = gl + G * (j0 + jj);
-                     if constexpr (!REGC) c[jj] = Cin[q];
+                     if constexpr (!REGC) c[jj] = ld16(Cin, q);
 #pragma unroll
-                     for (int k = 0; k < K; ++k) a[k][jj] = S[k][q];
+                     for (int k = 0; k < K; ++k) a[k][jj] = ld16(S[k], q);
                   }
                   if constexpr (REGC) {
 #pragma unroll
@@ -499,7 +518,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                         o = add4(c[jj], div4_by_k<K>(e));
                      }
                      m = hmin4(m, o);
-                     Cb[q] = o;
+                     st16(Cb, q, o);
 #if MGM_EXP != 1
                      __stcs(gout + q, o);
 #endif
@@ -531,16 +550,16 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                if (creg_mode) {   // this path reads the costs from the buffer: park the registers there first
 #pragma unroll
                   for (int j = 0; j < NJR; ++j)
-                     if (j < nj) Cb[gl + G * j] = creg[j];
+                     if (j < nj) st16(Cb, gl + G * j, creg[j]);
                }
                for (int j = 0; j < nj; ++j) {
                   const int q = gl + G * j;
-                  const float4 c = Cb[q];
+                  const float4 c = ld16(Cb, q);
                   float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                   for (int k = 0; k < K; ++k) {
                      const float *sf = reinterpret_cast<const float *>(S[k]);
-                     const float4 v = S[k][q];
+                     const float4 v = ld16(S[k], q);
                      const float lft = (q > 0) ? sf[4 * q - 1] : MGM_INF;
                      const float rgt = (q + 1 < nq) ? sf[4 * q + 4] : MGM_INF;
                      e.x += sgm_x(lft, v.x, v.y, pw[k], cap[k], mk[k]);
@@ -550,7 +569,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                   }
                   const float4 o = add4(c, div4_by_k<K>(e));
                   m = hmin4(m, o);
-                  Cb[q] = o;
+                  st16(Cb, q, o);
                   __stcs(gout + q, o);
                }
             }
@@ -577,9 +596,8 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
             float *dst = on ? row_base(crow) + (cxs % R) * VS : thr;
             const float *src = on ? (creg_mode ? dst : cbuf_of(crow, cxs)) : thr;
             if (MGM_EXP == 4) {}
-            else if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
-            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
-            if (on && has_next && crow == nrows - 1) fence_proxy_async_smem();   // read by the boundary TMA store
+            else if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
+            else minconv_half<1>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
          }
       } else if (act) {
          if constexpr (!WEIGHTED) {
@@ -593,7 +611,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 #pragma unroll
                for (int jj = 0; jj < B; ++jj) {
                   const int q = gl + G * (j0 + jj);
-                  v[jj] = Cb[q];
+                  v[jj] = ld16(Cb, q);
                   lft[jj] = (q > 0) ? Cbf[4 * q - 1] : MGM_INF;
                   rgt[jj] = (q + 1 < nq) ? Cbf[4 * q + 4] : MGM_INF;
                }
@@ -605,36 +623,31 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                   a.y = sgm_x(v[jj].x, v[jj].y, v[jj].z, p1, cap, m) * sc;
                   a.z = sgm_x(v[jj].y, v[jj].z, v[jj].w, p1, cap, m) * sc;
                   a.w = sgm_x(v[jj].z, v[jj].w, rgt[jj], p1, cap, m) * sc;
-                  cur[q] = a;
+                  st16(cur, q, a);
                }
             };
             int j0 = 0;
             for (; j0 + 4 <= nj; j0 += 4) tbatch(std::integral_constant<int, 4>{}, j0);
             for (; j0 < nj; ++j0) tbatch(std::integral_constant<int, 1>{}, j0);
          } else {
-            for (int j = 0; j < nj; ++j) cur[gl + G * j] = Cb[gl + G * j];   // weighted paths keep the raw message
+            for (int j = 0; j < nj; ++j) st16(cur, gl + G * j, ld16(Cb, gl + G * j));   // weighted paths keep the raw message
          }
-         if (last_row) fence_proxy_async_smem();
       }
       grp.sync();
 
-      // ---------------- hand the boundary row to the next band (producer thread, TMA bulk store)
-      if (is_pub && has_next) {
+      // ---------------- hand the boundary row to the next band: the publisher warp copies the transformed vector
+      // of the last row to the boundary line and releases the counter right away (pixels [0,xl] are in memory)
+      if (pub_warp && has_next) {
          const int xl = s - SIG * (nrows - 1);
          if (xl >= 0 && xl < maxii) {
-            if (NEEDM) bndm_out[xl] = msr[(nrows - 1) * 4 + (xl % R)];
-            tma_store_1d(bnd_out + (size_t)xl * VS, slot_of(nrows - 1, xl), vbytes);
-            tma_commit();
+            if (NEEDM && lane_id == 0) bndm_out[xl] = msr[(nrows - 1) * 4 + (xl % R)];
+            warp_copy_vector(bnd_out + (size_t)xl * VS, slot_of(nrows - 1, xl), VS, lane_id);
+            warp_publish(prog_out, xl + 1, lane_id);
          }
       }
    }
 
-   // epilogue: drain the boundary stores, publish the full boundary row, save mbarrier parities
-   if (is_pub && has_next) {
-      tma_wait_all<0>();
-      fence_proxy_async();
-      st_release(prog_out, maxii);
-   }
+   // epilogue: save mbarrier parities
    cp_async_wait<0>();
    if (tid == 0) phase[vph_idx] = vph;
    __syncthreads();
@@ -673,7 +686,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
    const int tid = threadIdx.x;
    const int ncomp = blockDim.x - 64;
    const bool is_prod = (tid == ncomp);
-   const bool is_pub = (tid == ncomp + 32);
+   const bool pub_warp = (tid >= ncomp + 32);
    const int u0 = band * T;
    const int nrows = min(T, nu - u0);
    const bool has_prev = band > 0;
@@ -750,8 +763,8 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
       }
       if (go) {
          const float4 *src = reinterpret_cast<const float4 *>(ccv + (size_t)(pix_u + (long long)vn * dv) * VS);
-         float4 *dst = reinterpret_cast<float4 *>(cbuf_of(r, vn));
-         for (int j = 0; j < nj; ++j) cp_async16(dst + gl + G * j, src + gl + G * j);
+         float *dst = cbuf_of(r, vn);   // 16-byte aligned in this mode (agg_plan)
+         for (int j = 0; j < nj; ++j) cp_async16(dst + 4 * (gl + G * j), src + gl + G * j);
       }
       cp_async_commit();
    };
@@ -760,12 +773,6 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
 
    for (int v = sb; v <= se; ++v) {
       if (!late_prefetch && !creg_mode) prefetch_cost(v);
-      if (is_pub && has_next && v > sb) {
-         // the stores of position v-1 were issued at the end of the previous step; everything before is complete
-         tma_wait_all<1>();
-         fence_proxy_async();
-         st_release(prog_out, v - 1);   // positions < v-1 of both boundary workers are in global memory
-      }
       if (is_prod && pf_hi >= pf_lo) {
          // position v is read in the NEXT step (blocking); up to v+PF are fetched ahead when already published
          const int need = min(pf_hi, v);
@@ -804,9 +811,9 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
       const bool act = rowok && v >= my_lo && v <= my_hi;
       const int xs = u - v;
       const long long pix = pix_u + (long long)v * dv;
-      float4 *cur = reinterpret_cast<float4 *>(row_base(r) + (v & 1) * VS);
+      float2 *cur = reinterpret_cast<float2 *>(row_base(r) + (v & 1) * VS);
       float *Cbf = inplace ? reinterpret_cast<float *>(cur) : cbuf_of(r, v);   // where the message is built
-      float4 *Cb = reinterpret_cast<float4 *>(Cbf);
+      float2 *Cb = reinterpret_cast<float2 *>(Cbf);
       float4 *gout = reinterpret_cast<float4 *>(ldir + (size_t)(act ? pix : 0) * VS);
       const bool border = (xs == 0) || (v == 0) || (xs == maxii - 1);
       float m = MGM_INF;
@@ -821,27 +828,27 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
                   if (j < nj) {
                      const int q = gl + G * j;
                      m = hmin4(m, creg[j]);
-                     Cb[q] = creg[j];
+                     st16(Cb, q, creg[j]);
                      __stcs(gout + q, creg[j]);
                   }
                }
             } else {
-               const float4 *Cin = reinterpret_cast<const float4 *>(cbuf_of(r, v));
+               const float2 *Cin = reinterpret_cast<const float2 *>(cbuf_of(r, v));
                for (int j = 0; j < nj; ++j) {
                   const int q = gl + G * j;
-                  const float4 c = Cin[q];
+                  const float4 c = ld16(Cin, q);
                   m = hmin4(m, c);
                   __stcs(gout + q, c);
                }
             }
          } else {
-            const float4 *Cin = reinterpret_cast<const float4 *>(cbuf_of(r, v));   // costs (cp.async mode)
-            const float4 *S[K];
+            const float2 *Cin = reinterpret_cast<const float2 *>(cbuf_of(r, v));   // costs (cp.async mode)
+            const float2 *S[K];
             float mk[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                const int prow = (k == 0) ? r : (k == 1 ? r - 2 : r - 1);   // (+1,-1), (-1,-1), (0,-1)
-               S[k] = reinterpret_cast<const float4 *>(slot_of(prow, v - 1));
+               S[k] = reinterpret_cast<const float2 *>(slot_of(prow, v - 1));
                mk[k] = NEEDM ? m_of(prow, v - 1) : 0.f;
             }
             auto batch = [&](auto jbc, int j0, auto regc) {
@@ -851,9 +858,9 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
 #pragma unroll
                for (int jj = 0; jj < B; ++jj) {
                   const int q = gl + G * (j0 + jj);
-                  if constexpr (!REGC) c[jj] = Cin[q];
+                  if constexpr (!REGC) c[jj] = ld16(Cin, q);
 #pragma unroll
-                  for (int k = 0; k < K; ++k) a[k][jj] = S[k][q];
+                  for (int k = 0; k < K; ++k) a[k][jj] = ld16(S[k], q);
                }
                if constexpr (REGC) {
 #pragma unroll
@@ -874,7 +881,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
                      o = add4(c[jj], div4_by_k<K>(e));
                   }
                   m = hmin4(m, o);
-                  Cb[q] = o;
+                  st16(Cb, q, o);
                   __stcs(gout + q, o);
                }
             };
@@ -915,9 +922,8 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
             const float cm = on ? msr[crow * 4 + (v & 1)] : 0.f;
             float *dst = on ? row_base(crow) + (v & 1) * VS : thr;
             const float *src = on ? (inplace ? dst : cbuf_of(crow, v)) : thr;
-            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
-            else minconv_half<1>(on, reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
-            if (on && has_next && crow >= nrows - 2) fence_proxy_async_smem();   // read by the boundary TMA stores
+            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
+            else minconv_half<1>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
          }
       } else if (act) {
          // SGM transform, label-parallel: A(o) = min3(L(o), min(L(o-1),L(o+1))+P1, m+P2) - m  [x 1/2 for K=2]
@@ -925,7 +931,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
          const float sc = (K == 2) ? 0.5f : 1.0f;
          for (int j = 0; j < nj; ++j) {
             const int q = gl + G * j;
-            const float4 x = Cb[q];
+            const float4 x = ld16(Cb, q);
             const float lft = (q > 0) ? Cbf[4 * q - 1] : MGM_INF;
             const float rgt = (q + 1 < nq) ? Cbf[4 * q + 4] : MGM_INF;
             float4 a;
@@ -933,31 +939,26 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
             a.y = sgm_x(x.x, x.y, x.z, p1, cap, m) * sc;
             a.z = sgm_x(x.y, x.z, x.w, p1, cap, m) * sc;
             a.w = sgm_x(x.z, x.w, rgt, p1, cap, m) * sc;
-            cur[q] = a;
+            st16(cur, q, a);
          }
-         if (has_next && r >= nrows - 2) fence_proxy_async_smem();
       }
       grp.sync();
 
-      // ---------------- hand the two boundary workers to the next band
-      if (is_pub && has_next) {
+      // ---------------- hand the two boundary workers to the next band (publisher warp, see run_band)
+      if (pub_warp && has_next) {
 #pragma unroll
          for (int line = 0; line < 2; ++line) {
             const int br = nrows - 1 - line;
             if (v >= vlo(u0 + br) && v <= vhi(u0 + br)) {
-               if (NEEDM) bndm_out[(size_t)line * maxjj + v] = msr[br * 4 + (v & 1)];
-               tma_store_1d(bnd_out + ((size_t)line * maxjj + v) * VS, slot_of(br, v), vbytes);
+               if (NEEDM && lane_id == 0) bndm_out[(size_t)line * maxjj + v] = msr[br * 4 + (v & 1)];
+               warp_copy_vector(bnd_out + ((size_t)line * maxjj + v) * VS, slot_of(br, v), VS, lane_id);
             }
          }
-         tma_commit();   // one (possibly empty) group per step
+         warp_publish(prog_out, v + 1, lane_id);   // positions <= v of both boundary workers are in global memory
       }
    }
 
-   if (is_pub && has_next) {
-      tma_wait_all<0>();
-      fence_proxy_async();
-      st_release(prog_out, 0x7fffffff);
-   }
+   if (pub_warp && has_next) warp_publish(prog_out, 0x7fffffff, lane_id);
    cp_async_wait<0>();
    if (tid == 0) phase[vph_idx] = vph;
    __syncthreads();
@@ -1085,7 +1086,8 @@ static void agg_plan_try(AggPlan *plan, int L, int K, int pot, bool weighted, in
    for (int cls = 0; cls < 2; ++cls) {
       int nbuf = ((cls == 1 && shear) ? 2 : ring_slots(cls, K)) + ncbuf + xtra;
       int TS = nbuf * VS;
-      if (((TS >> 2) & 1) == 0) TS += 4;   // odd number of 16-byte units: rows start in different bank groups
+      if (plan->ncb == 1) TS += 2;                // 8 bytes modulo 128: 64-bit accesses of 16 consecutive rows tile the banks
+      else if (((TS >> 2) & 1) == 0) TS += 4;     // cp.async mode needs 16-byte aligned rows: odd number of 16-byte units
       plan->TS[cls] = TS;
       size_t fixed = 1024 + (size_t)nvirt * RV * VS * 4 + (size_t)tcap * (16 + 16 + 4) + RV * 16;
       long avail = (long)max_smem - (long)fixed;
