@@ -94,11 +94,18 @@ __device__ __forceinline__ float4 div3_4(const float4 &e) {
 // the kernel is bound by the LSU, so this layout is worth 2x on the gather loads and 1.3x on the chain loads.
 // Rows are then only 8-byte aligned: chunk q of a vector is the pair of float2 elements 2q, 2q+1 and no float4
 // pointer is ever formed on row memory.
+// A16: the rows are 16-byte aligned and the chunk moves as one 16-byte access (truncated-linear kernels: their
+// chain lanes read one chunk per ROW, a pattern that gains little from 8-byte halves and pays for the extra
+// instructions in its dependent stream -- measured).
+template <bool A16>
 __device__ __forceinline__ float4 ld16(const float2 *p, int q) {
+   if (A16) return *reinterpret_cast<const float4 *>(p + 2 * q);
    const float2 a = p[2 * q], b = p[2 * q + 1];
    return make_float4(a.x, a.y, b.x, b.y);
 }
+template <bool A16>
 __device__ __forceinline__ void st16(float2 *p, int q, const float4 &v) {
+   if (A16) { *reinterpret_cast<float4 *>(p + 2 * q) = v; return; }
    p[2 * q] = make_float2(v.x, v.y);
    p[2 * q + 1] = make_float2(v.z, v.w);
 }
@@ -216,22 +223,22 @@ __device__ __forceinline__ void minconv_half(bool on, const float2 *src, float2 
    float run = MGM_INF;
    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
    if (on) {
-      v = ld16(src, q);
+      v = ld16<true>(src, q);
       for (int i = 0; i < h; ++i, q += dq) {
-         const float4 vn = ld16(src, q + dq);   // chunk i+1 always exists (h < nq)
+         const float4 vn = ld16<true>(src, q + dq);   // chunk i+1 always exists (h < nq)
          if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
-         st16(dst, q, v);
+         st16<true>(dst, q, v);
          v = vn;
       }
    }
    pair_barrier(bar_id);   // partner's partial values are now in dst
    if (on) {
-      v = ld16(dst, q);
+      v = ld16<true>(dst, q);
       for (int i = h; i < nq; ++i, q += dq) {
-         const float4 vn = ld16(dst, (i + 1 < nq) ? q + dq : q);
+         const float4 vn = ld16<true>(dst, (i + 1 < nq) ? q + dq : q);
          if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
          v = add4s(make_float4(fminf(v.x, cap), fminf(v.y, cap), fminf(v.z, cap), fminf(v.w, cap)), -sub);
-         st16(dst, q, v);
+         st16<true>(dst, q, v);
          v = vn;
       }
    }
@@ -253,6 +260,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    constexpr bool WTRUNC = WEIGHTED && POT == POT_TRUNC;
    constexpr bool CHAINS = !WEIGHTED && POT == POT_TRUNC;   // phase-2 transform done by lane pairs
    constexpr int CLS = DIAG ? 1 : 0;
+   constexpr bool A16 = (POT == POT_TRUNC);   // 16-byte aligned rows and accesses (ld16 / st16)
    constexpr int JB = (K <= 3) ? MGM_JB : 2;   // chunks per lane whose loads are issued together in the gather
    constexpr int NJR = MGM_AGG_CREG;      // cost chunks per lane that can be prefetched into registers
 
@@ -455,7 +463,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                   if (j < nj) {
                      const int q = gl + G * j;
                      m = hmin4(m, creg[j]);
-                     st16(Cb, q, creg[j]);
+                     st16<A16>(Cb, q, creg[j]);
                      __stcs(gout + q, creg[j]);
                   }
                }
@@ -463,9 +471,9 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                const float2 *Cin = reinterpret_cast<const float2 *>(cbuf_of(r, xs));
                for (int j = 0; j < nj; ++j) {
                   const int q = gl + G * j;
-                  const float4 c = ld16(Cin, q);
+                  const float4 c = ld16<A16>(Cin, q);
                   m = hmin4(m, c);
-                  if (CHAINS) st16(Cb, q, c);
+                  if (CHAINS) st16<A16>(Cb, q, c);
                   __stcs(gout + q, c);
                }
             }
@@ -492,9 +500,9 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 #pragma unroll
                   for (int jj = 0; jj < B; ++jj) {
                      const int q = gl + G * (j0 + jj);
-                     if constexpr (!REGC) c[jj] = ld16(Cin, q);
+                     if constexpr (!REGC) c[jj] = ld16<A16>(Cin, q);
 #pragma unroll
-                     for (int k = 0; k < K; ++k) a[k][jj] = ld16(S[k], q);
+                     for (int k = 0; k < K; ++k) a[k][jj] = ld16<A16>(S[k], q);
                   }
                   if constexpr (REGC) {
 #pragma unroll
@@ -518,7 +526,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                         o = add4(c[jj], div4_by_k<K>(e));
                      }
                      m = hmin4(m, o);
-                     st16(Cb, q, o);
+                     st16<A16>(Cb, q, o);
 #if MGM_EXP != 1
                      __stcs(gout + q, o);
 #endif
@@ -550,16 +558,16 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                if (creg_mode) {   // this path reads the costs from the buffer: park the registers there first
 #pragma unroll
                   for (int j = 0; j < NJR; ++j)
-                     if (j < nj) st16(Cb, gl + G * j, creg[j]);
+                     if (j < nj) st16<A16>(Cb, gl + G * j, creg[j]);
                }
                for (int j = 0; j < nj; ++j) {
                   const int q = gl + G * j;
-                  const float4 c = ld16(Cb, q);
+                  const float4 c = ld16<A16>(Cb, q);
                   float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                   for (int k = 0; k < K; ++k) {
                      const float *sf = reinterpret_cast<const float *>(S[k]);
-                     const float4 v = ld16(S[k], q);
+                     const float4 v = ld16<A16>(S[k], q);
                      const float lft = (q > 0) ? sf[4 * q - 1] : MGM_INF;
                      const float rgt = (q + 1 < nq) ? sf[4 * q + 4] : MGM_INF;
                      e.x += sgm_x(lft, v.x, v.y, pw[k], cap[k], mk[k]);
@@ -569,7 +577,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                   }
                   const float4 o = add4(c, div4_by_k<K>(e));
                   m = hmin4(m, o);
-                  st16(Cb, q, o);
+                  st16<A16>(Cb, q, o);
                   __stcs(gout + q, o);
                }
             }
@@ -611,7 +619,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 #pragma unroll
                for (int jj = 0; jj < B; ++jj) {
                   const int q = gl + G * (j0 + jj);
-                  v[jj] = ld16(Cb, q);
+                  v[jj] = ld16<A16>(Cb, q);
                   lft[jj] = (q > 0) ? Cbf[4 * q - 1] : MGM_INF;
                   rgt[jj] = (q + 1 < nq) ? Cbf[4 * q + 4] : MGM_INF;
                }
@@ -623,14 +631,14 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                   a.y = sgm_x(v[jj].x, v[jj].y, v[jj].z, p1, cap, m) * sc;
                   a.z = sgm_x(v[jj].y, v[jj].z, v[jj].w, p1, cap, m) * sc;
                   a.w = sgm_x(v[jj].z, v[jj].w, rgt[jj], p1, cap, m) * sc;
-                  st16(cur, q, a);
+                  st16<A16>(cur, q, a);
                }
             };
             int j0 = 0;
             for (; j0 + 4 <= nj; j0 += 4) tbatch(std::integral_constant<int, 4>{}, j0);
             for (; j0 < nj; ++j0) tbatch(std::integral_constant<int, 1>{}, j0);
          } else {
-            for (int j = 0; j < nj; ++j) st16(cur, gl + G * j, ld16(Cb, gl + G * j));   // weighted paths keep the raw message
+            for (int j = 0; j < nj; ++j) st16<A16>(cur, gl + G * j, ld16<A16>(Cb, gl + G * j));   // weighted paths keep the raw message
          }
       }
       grp.sync();
@@ -669,6 +677,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
    static_assert(K <= 3, "the sheared wavefront needs predecessors in the row above only");
    constexpr bool NEEDM = (POT == POT_TRUNC && K == 2);
    constexpr bool CHAINS = (POT == POT_TRUNC);
+   constexpr bool A16 = (POT == POT_TRUNC);   // 16-byte aligned rows and accesses (ld16 / st16)
    constexpr int JB = MGM_JB;
    constexpr int NJR = MGM_AGG_CREG;
 
@@ -828,7 +837,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
                   if (j < nj) {
                      const int q = gl + G * j;
                      m = hmin4(m, creg[j]);
-                     st16(Cb, q, creg[j]);
+                     st16<A16>(Cb, q, creg[j]);
                      __stcs(gout + q, creg[j]);
                   }
                }
@@ -836,7 +845,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
                const float2 *Cin = reinterpret_cast<const float2 *>(cbuf_of(r, v));
                for (int j = 0; j < nj; ++j) {
                   const int q = gl + G * j;
-                  const float4 c = ld16(Cin, q);
+                  const float4 c = ld16<A16>(Cin, q);
                   m = hmin4(m, c);
                   __stcs(gout + q, c);
                }
@@ -858,9 +867,9 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
 #pragma unroll
                for (int jj = 0; jj < B; ++jj) {
                   const int q = gl + G * (j0 + jj);
-                  if constexpr (!REGC) c[jj] = ld16(Cin, q);
+                  if constexpr (!REGC) c[jj] = ld16<A16>(Cin, q);
 #pragma unroll
-                  for (int k = 0; k < K; ++k) a[k][jj] = ld16(S[k], q);
+                  for (int k = 0; k < K; ++k) a[k][jj] = ld16<A16>(S[k], q);
                }
                if constexpr (REGC) {
 #pragma unroll
@@ -881,7 +890,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
                      o = add4(c[jj], div4_by_k<K>(e));
                   }
                   m = hmin4(m, o);
-                  st16(Cb, q, o);
+                  st16<A16>(Cb, q, o);
                   __stcs(gout + q, o);
                }
             };
@@ -931,7 +940,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
          const float sc = (K == 2) ? 0.5f : 1.0f;
          for (int j = 0; j < nj; ++j) {
             const int q = gl + G * j;
-            const float4 x = ld16(Cb, q);
+            const float4 x = ld16<A16>(Cb, q);
             const float lft = (q > 0) ? Cbf[4 * q - 1] : MGM_INF;
             const float rgt = (q + 1 < nq) ? Cbf[4 * q + 4] : MGM_INF;
             float4 a;
@@ -939,7 +948,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
             a.y = sgm_x(x.x, x.y, x.z, p1, cap, m) * sc;
             a.z = sgm_x(x.y, x.z, x.w, p1, cap, m) * sc;
             a.w = sgm_x(x.z, x.w, rgt, p1, cap, m) * sc;
-            st16(cur, q, a);
+            st16<A16>(cur, q, a);
          }
       }
       grp.sync();
@@ -1086,8 +1095,8 @@ static void agg_plan_try(AggPlan *plan, int L, int K, int pot, bool weighted, in
    for (int cls = 0; cls < 2; ++cls) {
       int nbuf = ((cls == 1 && shear) ? 2 : ring_slots(cls, K)) + ncbuf + xtra;
       int TS = nbuf * VS;
-      if (plan->ncb == 1) TS += 2;                // 8 bytes modulo 128: 64-bit accesses of 16 consecutive rows tile the banks
-      else if (((TS >> 2) & 1) == 0) TS += 4;     // cp.async mode needs 16-byte aligned rows: odd number of 16-byte units
+      if (plan->ncb == 1 && pot == POT_SGM) TS += 2;   // 8 bytes modulo 128: 64-bit accesses of adjacent rows tile the banks
+      else if (((TS >> 2) & 1) == 0) TS += 4;          // 16-byte aligned rows (truncated linear, cp.async mode): odd number of 16-byte units
       plan->TS[cls] = TS;
       size_t fixed = 1024 + (size_t)nvirt * RV * VS * 4 + (size_t)tcap * (16 + 16 + 4) + RV * 16;
       long avail = (long)max_smem - (long)fixed;
