@@ -100,6 +100,36 @@ int mgmb200_mgm_labelmajor(mgmb200_ctx *ctx, const float *costs, const float *w,
 int mgmb200_subpixel_refinement_sgm(mgmb200_ctx *ctx, const float *S, int nx, int ny, int dmin, int dmax,
                                     float *out, float *outcost, const char *refinement);
 
+/* ---- per-pixel disparity ranges: the dminI / dmaxI images of the three functions above (-m / -M range files
+ * mgm.cc:342-353, range updates between TSGM_ITER iterations mgm.cc:377-395).  A Dvec only holds its own
+ * [min,max] (dvec.cc:49-131); here volumes stay DENSE over an envelope [emin,emax] (L = emax-emin+1 labels per
+ * pixel) and a label outside a pixel's range holds +INF, which is what Dvec::operator[] returns for it.
+ * Range images are floats and are truncated to int like Dvec::init does (mgm_costvolume.h:323).          */
+
+/* allocate_and_fill_sgm_costvolume(in_u, in_v, dminI, dmaxI, ...)                 mgm_costvolume.h:337-424
+ * cc_out: nx*ny*L floats, +INF outside [dminI,dmaxI]. */
+int mgmb200_costvolume_ranges(mgmb200_ctx *ctx, const float *u, const float *v, int nx, int ny, int nch, int vnx,
+                              int vny, const float *dminI, const float *dmaxI, int emin, int emax,
+                              const char *prefilter, const char *distance, float truncDist, int census_ncc_win,
+                              float *cc_out);
+
+/* mgm(CC, in_w, dminI, dmaxI, ...)                                                   mgm_core.cc:408-613
+ * cc: nx*ny*L floats whose vectors have the ranges [ccmin,ccmax] (entries outside are ignored); dminI/dmaxI: the
+ * ranges of the returned volume S, over which the winner is taken (they differ from the former from the second
+ * TSGM_ITER iteration on, mgm.cc:377-395).  S_out: NULL or nx*ny*L floats, +INF outside [dminI,dmaxI].
+ * Truncated-linear potentials with non-uniform cost ranges are supported for MGM=2 without image-dependent
+ * weights (the variant that folds out-of-range labels back in, mgm_core.cc:166-219); MGMB200_EUNSUPPORTED else. */
+int mgmb200_mgm_ranges(mgmb200_ctx *ctx, const float *cc, const float *ccmin, const float *ccmax, const float *w,
+                       int nx, int ny, int emin, int emax, const float *dminI, const float *dmaxI, float P1,
+                       float P2, int NDIR, int MGM, int use_felzenszwalb_potentials, int sgm_fix_overcount,
+                       float *out, float *outcost, float *S_out);
+
+/* subpixel_refinement_sgm(S, out, outcost, refinement) on a volume with the ranges [dminI,dmaxI]
+ * (the test against S[i].min / S[i].max of mgm_refine.h:58). */
+int mgmb200_subpixel_refinement_sgm_ranges(mgmb200_ctx *ctx, const float *S, const float *dminI, const float *dmaxI,
+                                           int nx, int ny, int emin, int emax, float *out, float *outcost,
+                                           const char *refinement);
+
 /* The whole hot path as mgm.cc:356-385 strings it together for one direction of the LR pair:
  * weights(u) -> cost volume(u,v) -> mgm -> sub-pixel, nothing but the images going in and the two
  * maps coming out.  P1/P2 are the command-line values: they are multiplied by nch here exactly

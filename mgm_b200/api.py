@@ -171,6 +171,55 @@ class Context:
                                          _fp(outcost), _fp(S)))
         return dict(out=out, outcost=outcost, S=S)
 
+    # ------------------------------------------------------------------ per-pixel disparity ranges (dminI / dmaxI)
+    @staticmethod
+    def _range_imgs(lo, hi, ny, nx):
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, np.float32), (ny, nx)))
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, np.float32), (ny, nx)))
+        return lo, hi
+
+    def costvolume_ranges(self, u, v, dminI, dmaxI, emin, emax, prefilter="none", distance="ad", truncDist=np.inf,
+                          census_ncc_win=3):
+        """allocate_and_fill_sgm_costvolume with range images -> dense (H,W,emax-emin+1), +INF outside the ranges."""
+        u, nx, ny, nch = _img(u)
+        v, vnx, vny, vnch = _img(v)
+        lo, hi = self._range_imgs(dminI, dmaxI, ny, nx)
+        cc = np.empty((ny, nx, emax - emin + 1), np.float32)
+        self._check(self.lib.mgmb200_costvolume_ranges(self._ctx, _fp(u), _fp(v), nx, ny, nch, vnx, vny, _fp(lo), _fp(hi),
+                                                       int(emin), int(emax), prefilter.encode(), distance.encode(),
+                                                       ctypes.c_float(truncDist), int(census_ncc_win), _fp(cc)))
+        return cc
+
+    def mgm_ranges(self, cc, ccmin, ccmax, w, emin, dminI, dmaxI, P1, P2, NDIR, MGM, use_felzenszwalb_potentials=0,
+                   sgm_fix_overcount=1, want_S=True):
+        """mgm() with per-pixel ranges: cc dense over [emin, emin+L-1] with vector ranges [ccmin,ccmax]; dminI/dmaxI
+        are the ranges of the returned volume."""
+        cc = _f32(cc)
+        ny, nx, L = cc.shape
+        clo, chi = self._range_imgs(ccmin, ccmax, ny, nx)
+        slo, shi = self._range_imgs(dminI, dmaxI, ny, nx)
+        if w is not None:
+            w = _f32(w)
+        out = np.empty((ny, nx), np.float32)
+        outcost = np.empty((ny, nx), np.float32)
+        S = np.empty_like(cc) if want_S else None
+        self._check(self.lib.mgmb200_mgm_ranges(self._ctx, _fp(cc), _fp(clo), _fp(chi), _fp(w), nx, ny, int(emin),
+                                                int(emin) + L - 1, _fp(slo), _fp(shi), ctypes.c_float(P1),
+                                                ctypes.c_float(P2), int(NDIR), int(MGM), int(use_felzenszwalb_potentials),
+                                                int(sgm_fix_overcount), _fp(out), _fp(outcost), _fp(S)))
+        return dict(out=out, outcost=outcost, S=S)
+
+    def subpixel_refinement_sgm_ranges(self, S, dminI, dmaxI, emin, out, outcost, refinement):
+        S = _f32(S)
+        ny, nx, L = S.shape
+        slo, shi = self._range_imgs(dminI, dmaxI, ny, nx)
+        out = np.array(out, np.float32, copy=True)
+        outcost = np.array(outcost, np.float32, copy=True)
+        self._check(self.lib.mgmb200_subpixel_refinement_sgm_ranges(self._ctx, _fp(S), _fp(slo), _fp(shi), nx, ny,
+                                                                    int(emin), int(emin) + L - 1, _fp(out), _fp(outcost),
+                                                                    refinement.encode()))
+        return out, outcost
+
     def mgm_labelmajor(self, costs, w, P1, P2, NDIR, MGM, use_felzenszwalb_potentials=0):
         """matlab/mgm_o.cc protocol: costs (L,H,W) label-major planes -> labels (H,W)."""
         costs = _f32(costs)

@@ -59,7 +59,9 @@ struct mgmb200_ctx {
    cudaStream_t own_stream = nullptr, stream = nullptr;
    int rows_override = 0;
    // scratch (grow-only, reused across calls)
-   DevBuf u, v, fu, fv, ftmp, cu, cv, w, cc, dense, out, outcost, flags, progress, bnd, bndm;
+   DevBuf u, v, fu, fv, ftmp, cu, cv, w, cc, dense, out, outcost, flags, progress, bnd, bndm, rg[4];
+   // per-pixel ranges of the call in flight (device pointers or nullptr): S range, cost-vector range
+   const float *r_smin = nullptr, *r_smax = nullptr, *r_ccmin = nullptr, *r_ccmax = nullptr;
    DevBuf sweep[8];
    DevBuf dbgbuf;
    size_t sweep_bytes = 0;
@@ -133,7 +135,8 @@ extern "C" void mgmb200_destroy(mgmb200_ctx *c) {
    cudaSetDevice(c->device);
    cudaStreamSynchronize(c->stream);
    DevBuf *bufs[] = {&c->u, &c->v, &c->fu, &c->fv, &c->cu, &c->cv, &c->w, &c->cc, &c->dense, &c->out,
-                     &c->outcost, &c->flags, &c->ftmp, &c->progress, &c->bnd, &c->bndm};
+                     &c->outcost, &c->flags, &c->ftmp, &c->progress, &c->bnd, &c->bndm, &c->rg[0], &c->rg[1],
+                     &c->rg[2], &c->rg[3]};
    for (DevBuf *b : bufs) b->release();
    for (int i = 0; i < 8; i++) c->sweep[i].release();
    if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -215,9 +218,18 @@ extern "C" int mgmb200_weights_dev(mgmb200_ctx *c, const float *d_u, int nx, int
    return 0;
 }
 
+static int costvolume_dev_impl(mgmb200_ctx *c, const float *d_u, const float *d_v, int nx, int ny, int nch, int vnx,
+                               int vny, int dmin, int dmax, int pf, int dist, float truncDist, int win,
+                               const float *d_rlo, const float *d_rhi, float *d_cc);
 extern "C" int mgmb200_costvolume_dev(mgmb200_ctx *c, const float *d_u, const float *d_v, int nx, int ny, int nch,
                                       int vnx, int vny, int dmin, int dmax, int pf, int dist, float truncDist,
                                       int win, float *d_cc) {
+   return costvolume_dev_impl(c, d_u, d_v, nx, ny, nch, vnx, vny, dmin, dmax, pf, dist, truncDist, win, nullptr, nullptr,
+                              d_cc);
+}
+static int costvolume_dev_impl(mgmb200_ctx *c, const float *d_u, const float *d_v, int nx, int ny, int nch, int vnx,
+                               int vny, int dmin, int dmax, int pf, int dist, float truncDist, int win,
+                               const float *d_rlo, const float *d_rhi, float *d_cc) {
    if (!c || !d_u || !d_v || !d_cc) return fail(MGMB200_EINVAL, "NULL argument");
    RET(check_dims(nx, ny, dmin, dmax));
    if (vnx < 1 || vny < 1 || nch < 1) return fail(MGMB200_EINVAL, "image v %dx%dx%d", vnx, vny, nch);
@@ -255,7 +267,7 @@ extern "C" int mgmb200_costvolume_dev(mgmb200_ctx *c, const float *d_u, const fl
       CU(gblur_launch(d_v, vnx, vny, nch, 1.0f, c->ftmp.as<float>(), c->fv.as<float>(), c->stream));
       uu = c->fu.as<float>(); vv = c->fv.as<float>();
    }
-   CU(costvolume_launch(dist, uu, vv, cu, cv, nx, ny, vnx, vny, cnch, win, dmin, L, VS, truncDist, d_cc,
+   CU(costvolume_launch(dist, uu, vv, cu, cv, nx, ny, vnx, vny, cnch, win, dmin, L, VS, truncDist, d_rlo, d_rhi, d_cc,
                         c->num_sms, c->stream));
    return 0;
 }
@@ -378,6 +390,7 @@ static int finish_rows(mgmb200_ctx *c, const float *const *d_sweeps, const float
    W.pix_begin = (long long)row_begin * nx; W.pix_end = (long long)row_end * nx;
    W.ndir = NDIR; W.L = L; W.VS = mgmb200_padded_labels(L); W.dmin = dmin;
    W.fix = (fix == 1); W.refine = refine;
+   W.smin = c->r_smin; W.smax = c->r_smax; W.ccmin = c->r_ccmin; W.ccmax = c->r_ccmax;
    CU(wta_launch(W, c->num_sms, c->stream));
    c->n_launches++;
    return 0;
@@ -591,8 +604,134 @@ extern "C" int mgmb200_subpixel_refinement_sgm(mgmb200_ctx *c, const float *S, i
    RET(upload(c, c->dense, S, np * L * 4));
    RET(upload(c, c->out, out, np * 4));
    RET(upload(c, c->outcost, outcost, np * 4));
-   CU(refine_launch(c->dense.as<float>(), (long long)np, L, dmin, m, c->out.as<float>(), c->outcost.as<float>(),
-                    c->stream));
+   CU(refine_launch(c->dense.as<float>(), (long long)np, L, dmin, m, nullptr, nullptr, c->out.as<float>(),
+                    c->outcost.as<float>(), c->stream));
+   RET(download(c, out, c->out.p, np * 4));
+   RET(download(c, outcost, c->outcost.p, np * 4));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+
+// ------------------------------------------------------------------------------------------ per-pixel ranges
+// (-m/-M range images, TSGM_ITER > 1.)  Volumes cross the boundary DENSE over an envelope [emin,emax];
+// a label outside a pixel's range does not exist in the reference's Dvec: +INF in the dense array.
+struct RangeScan { bool ok, ragged; };
+static RangeScan scan_ranges(const float *lo, const float *hi, size_t np, int emin, int emax) {
+   RangeScan r = {true, false};
+   for (size_t i = 0; i < np; i++) {
+      const int a = (int)lo[i], b = (int)hi[i];
+      if (!(lo[i] == lo[i]) || !(hi[i] == hi[i]) || a > b || a < emin || b > emax) { r.ok = false; return r; }
+      if (a != emin || b != emax) r.ragged = true;
+   }
+   return r;
+}
+
+extern "C" int mgmb200_costvolume_ranges(mgmb200_ctx *c, const float *u, const float *v, int nx, int ny, int nch,
+                                         int vnx, int vny, const float *dminI, const float *dmaxI, int emin, int emax,
+                                         const char *prefilter, const char *distance, float truncDist, int win,
+                                         float *cc_out) {
+   if (!c || !u || !v || !dminI || !dmaxI || !cc_out) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, emin, emax));
+   const size_t np = (size_t)nx * ny;
+   if (!scan_ranges(dminI, dmaxI, np, emin, emax).ok)
+      return fail(MGMB200_EINVAL, "a disparity range is empty, NaN or outside the envelope [%d,%d]", emin, emax);
+   CU(cudaSetDevice(c->device));
+   int pf = mgmb200_prefilter_index(prefilter), di = mgmb200_distance_index(distance);
+   if (di == DIST_CENSUS) pf = PF_CENSUS;
+   const int L = emax - emin + 1, VS = mgmb200_padded_labels(L);
+   RET(upload(c, c->u, u, np * nch * 4));
+   RET(upload(c, c->v, v, (size_t)vnx * vny * nch * 4));
+   RET(upload(c, c->rg[0], dminI, np * 4));
+   RET(upload(c, c->rg[1], dmaxI, np * 4));
+   RET(c->cc.reserve(np * VS * 4));
+   RET(costvolume_dev_impl(c, c->u.as<float>(), c->v.as<float>(), nx, ny, nch, vnx, vny, emin, emax, pf, di, truncDist,
+                           win, c->rg[0].as<float>(), c->rg[1].as<float>(), c->cc.as<float>()));
+   if (VS == L) {
+      RET(download(c, cc_out, c->cc.p, np * L * 4));
+   } else {
+      RET(c->dense.reserve(np * L * 4));
+      CU(unpad_volume_launch(c->cc.as<float>(), c->dense.as<float>(), (long long)np, L, VS, c->stream));
+      RET(download(c, cc_out, c->dense.p, np * L * 4));
+   }
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+
+extern "C" int mgmb200_mgm_ranges(mgmb200_ctx *c, const float *cc, const float *ccmin, const float *ccmax,
+                                  const float *w, int nx, int ny, int emin, int emax, const float *dminI,
+                                  const float *dmaxI, float P1, float P2, int NDIR, int K, int felz, int fix,
+                                  float *out, float *outcost, float *S_out) {
+   if (!c || !cc || !ccmin || !ccmax || !dminI || !dmaxI || !out || !outcost) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, emin, emax));
+   const int L = emax - emin + 1, VS = mgmb200_padded_labels(L);
+   const size_t np = (size_t)nx * ny;
+   const RangeScan rc = scan_ranges(ccmin, ccmax, np, emin, emax), rs = scan_ranges(dminI, dmaxI, np, emin, emax);
+   if (!rc.ok || !rs.ok)
+      return fail(MGMB200_EINVAL, "a disparity range is empty, NaN or outside the envelope [%d,%d]", emin, emax);
+   bool weighted = false;
+   if (w) for (size_t i = 0; i < np * 8 && !weighted; i++) weighted = (w[i] != 1.0f);
+   // Truncated-linear potentials convolve inside the RECEIVING pixel's range (mgm_core.cc:229-281); only the
+   // two-neighbour unweighted variant folds the rest back in (FixBounrady..., :166-186, :197-219) and thereby
+   // equals the dense-envelope result.  The other variants with non-uniform ranges are not implemented.
+   if (felz && rc.ragged && !(K == 2 && !weighted))
+      return fail(MGMB200_EUNSUPPORTED, "truncated-linear potentials with per-pixel cost ranges need TSGM=2 without "
+                                        "image-dependent weights");
+   CU(cudaSetDevice(c->device));
+   RET(upload(c, c->rg[0], ccmin, np * 4));
+   RET(upload(c, c->rg[1], ccmax, np * 4));
+   RET(upload(c, c->rg[2], dminI, np * 4));
+   RET(upload(c, c->rg[3], dmaxI, np * 4));
+   // dense envelope -> padded volume, entries outside the cost ranges forced to +INF, preconditions checked
+   RET(c->cc.reserve(np * VS * 4));
+   RET(upload(c, c->dense, cc, np * L * 4));
+   CU(pad_volume_launch(c->dense.as<float>(), c->cc.as<float>(), (long long)np, L, VS, 0, c->stream));
+   CU(mask_volume_launch(c->cc.as<float>(), (long long)np, L, VS, emin, c->rg[0].as<float>(), c->rg[1].as<float>(),
+                         c->stream));
+   RET(clear_flags(c));
+   CU(validate_volume_launch(c->cc.as<float>(), (long long)np, L, VS, c->flags.as<int>(), c->num_sms, c->stream));
+   int fl = 0;
+   RET(read_flags(c, &fl));
+   if (fl)
+      return fail(MGMB200_EUNSUPPORTED, "cost volume outside the supported envelope:%s%s%s",
+                  (fl & 1) ? " a pixel without any finite cost" : "", (fl & 2) ? " NaN cost" : "",
+                  (fl & 4) ? " -INF cost" : "");
+   if (w) RET(upload(c, c->w, w, np * 8 * 4));
+   RET(c->out.reserve(np * 4));
+   RET(c->outcost.reserve(np * 4));
+   float *dS = nullptr;
+   if (S_out) { RET(c->dense.reserve(np * L * 4)); dS = c->dense.as<float>(); }
+   c->r_ccmin = c->rg[0].as<float>(); c->r_ccmax = c->rg[1].as<float>();
+   c->r_smin = c->rg[2].as<float>(); c->r_smax = c->rg[3].as<float>();
+   const int rc2 = mgmb200_aggregate_dev(c, c->cc.as<float>(), w ? c->w.as<float>() : nullptr, w ? 2 : 0, nx, ny, emin,
+                                         emax, P1, P2, NDIR, K, felz, fix, 0, c->out.as<float>(), c->outcost.as<float>(), dS);
+   c->r_ccmin = c->r_ccmax = c->r_smin = c->r_smax = nullptr;
+   if (rc2) return rc2;
+   RET(download(c, out, c->out.p, np * 4));
+   RET(download(c, outcost, c->outcost.p, np * 4));
+   if (S_out) RET(download(c, S_out, dS, np * L * 4));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+
+extern "C" int mgmb200_subpixel_refinement_sgm_ranges(mgmb200_ctx *c, const float *S, const float *dminI,
+                                                      const float *dmaxI, int nx, int ny, int emin, int emax,
+                                                      float *out, float *outcost, const char *refinement) {
+   if (!c || !S || !dminI || !dmaxI || !out || !outcost) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, emin, emax));
+   const int m = mgmb200_refinement_index(refinement);
+   if (m == 0) return 0;
+   const int L = emax - emin + 1;
+   const size_t np = (size_t)nx * ny;
+   if (!scan_ranges(dminI, dmaxI, np, emin, emax).ok)
+      return fail(MGMB200_EINVAL, "a disparity range is empty, NaN or outside the envelope [%d,%d]", emin, emax);
+   CU(cudaSetDevice(c->device));
+   RET(upload(c, c->dense, S, np * L * 4));
+   RET(upload(c, c->out, out, np * 4));
+   RET(upload(c, c->outcost, outcost, np * 4));
+   RET(upload(c, c->rg[2], dminI, np * 4));
+   RET(upload(c, c->rg[3], dmaxI, np * 4));
+   CU(refine_launch(c->dense.as<float>(), (long long)np, L, emin, m, c->rg[2].as<float>(), c->rg[3].as<float>(),
+                    c->out.as<float>(), c->outcost.as<float>(), c->stream));
    RET(download(c, out, c->out.p, np * 4));
    RET(download(c, outcost, c->outcost.p, np * 4));
    CU(cudaStreamSynchronize(c->stream));

@@ -194,8 +194,12 @@ __device__ __forceinline__ float cell_cost(const CostArgs &A, int px, int py, in
 }
 
 // ------------------------------------------------------------------ K2 cost volume: one warp per pixel
+// rlo/rhi (optional): per-pixel disparity ranges as float images, truncated to int like Dvec::init
+// (mgm_costvolume.h:323); labels outside a pixel's range do not exist in the reference: +INF here.
 template <int DIST>
 __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, int dmin, int L, int VS, float cap,
+                                                             const float *__restrict__ rlo,
+                                                             const float *__restrict__ rhi,
                                                              float *__restrict__ cc) {
    const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const long long np = (long long)A.nx * A.ny;
@@ -210,6 +214,11 @@ __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, i
       const int x = (int)(p % A.nx), y = (int)(p / A.nx);
       float4 *dst = reinterpret_cast<float4 *>(cc + (size_t)p * VS);
       bool anyfinite = false;
+      int klo = 0, khi = L - 1;   // the pixel's own range, as label indices of the dense envelope
+      if (rlo) {
+         klo = max((int)rlo[p] - dmin, 0);
+         khi = min((int)rhi[p] - dmin, L - 1);
+      }
       if (fast) {
          uint32_t lw[4] = {0u, 0u, 0u, 0u};     // left census words, or the bits of the left channel values
          const uint32_t *rrow[4] = {nullptr, nullptr, nullptr, nullptr};   // right image row, per channel / word
@@ -232,8 +241,8 @@ __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, i
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                const int k = q * 4 + j;
-               float e = MGM_INF;   // padding labels
-               if (k < L) {
+               float e = MGM_INF;   // padding labels, labels outside the pixel's range
+               if (k >= klo && k <= khi) {
                   const int qx = qx0 + k;
                   e = cap;
                   if (vy_ok && (unsigned)qx < (unsigned)A.vnx) {
@@ -265,8 +274,8 @@ __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, i
 #pragma unroll
          for (int j = 0; j < 4; ++j) {
             const int k = q * 4 + j;
-            float e = MGM_INF;   // padding labels
-            if (k < L) {
+            float e = MGM_INF;   // padding labels, labels outside the pixel's range
+            if (k >= klo && k <= khi) {
                const int qx = x + dmin + k;
                e = cap;   // truncDist * nch' when the match falls outside v (mgm_costvolume.h:398-400)
                if (qx >= 0 && qx < A.vnx && y < A.vny) e = cell_cost<DIST>(A, x, y, qx, y);
@@ -280,8 +289,8 @@ __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, i
       if (!__any_sync(0xffffffffu, anyfinite)) {   // no valid hypothesis: all costs become 0 (:414-421)
          for (int q = lane; q < nq; q += 32) {
             const int k = q * 4;
-            dst[q] = make_float4(k < L ? 0.f : MGM_INF, k + 1 < L ? 0.f : MGM_INF, k + 2 < L ? 0.f : MGM_INF,
-                                 k + 3 < L ? 0.f : MGM_INF);
+            auto z = [&](int kk) { return (kk >= klo && kk <= khi) ? 0.f : MGM_INF; };
+            dst[q] = make_float4(z(k), z(k + 1), z(k + 2), z(k + 3));
          }
       }
    }
@@ -305,6 +314,16 @@ __global__ void mgm_unpad_volume_kernel(const float *__restrict__ src, float *__
    const long long p = i / L;
    const int o = (int)(i - p * L);
    dst[i] = src[p * VS + o];
+}
+
+// entries of a padded volume outside the per-pixel range [rlo,rhi] become +INF (they do not exist in a Dvec)
+__global__ void mgm_mask_volume_kernel(float *__restrict__ cc, long long npix, int L, int VS, int dmin,
+                                       const float *__restrict__ rlo, const float *__restrict__ rhi) {
+   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= npix * VS) return;
+   const long long p = i / VS;
+   const int k = (int)(i - p * VS);
+   if (k < L && (k < (int)rlo[p] - dmin || k > (int)rhi[p] - dmin)) cc[i] = MGM_INF;
 }
 
 // flags: bit0 a vector without any finite entry, bit1 NaN, bit2 -INF (fast-path preconditions)
@@ -391,7 +410,8 @@ cudaError_t gblur_launch(const float *d_u, int nx, int ny, int nch, float sigma,
 
 cudaError_t costvolume_launch(int dist, const float *d_u, const float *d_v, const uint32_t *d_cu,
                               const uint32_t *d_cv, int nx, int ny, int vnx, int vny, int nch, int win, int dmin,
-                              int L, int VS, float truncDist, float *d_cc, int num_sms, cudaStream_t st) {
+                              int L, int VS, float truncDist, const float *d_rlo, const float *d_rhi, float *d_cc,
+                              int num_sms, cudaStream_t st) {
    CostArgs A;
    A.u = d_u; A.v = d_v; A.cu = d_cu; A.cv = d_cv;
    A.nx = nx; A.ny = ny; A.vnx = vnx; A.vny = vny; A.nch = nch; A.win = win;
@@ -401,12 +421,12 @@ cudaError_t costvolume_launch(int dist, const float *d_u, const float *d_v, cons
    unsigned grid = (unsigned)((want < (long long)num_sms * 16) ? want : (long long)num_sms * 16);
    if (grid < 1) grid = 1;
    switch (dist) {
-   case DIST_AD: mgm_costvolume_kernel<DIST_AD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_cc); break;
-   case DIST_SD: mgm_costvolume_kernel<DIST_SD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_cc); break;
-   case DIST_CENSUS: mgm_costvolume_kernel<DIST_CENSUS><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_cc); break;
-   case DIST_NCC: mgm_costvolume_kernel<DIST_NCC><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_cc); break;
-   case DIST_BTAD: mgm_costvolume_kernel<DIST_BTAD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_cc); break;
-   default: mgm_costvolume_kernel<DIST_BTSD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_cc); break;
+   case DIST_AD: mgm_costvolume_kernel<DIST_AD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, d_cc); break;
+   case DIST_SD: mgm_costvolume_kernel<DIST_SD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, d_cc); break;
+   case DIST_CENSUS: mgm_costvolume_kernel<DIST_CENSUS><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, d_cc); break;
+   case DIST_NCC: mgm_costvolume_kernel<DIST_NCC><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, d_cc); break;
+   case DIST_BTAD: mgm_costvolume_kernel<DIST_BTAD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, d_cc); break;
+   default: mgm_costvolume_kernel<DIST_BTSD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, d_cc); break;
    }
    return cudaGetLastError();
 }
@@ -419,6 +439,11 @@ cudaError_t pad_volume_launch(const float *d_src, float *d_dst, long long npix, 
 }
 cudaError_t unpad_volume_launch(const float *d_src, float *d_dst, long long npix, int L, int VS, cudaStream_t st) {
    mgm_unpad_volume_kernel<<<blocks_for(npix * L, 256), 256, 0, st>>>(d_src, d_dst, npix, L, VS);
+   return cudaGetLastError();
+}
+cudaError_t mask_volume_launch(float *d_cc, long long npix, int L, int VS, int dmin, const float *d_rlo,
+                               const float *d_rhi, cudaStream_t st) {
+   mgm_mask_volume_kernel<<<blocks_for(npix * VS, 256), 256, 0, st>>>(d_cc, npix, L, VS, dmin, d_rlo, d_rhi);
    return cudaGetLastError();
 }
 cudaError_t validate_volume_launch(const float *d_cc, long long npix, int L, int VS, int *d_flags, int num_sms,

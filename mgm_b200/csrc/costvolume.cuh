@@ -23,7 +23,10 @@ cudaError_t gblur_launch(const float *d_u, int nx, int ny, int nch, float sigma,
                          cudaStream_t st);
 cudaError_t costvolume_launch(int dist, const float *d_u, const float *d_v, const uint32_t *d_cu,
                               const uint32_t *d_cv, int nx, int ny, int vnx, int vny, int nch, int win, int dmin,
-                              int L, int VS, float truncDist, float *d_cc, int num_sms, cudaStream_t st);
+                              int L, int VS, float truncDist, const float *d_rlo, const float *d_rhi, float *d_cc,
+                              int num_sms, cudaStream_t st);
+cudaError_t mask_volume_launch(float *d_cc, long long npix, int L, int VS, int dmin, const float *d_rlo,
+                               const float *d_rhi, cudaStream_t st);
 cudaError_t pad_volume_launch(const float *d_src, float *d_dst, long long npix, int L, int VS, int label_major,
                               cudaStream_t st);
 cudaError_t unpad_volume_launch(const float *d_src, float *d_dst, long long npix, int L, int VS, cudaStream_t st);

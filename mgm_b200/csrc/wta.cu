@@ -87,6 +87,11 @@ __global__ void __launch_bounds__(256) mgm_wta_kernel(const WtaParams P) {
       float best = MGM_INF;
       int besto = -1;
       const size_t base = (size_t)pix * P.VS;
+      // per-pixel ranges as label indices (defaults: the whole envelope)
+      int slo = 0, shi = P.L - 1, clo = 0, chi = P.L - 1;
+      if (P.smin) { slo = (int)P.smin[pix] - P.dmin; shi = (int)P.smax[pix] - P.dmin; }
+      if (P.ccmin) { clo = (int)P.ccmin[pix] - P.dmin; chi = (int)P.ccmax[pix] - P.dmin; }
+      const bool ranged = (P.smin != nullptr) || (P.ccmin != nullptr);
       for (int q = lane; q < nq; q += 32) {
          const size_t off = base + (size_t)q * 4;
          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -95,10 +100,24 @@ __global__ void __launch_bounds__(256) mgm_wta_kernel(const WtaParams P) {
             const float4 l = __ldcs(reinterpret_cast<const float4 *>(P.ldir[p] + off));
             s.x += l.x; s.y += l.y; s.z += l.z; s.w += l.w;
          }
+         if (ranged) {   // S is only incremented inside the cost vector's range: it stays 0 elsewhere
+            const int o0 = q * 4;
+            if (o0 + 0 < clo || o0 + 0 > chi) s.x = 0.f;
+            if (o0 + 1 < clo || o0 + 1 > chi) s.y = 0.f;
+            if (o0 + 2 < clo || o0 + 2 > chi) s.z = 0.f;
+            if (o0 + 3 < clo || o0 + 3 > chi) s.w = 0.f;
+         }
          if (P.fix) {   // mgm_core.cc:598-599
             const float4 c = __ldcs(reinterpret_cast<const float4 *>(P.cc + off));
             s.x = s.x - fixmul * c.x; s.y = s.y - fixmul * c.y;
             s.z = s.z - fixmul * c.z; s.w = s.w - fixmul * c.w;
+         }
+         if (ranged) {   // labels outside S's range do not exist: they read as +INF and never win
+            const int o0 = q * 4;
+            if (o0 + 0 < slo || o0 + 0 > shi) s.x = MGM_INF;
+            if (o0 + 1 < slo || o0 + 1 > shi) s.y = MGM_INF;
+            if (o0 + 2 < slo || o0 + 2 > shi) s.z = MGM_INF;
+            if (o0 + 3 < slo || o0 + 3 > shi) s.w = MGM_INF;
          }
          *reinterpret_cast<float4 *>(sS + q * 4) = s;
          if (P.S_out) {
@@ -134,7 +153,7 @@ __global__ void __launch_bounds__(256) mgm_wta_kernel(const WtaParams P) {
             minP = (float)o;
             if (P.refine != 0) {
                const int oi = (int)minP;   // mgm_refine.h:57
-               if (oi - 1 >= P.dmin && oi + 2 <= P.dmin + P.L - 1) {
+               if (oi - 1 >= P.dmin + slo && oi + 2 <= P.dmin + shi) {   // S[i].min / S[i].max, mgm_refine.h:58
                   const float *v = sS + (besto - 1);
                   float dx = 0.f;
                   if (P.refine == 1) fit_vshape(v, &minL, &dx);
@@ -156,13 +175,15 @@ __global__ void __launch_bounds__(256) mgm_wta_kernel(const WtaParams P) {
 // (subpixel_refinement_sgm mgm_refine.h:40-70, for callers that keep the reference's
 // two-call sequence mgm() -> refine()).
 __global__ void mgm_refine_kernel(const float *__restrict__ S, long long npix, int L, int dmin, int method,
+                                  const float *__restrict__ smin, const float *__restrict__ smax,
                                   float *__restrict__ out, float *__restrict__ outcost) {
    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= npix) return;
    float minP = out[i], minL = outcost[i];
    if (minP != minP) return;   // no finite label (undefined in the reference)
    const int o = (int)minP;
-   if (o - 1 >= dmin && o + 2 <= dmin + L - 1) {
+   const int lo = smin ? (int)smin[i] : dmin, hi = smax ? (int)smax[i] : dmin + L - 1;
+   if (o - 1 >= lo && o + 2 <= hi) {
       const float *s = S + (size_t)i * L + (o - dmin);
       const float v[4] = {s[-1], s[0], s[1], s[2]};
       float dx = 0.f;
@@ -176,9 +197,10 @@ __global__ void mgm_refine_kernel(const float *__restrict__ S, long long npix, i
    outcost[i] = minL;
 }
 
-cudaError_t refine_launch(const float *d_S, long long npix, int L, int dmin, int method, float *d_out,
-                          float *d_outcost, cudaStream_t st) {
-   mgm_refine_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(d_S, npix, L, dmin, method, d_out, d_outcost);
+cudaError_t refine_launch(const float *d_S, long long npix, int L, int dmin, int method, const float *d_smin,
+                          const float *d_smax, float *d_out, float *d_outcost, cudaStream_t st) {
+   mgm_refine_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(d_S, npix, L, dmin, method, d_smin, d_smax, d_out,
+                                                                      d_outcost);
    return cudaGetLastError();
 }
 

@@ -9,7 +9,10 @@ struct WtaParams {
    const float *cc;         // matching costs [npix][VS]
    float *out;              // [npix] disparity (integer WTA label + sub-pixel offset)
    float *outcost;          // [npix]
-   float *S_out;            // optional dense [npix][L] corrected aggregated volume
+   float *S_out;            // optional dense [npix][L] corrected aggregated volume (+INF outside [smin,smax])
+   // per-pixel ranges (optional), float images truncated to int like Dvec::init:
+   const float *smin, *smax;     // range of the output volume S = the dminI/dmaxI arguments of mgm() (mgm_core.cc:408)
+   const float *ccmin, *ccmax;   // range of the cost vectors: S is only incremented there (mgm_core.cc:582-587)
    long long pix_begin, pix_end;
    int ndir, L, VS, dmin;
    int fix;                 // SGM_FIX_OVERCOUNT
@@ -17,7 +20,7 @@ struct WtaParams {
 };
 
 cudaError_t wta_launch(const WtaParams &P, int num_sms, cudaStream_t st);
-cudaError_t refine_launch(const float *d_S, long long npix, int L, int dmin, int method, float *d_out,
-                          float *d_outcost, cudaStream_t st);
+cudaError_t refine_launch(const float *d_S, long long npix, int L, int dmin, int method, const float *d_smin,
+                          const float *d_smax, float *d_out, float *d_outcost, cudaStream_t st);
 
 }  // namespace mgm

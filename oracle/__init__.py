@@ -155,6 +155,59 @@ def orc_pipeline(u, v, dmin, dmax, P1=8.0, P2=32.0, NDIR=4, K=4, felz=0, fix=1, 
     return dict(out=out, outcost=outcost, S=r["S"], cc=cc, w=w, wta=r["out"])
 
 
+def _ranges(lo, hi, ny, nx):
+    lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, np.float32), (ny, nx)))
+    hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, np.float32), (ny, nx)))
+    return lo, hi
+
+
+def orc_costvolume_ranges(u, v, dminI, dmaxI, emin, emax, prefilter="none", distance="ad", truncDist=np.inf, win=3):
+    """per-pixel ranges: dense (H,W,emax-emin+1) volume, +INF outside [dminI,dmaxI]"""
+    u, nx, ny, nch = _img(u)
+    v, vnx, vny, vnch = _img(v)
+    lib = orc_lib()
+    pf = lib.orc_prefilter_index(prefilter.encode())
+    di = lib.orc_distance_index(distance.encode())
+    if pf == 1 or di == 2:
+        if di != 2:
+            raise ValueError("-p census with a non-census distance is not modelled")
+        pf, di = 1, 2
+    lo, hi = _ranges(dminI, dmaxI, ny, nx)
+    cc = np.empty((ny, nx, emax - emin + 1), np.float32)
+    rc = lib.orc_costvolume_ranges(_fp(u), _fp(v), nx, ny, nch, vnx, vny, _fp(lo), _fp(hi), emin, emax, pf, di,
+                                   ctypes.c_float(truncDist), win, _fp(cc))
+    if rc != 0:
+        raise ValueError("orc_costvolume_ranges: unsupported combination (%d)" % rc)
+    return cc
+
+
+def orc_mgm_ranges(cc, ccmin, ccmax, w, emin, smin, smax, P1, P2, NDIR, K, felz=0, fix=1):
+    cc = np.ascontiguousarray(cc, np.float32)
+    ny, nx, L = cc.shape
+    clo, chi = _ranges(ccmin, ccmax, ny, nx)
+    slo, shi = _ranges(smin, smax, ny, nx)
+    if w is not None:
+        w = np.ascontiguousarray(w, np.float32)
+    out = np.empty((ny, nx), np.float32)
+    outcost = np.empty((ny, nx), np.float32)
+    S = np.empty_like(cc)
+    orc_lib().orc_mgm_ranges(_fp(cc), _fp(clo), _fp(chi), _fp(w), nx, ny, L, emin, _fp(slo), _fp(shi),
+                             ctypes.c_float(P1), ctypes.c_float(P2), NDIR, K, felz, fix, _fp(out), _fp(outcost), _fp(S))
+    return dict(out=out, outcost=outcost, S=S)
+
+
+def orc_refine_ranges(S, smin, smax, emin, out, outcost, refinement="none"):
+    S = np.ascontiguousarray(S, np.float32)
+    ny, nx, L = S.shape
+    slo, shi = _ranges(smin, smax, ny, nx)
+    out = np.array(out, np.float32, copy=True)
+    outcost = np.array(outcost, np.float32, copy=True)
+    lib = orc_lib()
+    lib.orc_refine_ranges(_fp(S), _fp(slo), _fp(shi), nx, ny, emin, L, _fp(out), _fp(outcost),
+                          lib.orc_refinement_index(refinement.encode()))
+    return out, outcost
+
+
 def orc_scan_preds(p, nx=9, ny=7):
     o = (ctypes.c_int * 8)()
     orc_lib().orc_pass_scan_preds(p, nx, ny, o)
@@ -216,3 +269,42 @@ def ref_pipeline(u, v, dmin, dmax, P1=8.0, P2=32.0, NDIR=4, K=4, felz=0, fix=1, 
                                   refinement.encode(), _fp(out), _fp(outcost), times)
     return dict(out=out, outcost=outcost, times=dict(weights=times[0], costvolume=times[1], mgm=times[2],
                                                      refine=times[3]))
+
+
+def ref_costvolume_ranges(u, v, dminI, dmaxI, emin, emax, prefilter="none", distance="ad", truncDist=np.inf, win=3,
+                          flavour=""):
+    u, nx, ny, nch = _img(u)
+    v, vnx, vny, vnch = _img(v)
+    lo, hi = _ranges(dminI, dmaxI, ny, nx)
+    cc = np.empty((ny, nx, emax - emin + 1), np.float32)
+    ref_lib(flavour).ref_costvolume_ranges(_fp(u), _fp(v), nx, ny, nch, vnx, vny, _fp(lo), _fp(hi), emin, emax,
+                                           prefilter.encode(), distance.encode(), ctypes.c_float(truncDist), win, _fp(cc))
+    return cc
+
+
+def ref_mgm_ranges(cc, ccmin, ccmax, w, emin, smin, smax, P1, P2, NDIR, K, felz=0, fix=1, flavour=""):
+    cc = np.ascontiguousarray(cc, np.float32)
+    ny, nx, L = cc.shape
+    clo, chi = _ranges(ccmin, ccmax, ny, nx)
+    slo, shi = _ranges(smin, smax, ny, nx)
+    if w is not None:
+        w = np.ascontiguousarray(w, np.float32)
+    out = np.empty((ny, nx), np.float32)
+    outcost = np.empty((ny, nx), np.float32)
+    S = np.empty_like(cc)
+    lib = ref_lib(flavour)
+    lib.ref_mgm_ranges.restype = ctypes.c_double
+    lib.ref_mgm_ranges(_fp(cc), _fp(clo), _fp(chi), _fp(w), nx, ny, emin, emin + L - 1, _fp(slo), _fp(shi),
+                       ctypes.c_float(P1), ctypes.c_float(P2), NDIR, K, felz, fix, _fp(out), _fp(outcost), _fp(S))
+    return dict(out=out, outcost=outcost, S=S)
+
+
+def ref_refine_ranges(S, smin, smax, emin, out, outcost, refinement="none", flavour=""):
+    S = np.ascontiguousarray(S, np.float32)
+    ny, nx, L = S.shape
+    slo, shi = _ranges(smin, smax, ny, nx)
+    out = np.array(out, np.float32, copy=True)
+    outcost = np.array(outcost, np.float32, copy=True)
+    ref_lib(flavour).ref_refine_ranges(_fp(S), _fp(slo), _fp(shi), nx, ny, emin, emin + L - 1, _fp(out), _fp(outcost),
+                                       refinement.encode())
+    return out, outcost

@@ -182,4 +182,59 @@ void ref_pipeline(const float *u, const float *v, int nx, int ny, int nch, int d
    }
 }
 
+// ---------------------------------------------------------------- per-pixel disparity ranges
+// Volumes cross the harness as DENSE arrays over an envelope [emin, emax] (Le labels per pixel); a pixel's Dvec
+// only holds [min_i, max_i]: entries outside are ignored on input and read back as +INF (Dvec::operator[]).
+// Range images are floats, truncated by Dvec::init like in the reference (mgm_costvolume.h:323).
+static costvolume_t volume_from_dense(const float *cc, Img &lo, Img &hi, int emin, int Le) {
+   costvolume_t CC = allocate_costvolume(lo, hi);
+   int npix = lo.nx * lo.ny;
+   for (int i = 0; i < npix; i++)
+      for (int o = CC[i].min; o <= CC[i].max; o++)
+         if (o >= emin && o < emin + Le) CC[i].set_nolock(o, cc[(size_t)i * Le + (o - emin)]);
+   return CC;
+}
+
+void ref_costvolume_ranges(const float *u, const float *v, int nx, int ny, int nch, int vnx, int vny,
+                           const float *dminI, const float *dmaxI, int emin, int emax, const char *prefilter,
+                           const char *distance, float truncDist, int census_ncc_win, float *cc_out) {
+   harness_value_CENSUS_NCC_WIN = census_ncc_win;
+   Img U = make_img(u, nx, ny, nch), V = make_img(v, vnx, vny, nch);
+   Img lo = make_img(dminI, nx, ny, 1), hi = make_img(dmaxI, nx, ny, 1);
+   costvolume_t CC = allocate_and_fill_sgm_costvolume(U, V, lo, hi, (char *)prefilter, (char *)distance, truncDist);
+   volume_to_flat(CC, cc_out, nx * ny, emin, emax - emin + 1);
+}
+
+// mgm() with a cost volume whose vectors have the ranges [ccmin, ccmax] and an output volume with the ranges
+// [smin, smax] (the dminI/dmaxI arguments of mgm_core.cc:408-413; different from the former when TSGM_ITER > 1)
+double ref_mgm_ranges(const float *cc, const float *ccmin, const float *ccmax, const float *w, int nx, int ny,
+                      int emin, int emax, const float *smin, const float *smax, float P1, float P2, int NDIR,
+                      int MGM, int felz, int fix, float *out, float *outcost, float *S_out) {
+   int Le = emax - emin + 1;
+   Img clo = make_img(ccmin, nx, ny, 1), chi = make_img(ccmax, nx, ny, 1);
+   Img slo = make_img(smin, nx, ny, 1), shi = make_img(smax, nx, ny, 1);
+   Img W = make_img(w, nx, ny, 8);
+   if (!w) for (size_t i = 0; i < W.data.size(); i++) W[i] = 1.0f;
+   costvolume_t CC = volume_from_dense(cc, clo, chi, emin, Le);
+   Img o(nx, ny), oc(nx, ny);
+   QuietStdout quiet;
+   auto t0 = std::chrono::steady_clock::now();
+   costvolume_t S = mgm(CC, W, slo, shi, &o, &oc, P1, P2, NDIR, MGM, felz, fix);
+   auto t1 = std::chrono::steady_clock::now();
+   memcpy(out, &o.data[0], sizeof(float) * (size_t)nx * ny);
+   memcpy(outcost, &oc.data[0], sizeof(float) * (size_t)nx * ny);
+   if (S_out) volume_to_flat(S, S_out, nx * ny, emin, Le);
+   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+void ref_refine_ranges(const float *S, const float *smin, const float *smax, int nx, int ny, int emin, int emax,
+                       float *out, float *outcost, const char *refinement) {
+   Img slo = make_img(smin, nx, ny, 1), shi = make_img(smax, nx, ny, 1);
+   costvolume_t SS = volume_from_dense(S, slo, shi, emin, emax - emin + 1);
+   std::vector<float> o(out, out + (size_t)nx * ny), oc(outcost, outcost + (size_t)nx * ny);
+   subpixel_refinement_sgm(SS, o, oc, (char *)refinement);
+   memcpy(out, &o[0], sizeof(float) * o.size());
+   memcpy(outcost, &oc[0], sizeof(float) * oc.size());
+}
+
 }  // extern "C"

@@ -192,6 +192,51 @@ def test_sweep_sharding_api_single_gpu(ctx):
     assert same(dout.cpu().numpy(), ro) and same(dcost.cpu().numpy(), rc)
 
 
+# ------------------------------------------------------------------------------------------ per-pixel ranges
+def _ragged(nx, ny, emin, emax, seed):
+    rng = np.random.default_rng(seed)
+    lo = rng.integers(emin, emin + 6, (ny, nx)).astype(np.float32)
+    hi = (lo + rng.integers(3, 9, (ny, nx))).clip(max=emax).astype(np.float32)
+    return lo, hi
+
+
+def test_ranges_costvolume_mgm_refine(ctx):
+    """dminI / dmaxI images: cost volume, aggregation of the INF-masked dense volume, WTA over a
+    second set of ranges (as from the second TSGM_ITER iteration on), refinement -- bit-exact against the oracle"""
+    import mgm_b200
+    nx, ny, emin, emax = 67, 41, -20, 5
+    u, v = synth_pair(nx, ny, 22, seed=3, nch=1)
+    lo, hi = _ragged(nx, ny, emin, emax, 1)
+    for dist in ["ad", "census", "ncc"]:
+        assert same(ctx.costvolume_ranges(u, v, lo, hi, emin, emax, "none", dist, np.inf, 3),
+                    O.orc_costvolume_ranges(u, v, lo, hi, emin, emax, "none", dist, np.inf, 3)), dist
+    cc = O.orc_costvolume_ranges(u, v, lo, hi, emin, emax, "none", "ad", np.inf, 3)
+    srs = [(lo, hi), (lo + 1, np.maximum(hi - 1, lo + 1)), (np.maximum(lo - 2, emin), np.minimum(hi + 2, emax))]
+    cases = [(K, 0, wt) for K in (1, 2, 3, 4) for wt in (0, 1)] + [(2, 1, 0)]
+    for (K, felz, weighted), fix in itertools.product(cases, [0, 1]):
+        w = synth_weights(nx, ny, seed=K) if weighted else None
+        P1, P2 = (8, 32) if not felz else (2, 20000)
+        for slo, shi in srs:
+            r = ctx.mgm_ranges(cc, lo, hi, w, emin, slo, shi, P1, P2, 8, K, felz, fix)
+            o = O.orc_mgm_ranges(cc, lo, hi, w, emin, slo, shi, P1, P2, 8, K, felz, fix)
+            tag = (K, felz, weighted, fix, mism(r["S"], o["S"]), mism(r["out"], o["out"]))
+            assert same(r["S"], o["S"]), tag
+            assert same(r["out"], o["out"]) and same(r["outcost"], o["outcost"]), tag
+            a = ctx.subpixel_refinement_sgm_ranges(o["S"], slo, shi, emin, o["out"], o["outcost"], "vfit")
+            b = O.orc_refine_ranges(o["S"], slo, shi, emin, o["out"], o["outcost"], "vfit")
+            assert same(a[0], b[0]) and same(a[1], b[1]), tag
+    # uniform ranges through the same entry point == the plain call; truncated linear with TSGM=3 needs uniform ranges
+    full_lo, full_hi = np.full((ny, nx), emin, np.float32), np.full((ny, nx), emax, np.float32)
+    ccu = O.orc_costvolume(u, v, emin, emax, "none", "ad", np.inf, 3)
+    r = ctx.mgm_ranges(ccu, full_lo, full_hi, None, emin, full_lo, full_hi, 2, 20000, 8, 3, 1, 1)
+    o = O.orc_mgm(ccu, None, emin, 2, 20000, 8, 3, 1, 1)
+    assert same(r["S"], o["S"]) and same(r["out"], o["out"])
+    with pytest.raises(mgm_b200.MgmError):
+        ctx.mgm_ranges(cc, lo, hi, None, emin, lo, hi, 2, 20000, 8, 3, 1, 1)
+    with pytest.raises(mgm_b200.MgmError):
+        ctx.mgm_ranges(cc, hi, lo, None, emin, lo, hi, 8, 32, 8, 2, 0, 1)   # empty ranges
+
+
 # ------------------------------------------------------------------------------------------ golden vectors
 @pytest.mark.parametrize("path", golden_files("pipeline"))
 def test_golden_pipeline(ctx, path):

@@ -138,3 +138,36 @@ def test_port_pipeline_vs_ref():
         a = O.orc_pipeline(u, v, -19, 0, **kw)
         b = O.ref_pipeline(u, v, -19, 0, **kw)
         assert same(a["out"], b["out"]) and same(a["outcost"], b["outcost"]), kw
+
+
+def _ragged(nx, ny, emin, emax, seed):
+    rng = np.random.default_rng(seed)
+    lo = rng.integers(emin, emin + 6, (ny, nx)).astype(np.float32)
+    hi = (lo + rng.integers(3, 9, (ny, nx))).clip(max=emax).astype(np.float32)
+    return lo, hi
+
+
+@needs_ref
+def test_port_ranges_vs_ref():
+    """per-pixel disparity ranges: cost volume, every message update variant, WTA restricted to a
+    second set of ranges (shrunk, and grown beyond the cost ranges as update_dmin_dmax does), refinement"""
+    nx, ny, emin, emax = 31, 19, -12, 3
+    u, v = synth_pair(nx, ny, 14, seed=3, nch=1)
+    lo, hi = _ragged(nx, ny, emin, emax, 0)
+    for dist in ["ad", "census", "ncc", "btsd"]:
+        assert same(O.orc_costvolume_ranges(u, v, lo, hi, emin, emax, "none", dist, np.inf, 3),
+                    O.ref_costvolume_ranges(u, v, lo, hi, emin, emax, "none", dist, np.inf, 3)), dist
+    cc = O.ref_costvolume_ranges(u, v, lo, hi, emin, emax, "none", "ad", np.inf, 3)
+    srs = [(lo, hi), (lo + 1, np.maximum(hi - 1, lo + 1)), (np.maximum(lo - 2, emin), np.minimum(hi + 2, emax))]
+    for K, felz, weighted, fix in itertools.product([1, 2, 3, 4], [0, 1], [0, 1], [0, 1]):
+        w = synth_weights(nx, ny, seed=K) if weighted else None
+        P1, P2 = (8, 32) if not felz else (2, 20000)
+        for slo, shi in srs:
+            a = O.orc_mgm_ranges(cc, lo, hi, w, emin, slo, shi, P1, P2, 8, K, felz, fix)
+            b = O.ref_mgm_ranges(cc, lo, hi, w, emin, slo, shi, P1, P2, 8, K, felz, fix)
+            ok = np.isfinite(b["outcost"])   # the reference leaves the label uninitialised when nothing is finite
+            assert same(a["S"], b["S"]) and same(a["outcost"], b["outcost"]), (K, felz, weighted, fix)
+            assert same(a["out"][ok], b["out"][ok]), (K, felz, weighted, fix)
+            ra = O.orc_refine_ranges(a["S"], slo, shi, emin, b["out"], b["outcost"], "vfit")
+            rb = O.ref_refine_ranges(b["S"], slo, shi, emin, b["out"], b["outcost"], "vfit")
+            assert same(ra[0][ok], rb[0][ok]) and same(ra[1][ok], rb[1][ok])
