@@ -621,7 +621,7 @@ static RangeScan scan_ranges(const float *lo, const float *hi, size_t np, int em
    for (size_t i = 0; i < np; i++) {
       const int a = (int)lo[i], b = (int)hi[i];
       if (!(lo[i] == lo[i]) || !(hi[i] == hi[i]) || a > b || a < emin || b > emax) { r.ok = false; return r; }
-      if (a != emin || b != emax) r.ragged = true;
+      if (a != (int)lo[0] || b != (int)hi[0]) r.ragged = true;   // ragged = the pixels do not all have the same range
    }
    return r;
 }

@@ -2,8 +2,10 @@
 // outputs as the reference CLI (mgm.cc:266-450), with the hot path (weights, cost volume, aggregation, WTA,
 // sub-pixel: mgm.cc:372-385 and :405-414) executed by libmgmb200 on the GPU.  The O(W*H) post-processing
 // around it (left-right test mgm.cc:68-91, median img_tools.h:203-238, back-projection mgm.cc:432-443) is
-// host code here.  Not supported yet (exit code 2 with a message, never a silent fallback): -m/-M range
-// images, TSGM_ITER > 1, WITH_MGM2, -O 16.
+// host code here.  -m/-M range images and TSGM_ITER > 1 take the call-by-call sequence of mgm.cc:372-395 (cost
+// volume, then mgm + refinement + range update per iteration) instead of the fused mgmb200_stereo.  Not supported
+// (exit code 2 or 3 with a message, never a silent fallback): -O 16, truncated-linear potentials with per-pixel
+// ranges unless TSGM=2 without weights.
 #include <algorithm>
 #include <cmath>
 
@@ -77,6 +79,49 @@ static Img median_filter(const Img &u, int radius) {
    return M;
 }
 
+// image_minmax, img_tools.h:183-200
+static std::pair<float, float> image_minmax(const Img &u) {
+   float gmin = INFINITY, gmax = -INFINITY;
+   for (float v : u.data)
+      if (std::isfinite(v)) {
+         if (v < gmin) gmin = v;
+         if (v > gmax) gmax = v;
+      }
+   return std::pair<float, float>(gmin, gmax);
+}
+
+// update_dmin_dmax, mgm.cc:120-158 (slack 3, radius 2, Neumann borders)
+static std::pair<float, float> update_dmin_dmax(const Img &outoff, Img *dminI, Img *dmaxI, int slack = 3, int radius = 2) {
+   Img dminI2(*dminI), dmaxI2(*dmaxI);
+   const int nx = outoff.nx, ny = outoff.ny;
+   const std::pair<float, float> gminmax = image_minmax(outoff);
+   const float gmin = gminmax.first, gmax = gminmax.second;
+   if (slack < 0) slack = -slack;
+   const int r = radius;
+   for (int j = 0; j < ny; j++)
+      for (int i = 0; i < nx; i++) {
+         float dmin = INFINITY, dmax = -INFINITY;
+         for (int dj = -r; dj <= r; dj++)
+            for (int di = -r; di <= r; di++) {
+               int xx = i + di, yy = j + dj;
+               xx = xx >= 0 ? xx : 0; xx = xx < nx ? xx : nx - 1;
+               yy = yy >= 0 ? yy : 0; yy = yy < ny ? yy : ny - 1;
+               const float v = outoff.data[xx + (size_t)yy * nx];
+               if (std::isfinite(v)) {
+                  dmin = fmin(dmin, v - slack);
+                  dmax = fmax(dmax, v + slack);
+               } else {
+                  dmin = fmin(dmin, gmin - slack);
+                  dmax = fmax(dmax, gmax + slack);
+               }
+            }
+         if (std::isfinite(dmin)) { dminI2[i + j * nx] = dmin; dmaxI2[i + j * nx] = dmax; }
+      }
+   *dminI = dminI2;
+   *dmaxI = dmaxI2;
+   return gminmax;
+}
+
 static const char *help_usage = "usage:\n\tmgm [-options] u v out [cost [backflow]]";
 
 int main(int argc, char *argv[]) {
@@ -125,11 +170,8 @@ int main(int argc, char *argv[]) {
 
       printf("%d %d\n", dmin, dmax);
 
-      if (strcmp(in_min_disp_file, "") != 0 || strcmp(in_max_disp_file, "") != 0) {
-         fprintf(stderr, "mgm_b200: per-pixel disparity range files (-m/-M) are not supported yet\n");
-         return 2;
-      }
-      if ((int)TSGM_ITER() != 1) { fprintf(stderr, "mgm_b200: TSGM_ITER != 1 is not supported yet\n"); return 2; }
+      const bool have_ranges = strcmp(in_min_disp_file, "") != 0;   // mgm.cc:342 tests the -m file only
+      const bool stepwise = have_ranges || (int)TSGM_ITER() != 1;
       if (WITH_MGM2()) fprintf(stderr, "mgm_b200: WITH_MGM2 ignored (the sweeps always run concurrently, summed in order)\n");
 
       Img u = io::read_image(filename_u);
@@ -154,18 +196,48 @@ int main(int argc, char *argv[]) {
       p.refinement = refine;
 
       Img outoff(u.nx, u.ny), outcost(u.nx, u.ny), outoffR(v.nx, v.ny), outcostR(v.nx, v.ny);
-      auto run = [&](Img &a, Img &b, int lo, int hi, Img &off, Img &cost) {
-         p.dmin = lo; p.dmax = hi;
-         check(mgmb200_stereo(context(), a.data.data(), b.data.data(), a.nx, a.ny, a.nch, &p, off.data.data(), cost.data.data()));
-         for (int pass = 0; pass < NDIR; pass++) printf("%d", pass);   // mgm_core.cc:491
-         printf("\n");                                                  // print_solution_energy, mgm_print_energy.h:110
+      // range images, mgm.cc:338-353 (L->R) and :366-368 (R->L: always the uniform mirrored range)
+      Img dminI(u.nx, u.ny), dmaxI(u.nx, u.ny), dminRI(v.nx, v.ny), dmaxRI(v.nx, v.ny);
+      for (int k = 0; k < u.npix; k++) { dminI[k] = dmin; dmaxI[k] = dmax; }
+      for (int k = 0; k < v.npix; k++) { dminRI[k] = -dmax; dmaxRI[k] = -dmin; }
+      if (have_ranges) {
+         dminI = io::read_image(in_min_disp_file);
+         dmaxI = io::read_image(in_max_disp_file);
+         if (dminI.npix != u.npix || dmaxI.npix != u.npix) { fprintf(stderr, "mgm_b200: range images must have the size of u\n"); return 2; }
+         remove_nonfinite_values_Img(dminI, dmin);
+         remove_nonfinite_values_Img(dmaxI, dmax);
+         for (int k = 0; k < u.npix; k++)
+            if (dmaxI[k] < dminI[k] + 1) dmaxI[k] = ceil(dminI[k] + 1);
+      }
+      auto run = [&](Img &a, Img &b, int lo, int hi, Img &off, Img &cost, Img &loI, Img &hiI) {
+         if (!stepwise) {
+            p.dmin = lo; p.dmax = hi;
+            check(mgmb200_stereo(context(), a.data.data(), b.data.data(), a.nx, a.ny, a.nch, &p, off.data.data(), cost.data.data()));
+            for (int pass = 0; pass < NDIR; pass++) printf("%d", pass);   // mgm_core.cc:491
+            printf("\n");                                                  // print_solution_energy, mgm_print_energy.h:110
+            return;
+         }
+         // mgm.cc:372-395 call by call: the cost volume keeps its ranges, every iteration aggregates, refines and
+         // updates the range images the next winner-take-all is restricted to
+         Img w = compute_mgm_weights(a, aP2, aThresh);
+         costvolume_t CC = allocate_and_fill_sgm_costvolume(a, b, loI, hiI, prefilter, distance, truncDist);
+         const float P1s = P1 * a.nch, P2s = P2 * a.nch;   // mgm.cc:356-357
+         for (int it = 0; it < (int)TSGM_ITER(); it++) {
+            costvolume_t S = mgm(CC, w, loI, hiI, &off, &cost, P1s, P2s, NDIR, (int)TSGM(),
+                                 (int)USE_TRUNCATED_LINEAR_POTENTIALS(), (int)TSGM_FIX_OVERCOUNT());
+            printf("\n");
+            subpixel_refinement_sgm(S, off.data, cost.data, refine);
+            const std::pair<float, float> gminmax = update_dmin_dmax(off, &loI, &hiI);
+            remove_nonfinite_values_Img(loI, gminmax.first);
+            remove_nonfinite_values_Img(hiI, gminmax.second);
+         }
       };
-      run(u, v, dmin, dmax, outoff, outcost);
+      run(u, v, dmin, dmax, outoff, outcost, dminI, dmaxI);
       if (MEDIAN()) outoff = median_filter(outoff, (int)MEDIAN());
       if (0 != strcmp(nolr_disp_file, "")) io::write_image(nolr_disp_file, outoff);
 
       if (TESTLRRL()) {
-         run(v, u, -dmax, -dmin, outoffR, outcostR);
+         run(v, u, -dmax, -dmin, outoffR, outcostR, dminRI, dmaxRI);
          if (MEDIAN()) outoffR = median_filter(outoffR, (int)MEDIAN());
          Img tmpL(outoff), tmpR(outoffR);
          leftright_test(outoffR, tmpL, (float)TESTLRRL_TAU());

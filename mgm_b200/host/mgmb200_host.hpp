@@ -3,7 +3,8 @@
 // caller written against mgm.cc:372-385 / matlab/readme.txt:67-98 compiles unchanged:
 //
 //   struct Img                                  img.h:9-59 (planar float, data[x + y*nx + c*nx*ny])
-//   struct costvolume_t                         mgm_costvolume.h:311-315 (dense here: uniform [dmin,dmax])
+//   struct costvolume_t                         mgm_costvolume.h:311-315 (dense here over an envelope [dmin,dmax];
+//                                               per-pixel ranges are kept beside it, +INF outside them)
 //   Img compute_mgm_weights(Img&, aP, aThresh)  mgm_weights.h:63
 //   costvolume_t allocate_and_fill_sgm_costvolume(Img&, Img&, Img&, Img&, char*, char*, float)
 //                                               mgm_costvolume.h:337
@@ -55,14 +56,19 @@ struct Img {
    float val(int i, int j, int c) const { return data[i + j * nx + (size_t)c * nx * ny]; }
 };
 
-// dense stand-in for std::vector<Dvec>: values[(x + y*nx)*L + (o - dmin)]
+// dense stand-in for std::vector<Dvec>: values[(x + y*nx)*L + (o - dmin)] over the envelope [dmin,dmax];
+// lo/hi (empty = every pixel spans the envelope) are the per-pixel Dvec ranges, truncated to int
 struct costvolume_t {
    std::vector<float> values;
    int nx = 0, ny = 0, dmin = 0, dmax = -1;
+   std::vector<float> lo, hi;
    int nlabels() const { return dmax - dmin + 1; }
+   bool uniform() const { return lo.empty(); }
+   int min_of(int pix) const { return lo.empty() ? dmin : (int)lo[pix]; }
+   int max_of(int pix) const { return hi.empty() ? dmax : (int)hi[pix]; }
    // Dvec::operator[] (dvec.cc:129): +INF outside the range
    float at(int pix, int o) const {
-      return (o >= dmin && o <= dmax) ? values[(size_t)pix * nlabels() + (o - dmin)] : INFINITY;
+      return (o >= min_of(pix) && o <= max_of(pix)) ? values[(size_t)pix * nlabels() + (o - dmin)] : INFINITY;
    }
 };
 
@@ -79,14 +85,20 @@ inline void check(int rc) {
    if (rc != 0) throw std::runtime_error(std::string("mgmb200: ") + mgmb200_last_error());
 }
 
-// the reference takes per-pixel range images; the GPU path supports the uniform case
-inline void uniform_range(const Img &dminI, const Img &dmaxI, int *dmin, int *dmax) {
+// range images -> envelope [*dmin,*dmax]; returns true when every pixel spans the whole envelope.
+// allocate_costvolume truncates float -> int (mgm_costvolume.h:323).
+inline bool range_envelope(const Img &dminI, const Img &dmaxI, int *dmin, int *dmax) {
    if (dminI.data.empty() || dmaxI.data.size() != dminI.data.size()) throw std::runtime_error("mgmb200: empty range images");
-   const int lo = (int)dminI[0], hi = (int)dmaxI[0];   // allocate_costvolume truncates float->int (mgm_costvolume.h:323)
-   for (size_t i = 0; i < dminI.data.size(); i++)
-      if ((int)dminI.data[i] != lo || (int)dmaxI.data[i] != hi)
-         throw std::runtime_error("mgmb200: per-pixel disparity ranges (-m/-M) are not supported yet");
+   int lo = (int)dminI[0], hi = (int)dmaxI[0];
+   bool uniform = true;
+   for (size_t i = 0; i < dminI.data.size(); i++) {
+      const int a = (int)dminI.data[i], b = (int)dmaxI.data[i];
+      if (a != (int)dminI[0] || b != (int)dmaxI[0]) uniform = false;
+      lo = a < lo ? a : lo;
+      hi = b > hi ? b : hi;
+   }
    *dmin = lo; *dmax = hi;
+   return uniform;
 }
 
 MGMB200_SMART_PARAMETER(CENSUS_NCC_WIN, 3)
@@ -100,11 +112,19 @@ inline Img compute_mgm_weights(Img &u, float aP, float aThresh) {
 inline costvolume_t allocate_and_fill_sgm_costvolume(Img &in_u, Img &in_v, Img &dminI, Img &dmaxI, char *prefilter,
                                                      char *distance, float truncDist) {
    costvolume_t CC;
-   uniform_range(dminI, dmaxI, &CC.dmin, &CC.dmax);
+   const bool uniform = range_envelope(dminI, dmaxI, &CC.dmin, &CC.dmax);
    CC.nx = in_u.nx; CC.ny = in_u.ny;
    CC.values.resize((size_t)CC.nx * CC.ny * CC.nlabels());
-   check(mgmb200_costvolume(context(), in_u.data.data(), in_v.data.data(), in_u.nx, in_u.ny, in_u.nch, in_v.nx, in_v.ny,
-                            CC.dmin, CC.dmax, prefilter, distance, truncDist, (int)CENSUS_NCC_WIN(), CC.values.data()));
+   if (uniform) {
+      check(mgmb200_costvolume(context(), in_u.data.data(), in_v.data.data(), in_u.nx, in_u.ny, in_u.nch, in_v.nx,
+                               in_v.ny, CC.dmin, CC.dmax, prefilter, distance, truncDist, (int)CENSUS_NCC_WIN(),
+                               CC.values.data()));
+   } else {
+      CC.lo = dminI.data; CC.hi = dmaxI.data;
+      check(mgmb200_costvolume_ranges(context(), in_u.data.data(), in_v.data.data(), in_u.nx, in_u.ny, in_u.nch, in_v.nx,
+                                      in_v.ny, CC.lo.data(), CC.hi.data(), CC.dmin, CC.dmax, prefilter, distance,
+                                      truncDist, (int)CENSUS_NCC_WIN(), CC.values.data()));
+   }
    return CC;
 }
 
@@ -112,27 +132,62 @@ inline costvolume_t mgm(costvolume_t CC, const Img &in_w, const Img &dminI, cons
                         const float P1, const float P2, const int NDIR, const int MGM,
                         const int USE_FELZENSZWALB_POTENTIALS = 0, int SGM_FIX_OVERCOUNT = 1) {
    int dmin, dmax;
-   uniform_range(dminI, dmaxI, &dmin, &dmax);
-   if (dmin != CC.dmin || dmax != CC.dmax) throw std::runtime_error("mgmb200: cost volume / range mismatch");
+   const bool s_uniform = range_envelope(dminI, dmaxI, &dmin, &dmax);
+   const size_t np = (size_t)CC.nx * CC.ny;
+   if (dminI.data.size() != np) throw std::runtime_error("mgmb200: cost volume / range image size mismatch");
    costvolume_t S;
-   S.nx = CC.nx; S.ny = CC.ny; S.dmin = dmin; S.dmax = dmax;
-   S.values.resize(CC.values.size());
+   S.nx = CC.nx; S.ny = CC.ny;
    if (out->npix != CC.nx * CC.ny) *out = Img(CC.nx, CC.ny);
    if (outcost->npix != CC.nx * CC.ny) *outcost = Img(CC.nx, CC.ny);
    const float *w = in_w.data.empty() ? nullptr : in_w.data.data();
-   check(mgmb200_mgm(context(), CC.values.data(), w, CC.nx, CC.ny, dmin, dmax, P1, P2, NDIR, MGM,
-                     USE_FELZENSZWALB_POTENTIALS, SGM_FIX_OVERCOUNT, out->data.data(), outcost->data.data(),
-                     S.values.data()));
+   if (s_uniform && CC.uniform() && dmin == CC.dmin && dmax == CC.dmax) {
+      S.dmin = dmin; S.dmax = dmax;
+      S.values.resize(CC.values.size());
+      check(mgmb200_mgm(context(), CC.values.data(), w, CC.nx, CC.ny, dmin, dmax, P1, P2, NDIR, MGM,
+                        USE_FELZENSZWALB_POTENTIALS, SGM_FIX_OVERCOUNT, out->data.data(), outcost->data.data(),
+                        S.values.data()));
+   } else {
+      // per-pixel ranges: the returned volume has the ranges [dminI,dmaxI], the cost vectors keep theirs; both live
+      // in one dense envelope that covers the two
+      const int emin = dmin < CC.dmin ? dmin : CC.dmin, emax = dmax > CC.dmax ? dmax : CC.dmax;
+      const int Le = emax - emin + 1, Lc = CC.nlabels();
+      std::vector<float> cclo(np), cchi(np), dense;
+      for (size_t i = 0; i < np; i++) { cclo[i] = (float)CC.min_of((int)i); cchi[i] = (float)CC.max_of((int)i); }
+      const float *ccp = CC.values.data();
+      if (emin != CC.dmin || emax != CC.dmax) {   // re-base the cost volume into the wider envelope
+         dense.assign(np * Le, INFINITY);
+         for (size_t i = 0; i < np; i++)
+            memcpy(&dense[i * Le + (CC.dmin - emin)], &CC.values[i * Lc], sizeof(float) * Lc);
+         ccp = dense.data();
+      }
+      S.dmin = emin; S.dmax = emax; S.lo = dminI.data; S.hi = dmaxI.data;
+      S.values.resize(np * Le);
+      check(mgmb200_mgm_ranges(context(), ccp, cclo.data(), cchi.data(), w, CC.nx, CC.ny, emin, emax, S.lo.data(),
+                               S.hi.data(), P1, P2, NDIR, MGM, USE_FELZENSZWALB_POTENTIALS, SGM_FIX_OVERCOUNT,
+                               out->data.data(), outcost->data.data(), S.values.data()));
+   }
    // side effect kept for drop-in parity of the console output: the sweep digits of mgm_core.cc:491
    for (int pass = 0; pass < NDIR; pass++) printf("%d", pass);
    fflush(stdout);
    return S;
 }
 
+// mgm_naive_parallelism (mgm_core.cc:632): one thread per sweep, S accumulated in completion order.  Here the sweeps
+// always run concurrently and are summed in sweep order, so it is the same call.
+inline costvolume_t mgm_naive_parallelism(costvolume_t CC, const Img &in_w, const Img &dminI, const Img &dmaxI, Img *out,
+                                          Img *outcost, const float P1, const float P2, const int NDIR, const int MGM,
+                                          const int USE_FELZENSZWALB_POTENTIALS = 0, int SGM_FIX_OVERCOUNT = 1) {
+   return mgm(CC, in_w, dminI, dmaxI, out, outcost, P1, P2, NDIR, MGM, USE_FELZENSZWALB_POTENTIALS, SGM_FIX_OVERCOUNT);
+}
+
 inline void subpixel_refinement_sgm(costvolume_t &S, std::vector<float> &out, std::vector<float> &outcost,
                                     char *refinement) {
-   check(mgmb200_subpixel_refinement_sgm(context(), S.values.data(), S.nx, S.ny, S.dmin, S.dmax, out.data(),
-                                         outcost.data(), refinement));
+   if (S.uniform())
+      check(mgmb200_subpixel_refinement_sgm(context(), S.values.data(), S.nx, S.ny, S.dmin, S.dmax, out.data(),
+                                            outcost.data(), refinement));
+   else
+      check(mgmb200_subpixel_refinement_sgm_ranges(context(), S.values.data(), S.lo.data(), S.hi.data(), S.nx, S.ny,
+                                                   S.dmin, S.dmax, out.data(), outcost.data(), refinement));
 }
 
 }  // namespace mgmb200

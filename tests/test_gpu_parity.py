@@ -339,13 +339,28 @@ def _pnm(path, a):
     (dict(MEDIAN="1", USE_TRUNCATED_LINEAR_POTENTIALS="1", TSGM="3"),
      ["-P2", "20000", "-P1", "4", "-r", "-23", "-R", "4", "-p", "sobel_x", "-truncDist", "63", "-s", "vfit", "-O", "8"], 3),  # Makefile:18
     (dict(TESTLRRL="0"), ["-r", "-23", "-R", "4", "-aP2", "4", "-aThresh", "9", "-s", "cubic", "-O", "8"], 1),  # CLI defaults, weights
+    (dict(TSGM_ITER="2", TSGM="2"), ["-r", "-23", "-R", "4", "-t", "census", "-s", "vfit", "-O", "8"], 1),        # range update between iterations
+    (dict(TSGM_ITER="3", TSGM="3", USE_TRUNCATED_LINEAR_POTENTIALS="1", MEDIAN="1"),
+     ["-P1", "2", "-P2", "20000", "-r", "-23", "-R", "4", "-t", "census", "-s", "vfit", "-O", "8"], 1),
+    (dict(TSGM="4", RANGES="1"), ["-r", "-23", "-R", "4", "-t", "ad", "-s", "parabola", "-O", "4", "-p", "gblur"], 3),  # -m/-M range images
+    (dict(TSGM="2", RANGES="1", USE_TRUNCATED_LINEAR_POTENTIALS="1", TSGM_ITER="2"),
+     ["-P1", "2", "-P2", "20000", "-r", "-23", "-R", "4", "-t", "sd", "-O", "8"], 1),
 ])
 def test_cli_matches_reference_cli(tmp_path, case):
     """the whole `mgm` command (both LR directions, median, LR test, back-projection, console output)"""
     env_extra, args, nch = case
+    env_extra = dict(env_extra)
     u, v = synth_pair(120, 64, 24, seed=4, nch=nch)
     _pnm(str(tmp_path / "u.pnm"), u)
     _pnm(str(tmp_path / "v.pnm"), v)
+    if env_extra.pop("RANGES", None):   # per-pixel range images around the true disparity (-m / -M, mgm.cc:342-353)
+        rng = np.random.default_rng(7)
+        lo = (-14 + rng.integers(-6, 3, (64, 120))).astype(np.float32)
+        hi = (lo + rng.integers(0, 14, (64, 120))).astype(np.float32)   # some max < min+1: the CLI repairs them
+        lo[5, 7] = np.nan
+        np.save(str(tmp_path / "dmin.npy"), lo)
+        np.save(str(tmp_path / "dmax.npy"), hi)
+        args = args + ["-m", str(tmp_path / "dmin.npy"), "-M", str(tmp_path / "dmax.npy")]
     outs = {}
     for tag, exe in (("ref", REF_MGM), ("our", OUR_MGM)):
         names = [str(tmp_path / ("%s_%s.npy" % (tag, k))) for k in ("disp", "cost", "back")]
