@@ -196,7 +196,8 @@ __device__ __forceinline__ float cell_cost(const CostArgs &A, int px, int py, in
 // ------------------------------------------------------------------ K2 cost volume: one warp per pixel
 // rlo/rhi (optional): per-pixel disparity ranges as float images, truncated to int like Dvec::init
 // (mgm_costvolume.h:323); labels outside a pixel's range do not exist in the reference: +INF here.
-template <int DIST>
+// NCT: compile-time number of channels / census words (1..4) for the fast path, 0 = generic cell_cost
+template <int DIST, int NCT>
 __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, int dmin, int L, int VS, float cap,
                                                              const float *__restrict__ rlo,
                                                              const float *__restrict__ rhi,
@@ -207,8 +208,7 @@ __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, i
    // Fast path (AD, SD, census with up to four channels / census words): everything that depends on the pixel
    // only -- the left pixel's values, the row pointers of the right image -- is hoisted out of the label loop and
    // the loop indexes with 32-bit offsets; same operations in the same order as cell_cost.
-   constexpr bool FASTDIST = (DIST == DIST_AD || DIST == DIST_SD || DIST == DIST_CENSUS);
-   const bool fast = FASTDIST && A.nch <= 4;
+   constexpr bool fast = (NCT > 0);
    const long long vnp = (long long)A.vnx * A.vny;
    for (long long p = (long long)blockIdx.x * warps + wid; p < np; p += (long long)gridDim.x * warps) {
       const int x = (int)(p % A.nx), y = (int)(p / A.nx);
@@ -219,20 +219,19 @@ __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, i
          klo = max((int)rlo[p] - dmin, 0);
          khi = min((int)rhi[p] - dmin, L - 1);
       }
-      if (fast) {
-         uint32_t lw[4] = {0u, 0u, 0u, 0u};     // left census words, or the bits of the left channel values
-         const uint32_t *rrow[4] = {nullptr, nullptr, nullptr, nullptr};   // right image row, per channel / word
+      if constexpr (fast) {
+         constexpr int NC = NCT > 0 ? NCT : 1;
+         uint32_t lw[NC];            // left census words, or the bits of the left channel values
+         const uint32_t *rrow[NC];   // right image row, per channel / word
          const bool vy_ok = y < A.vny;
 #pragma unroll
-         for (int t = 0; t < 4; ++t) {
-            if (t < A.nch) {
-               if (DIST == DIST_CENSUS) {
-                  lw[t] = __ldg(A.cu + p + t * np);
-                  rrow[t] = A.cv + (long long)y * A.vnx + t * vnp;
-               } else {
-                  lw[t] = __float_as_uint(__ldg(A.u + p + t * np));
-                  rrow[t] = reinterpret_cast<const uint32_t *>(A.v + (long long)y * A.vnx + t * vnp);
-               }
+         for (int t = 0; t < NC; ++t) {
+            if (DIST == DIST_CENSUS) {
+               lw[t] = __ldg(A.cu + p + t * np);
+               rrow[t] = A.cv + (long long)y * A.vnx + t * vnp;
+            } else {
+               lw[t] = __float_as_uint(__ldg(A.u + p + t * np));
+               rrow[t] = reinterpret_cast<const uint32_t *>(A.v + (long long)y * A.vnx + t * vnp);
             }
          }
          const int qx0 = x + dmin;
@@ -248,18 +247,16 @@ __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, i
                   if (vy_ok && (unsigned)qx < (unsigned)A.vnx) {
                      float acc = 0.f;
 #pragma unroll
-                     for (int t = 0; t < 4; ++t) {
-                        if (t < A.nch) {
-                           const uint32_t rv = __ldg(rrow[t] + qx);
-                           if (DIST == DIST_CENSUS) acc += (float)__popc(lw[t] ^ rv);
-                           else {
-                              float d = __uint_as_float(lw[t]) - __uint_as_float(rv);
-                              d = sel_max(d, -d);
-                              acc += (DIST == DIST_SD) ? d * d : d;
-                           }
+                     for (int t = 0; t < NC; ++t) {
+                        const uint32_t rv = __ldg(rrow[t] + qx);
+                        if (DIST == DIST_CENSUS) acc += (float)__popc(lw[t] ^ rv);
+                        else {
+                           float d = __uint_as_float(lw[t]) - __uint_as_float(rv);
+                           d = sel_max(d, -d);
+                           acc += (DIST == DIST_SD) ? d * d : d;
                         }
                      }
-                     e = (DIST == DIST_CENSUS && A.nch != 1) ? (float)((double)acc / (double)A.nch) : acc;
+                     e = (DIST == DIST_CENSUS && NC != 1) ? (float)((double)acc / (double)NC) : acc;
                   }
                   e = sel_min(e, cap);
                   anyfinite |= (fabsf(e) < MGM_INF);
@@ -420,14 +417,25 @@ cudaError_t costvolume_launch(int dist, const float *d_u, const float *d_v, cons
    long long want = (np + 7) / 8;
    unsigned grid = (unsigned)((want < (long long)num_sms * 16) ? want : (long long)num_sms * 16);
    if (grid < 1) grid = 1;
-   switch (dist) {
-   case DIST_AD: mgm_costvolume_kernel<DIST_AD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, d_cc); break;
-   case DIST_SD: mgm_costvolume_kernel<DIST_SD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, d_cc); break;
-   case DIST_CENSUS: mgm_costvolume_kernel<DIST_CENSUS><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, d_cc); break;
-   case DIST_NCC: mgm_costvolume_kernel<DIST_NCC><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, d_cc); break;
-   case DIST_BTAD: mgm_costvolume_kernel<DIST_BTAD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, d_cc); break;
-   default: mgm_costvolume_kernel<DIST_BTSD><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, d_cc); break;
+#define MGM_CV_LAUNCH(D, N) mgm_costvolume_kernel<D, N><<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, d_cc)
+#define MGM_CV_FAST(D)                                  \
+   switch (nch) {                                       \
+   case 1: MGM_CV_LAUNCH(D, 1); break;                  \
+   case 2: MGM_CV_LAUNCH(D, 2); break;                  \
+   case 3: MGM_CV_LAUNCH(D, 3); break;                  \
+   case 4: MGM_CV_LAUNCH(D, 4); break;                  \
+   default: MGM_CV_LAUNCH(D, 0); break;                 \
    }
+   switch (dist) {
+   case DIST_AD: MGM_CV_FAST(DIST_AD); break;
+   case DIST_SD: MGM_CV_FAST(DIST_SD); break;
+   case DIST_CENSUS: MGM_CV_FAST(DIST_CENSUS); break;
+   case DIST_NCC: MGM_CV_LAUNCH(DIST_NCC, 0); break;
+   case DIST_BTAD: MGM_CV_LAUNCH(DIST_BTAD, 0); break;
+   default: MGM_CV_LAUNCH(DIST_BTSD, 0); break;
+   }
+#undef MGM_CV_FAST
+#undef MGM_CV_LAUNCH
    return cudaGetLastError();
 }
 
