@@ -65,6 +65,23 @@ __global__ void k(float *out, int iters, long long *cyc) {
             const unsigned a = base + 4u * (r * TS + slot * 256) + 16u * (gl + 8 * j);
             sts64(a, make_float2(acc, 1.f)); sts64(a + 8u, make_float2(2.f, 3.f));
          }
+         if (MODE == 10 && crow < 56) {       // chain, planar halves: lanes (rows) contiguous
+            const unsigned e = (unsigned)(slot * 128 + 2 * ((j + it) & 63));
+            float2 p = lds64(base + 8u * (e * 57 + crow)), q = lds64(base + 8u * ((e + 1) * 57 + crow)); acc += p.x + q.y;
+         }
+         if (MODE == 11 && crow < 56) {       // chain STS, planar halves
+            const unsigned e = (unsigned)(slot * 128 + 2 * ((j + it) & 63));
+            sts64(base + 8u * (e * 57 + crow), make_float2(acc, 1.f)); sts64(base + 8u * ((e + 1) * 57 + crow), make_float2(2.f, 3.f));
+         }
+         if (MODE == 12 && r < 56) {          // gather LDS, planar halves: lane (r, gl) reads chunk gl+8j of row r-1
+            const int pr = r > 0 ? r - 1 : 0;
+            const unsigned e = (unsigned)(slot * 128 + 2 * (gl + 8 * j));
+            float2 p = lds64(base + 8u * (e * 57 + pr)), q = lds64(base + 8u * ((e + 1) * 57 + pr)); acc += p.x + q.y;
+         }
+         if (MODE == 13 && r < 56) {          // gather STS, planar halves
+            const unsigned e = (unsigned)(slot * 128 + 2 * (gl + 8 * j));
+            sts64(base + 8u * (e * 57 + r), make_float2(acc, 1.f)); sts64(base + 8u * ((e + 1) * 57 + r), make_float2(2.f, 3.f));
+         }
          if (MODE == 6 && r < 56) {           // gather STS.128 own slot
             sts128(base + 4u * (r * TS + slot * 256) + 16u * (gl + 8 * j), make_float4(acc, 1.f, 2.f, 3.f));
          }
@@ -78,14 +95,14 @@ int main() {
    float *out; long long *cyc;
    cudaMalloc(&out, 148 * 512 * 4); cudaMalloc(&cyc, 148 * 8);
    const int iters = 1000;
-   const char *names[] = {"", "", "", "", "", "", "", "chain 2xLDS.64 same order", "chain 2xSTS.64", "gather 2xSTS.64"};
+   const char *names[] = {"", "", "", "", "", "", "", "chain 2xLDS.64 same order", "chain 2xSTS.64", "gather 2xSTS.64", "PLANAR chain 2xLDS.64", "PLANAR chain 2xSTS.64", "PLANAR gather 2xLDS.64", "PLANAR gather 2xSTS.64"};
    const char *names0[] = {"gather LDS.128 (3 preds = x3)", "gather 2xLDS.64 alternating", "gather 2xLDS.64 same half", "chain LDS.128 (4 warps)", "chain 2xLDS.64 alternating", "chain STS.128", "gather STS.128"};
-   const size_t smem = 56 * TS * 4 + 256;
-   for (int mode = 0; mode < 10; ++mode) {
+   const size_t smem = 3 * 128 * 57 * 8 + 56 * 16 + 256 > 56 * TS * 4 + 256 ? 3 * 128 * 57 * 8 + 56 * 16 + 256 : 56 * TS * 4 + 256;
+   for (int mode = 0; mode < 14; ++mode) {
       if ((TS % 4) != 0 && (mode == 0 || mode == 3 || mode == 5 || mode == 6)) continue;   // 16-byte accesses need 16-byte aligned rows
-      auto kk = mode == 9 ? k<9> : mode == 8 ? k<8> : mode == 7 ? k<7> : mode == 0 ? k<0> : mode == 1 ? k<1> : mode == 2 ? k<2> : mode == 3 ? k<3> : mode == 4 ? k<4> : mode == 5 ? k<5> : k<6>;
+      auto kk = mode == 13 ? k<13> : mode == 12 ? k<12> : mode == 11 ? k<11> : mode == 10 ? k<10> : mode == 9 ? k<9> : mode == 8 ? k<8> : mode == 7 ? k<7> : mode == 0 ? k<0> : mode == 1 ? k<1> : mode == 2 ? k<2> : mode == 3 ? k<3> : mode == 4 ? k<4> : mode == 5 ? k<5> : k<6>;
       cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      const bool chain = (mode >= 3 && mode <= 5) || mode == 7 || mode == 8;
+      const bool chain = (mode >= 3 && mode <= 5) || mode == 7 || mode == 8 || mode == 10 || mode == 11;
       const int threads = chain ? 128 : 448;
       kk<<<148, threads, smem>>>(out, iters, cyc);
       cudaError_t e = cudaDeviceSynchronize();
