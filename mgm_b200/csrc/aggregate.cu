@@ -8,20 +8,20 @@
 // sweeps 4-7 in the order {(+1,-1),(-1,-1),(0,-1),(-1,0)}, TSGM=K keeps the first K.
 // Pixels with xs==0, ys==0 or xs==maxii-1 keep their matching cost (mgm_core.cc:538-541).
 //
-// Mapping to the machine:
-//   * one THREAD per scan row, sequential in xs; rows of a band of T consecutive
-//     rows run in lock step, row t trailing row t-1 by SIGMA pixels (1, or 2 when
-//     the (+1,-1) predecessor is used), one __syncthreads per pixel step;
-//   * all per-pixel label vectors live in shared memory: a ring of SIGMA+2 message
-//     slots per row, and two cost buffers per row that are filled by TMA bulk loads
-//     (cp.async.bulk + mbarrier) one pixel ahead and drained by TMA bulk stores of
-//     the finished message into the per-sweep volume;
-//   * the unweighted paths store in the ring the neighbour-side transform of the
-//     message (SGM min3 / truncated-linear min-convolution, minus its minimum),
-//     computed ONCE by the producer row instead of once per consumer;
-//   * bands are chained through a global boundary line (TMA store -> release flag
-//     -> acquire -> TMA load into a virtual "row -1" ring), and claimed from an
-//     atomic ticket in dependency order so any grid size is deadlock free.
+// Mapping to the machine (DESIGN.md section 4.1 has the measurements behind each choice):
+//   * work unit = a BAND of T consecutive workers of one sweep, run by one CTA in lock step, one label vector
+//     per worker and step.  Axis sweeps 0-3 (and every sweep with TSGM=4 or image-dependent weights): worker =
+//     scan row, row t trails row t-1 by SIGMA pixels (run_band).  Diagonal sweeps 4-7 with TSGM<=3: sheared
+//     wavefront, worker = anti-diagonal, no lag inside a band (run_band_shear);
+//   * 8 lanes per worker own interleaved 16-byte chunks of the label vector: phase 1 (gather) builds the message
+//     from the matching costs (streamed into registers one step ahead) and the predecessors' transformed
+//     vectors in a shared-memory ring, writes it to the sweep's volume and into the worker's ring slot;
+//   * phase 2 transforms the message IN PLACE into what its consumers add (SGM min3, or the exact sequential
+//     truncated-linear min-convolution by one lane pair per worker, minus its minimum) -- computed ONCE by the
+//     producer instead of once per consumer;
+//   * bands are chained through global boundary lines (publisher-warp copy -> release counter -> acquire ->
+//     TMA bulk load into a virtual-row ring, mbarrier completion) and claimed dynamically, in order within a
+//     sweep, ready axis bands first (claim_band), so any grid size is deadlock free.
 // Precondition of this fast path (enforced by the host): every cost
 // vector holds a finite value, no NaN / -INF, P1,P2 >= 0 and weights >= 0; then the
 // hardware min is bit-identical to the reference's compare-select forms.
