@@ -129,6 +129,36 @@ __device__ __forceinline__ float sgm_x(float l, float c, float r, float p1, floa
    return fminf(fminf(c, fminf(l, r) + p1), cap) - m;
 }
 
+// SGM transform of a whole message held in registers (register-cost mode, unweighted SGM kernels): lane gl of the
+// 8-lane group holds the chunks gl + 8j in v[j]; the labels next to a chunk live in the neighbouring lanes (same
+// j) or, at the ends of the group, in lane 7 / lane 0 of the previous / next j.  The message never goes through
+// shared memory and the step needs one barrier instead of two.
+template <int K, int NJR, bool A16>
+__device__ __forceinline__ void sgm_transform_regs(const float4 (&v)[NJR], int nj, int nq, int gl, unsigned gmask, float m,
+                                                   float p1, float p2, float2 *cur) {
+   const float cap = m + p2;
+   const float sc = (K == 2) ? 0.5f : 1.0f;
+#pragma unroll
+   for (int j = 0; j < NJR; ++j) {
+      if (j < nj) {
+         const int q = gl + G * j;
+         // last label of chunk q-1, first label of chunk q+1
+         const float l_same = __shfl_sync(gmask, v[j].w, (gl + G - 1) & (G - 1), G);               // lane gl-1, same j
+         const float l_prev = __shfl_sync(gmask, v[j > 0 ? j - 1 : 0].w, G - 1, G);                // lane 7, j-1
+         const float r_same = __shfl_sync(gmask, v[j].x, (gl + 1) & (G - 1), G);                   // lane gl+1, same j
+         const float r_next = __shfl_sync(gmask, v[j + 1 < NJR ? j + 1 : j].x, 0, G);              // lane 0, j+1
+         const float lft = (q == 0) ? MGM_INF : (gl > 0 ? l_same : l_prev);
+         const float rgt = (q + 1 >= nq) ? MGM_INF : (gl < G - 1 ? r_same : r_next);
+         float4 a;
+         a.x = sgm_x(lft, v[j].x, v[j].y, p1, cap, m) * sc;
+         a.y = sgm_x(v[j].x, v[j].y, v[j].z, p1, cap, m) * sc;
+         a.z = sgm_x(v[j].y, v[j].z, v[j].w, p1, cap, m) * sc;
+         a.w = sgm_x(v[j].z, v[j].w, rgt, p1, cap, m) * sc;
+         st16<A16>(cur, q, a);
+      }
+   }
+}
+
 // Truncated-linear min-convolution (minConvTruncatedLinear, mgm_core.cc:152-163) of src into dst by a PAIR
 // of adjacent lanes: lane dir=0 runs the forward recurrence F[o] = min(F[o-1]+c, M[o]) upwards, lane dir=1
 // the same recurrence downwards on the ORIGINAL values (Bp).  Because x -> RN(x+c) is monotone and
@@ -351,7 +381,10 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    for (int j = 0; j < NJR; ++j) creg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
    // CHAINS with register-resident costs: the message is written straight into its ring slot and the
    // min-convolution runs IN PLACE there (its second half no longer reads the source) -> no cost buffer at all
-   const int ncbuf = (CHAINS && creg_mode) ? 0 : ncb;
+   // unweighted SGM kernels in register mode: gather and transform fused, the message stays in creg[] (see
+   // sgm_transform_regs); one barrier per step, no cost buffer either
+   const bool fused = !WEIGHTED && POT == POT_SGM && P.fused_sgm != 0;
+   const int ncbuf = ((CHAINS && creg_mode) || fused) ? 0 : ncb;
    auto cbuf_of = [&](int rr, int px) -> float * { return row_base(rr) + (R + (ncb == 2 ? (px & 1) : 0)) * VS; };
    auto prefetch_cost = [&](int s) {
       const int px = s - SIG * r + 1;   // the pixel my row handles in the NEXT step
@@ -463,7 +496,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                   if (j < nj) {
                      const int q = gl + G * j;
                      m = hmin4(m, creg[j]);
-                     st16<A16>(Cb, q, creg[j]);
+                     if (!fused) st16<A16>(Cb, q, creg[j]);
                      __stcs(gout + q, creg[j]);
                   }
                }
@@ -526,7 +559,8 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
                         o = add4(c[jj], div4_by_k<K>(e));
                      }
                      m = hmin4(m, o);
-                     st16<A16>(Cb, q, o);
+                     if (REGC && fused) creg[(j0 + jj) < NJR ? (j0 + jj) : 0] = o;   // transformed from registers below
+                     else st16<A16>(Cb, q, o);
 #if MGM_EXP != 1
                      __stcs(gout + q, o);
 #endif
@@ -585,10 +619,15 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 #pragma unroll
          for (int d = 1; d < G; d <<= 1) m = fminf(m, __shfl_xor_sync(gmask, m, d));
          if (gl == 0) msr[r * 4 + (xs % R)] = m;
+         if constexpr (!WEIGHTED && POT == POT_SGM) {
+            if (fused) sgm_transform_regs<K, NJR, A16>(creg, nj, nq, gl, gmask, m, P.P1, P.P2, cur);
+         }
       }
       if (creg_mode) prefetch_cost(s);   // costs of the next pixel -> registers, in flight during phase 2
-      grp.gather_done(s == nsteps - 1);
-      grp.sync();
+      if (!fused) {
+         grp.gather_done(s == nsteps - 1);
+         grp.sync();
+      }
 
       // ---------------- phase 2: build the neighbour-side transform of the message in the ring slot
       if (late_prefetch) prefetch_cost(s);
@@ -607,7 +646,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
             else if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
             else minconv_half<1>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
          }
-      } else if (act) {
+      } else if (act && !fused) {
          if constexpr (!WEIGHTED) {
             // SGM transform, label-parallel: A(o) = min3(L(o), min(L(o-1),L(o+1))+P1, m+P2) - m  [x 1/2 for K=2]
             const float p1 = P.P1, cap = m + P.P2;
@@ -727,6 +766,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
    const int ncw = (TG + 31) >> 5;
    const int pair_id0 = 4 + grp.gi * 2;
    const bool inplace = CHAINS && creg_mode;   // message built in its ring slot, min-convolution in place
+   const bool fused = POT == POT_SGM && P.fused_sgm != 0;   // see run_band / sgm_transform_regs
 
    // per-worker shared memory: ring slots [2][VS] (position v&1) | cost buffers [ncb][VS] (none when in place)
    auto row_base = [&](int rr) -> float * { return thr + (size_t)rr * TS; };
@@ -837,7 +877,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
                   if (j < nj) {
                      const int q = gl + G * j;
                      m = hmin4(m, creg[j]);
-                     st16<A16>(Cb, q, creg[j]);
+                     if (!fused) st16<A16>(Cb, q, creg[j]);
                      __stcs(gout + q, creg[j]);
                   }
                }
@@ -890,7 +930,8 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
                      o = add4(c[jj], div4_by_k<K>(e));
                   }
                   m = hmin4(m, o);
-                  st16<A16>(Cb, q, o);
+                  if (REGC && fused) creg[(j0 + jj) < NJR ? (j0 + jj) : 0] = o;
+                  else st16<A16>(Cb, q, o);
                   __stcs(gout + q, o);
                }
             };
@@ -915,10 +956,15 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
 #pragma unroll
          for (int d = 1; d < G; d <<= 1) m = fminf(m, __shfl_xor_sync(gmask, m, d));
          if (gl == 0) msr[r * 4 + (v & 1)] = m;
+         if constexpr (POT == POT_SGM) {
+            if (fused) sgm_transform_regs<K, NJR, A16>(creg, nj, nq, gl, gmask, m, P.P1, P.P2, cur);
+         }
       }
       if (creg_mode) prefetch_cost(v);
-      grp.gather_done(v == se);
-      grp.sync();
+      if (!fused) {
+         grp.gather_done(v == se);
+         grp.sync();
+      }
 
       // ---------------- phase 2: neighbour-side transform of the message into ring slot v&1
       if (late_prefetch) prefetch_cost(v);
@@ -934,7 +980,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
             if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
             else minconv_half<1>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, P.P1, cm + P.P2, (K == 2) ? 0.0f : cm, pair_id0 + cw);
          }
-      } else if (act) {
+      } else if (act && !fused) {
          // SGM transform, label-parallel: A(o) = min3(L(o), min(L(o-1),L(o+1))+P1, m+P2) - m  [x 1/2 for K=2]
          const float p1 = P.P1, cap = m + P.P2;
          const float sc = (K == 2) ? 0.5f : 1.0f;
@@ -1089,9 +1135,11 @@ static void agg_plan_try(AggPlan *plan, int L, int K, int pot, bool weighted, in
    const int nvirt = shear ? 2 : 1;   // boundary workers kept per position
    // unweighted truncated-linear kernels with register-resident costs build the message in its ring slot and run
    // the min-convolution in place: no cost buffer
-   const int ncbuf = (pot == POT_TRUNC && !weighted && plan->ncb == 1) ? 0 : plan->ncb;
    int want_groups = 1;   // row groups per band (RowGroup in the kernel); measured: no gain, the LSU is the shared limit
    if (const char *e = getenv("MGMB200_GROUPS")) { const int v = atoi(e); if (!weighted && (v == 1 || v == 2 || v == 3)) want_groups = v; }
+   // ... and the unweighted SGM kernels transform the message straight from registers (one group only)
+   plan->fused_sgm = (!weighted && pot == POT_SGM && plan->ncb == 1 && want_groups == 1 && !getenv("MGMB200_NO_FUSED_SGM")) ? 1 : 0;
+   const int ncbuf = (!weighted && plan->ncb == 1 && (pot == POT_TRUNC || plan->fused_sgm)) ? 0 : plan->ncb;
    for (int cls = 0; cls < 2; ++cls) {
       int nbuf = ((cls == 1 && shear) ? 2 : ring_slots(cls, K)) + ncbuf + xtra;
       int TS = nbuf * VS;

@@ -27,6 +27,7 @@ struct AggParams {
    int ncb;                    // cost buffers per row (1: costs prefetched into registers, 2: cp.async ring)
    int shear;                  // 1: sweeps 4-7 run as sheared wavefronts (bands of anti-diagonals, run_band_shear)
    int ng[2];                  // row groups per band (axis / diagonal class), each on its own named barrier
+   int fused_sgm;              // 1: unweighted SGM kernels transform the message from registers (one barrier per step)
    float P1, P2;
    unsigned long long *dbg;    // optional 24-word phase-timing accumulator (profiling aid), or nullptr
    // dynamic shared memory carve-up (bytes)
@@ -34,7 +35,7 @@ struct AggParams {
 };
 
 struct AggPlan {
-   int VS, T[2], TS[2], ncb, shear, ng[2], block, num_sms;
+   int VS, T[2], TS[2], ncb, shear, ng[2], fused_sgm, block, num_sms;
    size_t smem;
    size_t off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };

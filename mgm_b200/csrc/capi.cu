@@ -369,7 +369,7 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
    P.nx = nx; P.ny = ny; P.L = L; P.VS = VS;
    P.T[0] = plan.T[0]; P.T[1] = plan.T[1];
    P.TS[0] = plan.TS[0]; P.TS[1] = plan.TS[1];
-   P.ncb = plan.ncb; P.shear = plan.shear; P.ng[0] = plan.ng[0]; P.ng[1] = plan.ng[1];
+   P.ncb = plan.ncb; P.shear = plan.shear; P.ng[0] = plan.ng[0]; P.ng[1] = plan.ng[1]; P.fused_sgm = plan.fused_sgm;
    P.P1 = P1; P.P2 = P2;
    P.dbg = nullptr;
    P.off_phase = (unsigned)plan.off_phase; P.off_cbar = (unsigned)plan.off_cbar; P.off_vbar = (unsigned)plan.off_vbar;
