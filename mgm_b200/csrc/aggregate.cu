@@ -43,7 +43,7 @@ namespace mgm {
 
 static constexpr int RV = 8;   // virtual-row ring (pixels of the previous band's last row)
 static constexpr int PF = 3;   // boundary prefetch distance in pixels
-static constexpr int G = MGM_AGG_GROUP;   // lanes cooperating on one scan row
+static constexpr int G = MGM_AGG_GROUP;   // lanes cooperating on one scan row (the band functions shadow it with their GL)
 
 enum PredType { PRED_SAME = 0, PRED_UP = 1, PRED_UPL = 2, PRED_UPR = 3 };
 
@@ -133,9 +133,10 @@ __device__ __forceinline__ float sgm_x(float l, float c, float r, float p1, floa
 // 8-lane group holds the chunks gl + 8j in v[j]; the labels next to a chunk live in the neighbouring lanes (same
 // j) or, at the ends of the group, in lane 7 / lane 0 of the previous / next j.  The message never goes through
 // shared memory and the step needs one barrier instead of two.
-template <int K, int NJR, bool A16>
+template <int K, int NJR, bool A16, int GL>
 __device__ __forceinline__ void sgm_transform_regs(const float4 (&v)[NJR], int nj, int nq, int gl, unsigned gmask, float m,
                                                    float p1, float p2, float2 *cur) {
+   constexpr int G = GL;
    const float cap = m + p2;
    const float sc = (K == 2) ? 0.5f : 1.0f;
 #pragma unroll
@@ -220,7 +221,7 @@ struct RowGroup {
       }
    }
 };
-__device__ __forceinline__ RowGroup make_row_group(int tid, int ncomp, int r, int NG, int TG) {
+__device__ __forceinline__ RowGroup make_row_group(int tid, int ncomp, int r, int NG, int TG, int G) {
    RowGroup g;
    g.ng = NG;
    g.gi = (tid < ncomp) ? min(r / TG, NG - 1) : (tid < ncomp + 32 ? 0 : NG - 1);   // consumer warp -> 0, publisher -> last
@@ -282,8 +283,9 @@ __device__ __forceinline__ float4 div4_by_k(const float4 &e) {   // e finite (se
    return div3_4(e);
 }
 
-template <int POT, int K, bool WEIGHTED, bool DIAG>
+template <int POT, int K, bool WEIGHTED, bool DIAG, int GL>
 __device__ void run_band(const AggParams &P, const int pass, const int band, unsigned char *smem) {
+   constexpr int G = GL;   // lanes per worker: 8, or 4 for short label vectors (unweighted SGM kernels, agg_plan)
    constexpr int SIG = (DIAG || K == 4) ? 2 : 1;
    constexpr int R = SIG + 2;
    constexpr bool NEEDM = WEIGHTED || (POT == POT_TRUNC && K == 2);
@@ -336,7 +338,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 
    // row groups (RowGroup above); the boundary consumer warp belongs to group 0, the publisher warp to the last
    const int NG = P.ng[CLS], TG = T / NG;
-   const RowGroup grp = make_row_group(tid, ncomp, r, NG, TG);
+   const RowGroup grp = make_row_group(tid, ncomp, r, NG, TG, G);
    const int gw0 = grp.first_tid >> 5;          // first warp of my group
    const int ncw = (TG + 31) >> 5;              // chain warps per direction and group (2 only when NG == 1)
    const int pair_id0 = 4 + grp.gi * 2;         // named barriers of my group's chain pairs
@@ -620,7 +622,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
          for (int d = 1; d < G; d <<= 1) m = fminf(m, __shfl_xor_sync(gmask, m, d));
          if (gl == 0) msr[r * 4 + (xs % R)] = m;
          if constexpr (!WEIGHTED && POT == POT_SGM) {
-            if (fused) sgm_transform_regs<K, NJR, A16>(creg, nj, nq, gl, gmask, m, P.P1, P.P2, cur);
+            if (fused) sgm_transform_regs<K, NJR, A16, G>(creg, nj, nq, gl, gmask, m, P.P1, P.P2, cur);
          }
       }
       if (creg_mode) prefetch_cost(s);   // costs of the next pixel -> registers, in flight during phase 2
@@ -711,8 +713,9 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 // maxii + 2*maxjj steps (row-per-worker, lag 2) to maxjj + (band hand-off) * #bands.
 // Everything else (register-resident cost prefetch, gather, exact min-convolution chains / SGM transform,
 // boundary lines through TMA stores + release/acquire counters + TMA loads) is as in run_band.
-template <int POT, int K>
+template <int POT, int K, int GL>
 __device__ void run_band_shear(const AggParams &P, const int pass, const int band, unsigned char *smem) {
+   constexpr int G = GL;
    static_assert(K <= 3, "the sheared wavefront needs predecessors in the row above only");
    constexpr bool NEEDM = (POT == POT_TRUNC && K == 2);
    constexpr bool CHAINS = (POT == POT_TRUNC);
@@ -761,7 +764,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
 
    // row groups (RowGroup): the boundary consumer warp belongs to group 0, the publisher warp to the last
    const int NG = P.ng[1], TG = T / NG;
-   const RowGroup grp = make_row_group(tid, ncomp, r, NG, TG);
+   const RowGroup grp = make_row_group(tid, ncomp, r, NG, TG, G);
    const int gw0 = grp.first_tid >> 5;
    const int ncw = (TG + 31) >> 5;
    const int pair_id0 = 4 + grp.gi * 2;
@@ -957,7 +960,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
          for (int d = 1; d < G; d <<= 1) m = fminf(m, __shfl_xor_sync(gmask, m, d));
          if (gl == 0) msr[r * 4 + (v & 1)] = m;
          if constexpr (POT == POT_SGM) {
-            if (fused) sgm_transform_regs<K, NJR, A16>(creg, nj, nq, gl, gmask, m, P.P1, P.P2, cur);
+            if (fused) sgm_transform_regs<K, NJR, A16, G>(creg, nj, nq, gl, gmask, m, P.P1, P.P2, cur);
          }
       }
       if (creg_mode) prefetch_cost(v);
@@ -1060,7 +1063,7 @@ __device__ int2 claim_band(const AggParams &P) {
    }
 }
 
-template <int POT, int K, bool WEIGHTED>
+template <int POT, int K, bool WEIGHTED, int GL>
 __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(const AggParams P) {
    extern __shared__ __align__(128) unsigned char smem[];
    __shared__ int2 s_ticket;
@@ -1084,20 +1087,20 @@ __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(c
       const int2 pb = s_ticket;
       __syncthreads();
       if (pb.x < 0) break;
-      if (pb.x < 4) run_band<POT, K, WEIGHTED, false>(P, pb.x, pb.y, smem);
+      if (pb.x < 4) run_band<POT, K, WEIGHTED, false, GL>(P, pb.x, pb.y, smem);
       else if constexpr (!WEIGHTED && K <= 3) {
-         if (P.shear) run_band_shear<POT, K>(P, pb.x, pb.y, smem);
-         else run_band<POT, K, WEIGHTED, true>(P, pb.x, pb.y, smem);
-      } else run_band<POT, K, WEIGHTED, true>(P, pb.x, pb.y, smem);
+         if (P.shear) run_band_shear<POT, K, GL>(P, pb.x, pb.y, smem);
+         else run_band<POT, K, WEIGHTED, true, GL>(P, pb.x, pb.y, smem);
+      } else run_band<POT, K, WEIGHTED, true, GL>(P, pb.x, pb.y, smem);
    }
 }
 
 // ---------------------------------------------------------------- host side
 static int ring_slots(int cls, int K) { return ((cls == 1 || K == 4) ? 2 : 1) + 2; }
 
-template <int POT, int K, bool WEIGHTED>
+template <int POT, int K, bool WEIGHTED, int GL = MGM_AGG_GROUP>
 static cudaError_t launch_t(const AggParams &P, const AggPlan &plan, cudaStream_t st) {
-   auto kern = mgm_aggregate_kernel<POT, K, WEIGHTED>;
+   auto kern = mgm_aggregate_kernel<POT, K, WEIGHTED, GL>;
    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
    if (e != cudaSuccess) return e;
    int per_sm = 0;
@@ -1115,6 +1118,16 @@ static cudaError_t launch_t(const AggParams &P, const AggPlan &plan, cudaStream_
 
 template <int POT, bool WEIGHTED>
 static cudaError_t launch_k(int K, const AggParams &P, const AggPlan &plan, cudaStream_t st) {
+   if constexpr (POT == POT_SGM && !WEIGHTED) {
+      if (plan.lanes == 4) {   // short label vectors: 4 lanes per worker, twice the workers per band
+         switch (K) {
+         case 1: return launch_t<POT, 1, WEIGHTED, 4>(P, plan, st);
+         case 2: return launch_t<POT, 2, WEIGHTED, 4>(P, plan, st);
+         case 3: return launch_t<POT, 3, WEIGHTED, 4>(P, plan, st);
+         default: return launch_t<POT, 4, WEIGHTED, 4>(P, plan, st);
+         }
+      }
+   }
    switch (K) {
    case 1: return launch_t<POT, 1, WEIGHTED>(P, plan, st);
    case 2: return launch_t<POT, 2, WEIGHTED>(P, plan, st);
@@ -1123,20 +1136,31 @@ static cudaError_t launch_k(int K, const AggParams &P, const AggPlan &plan, cuda
    }
 }
 
-static void agg_plan_try(AggPlan *plan, int L, int K, int pot, bool weighted, int max_smem, int num_sms, int t_override,
-                         int shear) {
+static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
+                         int t_override, int shear) {
    const int VS = (L + 31) & ~31;   // 8 lanes x 16 bytes per row and step
    plan->VS = VS;
    const int xtra = (weighted && pot == POT_TRUNC) ? K : 0;
-   const int tcap = (MGM_AGG_MAX_THREADS - 64) / MGM_AGG_GROUP;   // rows per CTA allowed by the thread budget
+   // lanes per worker: 8; 4 for the unweighted SGM kernels when the label vector is short (<= 128 labels), so that
+   // a lane still owns 8 chunks and a band holds twice the workers for the same per-step overhead
+   int want_groups = 1;   // row groups per band (RowGroup in the kernel); measured: no gain, the LSU is the shared limit
+   if (const char *e = getenv("MGMB200_GROUPS")) { const int v = atoi(e); if (!weighted && (v == 1 || v == 2 || v == 3)) want_groups = v; }
+   plan->lanes = MGM_AGG_GROUP;
+   if (pot == POT_SGM && !weighted && shear && want_groups == 1 && VS <= 16 * MGM_AGG_CREG && !getenv("MGMB200_NO_CREG") &&
+       !getenv("MGMB200_NO_FUSED_SGM") && !getenv("MGMB200_LANES8")) {
+      // only when the image still yields enough bands of that size to fill the machine twice (measured: with
+      // fewer, the longer hand-offs and the idle SMs cost more than the per-step overhead saved)
+      const int t4 = (MGM_AGG_MAX_THREADS - 64) / 4;
+      const long bands = 2L * ((ny + t4 - 1) / t4 + (nx + t4 - 1) / t4) + 4L * ((nx + ny + t4 - 2) / t4);
+      if (bands >= 2L * num_sms || getenv("MGMB200_LANES4")) plan->lanes = 4;
+   }
+   const int tcap = (MGM_AGG_MAX_THREADS - 64) / plan->lanes;   // rows per CTA allowed by the thread budget
    // costs prefetched into registers when a lane's share fits (one cost buffer per row), else a cp.async ring of two
-   plan->ncb = (VS / (4 * MGM_AGG_GROUP) <= MGM_AGG_CREG && !getenv("MGMB200_NO_CREG")) ? 1 : 2;
+   plan->ncb = (VS / (4 * plan->lanes) <= MGM_AGG_CREG && !getenv("MGMB200_NO_CREG")) ? 1 : 2;
    plan->shear = shear;
    const int nvirt = shear ? 2 : 1;   // boundary workers kept per position
    // unweighted truncated-linear kernels with register-resident costs build the message in its ring slot and run
    // the min-convolution in place: no cost buffer
-   int want_groups = 1;   // row groups per band (RowGroup in the kernel); measured: no gain, the LSU is the shared limit
-   if (const char *e = getenv("MGMB200_GROUPS")) { const int v = atoi(e); if (!weighted && (v == 1 || v == 2 || v == 3)) want_groups = v; }
    // ... and the unweighted SGM kernels transform the message straight from registers (one group only)
    plan->fused_sgm = (!weighted && pot == POT_SGM && plan->ncb == 1 && want_groups == 1 && !getenv("MGMB200_NO_FUSED_SGM")) ? 1 : 0;
    const int ncbuf = (!weighted && plan->ncb == 1 && (pot == POT_TRUNC || plan->fused_sgm)) ? 0 : plan->ncb;
@@ -1164,7 +1188,7 @@ static void agg_plan_try(AggPlan *plan, int L, int K, int pot, bool weighted, in
       plan->T[cls] = Tc;
    }
    const int tm = max(plan->T[0], plan->T[1]);
-   const int ncomp = (tm * MGM_AGG_GROUP + 31) & ~31;
+   const int ncomp = (tm * plan->lanes + 31) & ~31;
    plan->block = ncomp + 64;   // + boundary-consumer warp + boundary-publisher warp
    size_t off = 0;
    plan->off_phase = off; off += (size_t)(tm + 1) * 4; off = (off + 15) & ~(size_t)15;
@@ -1181,15 +1205,14 @@ static void agg_plan_try(AggPlan *plan, int L, int K, int pot, bool weighted, in
 
 void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
               int t_override) {
-   (void)nx; (void)ny;
    // diagonal sweeps as sheared wavefronts (run_band_shear): predecessors in the row above only, no image-dependent
    // weights, and room for at least two workers per band (the hand-off carries the last two)
    const bool want_shear = (K <= 3 && !weighted && !getenv("MGMB200_NO_SHEAR"));
    if (want_shear) {
-      agg_plan_try(plan, L, K, pot, weighted, max_smem, num_sms, t_override, 1);
+      agg_plan_try(plan, nx, ny, L, K, pot, weighted, max_smem, num_sms, t_override, 1);
       if (plan->T[0] >= 1 && plan->T[1] >= 2) return;
    }
-   agg_plan_try(plan, L, K, pot, weighted, max_smem, num_sms, t_override, 0);
+   agg_plan_try(plan, nx, ny, L, K, pot, weighted, max_smem, num_sms, t_override, 0);
 }
 
 cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st) {

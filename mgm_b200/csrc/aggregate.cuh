@@ -35,7 +35,7 @@ struct AggParams {
 };
 
 struct AggPlan {
-   int VS, T[2], TS[2], ncb, shear, ng[2], fused_sgm, block, num_sms;
+   int VS, T[2], TS[2], ncb, shear, ng[2], fused_sgm, lanes, block, num_sms;
    size_t smem;
    size_t off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };

@@ -42,6 +42,8 @@ else:
     (2048, 1536, 256, 3, 1, 0xFF, "full all trunc K3"),
     (2048, 1536, 256, 3, 0, 0xFF, "full all sgm K3"),
     (1920, 1080, 128, 2, 0, 0xFF, "cfg2 all sgm K2"),
+    (4096, 4096, 64, 2, 0, 0xFF, "big 4096x4096x64 sgm K2"),
+    (4096, 4096, 64, 4, 0, 0xFF, "big 4096x4096x64 sgm K4"),
 ]
 if __name__ == '__main__' and len(sys.argv) > 1:
     CASES = [c for c in CASES if sys.argv[1] in c[6]]
