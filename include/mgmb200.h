@@ -152,6 +152,38 @@ void mgmb200_stereo_params_default(mgmb200_stereo_params *p);   /* defaults of m
 int mgmb200_stereo(mgmb200_ctx *ctx, const float *u, const float *v, int nx, int ny, int nch,
                    const mgmb200_stereo_params *p, float *out, float *outcost);
 
+/* ---- the O(W*H) stages around the hot path in the CLI flow (mgm.cc:396-443), as small kernels so that the two
+ * directions, the median, the left-right tests and the back-projection stay on the device. */
+
+/* leftright_test(dx, Rdx, threshold)                                                        mgm.cc:68-91
+ * dx (nx*ny, tested in place) against the map of the other view Rdx (rnx*rny, rny >= ny). */
+int mgmb200_leftright_test(mgmb200_ctx *ctx, float *dx, int nx, int ny, const float *Rdx, int rnx, int rny,
+                           float threshold);
+/* median_filter(u, radius)                                                            img_tools.h:203-238
+ * NaN-aware median of the (2*radius+1)^2 window clipped to the image; radius 0..7. */
+int mgmb200_median_filter(mgmb200_ctx *ctx, const float *u, int nx, int ny, int nch, int radius, float *out);
+/* update_dmin_dmax(outoff, &dminI, &dmaxI, slack=3, radius=2)                             mgm.cc:120-158
+ * dminI/dmaxI updated in place; *gmin,*gmax (may be NULL) = the returned finite min/max of outoff. */
+int mgmb200_update_dmin_dmax(mgmb200_ctx *ctx, const float *outoff, int nx, int ny, float *dminI, float *dmaxI,
+                             int slack, int radius, float *gmin, float *gmax);
+/* the back-projected image of mgm.cc:432-443: v sampled at x + outoff where that is inside v, else u */
+int mgmb200_backproject(mgmb200_ctx *ctx, const float *outoff, const float *u, const float *v, int nx, int ny,
+                        int nch, int vnx, int vny, float *syn);
+
+/* The default command-line flow mgm.cc:372-443 (uniform range, TSGM_ITER=1) in one call: L->R run, median,
+ * R->L run with the mirrored range, median, both left-right tests, back-projection.  out/outcost are required;
+ * outR, outcostR (need testlrrl), out_nolr (the -l map: after the median, before the test) and backproj
+ * (nx*ny*nch) may be NULL. */
+typedef struct mgmb200_post_params {
+   int testlrrl;        /* env TESTLRRL */
+   float testlrrl_tau;  /* env TESTLRRL_TAU */
+   int median;          /* env MEDIAN: radius, 0 = off */
+} mgmb200_post_params;
+void mgmb200_post_params_default(mgmb200_post_params *q);   /* mgm.cc:194-196 */
+int mgmb200_stereo_lr(mgmb200_ctx *ctx, const float *u, const float *v, int nx, int ny, int nch,
+                      const mgmb200_stereo_params *p, const mgmb200_post_params *q, float *out, float *outcost,
+                      float *outR, float *outcostR, float *out_nolr, float *backproj);
+
 /* ------------------------------------------------------------------------------------------
  * Device-pointer entry points (inputs and outputs resident in HBM, asynchronous on the
  * context's stream).  d_cc is a padded volume.
@@ -188,6 +220,17 @@ int mgmb200_ipc_close(mgmb200_ctx *ctx, void *d_ptr);
 int mgmb200_finish_rows_dev(mgmb200_ctx *ctx, const float *const *d_sweeps, const float *d_cc, int nx, int ny,
                             int dmin, int dmax, int NDIR, int sgm_fix_overcount, int refinement_index,
                             int row_begin, int row_end, float *d_out, float *d_outcost);
+
+/* device-pointer forms of the post-processing stages; all out of place except update_dmin_dmax, whose
+ * d_minmax is 4 floats of scratch that receive the finite min and max of d_outoff in [0] and [1] */
+int mgmb200_leftright_test_dev(mgmb200_ctx *ctx, const float *d_dx, int nx, int ny, const float *d_Rdx, int rnx,
+                               int rny, float threshold, float *d_out);
+int mgmb200_median_filter_dev(mgmb200_ctx *ctx, const float *d_u, int nx, int ny, int nch, int radius,
+                              float *d_out);
+int mgmb200_update_dmin_dmax_dev(mgmb200_ctx *ctx, const float *d_outoff, int nx, int ny, float *d_dminI,
+                                 float *d_dmaxI, int slack, int radius, float *d_minmax);
+int mgmb200_backproject_dev(mgmb200_ctx *ctx, const float *d_outoff, const float *d_u, const float *d_v, int nx,
+                            int ny, int nch, int vnx, int vny, float *d_syn);
 
 /* device memory helpers so that non-CUDA hosts (ctypes, cgo, JNI) can drive the dev entry points */
 int mgmb200_malloc(mgmb200_ctx *ctx, size_t bytes, void **d_ptr);

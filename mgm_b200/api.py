@@ -54,6 +54,11 @@ class StereoParams(ctypes.Structure):
                 ("census_ncc_win", ctypes.c_int), ("refinement", ctypes.c_char_p)]
 
 
+class PostParams(ctypes.Structure):
+    """mgmb200_post_params: TESTLRRL, TESTLRRL_TAU, MEDIAN (mgm.cc:194-196)."""
+    _fields_ = [("testlrrl", ctypes.c_int), ("testlrrl_tau", ctypes.c_float), ("median", ctypes.c_int)]
+
+
 def load_library():
     """Load libmgmb200.so; raises if it has not been built (no fallback of any kind)."""
     global _LIB
@@ -265,6 +270,70 @@ class Context:
         self._check(self.lib.mgmb200_stereo(self._ctx, _fp(u), _fp(v), nx, ny, nch, ctypes.byref(p), _fp(out),
                                             _fp(outcost)))
         return out, outcost
+
+    # ------------------------------------------------------------------ post-processing of the CLI flow
+    def leftright_test(self, dx, Rdx, threshold=1.0):
+        """leftright_test (mgm.cc:68-91): returns the tested copy of dx."""
+        dx = np.array(dx, np.float32, copy=True)
+        Rdx = _f32(Rdx)
+        (ny, nx), (rny, rnx) = dx.shape, Rdx.shape
+        self._check(self.lib.mgmb200_leftright_test(self._ctx, _fp(dx), nx, ny, _fp(Rdx), rnx, rny,
+                                                    ctypes.c_float(threshold)))
+        return dx
+
+    def median_filter(self, u, radius):
+        """median_filter (img_tools.h:203-238) of an (H,W) or (C,H,W) image."""
+        a, nx, ny, nch = _img(u)
+        out = np.empty_like(a)
+        self._check(self.lib.mgmb200_median_filter(self._ctx, _fp(a), nx, ny, nch, int(radius), _fp(out)))
+        return out.reshape(np.shape(u))
+
+    def update_dmin_dmax(self, outoff, dminI, dmaxI, slack=3, radius=2):
+        """update_dmin_dmax (mgm.cc:120-158): returns (dminI, dmaxI, (gmin, gmax))."""
+        off = _f32(outoff)
+        ny, nx = off.shape
+        lo = np.array(dminI, np.float32, copy=True).reshape(ny, nx)
+        hi = np.array(dmaxI, np.float32, copy=True).reshape(ny, nx)
+        g0, g1 = ctypes.c_float(), ctypes.c_float()
+        self._check(self.lib.mgmb200_update_dmin_dmax(self._ctx, _fp(off), nx, ny, _fp(lo), _fp(hi), int(slack),
+                                                      int(radius), ctypes.byref(g0), ctypes.byref(g1)))
+        return lo, hi, (g0.value, g1.value)
+
+    def backproject(self, outoff, u, v):
+        """The back-projected image of mgm.cc:432-443."""
+        off = _f32(outoff)
+        u, nx, ny, nch = _img(u)
+        v, vnx, vny, vnch = _img(v)
+        if vnch != nch or off.shape != (ny, nx):
+            raise ValueError("outoff must have the size of u, and v its channels")
+        syn = np.empty_like(u)
+        self._check(self.lib.mgmb200_backproject(self._ctx, _fp(off), _fp(u), _fp(v), nx, ny, nch, vnx, vny, _fp(syn)))
+        return syn
+
+    def stereo_lr(self, u, v, dmin=-30, dmax=30, P1=8.0, P2=32.0, NDIR=4, MGM=4, use_felzenszwalb_potentials=0,
+                  sgm_fix_overcount=1, aP=1.0, aThresh=5.0, prefilter="none", distance="ad", truncDist=np.inf,
+                  census_ncc_win=3, refinement="none", testlrrl=1, testlrrl_tau=1.0, median=0, want_backproj=False):
+        """The default command-line flow mgm.cc:372-443 on the device: both directions, median, left-right tests,
+        back-projection.  Returns a dict with out, outcost, out_nolr and, with testlrrl, outR, outcostR."""
+        u, nx, ny, nch = _img(u)
+        v, vnx, vny, vnch = _img(v)
+        if (vnx, vny, vnch) != (nx, ny, nch):
+            raise ValueError("u and v must have the same shape")
+        p = StereoParams(int(dmin), int(dmax), P1, P2, int(NDIR), int(MGM), int(use_felzenszwalb_potentials),
+                         int(sgm_fix_overcount), aP, aThresh, prefilter.encode(), distance.encode(), truncDist,
+                         int(census_ncc_win), refinement.encode())
+        q = PostParams(int(testlrrl), testlrrl_tau, int(median))
+        r = dict(out=np.empty((ny, nx), np.float32), outcost=np.empty((ny, nx), np.float32),
+                 out_nolr=np.empty((ny, nx), np.float32))
+        if testlrrl:
+            r["outR"] = np.empty((ny, nx), np.float32)
+            r["outcostR"] = np.empty((ny, nx), np.float32)
+        if want_backproj:
+            r["backproj"] = np.empty((nch, ny, nx), np.float32)
+        self._check(self.lib.mgmb200_stereo_lr(self._ctx, _fp(u), _fp(v), nx, ny, nch, ctypes.byref(p), ctypes.byref(q),
+                                               _fp(r["out"]), _fp(r["outcost"]), _fp(r.get("outR")),
+                                               _fp(r.get("outcostR")), _fp(r["out_nolr"]), _fp(r.get("backproj"))))
+        return r
 
     # ------------------------------------------------------------------ device-pointer interface
     @staticmethod

@@ -11,6 +11,7 @@
 #include "aggregate.cuh"
 #include "costvolume.cuh"
 #include "wta.cuh"
+#include "post.cuh"
 
 using namespace mgm;
 
@@ -63,6 +64,7 @@ struct mgmb200_ctx {
    // per-pixel ranges of the call in flight (device pointers or nullptr): S range, cost-vector range
    const float *r_smin = nullptr, *r_smax = nullptr, *r_ccmin = nullptr, *r_ccmax = nullptr;
    DevBuf sweep[8];
+   DevBuf post[10];   // maps of the post-processing stages (N1/N2)
    DevBuf dbgbuf;
    size_t sweep_bytes = 0;
    // last launch info
@@ -139,6 +141,7 @@ extern "C" void mgmb200_destroy(mgmb200_ctx *c) {
                      &c->rg[2], &c->rg[3]};
    for (DevBuf *b : bufs) b->release();
    for (int i = 0; i < 8; i++) c->sweep[i].release();
+   for (DevBuf &b : c->post) b.release();
    if (c->own_stream) cudaStreamDestroy(c->own_stream);
    delete c;
 }
@@ -750,6 +753,27 @@ extern "C" void mgmb200_stereo_params_default(mgmb200_stereo_params *p) {
    p->refinement = "none";
 }
 
+// one direction of mgm.cc:372-385 on device-resident images: weights, cost volume, aggregation, WTA + refinement
+static int stereo_dev(mgmb200_ctx *c, const float *d_u, const float *d_v, int nx, int ny, int nch,
+                      const mgmb200_stereo_params *p, int dmin, int dmax, int pf, int di, float *d_out, float *d_outcost) {
+   const int L = dmax - dmin + 1, VS = mgmb200_padded_labels(L);
+   const size_t np = (size_t)nx * ny;
+   RET(c->w.reserve(np * 8 * 4));
+   RET(c->cc.reserve(np * VS * 4));
+   RET(clear_flags(c));
+   // weights + the "all ones?" scan of mgm_core.cc:420-422 in one kernel
+   CU(weights_launch(d_u, nx, ny, nch, p->aP, p->aThresh, c->w.as<float>(), c->flags.as<int>(), c->stream));
+   RET(mgmb200_costvolume_dev(c, d_u, d_v, nx, ny, nch, nx, ny, dmin, dmax, pf, di, p->truncDist, p->census_ncc_win,
+                              c->cc.as<float>()));
+   int fl = 0;
+   RET(read_flags(c, &fl));
+   if ((fl & 1) && !(p->aP >= 0.f && p->aP < INFINITY)) return fail(MGMB200_EUNSUPPORTED, "aP must be finite and >= 0");
+   const float P1 = p->P1 * nch, P2 = p->P2 * nch;   // mgm.cc:356-357
+   return mgmb200_aggregate_dev(c, c->cc.as<float>(), c->w.as<float>(), (fl & 1) ? 1 : 0, nx, ny, dmin, dmax, P1, P2, p->NDIR,
+                                p->MGM, p->use_felzenszwalb_potentials, p->sgm_fix_overcount,
+                                mgmb200_refinement_index(p->refinement), d_out, d_outcost, nullptr);
+}
+
 extern "C" int mgmb200_stereo(mgmb200_ctx *c, const float *u, const float *v, int nx, int ny, int nch,
                               const mgmb200_stereo_params *p, float *out, float *outcost) {
    if (!c || !u || !v || !p || !out || !outcost) return fail(MGMB200_EINVAL, "NULL argument");
@@ -761,25 +785,177 @@ extern "C" int mgmb200_stereo(mgmb200_ctx *c, const float *u, const float *v, in
    if (di == DIST_CENSUS) pf = PF_CENSUS;
    RET(upload(c, c->u, u, np * nch * 4));
    RET(upload(c, c->v, v, np * nch * 4));
-   RET(c->w.reserve(np * 8 * 4));
-   RET(c->cc.reserve(np * VS * 4));
    RET(c->out.reserve(np * 4));
    RET(c->outcost.reserve(np * 4));
-   RET(clear_flags(c));
-   // weights + the "all ones?" scan of mgm_core.cc:420-422 in one kernel
-   CU(weights_launch(c->u.as<float>(), nx, ny, nch, p->aP, p->aThresh, c->w.as<float>(), c->flags.as<int>(), c->stream));
-   RET(mgmb200_costvolume_dev(c, c->u.as<float>(), c->v.as<float>(), nx, ny, nch, nx, ny, p->dmin, p->dmax, pf, di,
-                              p->truncDist, p->census_ncc_win, c->cc.as<float>()));
-   int fl = 0;
-   RET(read_flags(c, &fl));
-   if ((fl & 1) && !(p->aP >= 0.f && p->aP < INFINITY)) return fail(MGMB200_EUNSUPPORTED, "aP must be finite and >= 0");
-   const float P1 = p->P1 * nch, P2 = p->P2 * nch;   // mgm.cc:356-357
-   RET(mgmb200_aggregate_dev(c, c->cc.as<float>(), c->w.as<float>(), (fl & 1) ? 1 : 0, nx, ny, p->dmin, p->dmax, P1, P2,
-                             p->NDIR, p->MGM, p->use_felzenszwalb_potentials, p->sgm_fix_overcount,
-                             mgmb200_refinement_index(p->refinement), c->out.as<float>(), c->outcost.as<float>(),
-                             nullptr));
+   RET(stereo_dev(c, c->u.as<float>(), c->v.as<float>(), nx, ny, nch, p, p->dmin, p->dmax, pf, di, c->out.as<float>(),
+                  c->outcost.as<float>()));
    RET(download(c, out, c->out.p, np * 4));
    RET(download(c, outcost, c->outcost.p, np * 4));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+
+// ------------------------------------------------------------------------------------------ post-processing (N1/N2)
+extern "C" int mgmb200_leftright_test_dev(mgmb200_ctx *c, const float *d_dx, int nx, int ny, const float *d_Rdx, int rnx,
+                                          int rny, float threshold, float *d_out) {
+   if (!c || !d_dx || !d_Rdx || !d_out) return fail(MGMB200_EINVAL, "NULL argument");
+   if (nx < 1 || ny < 1 || rnx < 1 || rny < ny) return fail(MGMB200_EINVAL, "maps %dx%d vs %dx%d: the other view needs at least as many rows", nx, ny, rnx, rny);
+   if (d_out == d_dx || d_out == d_Rdx) return fail(MGMB200_EINVAL, "the test is out of place (mgm.cc:421-424 passes copies)");
+   CU(cudaSetDevice(c->device));
+   CU(leftright_launch(d_dx, nx, ny, d_Rdx, rnx, threshold, d_out, c->stream));
+   return 0;
+}
+extern "C" int mgmb200_median_filter_dev(mgmb200_ctx *c, const float *d_u, int nx, int ny, int nch, int radius,
+                                         float *d_out) {
+   if (!c || !d_u || !d_out) return fail(MGMB200_EINVAL, "NULL argument");
+   if (nx < 1 || ny < 1 || nch < 1 || d_out == d_u) return fail(MGMB200_EINVAL, "image %dx%dx%d (out of place)", nx, ny, nch);
+   if (radius < 0 || radius > MGM_MEDIAN_MAX_RADIUS) return fail(MGMB200_EUNSUPPORTED, "median radius %d: 0..%d supported", radius, MGM_MEDIAN_MAX_RADIUS);
+   CU(cudaSetDevice(c->device));
+   CU(median_launch(d_u, nx, ny, nch, radius, d_out, c->stream));
+   return 0;
+}
+// d_minmax: 4 floats of device scratch; [0], [1] receive the finite min/max of d_outoff
+extern "C" int mgmb200_update_dmin_dmax_dev(mgmb200_ctx *c, const float *d_outoff, int nx, int ny, float *d_dminI,
+                                            float *d_dmaxI, int slack, int radius, float *d_minmax) {
+   if (!c || !d_outoff || !d_dminI || !d_dmaxI || !d_minmax) return fail(MGMB200_EINVAL, "NULL argument");
+   if (nx < 1 || ny < 1 || radius < 0) return fail(MGMB200_EINVAL, "image %dx%d radius %d", nx, ny, radius);
+   CU(cudaSetDevice(c->device));
+   const size_t np = (size_t)nx * ny;
+   RET(c->post[8].reserve(np * 4));
+   RET(c->post[9].reserve(np * 4));
+   CU(minmax_launch(d_outoff, (long long)np, d_minmax, c->num_sms, c->stream));
+   CU(update_range_launch(d_outoff, nx, ny, d_minmax, slack, radius, d_dminI, d_dmaxI, c->post[8].as<float>(),
+                          c->post[9].as<float>(), c->stream));
+   CU(cudaMemcpyAsync(d_dminI, c->post[8].p, np * 4, cudaMemcpyDeviceToDevice, c->stream));
+   CU(cudaMemcpyAsync(d_dmaxI, c->post[9].p, np * 4, cudaMemcpyDeviceToDevice, c->stream));
+   return 0;
+}
+extern "C" int mgmb200_backproject_dev(mgmb200_ctx *c, const float *d_outoff, const float *d_u, const float *d_v, int nx,
+                                       int ny, int nch, int vnx, int vny, float *d_syn) {
+   if (!c || !d_outoff || !d_u || !d_v || !d_syn) return fail(MGMB200_EINVAL, "NULL argument");
+   if (nx < 1 || ny < 1 || nch < 1 || vnx < 1 || vny < 1) return fail(MGMB200_EINVAL, "image %dx%dx%d / %dx%d", nx, ny, nch, vnx, vny);
+   CU(cudaSetDevice(c->device));
+   CU(backproject_launch(d_outoff, d_u, d_v, nx, ny, nch, vnx, vny, d_syn, c->stream));
+   return 0;
+}
+
+extern "C" int mgmb200_leftright_test(mgmb200_ctx *c, float *dx, int nx, int ny, const float *Rdx, int rnx, int rny,
+                                      float threshold) {
+   if (!c || !dx || !Rdx) return fail(MGMB200_EINVAL, "NULL argument");
+   if (nx < 1 || ny < 1 || rnx < 1 || rny < ny) return fail(MGMB200_EINVAL, "maps %dx%d vs %dx%d: the other view needs at least as many rows", nx, ny, rnx, rny);
+   CU(cudaSetDevice(c->device));
+   const size_t np = (size_t)nx * ny, rnp = (size_t)rnx * rny;
+   RET(upload(c, c->post[0], dx, np * 4));
+   RET(upload(c, c->post[1], Rdx, rnp * 4));
+   RET(c->post[2].reserve(np * 4));
+   RET(mgmb200_leftright_test_dev(c, c->post[0].as<float>(), nx, ny, c->post[1].as<float>(), rnx, rny, threshold,
+                                  c->post[2].as<float>()));
+   RET(download(c, dx, c->post[2].p, np * 4));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+extern "C" int mgmb200_median_filter(mgmb200_ctx *c, const float *u, int nx, int ny, int nch, int radius, float *out) {
+   if (!c || !u || !out) return fail(MGMB200_EINVAL, "NULL argument");
+   if (nx < 1 || ny < 1 || nch < 1) return fail(MGMB200_EINVAL, "image %dx%dx%d", nx, ny, nch);
+   CU(cudaSetDevice(c->device));
+   const size_t n = (size_t)nx * ny * nch;
+   RET(upload(c, c->post[0], u, n * 4));
+   RET(c->post[2].reserve(n * 4));
+   RET(mgmb200_median_filter_dev(c, c->post[0].as<float>(), nx, ny, nch, radius, c->post[2].as<float>()));
+   RET(download(c, out, c->post[2].p, n * 4));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+extern "C" int mgmb200_update_dmin_dmax(mgmb200_ctx *c, const float *outoff, int nx, int ny, float *dminI, float *dmaxI,
+                                        int slack, int radius, float *gmin, float *gmax) {
+   if (!c || !outoff || !dminI || !dmaxI) return fail(MGMB200_EINVAL, "NULL argument");
+   if (nx < 1 || ny < 1) return fail(MGMB200_EINVAL, "image %dx%d", nx, ny);
+   CU(cudaSetDevice(c->device));
+   const size_t np = (size_t)nx * ny;
+   RET(upload(c, c->post[0], outoff, np * 4));
+   RET(upload(c, c->post[1], dminI, np * 4));
+   RET(upload(c, c->post[2], dmaxI, np * 4));
+   RET(c->post[7].reserve(64));
+   RET(mgmb200_update_dmin_dmax_dev(c, c->post[0].as<float>(), nx, ny, c->post[1].as<float>(), c->post[2].as<float>(), slack,
+                                    radius, c->post[7].as<float>()));
+   float mm[2];
+   RET(download(c, dminI, c->post[1].p, np * 4));
+   RET(download(c, dmaxI, c->post[2].p, np * 4));
+   RET(download(c, mm, c->post[7].p, 8));
+   CU(cudaStreamSynchronize(c->stream));
+   if (gmin) *gmin = mm[0];
+   if (gmax) *gmax = mm[1];
+   return 0;
+}
+extern "C" int mgmb200_backproject(mgmb200_ctx *c, const float *outoff, const float *u, const float *v, int nx, int ny,
+                                   int nch, int vnx, int vny, float *syn) {
+   if (!c || !outoff || !u || !v || !syn) return fail(MGMB200_EINVAL, "NULL argument");
+   if (nx < 1 || ny < 1 || nch < 1 || vnx < 1 || vny < 1) return fail(MGMB200_EINVAL, "image %dx%dx%d / %dx%d", nx, ny, nch, vnx, vny);
+   CU(cudaSetDevice(c->device));
+   const size_t np = (size_t)nx * ny;
+   RET(upload(c, c->post[0], outoff, np * 4));
+   RET(upload(c, c->u, u, np * nch * 4));
+   RET(upload(c, c->v, v, (size_t)vnx * vny * nch * 4));
+   RET(c->post[2].reserve(np * nch * 4));
+   RET(mgmb200_backproject_dev(c, c->post[0].as<float>(), c->u.as<float>(), c->v.as<float>(), nx, ny, nch, vnx, vny,
+                               c->post[2].as<float>()));
+   RET(download(c, syn, c->post[2].p, np * nch * 4));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+
+extern "C" void mgmb200_post_params_default(mgmb200_post_params *q) {
+   if (!q) return;
+   q->testlrrl = 1; q->testlrrl_tau = 1.f; q->median = 0;   // mgm.cc:194-196
+}
+
+// The default CLI flow of mgm.cc:372-443 for uniform ranges and TSGM_ITER=1, resident on the device: the images go up
+// once, both directions run back to back, median + left-right tests + back-projection follow as small kernels, and
+// only the requested maps come back.
+extern "C" int mgmb200_stereo_lr(mgmb200_ctx *c, const float *u, const float *v, int nx, int ny, int nch,
+                                 const mgmb200_stereo_params *p, const mgmb200_post_params *q, float *out,
+                                 float *outcost, float *outR, float *outcostR, float *out_nolr, float *backproj) {
+   if (!c || !u || !v || !p || !q || !out || !outcost) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, p->dmin, p->dmax));
+   if (q->median < 0 || q->median > MGM_MEDIAN_MAX_RADIUS) return fail(MGMB200_EUNSUPPORTED, "median radius %d: 0..%d supported", q->median, MGM_MEDIAN_MAX_RADIUS);
+   if (!q->testlrrl && (outR || outcostR)) return fail(MGMB200_EINVAL, "outR/outcostR need testlrrl (the second run, mgm.cc:404)");
+   CU(cudaSetDevice(c->device));
+   const size_t np = (size_t)nx * ny;
+   int pf = mgmb200_prefilter_index(p->prefilter), di = mgmb200_distance_index(p->distance);
+   if (di == DIST_CENSUS) pf = PF_CENSUS;
+   RET(upload(c, c->u, u, np * nch * 4));
+   RET(upload(c, c->v, v, np * nch * 4));
+   for (int i = 0; i < 6; i++) RET(c->post[i].reserve(np * 4));
+   float *offL = c->post[0].as<float>(), *costL = c->post[1].as<float>(), *offR = c->post[2].as<float>(),
+         *costR = c->post[3].as<float>(), *t0 = c->post[4].as<float>(), *t1 = c->post[5].as<float>();
+   RET(stereo_dev(c, c->u.as<float>(), c->v.as<float>(), nx, ny, nch, p, p->dmin, p->dmax, pf, di, offL, costL));
+   if (q->median) {   // mgm.cc:396
+      CU(median_launch(offL, nx, ny, 1, q->median, t0, c->stream));
+      std::swap(offL, t0);
+   }
+   if (out_nolr) RET(download(c, out_nolr, offL, np * 4));   // mgm.cc:399-401
+   if (q->testlrrl) {
+      // mgm.cc:404-419: the other direction with the mirrored range
+      RET(stereo_dev(c, c->v.as<float>(), c->u.as<float>(), nx, ny, nch, p, -p->dmax, -p->dmin, pf, di, offR, costR));
+      if (q->median) {
+         CU(median_launch(offR, nx, ny, 1, q->median, t0, c->stream));
+         std::swap(offR, t0);
+      }
+      // mgm.cc:420-424: both tests read the untested maps
+      CU(leftright_launch(offR, nx, ny, offL, nx, q->testlrrl_tau, t0, c->stream));
+      CU(leftright_launch(offL, nx, ny, offR, nx, q->testlrrl_tau, t1, c->stream));
+      offR = t0;
+      offL = t1;
+      if (outR) RET(download(c, outR, offR, np * 4));
+      if (outcostR) RET(download(c, outcostR, costR, np * 4));
+   }
+   RET(download(c, out, offL, np * 4));
+   RET(download(c, outcost, costL, np * 4));
+   if (backproj) {
+      RET(c->post[6].reserve(np * nch * 4));
+      CU(backproject_launch(offL, c->u.as<float>(), c->v.as<float>(), nx, ny, nch, nx, ny, c->post[6].as<float>(), c->stream));
+      RET(download(c, backproj, c->post[6].p, np * nch * 4));
+   }
    CU(cudaStreamSynchronize(c->stream));
    return 0;
 }

@@ -1,9 +1,10 @@
 // `mgm` command line on the B200 hot path: same options, environment variables, console output and file
 // outputs as the reference CLI (mgm.cc:266-450), with the hot path (weights, cost volume, aggregation, WTA,
-// sub-pixel: mgm.cc:372-385 and :405-414) executed by libmgmb200 on the GPU.  The O(W*H) post-processing
-// around it (left-right test mgm.cc:68-91, median img_tools.h:203-238, back-projection mgm.cc:432-443) is
-// host code here.  -m/-M range images and TSGM_ITER > 1 take the call-by-call sequence of mgm.cc:372-395 (cost
-// volume, then mgm + refinement + range update per iteration) instead of the fused mgmb200_stereo.  Not supported
+// sub-pixel: mgm.cc:372-385 and :405-414) and the O(W*H) stages around it (left-right test mgm.cc:68-91, median
+// img_tools.h:203-238, range update mgm.cc:120-158, back-projection mgm.cc:432-443) executed by libmgmb200 on the
+// GPU.  The default flow is one mgmb200_stereo_lr call: the images go up once and the maps come back once.
+// -m/-M range images and TSGM_ITER > 1 take the call-by-call sequence of mgm.cc:372-395 (cost volume, then mgm +
+// refinement + range update per iteration) through the mirror functions of mgmb200_host.hpp.  Not supported
 // (exit code 2 or 3 with a message, never a silent fallback): -O 16, truncated-linear potentials with per-pixel
 // ranges unless TSGM=2 without weights.
 #include <algorithm>
@@ -39,87 +40,6 @@ MGMB200_SMART_PARAMETER(MEDIAN, 0)
 
 static void remove_nonfinite_values_Img(Img &u, float newval) {
    for (float &f : u.data) if (!std::isfinite(f)) f = newval;
-}
-
-// leftright_test, mgm.cc:68-91
-static void leftright_test(Img &dx, const Img &Rdx, float threshold) {
-   const int nc = dx.nx, nr = dx.ny, Rnc = Rdx.nx;
-   for (int y = 0; y < nr; y++)
-      for (int x = 0; x < nc; x++) {
-         const int i = x + y * nc;
-         const int Lx = (int)round(x + dx[i]);
-         if (Lx < Rnc && Lx >= 0) {
-            const float Rx = Lx + Rdx[Lx + y * Rnc];
-            if (fabs(Rx - x) > threshold) dx[i] = NAN;
-         } else
-            dx[i] = NAN;
-      }
-}
-
-// median_filter, img_tools.h:203-238 (NaN-aware, upper median)
-static Img median_filter(const Img &u, int radius) {
-   Img M = u;
-   std::vector<float> v;
-   for (int k = 0; k < u.nch; k++)
-      for (int y = 0; y < u.ny; y++)
-         for (int x = 0; x < u.nx; x++) {
-            v.clear();
-            for (int j = -radius; j <= radius; j++)
-               for (int i = -radius; i <= radius; i++) {
-                  const int xx = x + i, yy = y + j;
-                  if (xx < 0 || yy < 0 || xx >= u.nx || yy >= u.ny) continue;
-                  const float t = u.val(xx, yy, k);
-                  if (!std::isnan(t)) v.push_back(t);
-               }
-            if (!v.empty()) {
-               std::nth_element(v.begin(), v.begin() + v.size() / 2, v.end());
-               M.val(x, y, k) = v[v.size() / 2];
-            }
-         }
-   return M;
-}
-
-// image_minmax, img_tools.h:183-200
-static std::pair<float, float> image_minmax(const Img &u) {
-   float gmin = INFINITY, gmax = -INFINITY;
-   for (float v : u.data)
-      if (std::isfinite(v)) {
-         if (v < gmin) gmin = v;
-         if (v > gmax) gmax = v;
-      }
-   return std::pair<float, float>(gmin, gmax);
-}
-
-// update_dmin_dmax, mgm.cc:120-158 (slack 3, radius 2, Neumann borders)
-static std::pair<float, float> update_dmin_dmax(const Img &outoff, Img *dminI, Img *dmaxI, int slack = 3, int radius = 2) {
-   Img dminI2(*dminI), dmaxI2(*dmaxI);
-   const int nx = outoff.nx, ny = outoff.ny;
-   const std::pair<float, float> gminmax = image_minmax(outoff);
-   const float gmin = gminmax.first, gmax = gminmax.second;
-   if (slack < 0) slack = -slack;
-   const int r = radius;
-   for (int j = 0; j < ny; j++)
-      for (int i = 0; i < nx; i++) {
-         float dmin = INFINITY, dmax = -INFINITY;
-         for (int dj = -r; dj <= r; dj++)
-            for (int di = -r; di <= r; di++) {
-               int xx = i + di, yy = j + dj;
-               xx = xx >= 0 ? xx : 0; xx = xx < nx ? xx : nx - 1;
-               yy = yy >= 0 ? yy : 0; yy = yy < ny ? yy : ny - 1;
-               const float v = outoff.data[xx + (size_t)yy * nx];
-               if (std::isfinite(v)) {
-                  dmin = fmin(dmin, v - slack);
-                  dmax = fmax(dmax, v + slack);
-               } else {
-                  dmin = fmin(dmin, gmin - slack);
-                  dmax = fmax(dmax, gmax + slack);
-               }
-            }
-         if (std::isfinite(dmin)) { dminI2[i + j * nx] = dmin; dmaxI2[i + j * nx] = dmax; }
-      }
-   *dminI = dminI2;
-   *dmaxI = dmaxI2;
-   return gminmax;
 }
 
 static const char *help_usage = "usage:\n\tmgm [-options] u v out [cost [backflow]]";
@@ -209,14 +129,7 @@ int main(int argc, char *argv[]) {
          for (int k = 0; k < u.npix; k++)
             if (dmaxI[k] < dminI[k] + 1) dmaxI[k] = ceil(dminI[k] + 1);
       }
-      auto run = [&](Img &a, Img &b, int lo, int hi, Img &off, Img &cost, Img &loI, Img &hiI) {
-         if (!stepwise) {
-            p.dmin = lo; p.dmax = hi;
-            check(mgmb200_stereo(context(), a.data.data(), b.data.data(), a.nx, a.ny, a.nch, &p, off.data.data(), cost.data.data()));
-            for (int pass = 0; pass < NDIR; pass++) printf("%d", pass);   // mgm_core.cc:491
-            printf("\n");                                                  // print_solution_energy, mgm_print_energy.h:110
-            return;
-         }
+      auto run = [&](Img &a, Img &b, Img &off, Img &cost, Img &loI, Img &hiI) {
          // mgm.cc:372-395 call by call: the cost volume keeps its ranges, every iteration aggregates, refines and
          // updates the range images the next winner-take-all is restricted to
          Img w = compute_mgm_weights(a, aP2, aThresh);
@@ -232,33 +145,35 @@ int main(int argc, char *argv[]) {
             remove_nonfinite_values_Img(hiI, gminmax.second);
          }
       };
-      run(u, v, dmin, dmax, outoff, outcost, dminI, dmaxI);
-      if (MEDIAN()) outoff = median_filter(outoff, (int)MEDIAN());
-      if (0 != strcmp(nolr_disp_file, "")) io::write_image(nolr_disp_file, outoff);
-
-      if (TESTLRRL()) {
-         run(v, u, -dmax, -dmin, outoffR, outcostR, dminRI, dmaxRI);
-         if (MEDIAN()) outoffR = median_filter(outoffR, (int)MEDIAN());
-         Img tmpL(outoff), tmpR(outoffR);
-         leftright_test(outoffR, tmpL, (float)TESTLRRL_TAU());
-         leftright_test(outoff, tmpR, (float)TESTLRRL_TAU());
-      }
-
-      // back-projected image, mgm.cc:432-443
       Img syn(u.nx, u.ny, u.nch);
-      for (int x = 0; x < u.nx; x++)
-         for (int y = 0; y < u.ny; y++) {
-            const float qx = outoff[x + u.nx * y], qy = 0.f;
-            const float px = x + qx;
-            for (int c = 0; c < u.nch; c++) {
-               if (px >= 0 && px < v.nx) {   // check_inside_image(p+q, v) on float coordinates (NaN -> outside)
-                  // the reference indexes v.data with a FLOAT expression (mgm.cc:439): same arithmetic here
-                  const float fidx = x + qx + (y + qy) * v.nx + c * v.npix;
-                  syn.data[x + y * u.nx + (size_t)c * u.npix] = v.data[(size_t)fidx];
-               } else
-                  syn.data[x + y * u.nx + (size_t)c * u.npix] = u.data[x + y * u.nx + (size_t)c * u.npix];
-            }
+      if (!stepwise) {
+         // mgm.cc:372-443 in one device-resident call
+         mgmb200_post_params q;
+         q.testlrrl = TESTLRRL() ? 1 : 0;
+         q.testlrrl_tau = (float)TESTLRRL_TAU();
+         q.median = (int)MEDIAN();
+         p.dmin = dmin; p.dmax = dmax;
+         Img nolr(u.nx, u.ny);
+         check(mgmb200_stereo_lr(context(), u.data.data(), v.data.data(), u.nx, u.ny, u.nch, &p, &q, outoff.data.data(),
+                                 outcost.data.data(), NULL, NULL, nolr.data.data(), syn.data.data()));
+         for (int r = 0; r < (q.testlrrl ? 2 : 1); r++) {
+            for (int pass = 0; pass < NDIR; pass++) printf("%d", pass);   // mgm_core.cc:491
+            printf("\n");                                                  // print_solution_energy, mgm_print_energy.h:110
          }
+         if (0 != strcmp(nolr_disp_file, "")) io::write_image(nolr_disp_file, nolr);
+      } else {
+         run(u, v, outoff, outcost, dminI, dmaxI);
+         if (MEDIAN()) outoff = median_filter(outoff, (int)MEDIAN());
+         if (0 != strcmp(nolr_disp_file, "")) io::write_image(nolr_disp_file, outoff);
+         if (TESTLRRL()) {
+            run(v, u, outoffR, outcostR, dminRI, dmaxRI);
+            if (MEDIAN()) outoffR = median_filter(outoffR, (int)MEDIAN());
+            Img tmpL(outoff), tmpR(outoffR);
+            leftright_test(outoffR, tmpL, (float)TESTLRRL_TAU());
+            leftright_test(outoff, tmpR, (float)TESTLRRL_TAU());
+         }
+         syn = backproject(outoff, u, v);
+      }
 
       io::write_image(filename_out, outoff);
       if (filename_cost) io::write_image(filename_cost, outcost);

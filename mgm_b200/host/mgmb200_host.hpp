@@ -12,6 +12,8 @@
 //                    USE_FELZENSZWALB_POTENTIALS = 0, SGM_FIX_OVERCOUNT = 1)        mgm_core.cc:408
 //   void subpixel_refinement_sgm(costvolume_t&, std::vector<float>&, std::vector<float>&, char*)
 //                                               mgm_refine.h:40
+//   void leftright_test(Img&, Img&, float)      mgm.cc:68      Img median_filter(Img const&, int)  img_tools.h:203
+//   std::pair<float,float> update_dmin_dmax(Img, Img*, Img*, int, int)              mgm.cc:120
 // All arithmetic happens on the GPU; there is no host fallback (errors throw std::runtime_error).
 #pragma once
 #include <math.h>
@@ -21,6 +23,7 @@
 
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mgmb200.h"
@@ -188,6 +191,32 @@ inline void subpixel_refinement_sgm(costvolume_t &S, std::vector<float> &out, st
    else
       check(mgmb200_subpixel_refinement_sgm_ranges(context(), S.values.data(), S.lo.data(), S.hi.data(), S.nx, S.ny,
                                                    S.dmin, S.dmax, out.data(), outcost.data(), refinement));
+}
+
+// ---- the O(W*H) stages of the command-line flow, same signatures as the reference's
+// leftright_test, mgm.cc:68-91
+inline void leftright_test(Img &dx, Img &Rdx, float threshold = 1) {
+   check(mgmb200_leftright_test(context(), dx.data.data(), dx.nx, dx.ny, Rdx.data.data(), Rdx.nx, Rdx.ny, threshold));
+}
+// median_filter, img_tools.h:203-238
+inline Img median_filter(Img const &u, int radius) {
+   Img M(u.nx, u.ny, u.nch);
+   check(mgmb200_median_filter(context(), u.data.data(), u.nx, u.ny, u.nch, radius, M.data.data()));
+   return M;
+}
+// update_dmin_dmax, mgm.cc:120-158
+inline std::pair<float, float> update_dmin_dmax(const Img &outoff, Img *dminI, Img *dmaxI, int slack = 3, int radius = 2) {
+   float gmin = 0, gmax = 0;
+   check(mgmb200_update_dmin_dmax(context(), outoff.data.data(), outoff.nx, outoff.ny, dminI->data.data(),
+                                  dmaxI->data.data(), slack, radius, &gmin, &gmax));
+   return std::pair<float, float>(gmin, gmax);
+}
+// the back-projected image of mgm.cc:432-443
+inline Img backproject(const Img &outoff, const Img &u, const Img &v) {
+   Img syn(u.nx, u.ny, u.nch);
+   check(mgmb200_backproject(context(), outoff.data.data(), u.data.data(), v.data.data(), u.nx, u.ny, u.nch, v.nx, v.ny,
+                             syn.data.data()));
+   return syn;
 }
 
 }  // namespace mgmb200

@@ -208,6 +208,39 @@ def orc_refine_ranges(S, smin, smax, emin, out, outcost, refinement="none"):
     return out, outcost
 
 
+def orc_leftright(dx, Rdx, threshold=1.0):
+    dx = np.array(dx, np.float32, copy=True)
+    Rdx = np.ascontiguousarray(Rdx, np.float32)
+    orc_lib().orc_leftright(_fp(dx), _fp(Rdx), dx.shape[1], dx.shape[0], Rdx.shape[1], ctypes.c_float(threshold))
+    return dx
+
+
+def orc_median(u, radius):
+    u = np.ascontiguousarray(u, np.float32)
+    out = np.empty_like(u)
+    for a, o in zip(u.reshape(-1, *u.shape[-2:]), out.reshape(-1, *u.shape[-2:])):
+        orc_lib().orc_median(_fp(a), a.shape[1], a.shape[0], int(radius), _fp(o))
+    return out
+
+
+def orc_update_range(off, lo, hi, slack=3, radius=2):
+    off = np.ascontiguousarray(off, np.float32)
+    lo = np.array(lo, np.float32, copy=True)
+    hi = np.array(hi, np.float32, copy=True)
+    mm = np.zeros(2, np.float32)
+    orc_lib().orc_update_range(_fp(off), off.shape[1], off.shape[0], _fp(lo), _fp(hi), int(slack), int(radius), _fp(mm))
+    return lo, hi, (float(mm[0]), float(mm[1]))
+
+
+def orc_backproject(off, u, v):
+    off = np.ascontiguousarray(off, np.float32)
+    u, nx, ny, nch = _img(u)
+    v, vnx, vny, _ = _img(v)
+    syn = np.empty_like(u)
+    orc_lib().orc_backproject(_fp(off), _fp(u), _fp(v), nx, ny, nch, vnx, vny, _fp(syn))
+    return syn
+
+
 def orc_scan_preds(p, nx=9, ny=7):
     o = (ctypes.c_int * 8)()
     orc_lib().orc_pass_scan_preds(p, nx, ny, o)
@@ -308,3 +341,35 @@ def ref_refine_ranges(S, smin, smax, emin, out, outcost, refinement="none", flav
     ref_lib(flavour).ref_refine_ranges(_fp(S), _fp(slo), _fp(shi), nx, ny, emin, emin + L - 1, _fp(out), _fp(outcost),
                                        refinement.encode())
     return out, outcost
+
+
+# the reference's CLI translation unit as a library (oracle/ref_cli_harness.cc)
+def refcli_lib():
+    if "cli" not in _ref:
+        _ref["cli"] = _load(os.path.join(_HERE, "_ref", "libmgmref_cli.so"))
+    return _ref["cli"]
+
+
+def ref_leftright(dx, Rdx, threshold=1.0):
+    dx = np.array(dx, np.float32, copy=True)
+    Rdx = np.ascontiguousarray(Rdx, np.float32)
+    refcli_lib().refcli_leftright(_fp(dx), dx.shape[1], dx.shape[0], _fp(Rdx), Rdx.shape[1], Rdx.shape[0],
+                                  ctypes.c_float(threshold))
+    return dx
+
+
+def ref_median(u, radius):
+    a, nx, ny, nch = _img(u)
+    out = np.empty_like(a)
+    refcli_lib().refcli_median(_fp(a), nx, ny, nch, int(radius), _fp(out))
+    return out.reshape(np.shape(u))
+
+
+def ref_update_range(off, lo, hi, slack=3, radius=2):
+    off = np.ascontiguousarray(off, np.float32)
+    lo = np.array(lo, np.float32, copy=True)
+    hi = np.array(hi, np.float32, copy=True)
+    mm = np.zeros(2, np.float32)
+    refcli_lib().refcli_update_dmin_dmax(_fp(off), off.shape[1], off.shape[0], _fp(lo), _fp(hi), int(slack), int(radius),
+                                         _fp(mm))
+    return lo, hi, (float(mm[0]), float(mm[1]))

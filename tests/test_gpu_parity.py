@@ -323,6 +323,76 @@ OUR_MGM = os.path.join(ROOT, "mgm_b200", "bin", "mgm")
 OUR_MGM_O = os.path.join(ROOT, "mgm_b200", "bin", "mgm_o")
 
 
+# ------------------------------------------------------------------------------------------ N1/N2 post-processing
+def _disparity_maps(nx, ny, seed):
+    rng = np.random.default_rng(seed)
+    base = -np.round(6 + 4 * np.sin(0.11 * np.arange(nx))[None, :] * np.cos(0.07 * np.arange(ny))[:, None])
+    dl = (base + rng.integers(-1, 2, (ny, nx)) * (rng.random((ny, nx)) < 0.2)).astype(np.float32)
+    dl += (rng.random((ny, nx)) < 0.3) * rng.uniform(-0.5, 0.5, (ny, nx)).astype(np.float32)
+    dr = (-base + rng.integers(-2, 3, (ny, nx)) * (rng.random((ny, nx)) < 0.2)).astype(np.float32)
+    for d in (dl, dr):
+        d[rng.random((ny, nx)) < 0.05] = np.nan
+        d[rng.random((ny, nx)) < 0.01] = np.inf
+        d[rng.random((ny, nx)) < 0.01] = 1e9
+    return dl, dr
+
+
+@pytest.mark.parametrize("shape", [(37, 23), (300, 41), (3, 3), (1, 7), (64, 1)])
+def test_postprocessing_stages(ctx, shape):
+    """leftright_test (mgm.cc:68-91), median_filter (img_tools.h:203-238), update_dmin_dmax (mgm.cc:120-158),
+    back-projection (mgm.cc:432-443) against the oracle, NaN / INF / out-of-image disparities included"""
+    nx, ny = shape
+    dl, dr = _disparity_maps(nx, ny, nx + ny)
+    for tau in (1.0, 0.0, 2.5):
+        assert same(ctx.leftright_test(dl, dr, tau), O.orc_leftright(dl, dr, tau))
+        assert same(ctx.leftright_test(dr, dl, tau), O.orc_leftright(dr, dl, tau))
+    for r in (0, 1, 2, 3, 7):
+        assert same(ctx.median_filter(dl, r), O.orc_median(dl, r)), r
+    rgb = np.stack([dl, dr, dl + 1])
+    assert same(ctx.median_filter(rgb, 1), O.orc_median(rgb, 1))
+    lo = np.full((ny, nx), -12, np.float32)
+    hi = np.full((ny, nx), 3, np.float32)
+    for off, kw in ((dl, {}), (np.full((ny, nx), np.nan, np.float32), {}), (dl, dict(slack=-2, radius=1)), (dr, dict(slack=0, radius=0))):
+        a, b = ctx.update_dmin_dmax(off, lo, hi, **kw), O.orc_update_range(off, lo, hi, **kw)
+        assert same(a[0], b[0]) and same(a[1], b[1]) and a[2] == b[2], kw
+    for nch in (1, 3):
+        u, v = synth_pair(nx, ny, 8, seed=2, nch=nch)
+        off = np.where(np.isfinite(dl) & (np.abs(dl) < 1e6), dl, np.float32(np.nan))
+        assert same(ctx.backproject(off, u, v), O.orc_backproject(off, u, v))
+    with pytest.raises(Exception):
+        ctx.median_filter(dl, 8)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(distance="ad", MGM=2, NDIR=4, median=0, testlrrl=1),
+    dict(distance="census", MGM=3, NDIR=8, use_felzenszwalb_potentials=1, P1=2.0, P2=20000.0, refinement="vfit", median=1, testlrrl=1),
+    dict(distance="sd", MGM=4, NDIR=8, aP=4.0, aThresh=9.0, refinement="cubic", median=2, testlrrl=1, testlrrl_tau=2.0),
+    dict(distance="ad", MGM=1, NDIR=8, median=1, testlrrl=0),
+])
+def test_stereo_lr_flow(ctx, kw):
+    """mgmb200_stereo_lr = the CLI flow mgm.cc:372-443: L->R, median, R->L on the mirrored range, median, both
+    left-right tests on the untested maps, back-projection"""
+    kw = dict(kw)
+    median, lr, tau = kw.pop("median"), kw.pop("testlrrl"), kw.pop("testlrrl_tau", 1.0)
+    nch = 3 if kw["distance"] == "sd" else 1
+    u, v = synth_pair(97, 43, 20, seed=9, nch=nch)
+    r = ctx.stereo_lr(u, v, -19, 3, testlrrl=lr, testlrrl_tau=tau, median=median, want_backproj=True, **kw)
+    okw = dict(P1=kw.get("P1", 8.0), P2=kw.get("P2", 32.0), NDIR=kw["NDIR"], K=kw["MGM"], felz=kw.get("use_felzenszwalb_potentials", 0),
+               aP=kw.get("aP", 1.0), aThresh=kw.get("aThresh", 5.0), distance=kw["distance"], refinement=kw.get("refinement", "none"))
+    L = O.orc_pipeline(u, v, -19, 3, **okw)
+    offL = O.orc_median(L["out"], median) if median else L["out"]
+    assert same(r["out_nolr"], offL)
+    out = offL
+    if lr:
+        R = O.orc_pipeline(v, u, -3, 19, **okw)
+        offR = O.orc_median(R["out"], median) if median else R["out"]
+        out = O.orc_leftright(offL, offR, tau)
+        assert same(r["outR"], O.orc_leftright(offR, offL, tau)) and same(r["outcostR"], R["outcost"])
+        assert np.isnan(out).any() and np.isfinite(out).any()
+    assert same(r["out"], out) and same(r["outcost"], L["outcost"])
+    assert same(r["backproj"], O.orc_backproject(out, u, v))
+
+
 def _pnm(path, a):
     a = np.clip(a, 0, 255).astype(np.uint8)
     if a.shape[0] == 1:

@@ -171,3 +171,36 @@ def test_port_ranges_vs_ref():
             ra = O.orc_refine_ranges(a["S"], slo, shi, emin, b["out"], b["outcost"], "vfit")
             rb = O.ref_refine_ranges(b["S"], slo, shi, emin, b["out"], b["outcost"], "vfit")
             assert same(ra[0][ok], rb[0][ok]) and same(ra[1][ok], rb[1][ok])
+
+
+def _disparity_maps(nx, ny, seed):
+    """a pair of plausible L->R / R->L maps with sub-pixel parts, NaNs, infinities and outliers"""
+    rng = np.random.default_rng(seed)
+    base = -np.round(6 + 4 * np.sin(0.11 * np.arange(nx))[None, :] * np.cos(0.07 * np.arange(ny))[:, None])
+    dl = (base + rng.integers(-1, 2, (ny, nx)) * (rng.random((ny, nx)) < 0.2)).astype(np.float32)
+    dl += (rng.random((ny, nx)) < 0.3) * rng.uniform(-0.5, 0.5, (ny, nx)).astype(np.float32)
+    dr = (-base + rng.integers(-2, 3, (ny, nx)) * (rng.random((ny, nx)) < 0.2)).astype(np.float32)
+    for d in (dl, dr):
+        d[rng.random((ny, nx)) < 0.05] = np.nan
+        d[rng.random((ny, nx)) < 0.01] = np.inf
+        d[rng.random((ny, nx)) < 0.01] = 1e9
+    return dl, dr
+
+
+@pytest.mark.skipif(O.refcli_lib() is None, reason="oracle/_ref/libmgmref_cli.so not built")
+def test_port_postprocessing_vs_ref():
+    """leftright_test, median_filter, update_dmin_dmax of the port against the reference's own functions"""
+    for seed, (nx, ny) in enumerate([(37, 23), (64, 5), (3, 3), (1, 7)]):
+        dl, dr = _disparity_maps(nx, ny, seed)
+        for tau in (1.0, 0.0, 2.5):
+            assert same(O.orc_leftright(dl, dr, tau), O.ref_leftright(dl, dr, tau))
+            assert same(O.orc_leftright(dr, dl, tau), O.ref_leftright(dr, dl, tau))
+        for r in (1, 2, 3):
+            assert same(O.orc_median(dl, r), O.ref_median(dl, r))
+        lo = np.full((ny, nx), -12, np.float32)
+        hi = np.full((ny, nx), 3, np.float32)
+        for off in (dl, np.full((ny, nx), np.nan, np.float32)):
+            a, b = O.orc_update_range(off, lo, hi), O.ref_update_range(off, lo, hi)
+            assert same(a[0], b[0]) and same(a[1], b[1]) and a[2] == b[2]
+        a, b = O.orc_update_range(dl, lo, hi, slack=-2, radius=1), O.ref_update_range(dl, lo, hi, slack=-2, radius=1)
+        assert same(a[0], b[0]) and same(a[1], b[1]) and a[2] == b[2]
