@@ -339,6 +339,21 @@ def main():
             t = torch.tensor([ms_e2e], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e2e = float(t.item())
+    # secondary: the default command-line flow (SURVEY 8(d) "CLI-equivalent"): both directions, median of radius 1,
+    # left-right tests, all inside one mgmb200_stereo_lr call with host images in and host maps out
+    ms_lr = None
+    if world == 1:
+        def step_lr():
+            return ctx.stereo_lr(pu, pv, dmin=dmin, dmax=dmax, P1=wl["P1"], P2=wl["P2"], NDIR=NDIR, MGM=K,
+                                 use_felzenszwalb_potentials=wl["felz"], distance="census", census_ncc_win=wl["win"],
+                                 refinement=wl["refine"], testlrrl=1, median=1)
+        step_lr()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(min(args.steps, 3)):
+            step_lr()
+        torch.cuda.synchronize()
+        ms_lr = (time.perf_counter() - t0) * 1e3 / min(args.steps, 3)
     clocks = sampler.finish() if rank == 0 else None
 
     if rank != 0:
@@ -389,6 +404,11 @@ def main():
                        "h2d_bytes_per_step": nunits * 2 * W * H * 4, "d2h_bytes_per_step": nunits * 2 * W * H * 4,
                        "ms_per_step": round(ms_e2e, 3), "mpix_per_s": round(nunits * W * H / (ms_e2e * 1e-3) / 1e6, 2),
                        "call": "mgmb200_stereo (pinned host images in, pinned host maps out)"}
+    if ms_lr is not None:
+        line["e2e_cli_flow"] = {"ms_per_pair": round(ms_lr, 3), "mpix_per_s": round(W * H / (ms_lr * 1e-3) / 1e6, 2),
+                                "value": round(2 * updates / (ms_lr * 1e-3) / 1e9, 3), "unit": "Gdisp-updates/s",
+                                "call": "mgmb200_stereo_lr: L->R + R->L runs, median radius 1, left-right tests "
+                                        "(TESTLRRL=1 MEDIAN=1, mgm.cc:372-424); host images in, host maps out"}
     if not args.no_cpu_baseline and world == 1:
         try:
             _, cb = cpu_reference_rate(wl)
