@@ -117,8 +117,9 @@ int mgmb200_costvolume_ranges(mgmb200_ctx *ctx, const float *u, const float *v, 
  * cc: nx*ny*L floats whose vectors have the ranges [ccmin,ccmax] (entries outside are ignored); dminI/dmaxI: the
  * ranges of the returned volume S, over which the winner is taken (they differ from the former from the second
  * TSGM_ITER iteration on, mgm.cc:377-395).  S_out: NULL or nx*ny*L floats, +INF outside [dminI,dmaxI].
- * Truncated-linear potentials with non-uniform cost ranges are supported for MGM=2 without image-dependent
- * weights (the variant that folds out-of-range labels back in, mgm_core.cc:166-219); MGMB200_EUNSUPPORTED else. */
+ * Truncated-linear potentials with non-uniform cost ranges: MGM=2 without image-dependent weights folds the
+ * out-of-range labels back in (mgm_core.cc:166-219), every other variant convolves inside the receiving pixel's
+ * range (mgm_core.cc:229-281); both are reproduced. */
 int mgmb200_mgm_ranges(mgmb200_ctx *ctx, const float *cc, const float *ccmin, const float *ccmax, const float *w,
                        int nx, int ny, int emin, int emax, const float *dminI, const float *dmaxI, float P1,
                        float P2, int NDIR, int MGM, int use_felzenszwalb_potentials, int sgm_fix_overcount,

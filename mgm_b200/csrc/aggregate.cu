@@ -245,9 +245,20 @@ __device__ __forceinline__ RowGroup make_row_group(int tid, int ncomp, int r, in
 // hence Q[o] = min(Q[o+1]+c, F[o]) (and symmetrically Q[o] = min(Q[o-1]+c, B[o])): each lane continues ITS
 // recurrence over the partner's partial values only -- same additions in the same order as the reference,
 // one shared-memory read per label less (checked bit for bit in tests/micro/chain_bench.cu, form 6).
-template <int DIR>
+// MASK: labels outside [mlo,mhi] of the source read as +INF -- the min-convolution of a truncated-linear update
+// with per-pixel ranges runs inside the RECEIVING pixel's range (mgm_core.cc:229-281), which on dense vectors is
+// the convolution of the vector masked to that range.
+__device__ __forceinline__ float4 mask_labels(float4 v, int q, int mlo, int mhi) {
+   const int o = 4 * q;
+   v.x = (o >= mlo && o <= mhi) ? v.x : MGM_INF;
+   v.y = (o + 1 >= mlo && o + 1 <= mhi) ? v.y : MGM_INF;
+   v.z = (o + 2 >= mlo && o + 2 <= mhi) ? v.z : MGM_INF;
+   v.w = (o + 3 >= mlo && o + 3 <= mhi) ? v.w : MGM_INF;
+   return v;
+}
+template <int DIR, bool MASK = false>
 __device__ __forceinline__ void minconv_half(bool on, const float2 *src, float2 *dst, int nq, float c, float cap,
-                                             float sub, int bar_id) {
+                                             float sub, int bar_id, int mlo = 0, int mhi = 0) {
    const int h = nq >> 1;   // nq is even
    const int dq = DIR ? -1 : 1;
    int q = DIR ? (nq - 1) : 0;
@@ -255,8 +266,10 @@ __device__ __forceinline__ void minconv_half(bool on, const float2 *src, float2 
    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
    if (on) {
       v = ld16<true>(src, q);
+      if (MASK) v = mask_labels(v, q, mlo, mhi);
       for (int i = 0; i < h; ++i, q += dq) {
-         const float4 vn = ld16<true>(src, q + dq);   // chunk i+1 always exists (h < nq)
+         float4 vn = ld16<true>(src, q + dq);   // chunk i+1 always exists (h < nq)
+         if (MASK) vn = mask_labels(vn, q + dq, mlo, mhi);
          if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
          st16<true>(dst, q, v);
          v = vn;
@@ -471,18 +484,23 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
             const float *src = thr;
             float *dst = thr;
             float cw1 = 0.f, capv = 0.f, mk = 0.f;
+            int mlo = 0, mhi = VS;
             if (on) {
                int prow, ppx;
                pred_of(crow, cxs, ck, prow, ppx);
                const long long cpix = g.base0 + (long long)(row0 + crow) * g.dys + (long long)cxs * g.dxs;
-               const float wk = __ldg(P.w + (size_t)pass_weight_plane(pass, ck) * wplane + cpix);
+               const float wk = P.w ? __ldg(P.w + (size_t)pass_weight_plane(pass, ck) * wplane + cpix) : 1.0f;
+               if (P.win_lo) {   // per-pixel cost ranges: convolve inside the receiving pixel's range
+                  mlo = (int)__ldg(P.win_lo + cpix) - P.win_emin;
+                  mhi = (int)__ldg(P.win_hi + cpix) - P.win_emin;
+               }
                mk = m_of(prow, ppx);
                cw1 = P.P1 * wk; capv = mk + P.P2 * wk;
                src = slot_of(prow, ppx);
                dst = row_base(crow) + (R + ncbuf + ck) * VS;
             }
-            if (cdir == 0) minconv_half<0>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, cw1, capv, mk, 4 + cw);
-            else minconv_half<1>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, cw1, capv, mk, 4 + cw);
+            if (cdir == 0) minconv_half<0, true>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, cw1, capv, mk, 4 + cw, mlo, mhi);
+            else minconv_half<1, true>(on, reinterpret_cast<const float2 *>(src), reinterpret_cast<float2 *>(dst), nq, cw1, capv, mk, 4 + cw, mlo, mhi);
          }
          grp.sync();
       }

@@ -12,7 +12,9 @@ enum PotKind { POT_SGM = 0, POT_TRUNC = 1 };
 
 struct AggParams {
    const float *cc;            // matching costs [ny][nx][VS], labels >= L hold +INF
-   const float *w;             // 8 weight planes [8][ny][nx] (weighted kernels only)
+   const float *w;             // 8 weight planes [8][ny][nx] (weighted kernels only; nullptr = all ones)
+   const float *win_lo, *win_hi;   // per-pixel cost ranges (float images, truncated) or nullptr: the weighted
+   int win_emin;                   // truncated-linear kernels convolve inside the receiving pixel's range
    float *ldir[8];             // per-sweep message volumes [ny][nx][VS], indexed by sweep id
    float *bnd[8];              // per-sweep boundary lines [nbands][maxii][VS]
    float *bndm[8];             // per-sweep boundary minima [nbands][maxii]

@@ -63,6 +63,8 @@ struct mgmb200_ctx {
    DevBuf u, v, fu, fv, ftmp, cu, cv, w, cc, dense, out, outcost, flags, progress, bnd, bndm, rg[4];
    // per-pixel ranges of the call in flight (device pointers or nullptr): S range, cost-vector range
    const float *r_smin = nullptr, *r_smax = nullptr, *r_ccmin = nullptr, *r_ccmax = nullptr;
+   bool r_window = false;   // truncated-linear update inside the receiving pixel's cost range (consumer-side kernels)
+   int r_emin = 0;
    DevBuf sweep[8];
    DevBuf post[10];   // maps of the post-processing stages (N1/N2)
    DevBuf dbgbuf;
@@ -317,6 +319,9 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
       if (fl & 2) return fail(MGMB200_EUNSUPPORTED, "edge weights must be finite and >= 0");
    }
    if (weighted && !d_w) return fail(MGMB200_EINVAL, "weighted aggregation without weights");
+   // windowed truncated-linear updates need the consumer-side (per-edge) kernels, with or without weights
+   const bool window = c->r_window && pot == POT_TRUNC;
+   if (window) { if (!weighted) d_w = nullptr; weighted = true; }
 
    for (int p = 0; p < NDIR; p++)
       if (mask & (1u << p)) RET(c->sweep[p].reserve(vol));
@@ -359,6 +364,7 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
    AggParams P;
    memset(&P, 0, sizeof(P));
    P.cc = d_cc; P.w = d_w;
+   if (window) { P.win_lo = c->r_ccmin; P.win_hi = c->r_ccmax; P.win_emin = c->r_emin; }
    for (int p = 0; p < 8; p++) {
       P.ldir[p] = c->sweep[p].as<float>();
       P.bnd[p] = c->bnd.as<float>() + bnd_off[p];
@@ -675,10 +681,9 @@ extern "C" int mgmb200_mgm_ranges(mgmb200_ctx *c, const float *cc, const float *
    if (w) for (size_t i = 0; i < np * 8 && !weighted; i++) weighted = (w[i] != 1.0f);
    // Truncated-linear potentials convolve inside the RECEIVING pixel's range (mgm_core.cc:229-281); only the
    // two-neighbour unweighted variant folds the rest back in (FixBounrady..., :166-186, :197-219) and thereby
-   // equals the dense-envelope result.  The other variants with non-uniform ranges are not implemented.
-   if (felz && rc.ragged && !(K == 2 && !weighted))
-      return fail(MGMB200_EUNSUPPORTED, "truncated-linear potentials with per-pixel cost ranges need TSGM=2 without "
-                                        "image-dependent weights");
+   // equals the dense-envelope result.  The other variants with non-uniform ranges run on the consumer-side
+   // (per-edge) kernels, which mask the neighbour's vector to the receiving pixel's range before convolving.
+   const bool window = felz && rc.ragged && !(K == 2 && !weighted);
    CU(cudaSetDevice(c->device));
    RET(upload(c, c->rg[0], ccmin, np * 4));
    RET(upload(c, c->rg[1], ccmax, np * 4));
@@ -705,9 +710,11 @@ extern "C" int mgmb200_mgm_ranges(mgmb200_ctx *c, const float *cc, const float *
    if (S_out) { RET(c->dense.reserve(np * L * 4)); dS = c->dense.as<float>(); }
    c->r_ccmin = c->rg[0].as<float>(); c->r_ccmax = c->rg[1].as<float>();
    c->r_smin = c->rg[2].as<float>(); c->r_smax = c->rg[3].as<float>();
+   c->r_window = window; c->r_emin = emin;
    const int rc2 = mgmb200_aggregate_dev(c, c->cc.as<float>(), w ? c->w.as<float>() : nullptr, w ? 2 : 0, nx, ny, emin,
                                          emax, P1, P2, NDIR, K, felz, fix, 0, c->out.as<float>(), c->outcost.as<float>(), dS);
    c->r_ccmin = c->r_ccmax = c->r_smin = c->r_smax = nullptr;
+   c->r_window = false;
    if (rc2) return rc2;
    RET(download(c, out, c->out.p, np * 4));
    RET(download(c, outcost, c->outcost.p, np * 4));

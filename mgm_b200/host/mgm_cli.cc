@@ -5,8 +5,7 @@
 // GPU.  The default flow is one mgmb200_stereo_lr call: the images go up once and the maps come back once.
 // -m/-M range images and TSGM_ITER > 1 take the call-by-call sequence of mgm.cc:372-395 (cost volume, then mgm +
 // refinement + range update per iteration) through the mirror functions of mgmb200_host.hpp.  Not supported
-// (exit code 2 or 3 with a message, never a silent fallback): -O 16, truncated-linear potentials with per-pixel
-// ranges unless TSGM=2 without weights.
+// (exit code 2 or 3 with a message, never a silent fallback): -O 16, MEDIAN > 7.
 #include <algorithm>
 #include <cmath>
 

@@ -212,7 +212,9 @@ def test_ranges_costvolume_mgm_refine(ctx):
                     O.orc_costvolume_ranges(u, v, lo, hi, emin, emax, "none", dist, np.inf, 3)), dist
     cc = O.orc_costvolume_ranges(u, v, lo, hi, emin, emax, "none", "ad", np.inf, 3)
     srs = [(lo, hi), (lo + 1, np.maximum(hi - 1, lo + 1)), (np.maximum(lo - 2, emin), np.minimum(hi + 2, emax))]
-    cases = [(K, 0, wt) for K in (1, 2, 3, 4) for wt in (0, 1)] + [(2, 1, 0)]
+    # every update variant; truncated linear: (2,1,0) folds the out-of-range labels back in (mgm_core.cc:166-219),
+    # the others convolve inside the receiving pixel's range (:229-281, consumer-side kernels with masked loads)
+    cases = [(K, felz, wt) for K in (1, 2, 3, 4) for felz in (0, 1) for wt in (0, 1)]
     for (K, felz, weighted), fix in itertools.product(cases, [0, 1]):
         w = synth_weights(nx, ny, seed=K) if weighted else None
         P1, P2 = (8, 32) if not felz else (2, 20000)
@@ -225,14 +227,12 @@ def test_ranges_costvolume_mgm_refine(ctx):
             a = ctx.subpixel_refinement_sgm_ranges(o["S"], slo, shi, emin, o["out"], o["outcost"], "vfit")
             b = O.orc_refine_ranges(o["S"], slo, shi, emin, o["out"], o["outcost"], "vfit")
             assert same(a[0], b[0]) and same(a[1], b[1]), tag
-    # uniform ranges through the same entry point == the plain call; truncated linear with TSGM=3 needs uniform ranges
+    # uniform ranges through the same entry point == the plain call
     full_lo, full_hi = np.full((ny, nx), emin, np.float32), np.full((ny, nx), emax, np.float32)
     ccu = O.orc_costvolume(u, v, emin, emax, "none", "ad", np.inf, 3)
     r = ctx.mgm_ranges(ccu, full_lo, full_hi, None, emin, full_lo, full_hi, 2, 20000, 8, 3, 1, 1)
     o = O.orc_mgm(ccu, None, emin, 2, 20000, 8, 3, 1, 1)
     assert same(r["S"], o["S"]) and same(r["out"], o["out"])
-    with pytest.raises(mgm_b200.MgmError):
-        ctx.mgm_ranges(cc, lo, hi, None, emin, lo, hi, 2, 20000, 8, 3, 1, 1)
     with pytest.raises(mgm_b200.MgmError):
         ctx.mgm_ranges(cc, hi, lo, None, emin, lo, hi, 8, 32, 8, 2, 0, 1)   # empty ranges
 
@@ -415,6 +415,8 @@ def _pnm(path, a):
     (dict(TSGM="4", RANGES="1"), ["-r", "-23", "-R", "4", "-t", "ad", "-s", "parabola", "-O", "4", "-p", "gblur"], 3),  # -m/-M range images
     (dict(TSGM="2", RANGES="1", USE_TRUNCATED_LINEAR_POTENTIALS="1", TSGM_ITER="2"),
      ["-P1", "2", "-P2", "20000", "-r", "-23", "-R", "4", "-t", "sd", "-O", "8"], 1),
+    (dict(TSGM="3", RANGES="1", USE_TRUNCATED_LINEAR_POTENTIALS="1", MEDIAN="1"),                             # windowed min-convolution
+     ["-P1", "2", "-P2", "20000", "-r", "-23", "-R", "4", "-t", "census", "-s", "vfit", "-O", "8", "-aP2", "3"], 1),
 ])
 def test_cli_matches_reference_cli(tmp_path, case):
     """the whole `mgm` command (both LR directions, median, LR test, back-projection, console output)"""
