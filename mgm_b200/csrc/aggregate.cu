@@ -31,6 +31,7 @@
 #include <type_traits>
 
 #include "aggregate.cuh"
+#include "wta_device.cuh"
 
 #ifndef MGM_JB
 #define MGM_JB 2   // chunks per lane whose loads are issued together in the gather (measured: 2 < 4 < 8)
@@ -294,6 +295,15 @@ __device__ __forceinline__ float4 div4_by_k(const float4 &e) {   // e finite (se
    if (K == 2) return mul4s(e, 0.5f);    // exact: same real quotient, same rounding
    if (K == 4) return mul4s(e, 0.25f);
    return div3_4(e);
+}
+
+// Every message of the band is in memory (all threads have passed the barrier that follows their last store):
+// one thread publishes the completion flag the fused finish tiles wait for.
+__device__ __forceinline__ void band_finished(const AggParams &P, int pass, int band) {
+   if (P.fin_enabled && threadIdx.x == 0) {
+      __threadfence();
+      st_release(P.band_done[pass] + band, 1);
+   }
 }
 
 template <int POT, int K, bool WEIGHTED, bool DIAG, int GL>
@@ -718,6 +728,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    cp_async_wait<0>();
    if (tid == 0) phase[vph_idx] = vph;
    __syncthreads();
+   band_finished(P, pass, band);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1038,6 +1049,7 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
    cp_async_wait<0>();
    if (tid == 0) phase[vph_idx] = vph;
    __syncthreads();
+   band_finished(P, pass, band);
 }
 
 // Dynamic band scheduling (one thread per CTA).  Bands of a sweep are claimed strictly in order through a
@@ -1048,7 +1060,31 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
 //      remaining chain first -- the axis sweeps are the critical path;
 //   2. else the next band of the diagonal sweep that is least advanced (short hand-off: the filler work);
 //   3. else any remaining axis band (it waits inside run_band).
-__device__ int2 claim_band(const AggParams &P) {
+// A tile can be finished once every band (of every requested sweep) that holds one of its pixels is complete.
+// Band indices are monotone in the scan coordinates, which are affine in (x,y): the extremes are at the corners.
+__device__ bool tile_ready(const AggParams &P, int tile) {
+   const int x0 = (tile % P.fin_tiles_x) * P.fin_tw, y0 = (tile / P.fin_tiles_x) * P.fin_th;
+   const int x1 = min(x0 + P.fin_tw, P.nx) - 1, y1 = min(y0 + P.fin_th, P.ny) - 1;
+   int done = 1;
+   for (int p = 0; p < 8; ++p) {
+      if (!P.nb[p]) continue;
+      const int rm = (0x53 >> p) & 1, incx = (0xC5 >> p) & 1, incy = (0x99 >> p) & 1;   // pass_geometry
+      const int ax0 = incx ? x0 : P.nx - 1 - x1, ax1 = incx ? x1 : P.nx - 1 - x0;       // ascending along the scan
+      const int ay0 = incy ? y0 : P.ny - 1 - y1, ay1 = incy ? y1 : P.ny - 1 - y0;
+      const int xs0 = rm ? ax0 : ay0, xs1 = rm ? ax1 : ay1, ys0 = rm ? ay0 : ax0, ys1 = rm ? ay1 : ax1;
+      int b0, b1;
+      if (p >= 4 && P.shear) { b0 = (xs0 + ys0) / P.T[1]; b1 = (xs1 + ys1) / P.T[1]; }
+      else { const int T = P.T[p < 4 ? 0 : 1]; b0 = ys0 / T; b1 = ys1 / T; }
+      // relaxed loads (they pipeline), ordered before the tile's reads by the fence below
+      for (int b = b1; b >= b0; --b) done &= *reinterpret_cast<volatile const int *>(P.band_done[p] + b);
+   }
+   if (!done) return false;
+   __threadfence();
+   return true;
+}
+
+// `pending`: a finish tile this CTA has claimed but not run yet (-1 none, -2 no tiles left).
+__device__ int2 claim_band(const AggParams &P, int &pending) {
    for (;;) {
       int best = -1, bb = 0, bestrem = 0;
       for (int p = 0; p < 4; ++p) {
@@ -1068,6 +1104,19 @@ __device__ int2 claim_band(const AggParams &P) {
             if (b < nbp && b < bmin) { best = p; bb = b; bmin = b; }
          }
       }
+      if (best < 0 && P.fin_enabled) {
+         // 3. a finish tile (keeps the SM busy instead of parking on an axis band): tiles are claimed one by one in
+         // the expected order of readiness and run once the bands that hold their pixels are complete
+         if (pending == -1) {
+            const int t = atomicAdd(P.fin_next, 1);
+            pending = (t < P.fin_ntiles) ? P.fin_order[t] : -2;
+         }
+         if (pending >= 0 && tile_ready(P, pending)) {
+            const int tile = pending;
+            pending = -1;
+            return make_int2(8, tile);
+         }
+      }
       if (best < 0) {
          for (int p = 0; p < 4; ++p) {
             const int nbp = P.nb[p];
@@ -1076,9 +1125,40 @@ __device__ int2 claim_band(const AggParams &P) {
             if (b < nbp && nbp - b > bestrem) { best = p; bb = b; bestrem = nbp - b; }
          }
       }
-      if (best < 0) return make_int2(-1, 0);
+      if (best < 0) {
+         if (!P.fin_enabled || pending < 0) return make_int2(-1, 0);
+         __nanosleep(500);   // every band is claimed: wait for the bands that still hold this CTA's tile back
+         continue;
+      }
       if (atomicCAS(P.next_band + best, bb, bb + 1) == bb) return make_int2(best, bb);
    }
+}
+
+// One finish tile: fin_tw x fin_th pixels, one warp per pixel (wta_device.cuh); the rows region of the shared
+// memory is free between bands and holds one label vector per warp.
+__device__ __forceinline__ void run_finish_tile(const AggParams &P, int tile, unsigned char *smem) {
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+   float *sS = reinterpret_cast<float *>(smem + P.off_thr) + (size_t)warp * P.VS;
+   const int x0 = (tile % P.fin_tiles_x) * P.fin_tw, y0 = (tile / P.fin_tiles_x) * P.fin_th;
+   const int w = min(P.fin_tw, P.nx - x0), h = min(P.fin_th, P.ny - y0);
+   // 128-byte lines of one pixel: (ndir + 1) vectors of VS floats; the warp's next pixel is prefetched into L2
+   // while the current one is reduced (16 warps per SM cannot keep enough loads in flight otherwise)
+   const int lpv = P.VS >> 5, nlines = (P.fin.ndir + 1) * lpv;
+   auto prefetch_pixel = [&](int i) {
+      const long long pix = (long long)(y0 + i / w) * P.nx + x0 + i % w;
+      for (int l = lane; l < nlines; l += 32) {
+         const int v = l / lpv;
+         const float *base = (v < P.fin.ndir) ? P.fin.ldir[v] : P.fin.cc;
+         asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)pix * P.VS + (size_t)(l % lpv) * 32));
+      }
+   };
+   if (warp < w * h) prefetch_pixel(warp);
+   for (int i = warp; i < w * h; i += nwarps) {
+      if (i + nwarps < w * h) prefetch_pixel(i + nwarps);
+      const long long pix = (long long)(y0 + i / w) * P.nx + x0 + i % w;
+      wta_pixel<true>(P.fin, pix, sS, lane);
+   }
+   __syncthreads();
 }
 
 template <int POT, int K, bool WEIGHTED, int GL>
@@ -1099,13 +1179,15 @@ __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(c
       __syncthreads();
    }
 
+   int pending = -1;   // thread 0: claimed finish tile
    for (;;) {
-      if (t == 0) s_ticket = claim_band(P);
+      if (t == 0) s_ticket = claim_band(P, pending);
       __syncthreads();
       const int2 pb = s_ticket;
       __syncthreads();
       if (pb.x < 0) break;
-      if (pb.x < 4) run_band<POT, K, WEIGHTED, false, GL>(P, pb.x, pb.y, smem);
+      if (pb.x == 8) run_finish_tile(P, pb.y, smem);
+      else if (pb.x < 4) run_band<POT, K, WEIGHTED, false, GL>(P, pb.x, pb.y, smem);
       else if constexpr (!WEIGHTED && K <= 3) {
          if (P.shear) run_band_shear<POT, K, GL>(P, pb.x, pb.y, smem);
          else run_band<POT, K, WEIGHTED, true, GL>(P, pb.x, pb.y, smem);

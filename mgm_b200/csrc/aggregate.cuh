@@ -1,6 +1,7 @@
 // Parameters and launch plan of the aggregation kernel (aggregate.cu).
 #pragma once
 #include "common.cuh"
+#include "wta.cuh"
 
 #define MGM_AGG_GROUP 8           // lanes cooperating on one scan row
 #define MGM_AGG_MAX_THREADS 512   // 56 rows x 8 lanes + two service warps (boundary consumer / publisher); 128 registers per thread
@@ -31,6 +32,14 @@ struct AggParams {
    int ng[2];                  // row groups per band (axis / diagonal class), each on its own named barrier
    int fused_sgm;              // 1: unweighted SGM kernels transform the message from registers (one barrier per step)
    float P1, P2;
+   // fused finish (optional): CTAs without a band to run take tiles of pixels whose sweeps are all complete and do
+   // the ordered sum + over-count fix + WTA + sub-pixel there (wta_device.cuh), inside the same launch
+   int fin_enabled;
+   int fin_ntiles, fin_tw, fin_th, fin_tiles_x;   // tiles of fin_tw x fin_th pixels, fin_tiles_x per image row of tiles
+   const int *fin_order;       // tile ids in the expected order of readiness
+   int *fin_next;              // claim counter into fin_order
+   int *band_done[8];          // per-sweep [nbands]: 1 once every message of the band is in memory
+   WtaParams fin;
    unsigned long long *dbg;    // optional 24-word phase-timing accumulator (profiling aid), or nullptr
    // dynamic shared memory carve-up (bytes)
    unsigned off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;

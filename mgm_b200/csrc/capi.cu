@@ -67,6 +67,11 @@ struct mgmb200_ctx {
    int r_emin = 0;
    DevBuf sweep[8];
    DevBuf post[10];   // maps of the post-processing stages (N1/N2)
+   // fused finish: tile order (expected readiness) cached per geometry
+   DevBuf tiles;
+   std::vector<int> tile_order;
+   int tile_key[6] = {0, 0, 0, 0, 0, 0};
+   bool fin_done = false;   // the last run_sweeps finished the maps inside the aggregation launch
    DevBuf dbgbuf;
    size_t sweep_bytes = 0;
    // last launch info
@@ -144,6 +149,7 @@ extern "C" void mgmb200_destroy(mgmb200_ctx *c) {
    for (DevBuf *b : bufs) b->release();
    for (int i = 0; i < 8; i++) c->sweep[i].release();
    for (DevBuf &b : c->post) b.release();
+   c->tiles.release();
    if (c->own_stream) cudaStreamDestroy(c->own_stream);
    delete c;
 }
@@ -293,8 +299,11 @@ extern "C" int mgmb200_unpad_volume_dev(mgmb200_ctx *c, const float *d_padded, f
 }
 
 // Runs the sweeps in `mask` into c->sweep[p]; fills `weighted`.  d_cc padded.
+// fin != nullptr: all sweeps are requested and the finish stage (ordered sum, fix, WTA, sub-pixel) may run inside the
+// same launch on tiles whose bands are complete (c->fin_done tells whether it did).
 static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int weights_mode, int nx, int ny,
-                      int L, float P1, float P2, int NDIR, int K, int felz, unsigned mask) {
+                      int L, float P1, float P2, int NDIR, int K, int felz, unsigned mask, const WtaParams *fin = nullptr) {
+   c->fin_done = false;
    if (NDIR < 1 || NDIR > 8)
       return fail(MGMB200_EUNSUPPORTED, "NDIR=%d: the reference defines 8 sweeps (mgm_core.cc:463-471); "
                   "-O 16 indexes past its table", NDIR);
@@ -356,10 +365,45 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
    }
    if (nbands == 0) return 0;
 
-   RET(c->progress.reserve((prog_total + 16) * sizeof(int)));
+   // layout of the counters: [prog_total] progress, [16] claim counters (8 sweeps + the finish tiles), [prog_total] done flags
+   RET(c->progress.reserve((2 * prog_total + 16) * sizeof(int)));
    RET(c->bnd.reserve(bnd_total * sizeof(float)));
    RET(c->bndm.reserve(bndm_total * sizeof(float)));
-   CU(cudaMemsetAsync(c->progress.p, 0, (prog_total + 16) * sizeof(int), c->stream));
+   CU(cudaMemsetAsync(c->progress.p, 0, (2 * prog_total + 16) * sizeof(int), c->stream));
+
+   // fused finish: tiles of pixels in the order they are expected to become complete (the axis sweeps decide:
+   // band b of a sweep is done after about maxii + (b+1)*T steps)
+   int tw = 128, th = 16;
+   if (const char *e = getenv("MGMB200_FIN_TILE")) { int a = 0, b = 0; if (sscanf(e, "%dx%d", &a, &b) == 2 && a > 0 && b > 0) { tw = a; th = b; } }
+   const size_t rows_region = plan.smem - plan.off_thr;
+   const bool fuse = fin && !getenv("MGMB200_NO_FUSED_FINISH") && (size_t)(plan.block / 32) * VS * 4 <= rows_region;
+   const int tiles_x = (nx + tw - 1) / tw, tiles_y = (ny + th - 1) / th, ntiles = tiles_x * tiles_y;
+   if (fuse) {
+      const int key[6] = {nx, ny, plan.T[0], tw, th, NDIR};
+      if (memcmp(key, c->tile_key, sizeof(key)) != 0 || (int)c->tile_order.size() != ntiles) {
+         std::vector<std::pair<long long, int>> when(ntiles);
+         for (int t = 0; t < ntiles; t++) {
+            const int x0 = (t % tiles_x) * tw, y0 = (t / tiles_x) * th;
+            const int x1 = std::min(x0 + tw, nx) - 1, y1 = std::min(y0 + th, ny) - 1;
+            long long ready = 0;
+            for (int p = 0; p < 4 && p < NDIR; p++) {
+               const PassGeom g = pass_geometry(p, nx, ny);
+               const int rm = (0x53 >> p) & 1, incx = (0xC5 >> p) & 1, incy = (0x99 >> p) & 1;
+               const int ax1 = incx ? x1 : nx - 1 - x0, ay1 = incy ? y1 : ny - 1 - y0;
+               const int ys1 = rm ? ay1 : ax1;
+               ready = std::max(ready, (long long)g.maxii + (long long)(ys1 / plan.T[0] + 1) * plan.T[0]);
+            }
+            when[t] = std::make_pair(ready, t);
+         }
+         std::stable_sort(when.begin(), when.end());
+         c->tile_order.resize(ntiles);
+         for (int t = 0; t < ntiles; t++) c->tile_order[t] = when[t].second;
+         memcpy(c->tile_key, key, sizeof(key));
+         RET(c->tiles.reserve((size_t)ntiles * sizeof(int)));
+         CU(cudaMemcpyAsync(c->tiles.p, c->tile_order.data(), (size_t)ntiles * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+         CU(cudaStreamSynchronize(c->stream));   // the host vector may be rebuilt by the next call
+      }
+   }
 
    AggParams P;
    memset(&P, 0, sizeof(P));
@@ -372,6 +416,14 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
       P.progress[p] = c->progress.as<int>() + prog_off[p];
    }
    P.next_band = c->progress.as<int>() + prog_total;   // 8 per-sweep claim counters (zeroed above)
+   if (fuse) {
+      P.fin_enabled = 1;
+      P.fin_ntiles = ntiles; P.fin_tw = tw; P.fin_th = th; P.fin_tiles_x = tiles_x;
+      P.fin_order = c->tiles.as<int>();
+      P.fin_next = P.next_band + 8;
+      for (int p = 0; p < 8; p++) P.band_done[p] = c->progress.as<int>() + prog_total + 16 + prog_off[p];
+      P.fin = *fin;
+   }
    for (int p = 0; p < 8; p++) P.nb[p] = nb[p];
    P.nbands = nbands;
    P.static_order = getenv("MGMB200_STATIC_ORDER") ? 1 : 0;
@@ -386,12 +438,13 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
    P.off_thr = (unsigned)plan.off_thr;
    CU(agg_launch(P, plan, pot, K, weighted, c->stream));
    c->n_launches++;
+   c->fin_done = fuse;
    return 0;
 }
 
-static int finish_rows(mgmb200_ctx *c, const float *const *d_sweeps, const float *d_cc, int nx, int ny, int dmin,
-                       int L, int NDIR, int fix, int refine, int row_begin, int row_end, float *d_out,
-                       float *d_outcost, float *d_S) {
+static WtaParams finish_params(mgmb200_ctx *c, const float *const *d_sweeps, const float *d_cc, int nx, int dmin, int L,
+                               int NDIR, int fix, int refine, int row_begin, int row_end, float *d_out, float *d_outcost,
+                               float *d_S) {
    WtaParams W;
    memset(&W, 0, sizeof(W));
    for (int p = 0; p < NDIR; p++) W.ldir[p] = d_sweeps[p];
@@ -400,6 +453,13 @@ static int finish_rows(mgmb200_ctx *c, const float *const *d_sweeps, const float
    W.ndir = NDIR; W.L = L; W.VS = mgmb200_padded_labels(L); W.dmin = dmin;
    W.fix = (fix == 1); W.refine = refine;
    W.smin = c->r_smin; W.smax = c->r_smax; W.ccmin = c->r_ccmin; W.ccmax = c->r_ccmax;
+   return W;
+}
+
+static int finish_rows(mgmb200_ctx *c, const float *const *d_sweeps, const float *d_cc, int nx, int ny, int dmin,
+                       int L, int NDIR, int fix, int refine, int row_begin, int row_end, float *d_out,
+                       float *d_outcost, float *d_S) {
+   const WtaParams W = finish_params(c, d_sweeps, d_cc, nx, dmin, L, NDIR, fix, refine, row_begin, row_end, d_out, d_outcost, d_S);
    CU(wta_launch(W, c->num_sms, c->stream));
    c->n_launches++;
    return 0;
@@ -445,9 +505,15 @@ extern "C" int mgmb200_aggregate_dev(mgmb200_ctx *c, const float *d_cc, const fl
    CU(cudaSetDevice(c->device));
    const int L = dmax - dmin + 1;
    unsigned mask = (NDIR >= 1 && NDIR <= 8) ? ((1u << NDIR) - 1u) : 0u;
-   RET(run_sweeps(c, d_cc, d_w, weights_mode, nx, ny, L, P1, P2, NDIR, K, felz, mask));
+   if (NDIR < 1 || NDIR > 8) return run_sweeps(c, d_cc, d_w, weights_mode, nx, ny, L, P1, P2, NDIR, K, felz, mask);   // fails with the message
+   // the sweep volumes must exist before their addresses go into the finish parameters
+   const size_t vol = (size_t)nx * ny * mgmb200_padded_labels(L) * sizeof(float);
+   for (int p = 0; p < NDIR; p++) RET(c->sweep[p].reserve(vol));
    const float *sw[8];
    for (int p = 0; p < 8; p++) sw[p] = c->sweep[p].as<float>();
+   const WtaParams W = finish_params(c, sw, d_cc, nx, dmin, L, NDIR, fix, refine, 0, ny, d_out, d_outcost, d_S);
+   RET(run_sweeps(c, d_cc, d_w, weights_mode, nx, ny, L, P1, P2, NDIR, K, felz, mask, &W));
+   if (c->fin_done) return 0;   // finished tile by tile inside the aggregation launch
    return finish_rows(c, sw, d_cc, nx, ny, dmin, L, NDIR, fix, refine, 0, ny, d_out, d_outcost, d_S);
 }
 

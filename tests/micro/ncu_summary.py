@@ -29,6 +29,8 @@ for r in data:
             u = units[ix[k]].lower()
             return v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "tbyte": 1e12}.get(u, 1.0)
         rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+        if short == "mgm_aggregate_kernel" and rd > 1.5 * wr:   # the launch with the finish tiles fused in re-reads the sweeps
+            short = "mgm_aggregate_kernel_fused"
         traffic[short] = {"dram_bytes_read": rd, "dram_bytes_write": wr, "traffic": rd + wr, "round": 1}
 open(out_md, "w").write("\n".join(lines))
 tj = os.path.join(os.path.dirname(out_md), "traffic.json")

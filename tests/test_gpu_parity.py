@@ -95,10 +95,12 @@ def test_mgm_matches_oracle(ctx, K, felz, weighted):
 
 
 @pytest.mark.parametrize("knob", ["MGMB200_GROUPS=2", "MGMB200_GROUPS=3", "MGMB200_NO_SHEAR=1", "MGMB200_NO_CREG=1",
-                                  "MGMB200_STATIC_ORDER=1", "MGMB200_NO_FUSED_SGM=1", "MGMB200_LANES4=1"])
+                                  "MGMB200_STATIC_ORDER=1", "MGMB200_NO_FUSED_SGM=1", "MGMB200_LANES4=1",
+                                  "MGMB200_NO_FUSED_FINISH=1", "MGMB200_FIN_TILE=7x3", "MGMB200_FIN_TILE=4096x4096"])
 def test_mgm_alternative_kernel_layouts(ctx, knob, monkeypatch):
     """The aggregation kernel's alternative layouts (row groups on their own named barriers, row-per-worker diagonal
-    sweeps, cp.async cost ring, static band order) are selected by environment knobs read at every call: each must
+    sweeps, cp.async cost ring, static band order, finish stage as a separate launch or fused with other tile sizes) are
+    selected by environment knobs read at every call: each must
     give the same bits as the default layout, i.e. as the oracle."""
     name, val = knob.split("=")
     monkeypatch.setenv(name, val)
