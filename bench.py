@@ -343,10 +343,13 @@ def main():
     # left-right tests, all inside one mgmb200_stereo_lr call with host images in and host maps out
     ms_lr = None
     if world == 1:
+        lr_bufs = {k: torch.empty((H, W), dtype=torch.float32).pin_memory().numpy()
+                   for k in ("out", "outcost", "out_nolr", "outR", "outcostR")}
+
         def step_lr():
             return ctx.stereo_lr(pu, pv, dmin=dmin, dmax=dmax, P1=wl["P1"], P2=wl["P2"], NDIR=NDIR, MGM=K,
                                  use_felzenszwalb_potentials=wl["felz"], distance="census", census_ncc_win=wl["win"],
-                                 refinement=wl["refine"], testlrrl=1, median=1)
+                                 refinement=wl["refine"], testlrrl=1, median=1, buffers=lr_bufs)
         step_lr()
         torch.cuda.synchronize()
         t0 = time.perf_counter()

@@ -312,9 +312,11 @@ class Context:
 
     def stereo_lr(self, u, v, dmin=-30, dmax=30, P1=8.0, P2=32.0, NDIR=4, MGM=4, use_felzenszwalb_potentials=0,
                   sgm_fix_overcount=1, aP=1.0, aThresh=5.0, prefilter="none", distance="ad", truncDist=np.inf,
-                  census_ncc_win=3, refinement="none", testlrrl=1, testlrrl_tau=1.0, median=0, want_backproj=False):
+                  census_ncc_win=3, refinement="none", testlrrl=1, testlrrl_tau=1.0, median=0, want_backproj=False,
+                  buffers=None):
         """The default command-line flow mgm.cc:372-443 on the device: both directions, median, left-right tests,
-        back-projection.  Returns a dict with out, outcost, out_nolr and, with testlrrl, outR, outcostR."""
+        back-projection.  Returns a dict with out, outcost, out_nolr and, with testlrrl, outR, outcostR.
+        `buffers`: a dict returned by an earlier call with the same shapes, reused for the outputs."""
         u, nx, ny, nch = _img(u)
         v, vnx, vny, vnch = _img(v)
         if (vnx, vny, vnch) != (nx, ny, nch):
@@ -323,13 +325,16 @@ class Context:
                          int(sgm_fix_overcount), aP, aThresh, prefilter.encode(), distance.encode(), truncDist,
                          int(census_ncc_win), refinement.encode())
         q = PostParams(int(testlrrl), testlrrl_tau, int(median))
-        r = dict(out=np.empty((ny, nx), np.float32), outcost=np.empty((ny, nx), np.float32),
-                 out_nolr=np.empty((ny, nx), np.float32))
-        if testlrrl:
-            r["outR"] = np.empty((ny, nx), np.float32)
-            r["outcostR"] = np.empty((ny, nx), np.float32)
+        names = ["out", "outcost", "out_nolr"] + (["outR", "outcostR"] if testlrrl else [])
+        r = {k: np.empty((ny, nx), np.float32) for k in names}
         if want_backproj:
             r["backproj"] = np.empty((nch, ny, nx), np.float32)
+        if buffers is not None:
+            for k in r:
+                b = buffers.get(k)
+                if not (isinstance(b, np.ndarray) and b.dtype == np.float32 and b.shape == r[k].shape and b.flags["C_CONTIGUOUS"]):
+                    raise ValueError("buffers[%r] must be a C-contiguous float32 array of shape %s" % (k, r[k].shape))
+                r[k] = b
         self._check(self.lib.mgmb200_stereo_lr(self._ctx, _fp(u), _fp(v), nx, ny, nch, ctypes.byref(p), ctypes.byref(q),
                                                _fp(r["out"]), _fp(r["outcost"]), _fp(r.get("outR")),
                                                _fp(r.get("outcostR")), _fp(r["out_nolr"]), _fp(r.get("backproj"))))
