@@ -185,6 +185,14 @@ int mgmb200_stereo_lr(mgmb200_ctx *ctx, const float *u, const float *v, int nx, 
                       const mgmb200_stereo_params *p, const mgmb200_post_params *q, float *out, float *outcost,
                       float *outR, float *outcostR, float *out_nolr, float *backproj);
 
+/* One direction of mgm.cc:372-395 with per-pixel range images (-m / -M, or the uniform range) and TSGM_ITER
+ * iterations, device resident: cost volume over [dminI,dmaxI] once, then per iteration mgm() + sub-pixel refinement
+ * over the current ranges and update_dmin_dmax + remove_nonfinite_values_Img on them.  dminI/dmaxI (nx*ny, finite,
+ * min <= max after truncation) are updated in place; p->dmin / p->dmax are not used. */
+int mgmb200_stereo_ranges(mgmb200_ctx *ctx, const float *u, const float *v, int nx, int ny, int nch,
+                          const mgmb200_stereo_params *p, float *dminI, float *dmaxI, int tsgm_iter, float *out,
+                          float *outcost);
+
 /* ------------------------------------------------------------------------------------------
  * Device-pointer entry points (inputs and outputs resident in HBM, asynchronous on the
  * context's stream).  d_cc is a padded volume.

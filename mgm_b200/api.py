@@ -340,6 +340,24 @@ class Context:
                                                _fp(r.get("outcostR")), _fp(r["out_nolr"]), _fp(r.get("backproj"))))
         return r
 
+    def stereo_ranges(self, u, v, dminI, dmaxI, tsgm_iter=1, P1=8.0, P2=32.0, NDIR=4, MGM=4,
+                      use_felzenszwalb_potentials=0, sgm_fix_overcount=1, aP=1.0, aThresh=5.0, prefilter="none",
+                      distance="ad", truncDist=np.inf, census_ncc_win=3, refinement="none"):
+        """One direction of mgm.cc:372-395 with range images and TSGM_ITER iterations, device resident.
+        Returns (out, outcost, dminI, dmaxI) with the range images as updated by the last iteration."""
+        u, nx, ny, nch = _img(u)
+        v, vnx, vny, vnch = _img(v)
+        if (vnx, vny, vnch) != (nx, ny, nch):
+            raise ValueError("u and v must have the same shape")
+        lo = np.array(np.broadcast_to(np.asarray(dminI, np.float32), (ny, nx)), np.float32, copy=True)
+        hi = np.array(np.broadcast_to(np.asarray(dmaxI, np.float32), (ny, nx)), np.float32, copy=True)
+        p = StereoParams(0, 0, P1, P2, int(NDIR), int(MGM), int(use_felzenszwalb_potentials), int(sgm_fix_overcount), aP,
+                         aThresh, prefilter.encode(), distance.encode(), truncDist, int(census_ncc_win), refinement.encode())
+        out, outcost = np.empty((ny, nx), np.float32), np.empty((ny, nx), np.float32)
+        self._check(self.lib.mgmb200_stereo_ranges(self._ctx, _fp(u), _fp(v), nx, ny, nch, ctypes.byref(p), _fp(lo), _fp(hi),
+                                                   int(tsgm_iter), _fp(out), _fp(outcost)))
+        return out, outcost, lo, hi
+
     # ------------------------------------------------------------------ device-pointer interface
     @staticmethod
     def padded_labels(L):

@@ -1032,3 +1032,80 @@ extern "C" int mgmb200_stereo_lr(mgmb200_ctx *c, const float *u, const float *v,
    CU(cudaStreamSynchronize(c->stream));
    return 0;
 }
+
+// mgm.cc:372-395 for one direction with range images and TSGM_ITER iterations, resident on the device: the cost
+// volume is built once over an envelope wide enough for every iteration (update_dmin_dmax widens a range by its slack
+// of 3 per iteration), then each iteration aggregates + finishes over the current ranges and updates them from the
+// refined disparities.  dminI/dmaxI come back as left by the last update (mgm.cc:390-392).
+extern "C" int mgmb200_stereo_ranges(mgmb200_ctx *c, const float *u, const float *v, int nx, int ny, int nch,
+                                     const mgmb200_stereo_params *p, float *dminI, float *dmaxI, int tsgm_iter,
+                                     float *out, float *outcost) {
+   if (!c || !u || !v || !p || !dminI || !dmaxI || !out || !outcost) return fail(MGMB200_EINVAL, "NULL argument");
+   if (nx < 1 || ny < 1 || nch < 1) return fail(MGMB200_EINVAL, "image %dx%dx%d", nx, ny, nch);
+   if (tsgm_iter < 1) tsgm_iter = 0;   // the reference's loop simply does not run (outputs stay untouched)
+   const size_t np = (size_t)nx * ny;
+   int rmin = 0x7fffffff, rmax = -0x7fffffff;
+   for (size_t i = 0; i < np; i++) {
+      if (!(dminI[i] == dminI[i]) || !(dmaxI[i] == dmaxI[i]) || !(fabsf(dminI[i]) < 1e9f) || !(fabsf(dmaxI[i]) < 1e9f))
+         return fail(MGMB200_EINVAL, "non-finite disparity range at pixel %zu", i);
+      const int a = (int)dminI[i], b = (int)dmaxI[i];
+      if (a > b) return fail(MGMB200_EINVAL, "empty disparity range [%d,%d] at pixel %zu", a, b, i);
+      rmin = std::min(rmin, a); rmax = std::max(rmax, b);
+   }
+   const RangeScan rc = scan_ranges(dminI, dmaxI, np, rmin, rmax);
+   const int slack = 3, radius = 2;   // defaults of update_dmin_dmax, mgm.cc:120
+   const int grow = tsgm_iter > 1 ? slack * (tsgm_iter - 1) : 0;
+   const int emin = rmin - grow, emax = rmax + grow;
+   RET(check_dims(nx, ny, emin, emax));
+   if (tsgm_iter == 0) return 0;
+   CU(cudaSetDevice(c->device));
+   const int L = emax - emin + 1, VS = mgmb200_padded_labels(L);
+   int pf = mgmb200_prefilter_index(p->prefilter), di = mgmb200_distance_index(p->distance);
+   if (di == DIST_CENSUS) pf = PF_CENSUS;
+   RET(upload(c, c->u, u, np * nch * 4));
+   RET(upload(c, c->v, v, np * nch * 4));
+   RET(upload(c, c->rg[0], dminI, np * 4));   // ranges of the cost vectors: fixed (mgm.cc:376 builds CC once)
+   RET(upload(c, c->rg[1], dmaxI, np * 4));
+   RET(upload(c, c->rg[2], dminI, np * 4));   // ranges of S: updated after every iteration
+   RET(upload(c, c->rg[3], dmaxI, np * 4));
+   RET(c->w.reserve(np * 8 * 4));
+   RET(c->cc.reserve(np * VS * 4));
+   RET(c->out.reserve(np * 4));
+   RET(c->outcost.reserve(np * 4));
+   RET(c->post[7].reserve(64));
+   RET(clear_flags(c));
+   CU(weights_launch(c->u.as<float>(), nx, ny, nch, p->aP, p->aThresh, c->w.as<float>(), c->flags.as<int>(), c->stream));
+   RET(costvolume_dev_impl(c, c->u.as<float>(), c->v.as<float>(), nx, ny, nch, nx, ny, emin, emax, pf, di, p->truncDist,
+                           p->census_ncc_win, c->rg[0].as<float>(), c->rg[1].as<float>(), c->cc.as<float>()));
+   int fl = 0;
+   RET(read_flags(c, &fl));
+   const bool weighted = (fl & 1) != 0;
+   if (weighted && !(p->aP >= 0.f && p->aP < INFINITY)) return fail(MGMB200_EUNSUPPORTED, "aP must be finite and >= 0");
+   const int K = p->MGM, felz = p->use_felzenszwalb_potentials;
+   const float P1 = p->P1 * nch, P2 = p->P2 * nch;   // mgm.cc:356-357
+   const int refine = mgmb200_refinement_index(p->refinement);
+   float *mm = c->post[7].as<float>();
+   for (int it = 0; it < tsgm_iter; it++) {
+      c->r_ccmin = c->rg[0].as<float>(); c->r_ccmax = c->rg[1].as<float>();
+      c->r_smin = c->rg[2].as<float>(); c->r_smax = c->rg[3].as<float>();
+      c->r_window = felz && rc.ragged && !(K == 2 && !weighted);
+      c->r_emin = emin;
+      const int r = mgmb200_aggregate_dev(c, c->cc.as<float>(), c->w.as<float>(), weighted ? 1 : 0, nx, ny, emin, emax, P1, P2,
+                                          p->NDIR, K, felz, p->sgm_fix_overcount, refine, c->out.as<float>(),
+                                          c->outcost.as<float>(), nullptr);
+      c->r_ccmin = c->r_ccmax = c->r_smin = c->r_smax = nullptr;
+      c->r_window = false;
+      if (r) return r;
+      // update_dmin_dmax + remove_nonfinite_values_Img on both range images, mgm.cc:390-392
+      RET(mgmb200_update_dmin_dmax_dev(c, c->out.as<float>(), nx, ny, c->rg[2].as<float>(), c->rg[3].as<float>(), slack,
+                                       radius, mm));
+      CU(replace_nonfinite_launch(c->rg[2].as<float>(), (long long)np, mm + 0, c->stream));
+      CU(replace_nonfinite_launch(c->rg[3].as<float>(), (long long)np, mm + 1, c->stream));
+   }
+   RET(download(c, out, c->out.p, np * 4));
+   RET(download(c, outcost, c->outcost.p, np * 4));
+   RET(download(c, dminI, c->rg[2].p, np * 4));
+   RET(download(c, dmaxI, c->rg[3].p, np * 4));
+   CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}

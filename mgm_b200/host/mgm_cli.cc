@@ -3,8 +3,9 @@
 // sub-pixel: mgm.cc:372-385 and :405-414) and the O(W*H) stages around it (left-right test mgm.cc:68-91, median
 // img_tools.h:203-238, range update mgm.cc:120-158, back-projection mgm.cc:432-443) executed by libmgmb200 on the
 // GPU.  The default flow is one mgmb200_stereo_lr call: the images go up once and the maps come back once.
-// -m/-M range images and TSGM_ITER > 1 take the call-by-call sequence of mgm.cc:372-395 (cost volume, then mgm +
-// refinement + range update per iteration) through the mirror functions of mgmb200_host.hpp.  Not supported
+// -m/-M range images and TSGM_ITER > 1 take mgmb200_stereo_ranges per direction (mgm.cc:372-395 on the device: cost
+// volume once, then mgm + refinement + range update per iteration); MGMB200_STEPWISE=1 runs the same sequence call
+// by call through the mirror functions of mgmb200_host.hpp (volumes cross the host between the calls).  Not supported
 // (exit code 2 or 3 with a message, never a silent fallback): -O 16, MEDIAN > 7.
 #include <algorithm>
 #include <cmath>
@@ -128,7 +129,18 @@ int main(int argc, char *argv[]) {
          for (int k = 0; k < u.npix; k++)
             if (dmaxI[k] < dminI[k] + 1) dmaxI[k] = ceil(dminI[k] + 1);
       }
+      const bool call_by_call = getenv("MGMB200_STEPWISE") != NULL;   // keep every volume on the host between the calls
       auto run = [&](Img &a, Img &b, Img &off, Img &cost, Img &loI, Img &hiI) {
+         if (!call_by_call) {
+            // the same sequence resident on the device (cost volume built once, ranges updated in place)
+            check(mgmb200_stereo_ranges(context(), a.data.data(), b.data.data(), a.nx, a.ny, a.nch, &p, loI.data.data(),
+                                        hiI.data.data(), (int)TSGM_ITER(), off.data.data(), cost.data.data()));
+            for (int it = 0; it < (int)TSGM_ITER(); it++) {
+               for (int pass = 0; pass < NDIR; pass++) printf("%d", pass);   // mgm_core.cc:491
+               printf("\n");                                                  // mgm_print_energy.h:110
+            }
+            return;
+         }
          // mgm.cc:372-395 call by call: the cost volume keeps its ranges, every iteration aggregates, refines and
          // updates the range images the next winner-take-all is restricted to
          Img w = compute_mgm_weights(a, aP2, aThresh);

@@ -395,6 +395,41 @@ def test_stereo_lr_flow(ctx, kw):
     assert same(r["backproj"], O.orc_backproject(out, u, v))
 
 
+@pytest.mark.parametrize("kw", [
+    dict(distance="ad", MGM=2, NDIR=8, iters=3, ragged=True),
+    dict(distance="census", MGM=3, NDIR=8, use_felzenszwalb_potentials=1, P1=2.0, P2=20000.0, refinement="vfit", iters=2, ragged=True),
+    dict(distance="sd", MGM=4, NDIR=4, aP=4.0, aThresh=9.0, refinement="cubic", iters=2, ragged=False),
+    dict(distance="ad", MGM=2, NDIR=8, use_felzenszwalb_potentials=1, P1=2.0, P2=20000.0, iters=1, ragged=True),
+])
+def test_stereo_ranges_flow(ctx, kw):
+    """mgmb200_stereo_ranges = mgm.cc:372-395 on the device: cost volume over the range images once, then per
+    TSGM_ITER iteration mgm + refinement over the current ranges and update_dmin_dmax + non-finite repair"""
+    kw = dict(kw)
+    iters, ragged = kw.pop("iters"), kw.pop("ragged")
+    nch = 3 if kw["distance"] == "sd" else 1
+    nx, ny = 83, 37
+    u, v = synth_pair(nx, ny, 18, seed=11, nch=nch)
+    if ragged:
+        lo, hi = _ragged(nx, ny, -20, 5, 5)
+    else:
+        lo, hi = np.full((ny, nx), -17, np.float32), np.full((ny, nx), 2, np.float32)
+    out, cost, lo2, hi2 = ctx.stereo_ranges(u, v, lo, hi, tsgm_iter=iters, **kw)
+    # the oracle's composition, over an envelope wide enough for every iteration
+    emin, emax = int(lo.min()) - 3 * (iters - 1), int(hi.max()) + 3 * (iters - 1)
+    P1, P2 = np.float32(kw.get("P1", 8.0)) * nch, np.float32(kw.get("P2", 32.0)) * nch
+    w = O.orc_weights(u, kw.get("aP", 1.0), kw.get("aThresh", 5.0))
+    cc = O.orc_costvolume_ranges(u, v, lo, hi, emin, emax, "none", kw["distance"], np.inf, 3)
+    slo, shi = lo.copy(), hi.copy()
+    for _ in range(iters):
+        r = O.orc_mgm_ranges(cc, lo, hi, w, emin, slo, shi, P1, P2, kw["NDIR"], kw["MGM"], kw.get("use_felzenszwalb_potentials", 0), 1)
+        o, oc = O.orc_refine_ranges(r["S"], slo, shi, emin, r["out"], r["outcost"], kw.get("refinement", "none"))
+        slo, shi, (gmin, gmax) = O.orc_update_range(o, slo, shi)
+        slo[~np.isfinite(slo)] = gmin
+        shi[~np.isfinite(shi)] = gmax
+    assert same(out, o) and same(cost, oc), (mism(out, o), mism(cost, oc))
+    assert same(lo2, slo) and same(hi2, shi)
+
+
 def _pnm(path, a):
     a = np.clip(a, 0, 255).astype(np.uint8)
     if a.shape[0] == 1:
@@ -417,6 +452,9 @@ def _pnm(path, a):
     (dict(TSGM="4", RANGES="1"), ["-r", "-23", "-R", "4", "-t", "ad", "-s", "parabola", "-O", "4", "-p", "gblur"], 3),  # -m/-M range images
     (dict(TSGM="2", RANGES="1", USE_TRUNCATED_LINEAR_POTENTIALS="1", TSGM_ITER="2"),
      ["-P1", "2", "-P2", "20000", "-r", "-23", "-R", "4", "-t", "sd", "-O", "8"], 1),
+    (dict(TSGM="4", RANGES="1", MGMB200_STEPWISE="1"), ["-r", "-23", "-R", "4", "-t", "ad", "-s", "parabola", "-O", "4"], 3),  # call-by-call mirror functions
+    (dict(TSGM_ITER="2", TSGM="3", USE_TRUNCATED_LINEAR_POTENTIALS="1", MGMB200_STEPWISE="1"),
+     ["-P1", "2", "-P2", "20000", "-r", "-23", "-R", "4", "-t", "census", "-s", "vfit", "-O", "8"], 1),
     (dict(TSGM="3", RANGES="1", USE_TRUNCATED_LINEAR_POTENTIALS="1", MEDIAN="1"),                             # windowed min-convolution
      ["-P1", "2", "-P2", "20000", "-r", "-23", "-R", "4", "-t", "census", "-s", "vfit", "-O", "8", "-aP2", "3"], 1),
 ])
