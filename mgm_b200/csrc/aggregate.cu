@@ -1152,9 +1152,13 @@ __device__ __forceinline__ void run_finish_tile(const AggParams &P, int tile, un
          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)pix * P.VS + (size_t)(l % lpv) * 32));
       }
    };
-   if (warp < w * h) prefetch_pixel(warp);
+#ifndef MGM_FIN_PF
+#define MGM_FIN_PF 1   // prefetch distance in pixels of the warp
+#endif
+   for (int d = 0; d < MGM_FIN_PF; ++d)
+      if (warp + d * nwarps < w * h) prefetch_pixel(warp + d * nwarps);
    for (int i = warp; i < w * h; i += nwarps) {
-      if (i + nwarps < w * h) prefetch_pixel(i + nwarps);
+      if (i + MGM_FIN_PF * nwarps < w * h) prefetch_pixel(i + MGM_FIN_PF * nwarps);
       const long long pix = (long long)(y0 + i / w) * P.nx + x0 + i % w;
       wta_pixel<true>(P.fin, pix, sS, lane);
    }
