@@ -280,6 +280,29 @@ def test_stereo_matches_oracle(ctx, kw):
 
 
 # ------------------------------------------------------------------------------------------ full-size properties
+@pytest.mark.parametrize("cfg", [dict(W=2048, H=1536, L=256, dist="census", win=3, K=3, felz=1, P1=2.0, P2=20000.0),
+                                 dict(W=1920, H=1080, L=128, dist="census", win=5, K=2, felz=0, P1=8.0, P2=32.0),
+                                 dict(W=1242, H=375, L=192, dist="census", win=5, K=4, felz=0, P1=8.0, P2=32.0),
+                                 dict(W=4096, H=4096, L=64, dist="ncc", win=5, K=2, felz=0, P1=8.0, P2=32.0)])
+def test_full_size_finish_fused_vs_separate(ctx, cfg, monkeypatch):
+    """BASELINE.json configs 2-5 shapes: the finish stage run as tiles inside the aggregation launch (completion flags,
+    release/acquire across CTAs, thousands of tiles racing with the running bands) gives the bits of the separate
+    finish kernel, sub-pixel refinement included, and is reproducible from run to run."""
+    from bench import synth_pair as bench_pair
+    W, H, L = cfg["W"], cfg["H"], cfg["L"]
+    u, v = bench_pair(W, H, L, 1)
+    kw = dict(dmin=-(L - 1), dmax=0, P1=cfg["P1"], P2=cfg["P2"], MGM=cfg["K"], NDIR=8, refinement="vfit",
+              use_felzenszwalb_potentials=cfg["felz"], distance=cfg["dist"], census_ncc_win=cfg["win"])
+    runs = [ctx.stereo(u, v, **kw) for _ in range(3)]
+    assert ctx.last_launch_info()["kernel_launches"] == 1
+    monkeypatch.setenv("MGMB200_NO_FUSED_FINISH", "1")
+    ref = ctx.stereo(u, v, **kw)
+    assert ctx.last_launch_info()["kernel_launches"] == 2
+    for out, cost in runs:
+        assert same(out, ref[0]) and same(cost, ref[1]), (mism(out, ref[0]), mism(cost, ref[1]))
+    assert (ref[0] != np.round(ref[0])).any()   # sub-pixel offsets present (vfit may give NaN on flat minima, like the reference)
+
+
 @pytest.mark.parametrize("cfg", [dict(W=2048, H=1536, L=256, win=3, K=3, felz=1, P1=2.0, P2=20000.0),
                                  dict(W=1920, H=1080, L=128, win=5, K=2, felz=0, P1=8.0, P2=32.0)])
 def test_full_size_properties(ctx, cfg):
