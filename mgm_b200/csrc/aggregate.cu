@@ -1059,7 +1059,12 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
 //   1. an axis band whose predecessor has started publishing its boundary row (or a first band), longest
 //      remaining chain first -- the axis sweeps are the critical path;
 //   2. else the next band of the diagonal sweep that is least advanced (short hand-off: the filler work);
-//   3. else any remaining axis band (it waits inside run_band).
+//   3. else (fused finish) the finish tile this CTA holds, if the bands that cover it are complete;
+//   4. else any remaining axis band (it waits inside run_band);
+//   5. else, with a tile still pending, wait for it; without, the CTA is done.
+// Finish tiles never block: they are claimed one per CTA from a host-built order and only run when ready, so the
+// band argument above is unchanged.
+
 // A tile can be finished once every band (of every requested sweep) that holds one of its pixels is complete.
 // Band indices are monotone in the scan coordinates, which are affine in (x,y): the extremes are at the corners.
 __device__ bool tile_ready(const AggParams &P, int tile) {
