@@ -210,8 +210,11 @@ __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, i
    // the loop indexes with 32-bit offsets; same operations in the same order as cell_cost.
    constexpr bool fast = (NCT > 0);
    const long long vnp = (long long)A.vnx * A.vny;
+   const bool small = np < 0x7fffffffLL;   // 32-bit pixel arithmetic (the 64-bit division costs as much as a pixel)
    for (long long p = (long long)blockIdx.x * warps + wid; p < np; p += (long long)gridDim.x * warps) {
-      const int x = (int)(p % A.nx), y = (int)(p / A.nx);
+      int x, y;
+      if (small) { y = (int)((unsigned)p / (unsigned)A.nx); x = (int)((unsigned)p - (unsigned)y * (unsigned)A.nx); }
+      else { x = (int)(p % A.nx); y = (int)(p / A.nx); }
       float4 *dst = reinterpret_cast<float4 *>(cc + (size_t)p * VS);
       bool anyfinite = false;
       int klo = 0, khi = L - 1;   // the pixel's own range, as label indices of the dense envelope
@@ -235,8 +238,36 @@ __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, i
             }
          }
          const int qx0 = x + dmin;
+         // labels [va,vb] have a match inside the right image; a 16-byte chunk that lies entirely in there (all but
+         // two per pixel) takes the straight-line path without per-label range tests
+         const int va = vy_ok ? max(klo, -qx0) : 1, vb = vy_ok ? min(khi, A.vnx - 1 - qx0) : 0;
          for (int q = lane; q < nq; q += 32) {
             float e4[4];
+            if (q * 4 >= va && q * 4 + 3 <= vb) {
+               const int qb = qx0 + q * 4;
+#pragma unroll
+               for (int j = 0; j < 4; ++j) {
+                  float acc = 0.f;
+#pragma unroll
+                  for (int t = 0; t < NC; ++t) {
+                     const uint32_t rv = __ldg(rrow[t] + qb + j);
+                     if (DIST == DIST_CENSUS) {
+                        const float pc = __uint_as_float(0x4B000000u | (unsigned)__popc(lw[t] ^ rv)) - 8388608.0f;
+                        acc = (t == 0) ? pc : acc + pc;
+                     } else {
+                        float d = __uint_as_float(lw[t]) - __uint_as_float(rv);
+                        d = sel_max(d, -d);
+                        acc += (DIST == DIST_SD) ? d * d : d;
+                     }
+                  }
+                  float e = (DIST == DIST_CENSUS && NC != 1) ? (float)((double)acc / (double)NC) : acc;
+                  e = sel_min(e, cap);
+                  anyfinite |= (fabsf(e) < MGM_INF);
+                  e4[j] = e;
+               }
+               dst[q] = make_float4(e4[0], e4[1], e4[2], e4[3]);
+               continue;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                const int k = q * 4 + j;
@@ -249,7 +280,11 @@ __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, i
 #pragma unroll
                      for (int t = 0; t < NC; ++t) {
                         const uint32_t rv = __ldg(rrow[t] + qx);
-                        if (DIST == DIST_CENSUS) acc += (float)__popc(lw[t] ^ rv);
+                        if (DIST == DIST_CENSUS) {
+                           // (float)popc without the quarter-rate I2F: 2^23 + n is exact for n <= 32
+                           const float pc = __uint_as_float(0x4B000000u | (unsigned)__popc(lw[t] ^ rv)) - 8388608.0f;
+                           acc = (t == 0) ? pc : acc + pc;   // 0.f + pc == pc (pc >= +0)
+                        }
                         else {
                            float d = __uint_as_float(lw[t]) - __uint_as_float(rv);
                            d = sel_max(d, -d);
