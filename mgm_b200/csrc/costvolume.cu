@@ -13,12 +13,12 @@ namespace mgm {
 // ------------------------------------------------------------------ K3 weights
 __global__ void mgm_weights_kernel(const float *__restrict__ u, int nx, int ny, int nch, float aP, float aThresh,
                                    float *__restrict__ w, int *__restrict__ not_all_ones) {
+   // grid: x over columns, y = image row, z = weight plane (no index divisions: they dominated this kernel)
    const long long np = (long long)nx * ny;
-   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= np * 8) return;
-   const int k = (int)(i / np);
-   const long long p = i - (long long)k * np;
-   const int x = (int)(p % nx), y = (int)(p / nx);
+   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;
+   if (x >= nx) return;
+   const long long p = x + (long long)y * nx;
+   const long long i = p + (long long)k * np;
    // plane order W E S N NW NE SE SW (mgm_weights.h:69)
    const int ox = (k == 0 || k == 4 || k == 7) ? -1 : ((k == 1 || k == 5 || k == 6) ? 1 : 0);
    const int oy = (k == 3 || k == 4 || k == 5) ? -1 : ((k == 2 || k == 6 || k == 7) ? 1 : 0);
@@ -398,8 +398,8 @@ static inline unsigned blocks_for(long long n, int b) { return (unsigned)((n + b
 
 cudaError_t weights_launch(const float *d_u, int nx, int ny, int nch, float aP, float aThresh, float *d_w,
                            int *d_flag, cudaStream_t st) {
-   const long long n = (long long)nx * ny * 8;
-   mgm_weights_kernel<<<blocks_for(n, 256), 256, 0, st>>>(d_u, nx, ny, nch, aP, aThresh, d_w, d_flag);
+   if (ny > 65535) return cudaErrorInvalidValue;   // one grid row per image row
+   mgm_weights_kernel<<<dim3((nx + 255) / 256, ny, 8), 256, 0, st>>>(d_u, nx, ny, nch, aP, aThresh, d_w, d_flag);
    return cudaGetLastError();
 }
 
