@@ -190,7 +190,7 @@ inline Img read_tiff(const std::vector<uint8_t> &b) {
    if (u16(2) != 42) throw std::runtime_error("not a classic TIFF");
    size_t ifd = u32(4);
    const int n = u16(ifd);
-   uint32_t w = 0, h = 0, bps = 8, comp = 1, spp = 1, fmt = 1, rps = 0xffffffff, planar = 1;
+   uint32_t w = 0, h = 0, bps = 8, comp = 1, spp = 1, fmt = 1, planar = 1;
    std::vector<uint32_t> offs, counts;
    for (int i = 0; i < n; i++) {
       const size_t e = ifd + 2 + 12 * i;
@@ -202,7 +202,7 @@ inline Img read_tiff(const std::vector<uint8_t> &b) {
       };
       if (tag == 256) w = value(0); else if (tag == 257) h = value(0); else if (tag == 258) bps = value(0);
       else if (tag == 259) comp = value(0); else if (tag == 277) spp = value(0); else if (tag == 339) fmt = value(0);
-      else if (tag == 278) rps = value(0); else if (tag == 284) planar = value(0);
+      else if (tag == 284) planar = value(0);   // rows per strip (278) is implied by the strip offsets
       else if (tag == 273) { offs.resize(cnt); for (uint32_t j = 0; j < cnt; j++) offs[j] = value(j); }
       else if (tag == 279) { counts.resize(cnt); for (uint32_t j = 0; j < cnt; j++) counts[j] = value(j); }
    }
