@@ -13,28 +13,36 @@ namespace mgm {
 // ------------------------------------------------------------------ K3 weights
 __global__ void mgm_weights_kernel(const float *__restrict__ u, int nx, int ny, int nch, float aP, float aThresh,
                                    float *__restrict__ w, int *__restrict__ not_all_ones) {
-   // grid: x over columns, y = image row, z = weight plane (no index divisions: they dominated this kernel)
+   // grid: x over columns, y = image row; one thread writes the eight planes of its pixel (no index divisions,
+   // blocks with enough work: both dominated earlier versions of this kernel)
    const long long np = (long long)nx * ny;
-   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, k = blockIdx.z;
+   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
    if (x >= nx) return;
    const long long p = x + (long long)y * nx;
-   const long long i = p + (long long)k * np;
-   // plane order W E S N NW NE SE SW (mgm_weights.h:69)
-   const int ox = (k == 0 || k == 4 || k == 7) ? -1 : ((k == 1 || k == 5 || k == 6) ? 1 : 0);
-   const int oy = (k == 3 || k == 4 || k == 5) ? -1 : ((k == 2 || k == 6 || k == 7) ? 1 : 0);
-   const int qx = x + ox, qy = y + oy;
-   float wv = 1.0f;
-   if (qx >= 0 && qy >= 0 && qx < nx && qy < ny) {
-      float d = 0.f;
-      for (int c = 0; c < nch; ++c) {
-         const float diff = u[p + c * np] - u[qx + (long long)qy * nx + c * np];
-         d += diff * diff;
+   const float thr2 = aThresh * aThresh;
+   bool other = false;
+#pragma unroll
+   for (int k = 0; k < 8; ++k) {
+      // plane order W E S N NW NE SE SW (mgm_weights.h:69)
+      const int ox = (k == 0 || k == 4 || k == 7) ? -1 : ((k == 1 || k == 5 || k == 6) ? 1 : 0);
+      const int oy = (k == 3 || k == 4 || k == 5) ? -1 : ((k == 2 || k == 6 || k == 7) ? 1 : 0);
+      const int qx = x + ox, qy = y + oy;
+      float wv = 1.0f;
+      if (qx >= 0 && qy >= 0 && qx < nx && qy < ny) {
+         float d = 0.f;
+         for (int c = 0; c < nch; ++c) {
+            const float diff = u[p + c * np] - u[qx + (long long)qy * nx + c * np];
+            d += diff * diff;
+         }
+         d = __fdiv_rn(d, (float)nch);
+         if (fabsf(d) < thr2) wv = aP;
       }
-      d = __fdiv_rn(d, (float)nch);
-      if (fabsf(d) < aThresh * aThresh) wv = aP;
+      w[p + (long long)k * np] = wv;
+      other |= (wv != 1.0f);
    }
-   w[i] = wv;
-   if (wv != 1.0f && not_all_ones) atomicOr(not_all_ones, 1);   // the scan of mgm_core.cc:420-422
+   // the scan of mgm_core.cc:420-422: one atomic per warp that saw a weight other than 1
+   const unsigned am = __activemask();
+   if (__any_sync(am, other) && not_all_ones && (int)(threadIdx.x & 31) == __ffs(am) - 1) atomicOr(not_all_ones, 1);
 }
 
 // ------------------------------------------------------------------ K1 census transform
@@ -399,7 +407,7 @@ static inline unsigned blocks_for(long long n, int b) { return (unsigned)((n + b
 cudaError_t weights_launch(const float *d_u, int nx, int ny, int nch, float aP, float aThresh, float *d_w,
                            int *d_flag, cudaStream_t st) {
    if (ny > 65535) return cudaErrorInvalidValue;   // one grid row per image row
-   mgm_weights_kernel<<<dim3((nx + 255) / 256, ny, 8), 256, 0, st>>>(d_u, nx, ny, nch, aP, aThresh, d_w, d_flag);
+   mgm_weights_kernel<<<dim3((nx + 255) / 256, ny), 256, 0, st>>>(d_u, nx, ny, nch, aP, aThresh, d_w, d_flag);
    return cudaGetLastError();
 }
 
