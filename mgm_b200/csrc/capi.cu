@@ -338,6 +338,22 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
 
    AggPlan plan;
    agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, c->rows_override);
+   if (!c->rows_override && !getenv("MGMB200_ROWS_AXIS") && !getenv("MGMB200_ROWS_DIAG") && plan.T[0] > 40) {
+      // One or two sweeps on this GPU (sweep-sharded layouts): with fewer bands than SMs the launch is bound by the
+      // dependency depth alone, and bands of 40 workers step faster than bands of 56 (measured: one axis sweep of
+      // the headline shape 15.6 -> 13.9 ms, an axis + a diagonal sweep 15.9 -> 14.9 ms; small images with all
+      // eight sweeps do not gain)
+      long bands = 0;
+      int nsweeps = 0;
+      for (int p = 0; p < NDIR; p++) nsweeps += (mask >> p) & 1;
+      for (int p = 0; p < NDIR && nsweeps <= 2; p++) {
+         if (!(mask & (1u << p))) continue;
+         const PassGeom g = pass_geometry(p, nx, ny);
+         const int T = plan.T[p < 4 ? 0 : 1];
+         bands += (p >= 4 && plan.shear) ? (g.maxii + g.maxjj - 1 + T - 1) / T : (g.maxjj + T - 1) / T;
+      }
+      if (nsweeps <= 2 && bands < c->num_sms) agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 40);
+   }
    if (plan.T[0] < 1 || plan.T[1] < 1)
       return fail(MGMB200_EUNSUPPORTED, "%d labels do not fit the shared-memory wavefront (max_smem=%d)", L, c->max_smem);
    c->rows_axis = plan.T[0]; c->rows_diag = plan.T[1]; c->block = plan.block; c->smem = plan.smem;
