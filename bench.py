@@ -7,16 +7,24 @@ configuration (BASELINE.json configs[2], the one the metric is quoted on):
 
   value : Gdisp-updates/s = W*H*L*NDIR / t, t = device time from "cost volume resident in
           HBM" to "disparity + cost maps resident in HBM" (aggregation sweeps + ordered sum +
-          over-count fix + WTA + sub-pixel), CUDA events on the launching stream.
+          over-count fix + WTA + sub-pixel), CUDA events on the launching stream.  That region is ONE
+          kernel launch (the aggregation kernel with the finish stage fused in as tile work): `roofline`
+          describes it, with the two-launch split (sweeps only / finish only) measured beside it.
   e2e   : same metric through the reference-facing C-ABI call mgmb200_stereo() with HOST
           buffers: H2D of the two images, weights, cost volume, aggregation, refinement, D2H of
           the two maps, all inside the timed region.
   --impl reference : the reference's own CPU implementation (oracle/_ref, compiled from the
           unmodified sources) timed on the host cores on a bounded crop of the same workload.
 
-Multi-GPU (torchrun, one rank per GPU): the 8 sweeps are sharded over the ranks (sweep p on
-rank p mod N), every rank finishes a slab of rows reading the other ranks' sweep volumes over
-NVLink in sweep order (bit-identical to 1 GPU), the two maps are all-gathered with NCCL.
+  e2e_cli_flow : the default command-line flow (both directions, median, left-right tests)
+          through mgmb200_stereo_lr with host buffers.
+
+Multi-GPU (torchrun, one rank per GPU): `value` is the batch layout, one independent stereo pair
+per GPU and no data-path collective (weak scaling).  `sweep_sharded` reports the north_star
+layout beside it: the 8 sweeps of ONE pair sharded over the ranks (sweep p on rank p mod N),
+every rank finishes a slab of rows reading the other ranks' sweep volumes over NVLink in sweep
+order (bit-identical to 1 GPU), the two maps are all-gathered with NCCL (`--shard sweeps` makes
+it the timed step).
 """
 import argparse
 import json
