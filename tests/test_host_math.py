@@ -93,3 +93,42 @@ def test_minconv_second_half_runs_on_the_partner_partials_only():
             run = min(np.float32(run + c), F[o])
             Q[o] = run
         assert np.array_equal(Q, ref), (trial, n, float(c))
+
+
+def test_finish_tile_band_bounds():
+    """Fused finish (aggregate.cu tile_ready): the bands of a sweep that hold pixels of a rectangular tile are bounded
+    by the band indices of two opposite corners in SCAN coordinates, because the scan coordinates are affine in
+    (x, y) with slopes +-1 and the band index is monotone in them.  Restated here with the sweep table of
+    common.cuh (pass_geometry) and checked against the brute-force set of bands over every pixel of the tile."""
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        nx, ny = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        T0, T1 = int(rng.integers(1, 20)), int(rng.integers(1, 20))
+        shear = bool(rng.integers(0, 2))
+        tw, th = int(rng.integers(1, 25)), int(rng.integers(1, 25))
+        tx, ty = int(rng.integers(0, (nx + tw - 1) // tw)), int(rng.integers(0, (ny + th - 1) // th))
+        x0, y0 = tx * tw, ty * th
+        x1, y1 = min(x0 + tw, nx) - 1, min(y0 + th, ny) - 1
+        for p in range(8):
+            rm, incx, incy = (0x53 >> p) & 1, (0xC5 >> p) & 1, (0x99 >> p) & 1
+            maxii, maxjj = (nx, ny) if rm else (ny, nx)
+
+            def band(x, y):
+                ax = x if incx else nx - 1 - x
+                ay = y if incy else ny - 1 - y
+                xs, ys = (ax, ay) if rm else (ay, ax)
+                assert 0 <= xs < maxii and 0 <= ys < maxjj
+                return (xs + ys) // T1 if (p >= 4 and shear) else ys // (T0 if p < 4 else T1)
+            # the corner formula of tile_ready
+            ax0, ax1 = (x0, x1) if incx else (nx - 1 - x1, nx - 1 - x0)
+            ay0, ay1 = (y0, y1) if incy else (ny - 1 - y1, ny - 1 - y0)
+            xs0, xs1, ys0, ys1 = (ax0, ax1, ay0, ay1) if rm else (ay0, ay1, ax0, ax1)
+            if p >= 4 and shear:
+                b0, b1 = (xs0 + ys0) // T1, (xs1 + ys1) // T1
+            else:
+                T = T0 if p < 4 else T1
+                b0, b1 = ys0 // T, ys1 // T
+            brute = {band(x, y) for x in range(x0, x1 + 1) for y in range(y0, y1 + 1)}
+            assert min(brute) == b0 and max(brute) == b1, (p, nx, ny, shear)
+            nb = (maxii + maxjj - 1 + T1 - 1) // T1 if (p >= 4 and shear) else (maxjj + (T0 if p < 4 else T1) - 1) // (T0 if p < 4 else T1)
+            assert 0 <= b0 <= b1 < nb
