@@ -3,6 +3,7 @@
  (b) the reference itself, live, when oracle/_ref/libmgmref.so is present (build container, GPU box).
 Bit-exact everywhere: the port restates the same IEEE operations in the same order."""
 import itertools
+import os
 
 import numpy as np
 import pytest
@@ -204,3 +205,48 @@ def test_port_postprocessing_vs_ref():
             assert same(a[0], b[0]) and same(a[1], b[1]) and a[2] == b[2]
         a, b = O.orc_update_range(dl, lo, hi, slack=-2, radius=1), O.ref_update_range(dl, lo, hi, slack=-2, radius=1)
         assert same(a[0], b[0]) and same(a[1], b[1]) and a[2] == b[2]
+
+
+REF_MGM = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "mgm")
+
+
+def _pnm(path, a):
+    a = np.clip(a, 0, 255).astype(np.uint8)
+    if a.shape[0] == 1:
+        open(path, "wb").write(b"P5\n%d %d\n255\n" % (a.shape[2], a.shape[1]) + a[0].tobytes())
+    else:
+        open(path, "wb").write(b"P6\n%d %d\n255\n" % (a.shape[2], a.shape[1]) + np.transpose(a, (1, 2, 0)).tobytes())
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MGM), reason="oracle/_ref/mgm not built")
+@pytest.mark.parametrize("nch,median,refinement", [(1, 1, "vfit"), (3, 0, "none")])
+def test_port_cli_flow_vs_reference_cli(tmp_path, nch, median, refinement):
+    """The oracle's composition of the default command-line flow (both directions, median, left-right tests,
+    back-projection: the checker of mgmb200_stereo_lr) against the reference BINARY on the same files."""
+    import subprocess
+    u, v = synth_pair(70, 40, 14, seed=6, nch=nch)
+    u, v = np.round(np.clip(u, 0, 255)), np.round(np.clip(v, 0, 255))   # what the 8-bit files hold
+    if u.ndim == 2:
+        u, v = u[None], v[None]
+    _pnm(str(tmp_path / "u.pnm"), u)
+    _pnm(str(tmp_path / "v.pnm"), v)
+    names = [str(tmp_path / ("ref_%s.npy" % k)) for k in ("disp", "cost", "back")]
+    env = dict(os.environ, TSGM="3", MEDIAN=str(median), USE_TRUNCATED_LINEAR_POTENTIALS="1", CENSUS_NCC_WIN="3")
+    r = subprocess.run([REF_MGM, "-r", "-13", "-R", "2", "-t", "census", "-O", "8", "-P1", "2", "-P2", "20000", "-s", refinement,
+                        "-l", str(tmp_path / "ref_nolr.npy"), str(tmp_path / "u.pnm"), str(tmp_path / "v.pnm")] + names,
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    disp, cost, back = [np.load(n) for n in names]
+    nolr = np.squeeze(np.load(str(tmp_path / "ref_nolr.npy")))
+    disp, cost = np.squeeze(disp), np.squeeze(cost)
+    back = np.moveaxis(back, -1, 0) if back.ndim == 3 else back[None]
+    kw = dict(P1=2.0, P2=20000.0, NDIR=8, K=3, felz=1, distance="census", win=3, refinement=refinement)
+    uu, vv = u.astype(np.float32), v.astype(np.float32)
+    L = O.orc_pipeline(uu, vv, -13, 2, **kw)
+    R = O.orc_pipeline(vv, uu, -2, 13, **kw)
+    offL = O.orc_median(L["out"], median) if median else L["out"]
+    offR = O.orc_median(R["out"], median) if median else R["out"]
+    assert same(nolr, offL)
+    out = O.orc_leftright(offL, offR, 1.0)
+    assert same(disp, out) and same(cost, L["outcost"])
+    assert same(back, O.orc_backproject(out, uu, vv))
