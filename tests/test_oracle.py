@@ -250,3 +250,50 @@ def test_port_cli_flow_vs_reference_cli(tmp_path, nch, median, refinement):
     out = O.orc_leftright(offL, offR, 1.0)
     assert same(disp, out) and same(cost, L["outcost"])
     assert same(back, O.orc_backproject(out, uu, vv))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MGM), reason="oracle/_ref/mgm not built")
+@pytest.mark.parametrize("iters,ranges,felz,K", [(2, True, 0, 2), (3, False, 1, 3), (1, True, 1, 2), (2, True, 1, 3)])
+def test_port_ranges_iterations_vs_reference_cli(tmp_path, iters, ranges, felz, K):
+    """The oracle's composition of mgm.cc:372-395 (cost volume over the range images once, then per TSGM_ITER
+    iteration mgm + refinement over the current ranges and update_dmin_dmax + non-finite repair: the checker of
+    mgmb200_stereo_ranges) against the reference BINARY with -m/-M files and TSGM_ITER."""
+    import subprocess
+    nx, ny = 120, 64
+    u, v = synth_pair(nx, ny, 24, seed=4, nch=1)
+    u, v = np.round(np.clip(u, 0, 255)).reshape(1, ny, nx), np.round(np.clip(v, 0, 255)).reshape(1, ny, nx)
+    _pnm(str(tmp_path / "u.pnm"), u)
+    _pnm(str(tmp_path / "v.pnm"), v)
+    # -truncDist keeps every label finite: a pixel whose range holds no finite label has an UNINITIALISED disparity in
+    # the reference (mgm_core.cc:594), which update_dmin_dmax would then spread to its neighbours' ranges
+    args = ["-r", "-23", "-R", "4", "-t", "ad", "-O", "8", "-s", "vfit", "-truncDist", "40"] + (["-P1", "2", "-P2", "20000"] if felz else [])
+    if ranges:
+        rng = np.random.default_rng(7)
+        lo = (-14 + rng.integers(-6, 3, (ny, nx))).astype(np.float32)
+        hi = (lo + rng.integers(0, 14, (ny, nx))).astype(np.float32)
+        np.save(str(tmp_path / "dmin.npy"), lo)
+        np.save(str(tmp_path / "dmax.npy"), hi)
+        args += ["-m", str(tmp_path / "dmin.npy"), "-M", str(tmp_path / "dmax.npy")]
+        hi = np.where(hi < lo + 1, np.ceil(lo + 1), hi).astype(np.float32)   # the repair of mgm.cc:349-352
+    else:
+        lo, hi = np.full((ny, nx), -23, np.float32), np.full((ny, nx), 4, np.float32)
+    names = [str(tmp_path / ("ref_%s.npy" % k)) for k in ("disp", "cost")]
+    env = dict(os.environ, TSGM=str(K), TSGM_ITER=str(iters), TESTLRRL="0", USE_TRUNCATED_LINEAR_POTENTIALS=str(felz))
+    r = subprocess.run([REF_MGM] + args + [str(tmp_path / "u.pnm"), str(tmp_path / "v.pnm")] + names, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    disp, cost = [np.squeeze(np.load(n)) for n in names]
+    uu, vv = u.astype(np.float32), v.astype(np.float32)
+    emin, emax = int(lo.min()) - 3 * (iters - 1), int(hi.max()) + 3 * (iters - 1)
+    P1, P2 = (2.0, 20000.0) if felz else (8.0, 32.0)
+    w = O.orc_weights(uu, 1.0, 5.0)
+    cc = O.orc_costvolume_ranges(uu, vv, lo, hi, emin, emax, "none", "ad", 40.0, 3)
+    slo, shi = lo.copy(), hi.copy()
+    for _ in range(iters):
+        rr = O.orc_mgm_ranges(cc, lo, hi, w, emin, slo, shi, P1, P2, 8, K, felz, 1)
+        o, oc = O.orc_refine_ranges(rr["S"], slo, shi, emin, rr["out"], rr["outcost"], "vfit")
+        slo, shi, (gmin, gmax) = O.orc_update_range(o, slo, shi)
+        slo[~np.isfinite(slo)] = gmin
+        shi[~np.isfinite(shi)] = gmax
+    ok = np.isfinite(cost)   # the reference leaves the label uninitialised where no label of the range is finite
+    assert same(cost, oc) and same(disp[ok], o[ok]) and ok.mean() > 0.25
