@@ -261,6 +261,21 @@ def test_golden_volume(ctx, path):
     assert same(r["S"][r["S"].shape[0] // 2], g["S_row"])
 
 
+@pytest.mark.parametrize("path", golden_files("flow_lr"))
+def test_golden_flow_lr(ctx, path):
+    """mgmb200_stereo_lr against the output files of the reference binary (both directions, median, left-right tests,
+    -l map, back-projection; tests/golden/make_golden_flows.py)"""
+    from tests.flow_checks import check_flow_lr
+    check_flow_lr(load_golden(path), ctx)
+
+
+@pytest.mark.parametrize("path", golden_files("flow_ranges"))
+def test_golden_flow_ranges(ctx, path):
+    """mgmb200_stereo_ranges against the output files of the reference binary (-m/-M range images, TSGM_ITER)"""
+    from tests.flow_checks import check_flow_ranges
+    check_flow_ranges(load_golden(path), ctx)
+
+
 # ------------------------------------------------------------------------------------------ whole hot path
 @pytest.mark.parametrize("kw", [
     dict(distance="census", census_ncc_win=5, NDIR=8, MGM=2, refinement="vfit"),                       # BASELINE cfg 2 shape of flags

@@ -297,3 +297,31 @@ def test_port_ranges_iterations_vs_reference_cli(tmp_path, iters, ranges, felz, 
         shi[~np.isfinite(shi)] = gmax
     ok = np.isfinite(cost)   # the reference leaves the label uninitialised where no label of the range is finite
     assert same(cost, oc) and same(disp[ok], o[ok]) and ok.mean() > 0.25
+
+
+# ------------------------------------------------------------------------------------------ golden flows
+def test_flow_interface_matches_api():
+    """OracleImpl (tests/flow_checks.py) takes exactly the keywords of mgm_b200.api.Context for the two flow calls, so
+    that the same checks drive both."""
+    import inspect
+    from mgm_b200.api import Context
+    from tests.flow_checks import OracleImpl
+    for name in ("stereo_lr", "stereo_ranges"):
+        a = inspect.signature(getattr(Context, name)).parameters
+        b = inspect.signature(getattr(OracleImpl, name)).parameters
+        assert list(a) == list(b), (name, list(a), list(b))
+        for k in a:
+            if a[k].default is not inspect.Parameter.empty:
+                assert repr(a[k].default) == repr(b[k].default), (name, k)
+
+
+@pytest.mark.parametrize("path", golden_files("flow_lr"))
+def test_golden_flow_lr_oracle(path):
+    from tests.flow_checks import OracleImpl, check_flow_lr
+    check_flow_lr(load_golden(path), OracleImpl())
+
+
+@pytest.mark.parametrize("path", golden_files("flow_ranges"))
+def test_golden_flow_ranges_oracle(path):
+    from tests.flow_checks import OracleImpl, check_flow_ranges
+    check_flow_ranges(load_golden(path), OracleImpl())
