@@ -1,32 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- MGM hot-path benchmark (contract in the task statement).
 
-One "step" = one pass of the hot path over one synthetic stereo pair of the headline
-configuration (BASELINE.json configs[2], the one the metric is quoted on):
-2048x1536, 256 disparities, census 3x3, -O 8, TSGM=3, truncated-linear potentials.
+One "step" = one pass of the hot path over one batch of synthetic input of the named workload.  The default
+workload is the configuration the metric is quoted on (BASELINE.json configs[2]): ONE stereo pair 2048x1536,
+256 disparities, census 3x3, -O 8, TSGM=3, truncated-linear potentials.
 
-  value : Gdisp-updates/s = W*H*L*NDIR / t, t = device time from "cost volume resident in
-          HBM" to "disparity + cost maps resident in HBM" (aggregation sweeps + ordered sum +
-          over-count fix + WTA + sub-pixel), CUDA events on the launching stream.  That region is ONE
-          kernel launch (the aggregation kernel with the finish stage fused in as tile work): `roofline`
-          describes it, with the two-launch split (sweeps only / finish only) measured beside it.
-  e2e   : same metric through the reference-facing C-ABI call mgmb200_stereo() with HOST
-          buffers: H2D of the two images, weights, cost volume, aggregation, refinement, D2H of
-          the two maps, all inside the timed region.
-  --impl reference : the reference's own CPU implementation (oracle/_ref, compiled from the
-          unmodified sources) timed on the host cores on a bounded crop of the same workload.
+  value : Gdisp-updates/s = pairs*W*H*L*NDIR / t, t = device time from "cost volumes resident in HBM" to
+          "disparity + cost maps resident in HBM" (aggregation sweeps + ordered sum + over-count fix + WTA +
+          sub-pixel), CUDA events on the launching stream.  For one pair that region is ONE kernel launch (the
+          aggregation kernel with the finish stage fused in as tile work): `roofline` describes it.
+  e2e   : the same metric through the reference-facing C-ABI call mgmb200_stereo() with HOST buffers: H2D of the
+          images, weights, cost volume, aggregation, refinement, D2H of the two maps, all inside the timed region.
+  parity: (N=1, on by default) the UNMODIFIED reference (oracle/_ref, OpenMP, all host threads) run on the SAME
+          full-size synthetic pair; WTA labels, aggregated volume, costs and sub-pixel disparities of the CUDA path
+          are compared with it.  The same run is the `cpu_baseline`.
+  --impl reference : the reference's own mgm() on the host cores, full frame of the same workload per step.
 
-  e2e_cli_flow : the default command-line flow (both directions, median, left-right tests)
-          through mgmb200_stereo_lr with host buffers.
-
-Multi-GPU (torchrun, one rank per GPU): `value` is the batch layout, one independent stereo pair
-per GPU and no data-path collective (weak scaling).  `sweep_sharded` reports the north_star
-layout beside it: the 8 sweeps of ONE pair sharded over the ranks (sweep p on rank p mod N),
-every rank finishes a slab of rows reading the other ranks' sweep volumes over NVLink in sweep
-order (bit-identical to 1 GPU), the two maps are all-gathered with NCCL (`--shard sweeps` makes
-it the timed step).
+Multi-GPU (torchrun, one rank per GPU): `value` is the batch layout (independent stereo pairs sharded over the
+GPUs, no data-path collective); `sweep_sharded` reports the north_star layout beside it (the sweeps of ONE pair
+sharded over the ranks), `--shard sweeps` makes it the timed step.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -40,15 +35,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: W, H, L, census win, NDIR, TSGM, trunc-linear, P1, P2, refinement
-    "cfg3_2048x1536x256_census3_O8_TSGM3_trunclinear": dict(W=2048, H=1536, L=256, win=3, NDIR=8, K=3, felz=1,
-                                                            P1=2.0, P2=20000.0, refine="vfit"),
-    "cfg2_1920x1080x128_census5_O8_TSGM2": dict(W=1920, H=1080, L=128, win=5, NDIR=8, K=2, felz=0, P1=8.0, P2=32.0,
-                                                refine="vfit"),
-    "small_640x480x64_census3_O8_TSGM3_trunclinear": dict(W=640, H=480, L=64, win=3, NDIR=8, K=3, felz=1, P1=2.0,
-                                                          P2=20000.0, refine="vfit"),
+    # BASELINE.json configs[2] -- the configuration the metric is quoted on
+    "cfg3_2048x1536x256_census3_O8_TSGM3_trunclinear": dict(W=2048, H=1536, L=256, dist="census", win=3, NDIR=8, K=3,
+                                                            felz=1, P1=2.0, P2=20000.0, refine="vfit", pairs=1),
+    # configs[1]
+    "cfg2_1920x1080x128_census5_O8_TSGM2": dict(W=1920, H=1080, L=128, dist="census", win=5, NDIR=8, K=2, felz=0,
+                                                P1=8.0, P2=32.0, refine="vfit", pairs=1),
+    # configs[3]: 32 KITTI-shape pairs, command-line defaults otherwise (-t ad, TSGM=4, P1=8, P2=32; mgm.cc:186,303-318)
+    "cfg4_32x1242x375x192_ad_O8_TSGM4": dict(W=1242, H=375, L=192, dist="ad", win=3, NDIR=8, K=4, felz=0, P1=8.0,
+                                             P2=32.0, refine="none", pairs=32),
+    # configs[4]: satellite tile, NCC 5x5, 16 sweeps (sweeps 8-15 are DEFINED by this build)
+    "cfg5_4096x4096x64_ncc5_O16_TSGM4": dict(W=4096, H=4096, L=64, dist="ncc", win=5, NDIR=16, K=4, felz=0, P1=8.0,
+                                             P2=32.0, refine="none", pairs=1),
+    "small_640x480x64_census3_O8_TSGM3_trunclinear": dict(W=640, H=480, L=64, dist="census", win=3, NDIR=8, K=3, felz=1,
+                                                          P1=2.0, P2=20000.0, refine="vfit", pairs=1),
 }
 DEFAULT_WORKLOAD = "cfg3_2048x1536x256_census3_O8_TSGM3_trunclinear"
+METRIC = "Gdisp-updates/s (W*H*L*Ndirs)"
+UNIT = "Gdisp-updates/s"
 
 
 def synth_pair(W, H, L, seed=0):
@@ -118,45 +122,213 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference_rate(wl, target_seconds=12.0, seed=0):
-    """Times the reference's own mgm() (oracle/_ref, OpenMP, all host threads) on a crop of the workload.
-    Returns (Gupd/s, dict)."""
-    import oracle as O
-    flavour = "_flat" if O.ref_lib("_flat") is not None else ""
-    kind = "reference"
-    if O.ref_lib(flavour) is None:
-        kind = "port"   # oracle/_ref not built on this box: fall back to the C restatement
-    L, NDIR, K = wl["L"], wl["NDIR"], wl["K"]
-    cores = os.cpu_count() or 1
+def kernel_source_sha():
+    """Identifies the kernel sources an ncu traffic capture belongs to (profiles/traffic.json is refused when stale)."""
+    h = hashlib.sha256()
+    for f in ("aggregate.cu", "aggregate.cuh", "wta_device.cuh", "common.cuh"):
+        h.update(open(os.path.join(ROOT, "mgm_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
 
-    def run(cw, ch):
-        u, v = synth_pair(cw, ch, L, seed)
-        if kind == "reference":
-            cc = O.ref_costvolume(u, v, -(L - 1), 0, "census", "census", np.inf, wl["win"], flavour=flavour)
-            r = O.ref_mgm(cc, None, -(L - 1), wl["P1"], wl["P2"], NDIR, K, wl["felz"], 1, want_S=False, flavour=flavour)
-            t = r["seconds"]
-        else:
-            cc = O.orc_costvolume(u, v, -(L - 1), 0, "census", "census", np.inf, wl["win"])
+
+def recorded_traffic(workload, key):
+    """DRAM bytes per launch of the named kernel from the committed `ncu --set full` capture, or (None, why)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = t[workload][key]
+        if e.get("kernel_source_sha") != kernel_source_sha():
+            return None, "profiles/traffic.json was captured on other kernel sources (%s): refused" % e.get("kernel_source_sha")
+        return e["traffic"], "ncu dram__bytes_read.sum + dram__bytes_write.sum, %s" % e.get("capture", "profiles/")
+    except Exception as ex:
+        return None, "no capture recorded (%s)" % type(ex).__name__
+
+
+def config_of(name, wl):
+    W, H, L = wl["W"], wl["H"], wl["L"]
+    dist = wl["dist"] + (" %dx%d" % (wl["win"], wl["win"]) if wl["dist"] in ("census", "ncc") else "")
+    return {"workload": name, "pairs": wl["pairs"], "W": W, "H": H, "L": L, "NDIR": wl["NDIR"], "TSGM": wl["K"],
+            "potentials": "truncated-linear" if wl["felz"] else "sgm", "P1": wl["P1"], "P2": wl["P2"],
+            "distance": dist, "refinement": wl["refine"],
+            "l2": "inputs (%.2f GB of cost volumes per step) larger than L2" % (wl["pairs"] * W * H * L * 4 / 1e9)}
+
+
+# ------------------------------------------------------------------------------------------ the reference on the CPU
+class ReferenceRun:
+    """The unmodified reference (oracle/_ref) on one synthetic pair of the workload; falls back to the C port
+    (oracle/mgm_oracle.c, one thread) when oracle/_ref is absent or the workload is outside the reference's
+    defined range (NDIR > 8)."""
+
+    def __init__(self, wl, seed=0, crop=None):
+        import oracle as O
+        self.O, self.wl = O, wl
+        self.flavour = "_flat" if O.ref_lib("_flat") is not None else ""
+        self.kind = "reference" if (O.ref_lib(self.flavour) is not None and wl["NDIR"] <= 8) else "port"
+        self.W, self.H = crop if crop else (wl["W"], wl["H"])
+        self.L = wl["L"]
+        self.dmin, self.dmax = -(self.L - 1), 0
+        self.u, self.v = synth_pair(self.W, self.H, self.L, seed)
+        self.cores = (os.cpu_count() or 1) if self.kind == "reference" else 1
+        self.cc = None
+        self.t_cc = None
+
+    def costvolume(self):
+        if self.cc is None:
+            O, wl = self.O, self.wl
+            pf = "census" if wl["dist"] == "census" else "none"
             t0 = time.perf_counter()
-            O.orc_mgm(cc, None, -(L - 1), wl["P1"], wl["P2"], NDIR, K, wl["felz"], 1, want_S=False)
-            t = time.perf_counter() - t0
-        return cw * ch * L * NDIR / t / 1e9, t
+            if self.kind == "reference":
+                self.cc = O.ref_costvolume(self.u, self.v, self.dmin, self.dmax, pf, wl["dist"], np.inf, wl["win"],
+                                           flavour=self.flavour)
+            else:
+                self.cc = O.orc_costvolume(self.u, self.v, self.dmin, self.dmax, pf, wl["dist"], np.inf, wl["win"])
+            self.t_cc = time.perf_counter() - t0
+        return self.cc
 
-    # calibrate on a small crop, then size the sample for ~target_seconds
-    cw, ch = 256, 96
-    rate, t = run(cw, ch)
-    scale = max(1.0, min(target_seconds / max(t, 1e-3), wl["W"] * wl["H"] / (cw * ch)))
-    ch2 = int(min(wl["H"], max(ch, ch * np.sqrt(scale))))
-    cw2 = int(min(wl["W"], max(cw, cw * scale * ch / ch2)))
-    rate, t = run(cw2, ch2)
-    info = {"value": round(rate, 4), "unit": "Gdisp-updates/s", "cores": cores if kind == "reference" else 1,
-            "kind": kind,
-            "sample": "%s mgm() on a %dx%dx%d crop of the workload (%.1f s, OMP threads=%s, build flavour '%s')" %
-                      ("reference" if kind == "reference" else "oracle C port", cw2, ch2, L, t,
-                       os.environ.get("OMP_NUM_THREADS", "all"), flavour or "default")}
-    return rate, info
+    def mgm(self, want_S):
+        """-> dict(out, outcost, S, seconds): mgm() of the reference (mgm_core.cc:408-613)"""
+        O, wl = self.O, self.wl
+        cc = self.costvolume()
+        if self.kind == "reference":
+            return O.ref_mgm(cc, None, self.dmin, wl["P1"], wl["P2"], wl["NDIR"], wl["K"], wl["felz"], 1, want_S=want_S,
+                             flavour=self.flavour)
+        t0 = time.perf_counter()
+        r = O.orc_mgm(cc, None, self.dmin, wl["P1"], wl["P2"], wl["NDIR"], wl["K"], wl["felz"], 1, want_S=want_S)
+        r["seconds"] = time.perf_counter() - t0
+        return r
+
+    def refine(self, r):
+        O, wl = self.O, self.wl
+        if wl["refine"] == "none":
+            return r["out"], r["outcost"]
+        if self.kind == "reference":
+            return O.ref_refine(r["S"], self.dmin, r["out"], r["outcost"], wl["refine"], flavour=self.flavour)
+        return O.orc_refine(r["S"], self.dmin, r["out"], r["outcost"], wl["refine"])
+
+    def rate(self, seconds):
+        return self.W * self.H * self.L * self.wl["NDIR"] / seconds / 1e9
+
+    def describe(self, seconds):
+        what = ("unmodified reference mgm() (oracle/_ref, build flavour '%s', OpenMP)" % (self.flavour or "default")
+                if self.kind == "reference" else "oracle C port orc_mgm() (one thread)")
+        full = (self.W, self.H) == (self.wl["W"], self.wl["H"])
+        return "%s on %s %dx%dx%d pair of the workload, %d sweeps: %.2f s (cost volume %.2f s not counted), OMP threads=%s" % (
+            what, "the FULL" if full else "a cropped", self.W, self.H, self.L, self.wl["NDIR"], seconds, self.t_cc or 0.0,
+            os.environ.get("OMP_NUM_THREADS", "all"))
 
 
+def reference_crop(wl):
+    """The reference runs the full frame when it is defined for the workload and the frame costs about a minute or
+    less on 16 cores; otherwise (NDIR=16: C port, one thread) a bounded crop."""
+    if wl["NDIR"] <= 8:
+        return None
+    return (512, 384)
+
+
+def rel_err(a, b):
+    """max |a-b| / |b| over finite b != 0 (a, b float32 arrays), ignoring positions where both are non-finite"""
+    a = a.astype(np.float64).ravel(); b = b.astype(np.float64).ravel()
+    ok = np.isfinite(b) & (b != 0)
+    bad_nonfinite = int(np.count_nonzero(np.isfinite(a) != np.isfinite(b)))
+    if not ok.any():
+        return 0.0, bad_nonfinite
+    return float(np.max(np.abs(a[ok] - b[ok]) / np.abs(b[ok]))), bad_nonfinite
+
+
+def parity_check(ctx, wl, ref, torch):
+    """The CUDA path against the reference on the same pair.  Returns the `parity` object and the reference's
+    mgm() seconds."""
+    W, H, L, dmin, dmax = ref.W, ref.H, ref.L, ref.dmin, ref.dmax
+    r = ref.mgm(want_S=True)
+    ro, rc = ref.refine(r)
+    kw = dict(dmin=dmin, dmax=dmax, P1=wl["P1"], P2=wl["P2"], NDIR=wl["NDIR"], MGM=wl["K"],
+              use_felzenszwalb_potentials=wl["felz"], distance=wl["dist"], census_ncc_win=wl["win"])
+    go, gc = ctx.stereo(ref.u, ref.v, refinement="none", **kw)          # WTA labels + their costs
+    gro, grc = ctx.stereo(ref.u, ref.v, refinement=wl["refine"], **kw)  # refined
+    wta_mismatch = int(np.count_nonzero(~((go == r["out"]) | (np.isnan(go) & np.isnan(r["out"])))))
+    cost_rel, cost_nf = rel_err(gc, r["outcost"])
+    sub_rel, sub_nf = rel_err(gro, ro)
+    subc_rel, _ = rel_err(grc, rc)
+    par = {"against": ref.kind, "shape": "%dx%dx%d" % (W, H, L), "sweeps": wl["NDIR"], "wta_mismatch": wta_mismatch,
+           "cost_max_rel": cost_rel, "subpixel_max_rel": sub_rel, "subpixel_cost_max_rel": subc_rel,
+           "nonfinite_mismatch": cost_nf + sub_nf,
+           "disparity_bit_mismatch": int(np.count_nonzero(gro.view(np.int32) != ro.view(np.int32))),
+           "cost_bit_mismatch": int(np.count_nonzero(grc.view(np.int32) != rc.view(np.int32))),
+           "ref_seconds": round(r["seconds"], 3), "ref_costvolume_seconds": round(ref.t_cc or 0.0, 3)}
+    # aggregated volume S (after the over-count fix), compared on the device chunk by chunk
+    try:
+        VS = ctx.padded_labels(L)
+        du = torch.from_numpy(ref.u).cuda(); dv = torch.from_numpy(ref.v).cuda()
+        dcc = torch.empty((H, W, VS), dtype=torch.float32, device="cuda")
+        dS = torch.empty((H, W, L), dtype=torch.float32, device="cuda")   # dense [pix][L], like the reference's return value
+        do = torch.empty((H, W), dtype=torch.float32, device="cuda"); dc = torch.empty_like(do)
+        ctx.set_stream(0)
+        ctx.costvolume_dev(du.data_ptr(), dv.data_ptr(), W, H, 1, dmin, dmax, "census" if wl["dist"] == "census" else "none",
+                           wl["dist"], float("inf"), wl["win"], dcc.data_ptr())
+        ctx.aggregate_dev(dcc.data_ptr(), 0, 0, W, H, dmin, dmax, wl["P1"], wl["P2"], wl["NDIR"], wl["K"], wl["felz"], 1,
+                          "none", do.data_ptr(), dc.data_ptr(), dS.data_ptr())
+        ctx.synchronize()
+        bit_mis, max_rel, cc_mis = 0, 0.0, 0
+        rows = max(1, (256 << 20) // (W * L * 4))
+        for y0 in range(0, H, rows):
+            y1 = min(H, y0 + rows)
+            rs = torch.from_numpy(r["S"][y0:y1]).cuda()
+            gs = dS[y0:y1]
+            same = (gs.view(torch.int32) == rs.view(torch.int32)) | (torch.isnan(gs) & torch.isnan(rs))
+            bit_mis += int((~same).sum().item())
+            fin = torch.isfinite(rs) & (rs != 0)
+            if bool(fin.any()):
+                max_rel = max(max_rel, float(((gs[fin].double() - rs[fin].double()).abs() / rs[fin].double().abs()).max().item()))
+            rcc = torch.from_numpy(ref.cc[y0:y1]).cuda()
+            cc_mis += int((dcc[y0:y1, :, :L].view(torch.int32) != rcc.view(torch.int32)).sum().item())
+        par["S_bit_mismatch"] = bit_mis
+        par["S_max_rel"] = max_rel
+        par["costvolume_bit_mismatch"] = cc_mis
+        del du, dv, dcc, dS, do, dc
+        torch.cuda.empty_cache()
+    except Exception as e:   # pragma: no cover - reported, never hidden
+        par["S_error"] = str(e)[:200]
+    par["ok"] = bool(wta_mismatch == 0 and cost_rel <= 1e-4 and sub_rel <= 1e-4 and par["nonfinite_mismatch"] == 0 and
+                     par.get("S_max_rel", 0.0) <= 1e-4)
+    return par, r["seconds"]
+
+
+def run_reference_arm(args, name, wl):
+    """--impl reference: the reference's mgm() on the host cores, the full frame of the workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    if world > 1 or os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)   # torchrun pins it to 1; use all host threads
+    ref = ReferenceRun(wl, seed=0, crop=reference_crop(wl))
+    ref.costvolume()
+    t0 = time.perf_counter()
+    secs = []
+    budget = 300.0
+    for i in range(args.warmup + args.steps):
+        r = ref.mgm(want_S=False)
+        if i >= args.warmup:
+            secs.append(r["seconds"])
+        el = time.perf_counter() - t0
+        per = el / (i + 1)
+        # bounded run: skip the remaining warm-up steps / stop early when the budget would be exceeded
+        if i < args.warmup and el + per * (args.steps + args.warmup - i - 1) > budget:
+            args.warmup = i + 1
+        if secs and el + per > budget:
+            break
+    if not secs:
+        secs = [r["seconds"]]
+    sec = float(np.mean(secs))
+    val = ref.rate(sec)
+    info = {"value": round(val, 4), "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": ref.describe(sec)}
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(secs), "warmup": args.warmup, "ms_per_step": round(sec * 1e3 * wl["pairs"], 1),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(name, wl), "cpu_baseline": info,
+            "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ the CUDA arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,50 +336,31 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference run (parity + cpu_baseline)")
+    ap.add_argument("--no-parity", action="store_true", help="alias of --no-cpu-baseline")
     ap.add_argument("--rows-per-band", type=int, default=0)
     ap.add_argument("--shard", default="batch", choices=["batch", "sweeps"],
-                    help="N>1: 'batch' = one stereo pair per GPU, no data-path collective (weak scaling); "
-                         "'sweeps' = one pair, sweeps sharded over the GPUs + ordered peer-memory finish (strong)")
+                    help="N>1: 'batch' = independent pairs sharded over the GPUs, no data-path collective; "
+                         "'sweeps' = one pair, its sweeps sharded over the GPUs (north_star layout)")
+    ap.add_argument("--exchange", default="ordered", choices=["ordered", "allreduce"],
+                    help="sweeps layout: 'ordered' = sweep-ordered sum from slab-distributed volumes (bit-exact); "
+                         "'allreduce' = NCCL all-reduce of the per-GPU partial sums")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
-    W, H, L, NDIR, K = wl["W"], wl["H"], wl["L"], wl["NDIR"], wl["K"]
+    name = args.workload
+    wl = WORKLOADS[name]
+    if args.impl == "reference":
+        return run_reference_arm(args, name, wl)
+
+    W, H, L, NDIR, K, pairs = wl["W"], wl["H"], wl["L"], wl["NDIR"], wl["K"], wl["pairs"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    updates = W * H * L * NDIR
-    config = {"workload": args.workload, "W": W, "H": H, "L": L, "NDIR": NDIR, "TSGM": K,
-              "potentials": "truncated-linear" if wl["felz"] else "sgm", "P1": wl["P1"], "P2": wl["P2"],
-              "distance": "census %dx%d" % (wl["win"], wl["win"]), "refinement": wl["refine"],
-              "l2": "inputs (%.2f GB cost volume) larger than L2" % (W * H * L * 4 / 1e9)}
-
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        if world > 1 or os.environ.get("OMP_NUM_THREADS") == "1":
-            os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)   # torchrun pins it to 1; use all host threads
-        t0 = time.perf_counter()
-        rates = []
-        info = None
-        for i in range(args.warmup + args.steps):
-            r, info = cpu_reference_rate(wl, target_seconds=8.0, seed=i)
-            if i >= args.warmup:
-                rates.append(r)
-            if time.perf_counter() - t0 > 240 and len(rates) >= 1:
-                break
-        val = float(np.mean(rates))
-        info["value"] = round(val, 4)
-        line = {"impl": "reference", "metric": "Gdisp-updates/s (W*H*L*Ndirs)", "value": round(val, 4),
-                "unit": "Gdisp-updates/s", "n_gpus": args.gpus, "steps": len(rates), "warmup": args.warmup,
-                "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": info,
-                "e2e": {"value": round(val, 4), "unit": "Gdisp-updates/s", "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return
+    updates = W * H * L * NDIR          # per pair
+    config = config_of(name, wl)
 
     import torch
     import mgm_b200
+    from mgm_b200 import sharding
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -222,51 +375,57 @@ def main():
 
     dmin, dmax = -(L - 1), 0
     VS = ctx.padded_labels(L)
-    batch_mode = world > 1 and args.shard == "batch"
-    u, v = synth_pair(W, H, L, seed=rank if batch_mode else 0)
-    hu = torch.from_numpy(u).pin_memory()
-    hv = torch.from_numpy(v).pin_memory()
+    pf = "census" if wl["dist"] == "census" else "none"
+    batch_mode = world == 1 or args.shard == "batch"
+    # batch layout: a single-pair workload runs one pair per GPU (weak scaling); a multi-pair workload splits its
+    # pairs over the ranks (the whole job's work is fixed: strong scaling)
+    if pairs == 1:
+        my_pairs = [rank] if (world > 1 and batch_mode) else [0]
+        job_pairs = world if (world > 1 and batch_mode) else 1
+        scaling = "weak" if batch_mode else "strong"
+    else:
+        my_pairs = list(range(rank, pairs, world)) if batch_mode else list(range(pairs))
+        job_pairs = pairs
+        scaling = "strong" if world > 1 else "weak"
+    npair = len(my_pairs)
+
+    hu, hv, dcc = [], [], []
+    for s in my_pairs:
+        u, v = synth_pair(W, H, L, seed=s)
+        hu.append(torch.from_numpy(u).pin_memory()); hv.append(torch.from_numpy(v).pin_memory())
     hout = torch.empty((H, W), dtype=torch.float32).pin_memory()
     hcost = torch.empty((H, W), dtype=torch.float32).pin_memory()
-
     with torch.cuda.stream(stream):
-        du = hu.cuda(non_blocking=True)
-        dv = hv.cuda(non_blocking=True)
-        dcc = torch.empty((H, W, VS), dtype=torch.float32, device="cuda")
-        dout = torch.empty((H, W), dtype=torch.float32, device="cuda")
-        dcost = torch.empty((H, W), dtype=torch.float32, device="cuda")
-        ctx.costvolume_dev(du.data_ptr(), dv.data_ptr(), W, H, 1, dmin, dmax, "census", "census", float("inf"),
-                           wl["win"], dcc.data_ptr())
+        for i in range(npair):
+            du = hu[i].cuda(non_blocking=True); dv = hv[i].cuda(non_blocking=True)
+            c = torch.empty((H, W, VS), dtype=torch.float32, device="cuda")
+            ctx.costvolume_dev(du.data_ptr(), dv.data_ptr(), W, H, 1, dmin, dmax, pf, wl["dist"], float("inf"),
+                               wl["win"], c.data_ptr())
+            dcc.append(c)
+        dout = [torch.empty((H, W), dtype=torch.float32, device="cuda") for _ in range(npair)]
+        dcost = [torch.empty((H, W), dtype=torch.float32, device="cuda") for _ in range(npair)]
     stream.synchronize()
 
-    from mgm_b200 import sharding
-    my_mask = sharding.sweep_mask(NDIR, world, rank)
-    peer_ptrs = None
-    slabs = sharding.row_slabs(H, world)
-    rows = [a for a, _ in slabs] + [H]
-    if world > 1:
-        # (sweeps mode) one un-timed run so that the sweep volumes exist, then exchange their IPC handles once
-        ctx.aggregate_sweeps_dev(dcc.data_ptr(), 0, 0, W, H, dmin, dmax, wl["P1"], wl["P2"], NDIR, K, wl["felz"], my_mask)
-        ctx.synchronize()
-        peer_ptrs = sharding.exchange_sweep_handles(ctx, dist, NDIR, world, rank)
-        gout = [torch.empty((rows[r + 1] - rows[r], W), dtype=torch.float32, device="cuda") for r in range(world)]
-        gcost = [torch.empty((rows[r + 1] - rows[r], W), dtype=torch.float32, device="cuda") for r in range(world)]
+    agg_args = (W, H, dmin, dmax, wl["P1"], wl["P2"], NDIR, K, wl["felz"])
 
-    def step_device():
-        """cost volume resident -> maps resident (the metric's timed region)"""
-        if world == 1 or batch_mode:
-            ctx.aggregate_dev(dcc.data_ptr(), 0, 0, W, H, dmin, dmax, wl["P1"], wl["P2"], NDIR, K, wl["felz"], 1,
-                              wl["refine"], dout.data_ptr(), dcost.data_ptr())
+    def step_batch():
+        """cost volumes resident -> maps resident (the metric's timed region), this rank's pairs"""
+        if npair > 1 and hasattr(ctx, "aggregate_batch_dev"):
+            ctx.aggregate_batch_dev([c.data_ptr() for c in dcc], *agg_args, 1, wl["refine"],
+                                    [o.data_ptr() for o in dout], [o.data_ptr() for o in dcost])
         else:
-            ctx.aggregate_sweeps_dev(dcc.data_ptr(), 0, 0, W, H, dmin, dmax, wl["P1"], wl["P2"], NDIR, K, wl["felz"],
-                                     my_mask)
-            with torch.cuda.stream(stream):
-                dist.barrier()   # all sweeps of all ranks are complete before anyone reads peer memory
-            ctx.finish_rows_dev(peer_ptrs, dcc.data_ptr(), W, H, dmin, dmax, NDIR, 1, wl["refine"], rows[rank],
-                                rows[rank + 1], dout.data_ptr(), dcost.data_ptr())
-            with torch.cuda.stream(stream):
-                dist.all_gather(gout, dout[rows[rank]:rows[rank + 1]].contiguous())
-                dist.all_gather(gcost, dcost[rows[rank]:rows[rank + 1]].contiguous())
+            for i in range(npair):
+                ctx.aggregate_dev(dcc[i].data_ptr(), 0, 0, *agg_args, 1, wl["refine"], dout[i].data_ptr(), dcost[i].data_ptr())
+
+    # north_star layout (one pair, sweeps sharded over the ranks)
+    sw = None
+    if world > 1:
+        sw = sharding.SweepSharded(ctx, dist, torch, stream, W, H, dmin, dmax, wl["P1"], wl["P2"], NDIR, K, wl["felz"],
+                                   wl["refine"], world, rank)
+        sw.setup(dcc[0])
+
+    def step_sweeps():
+        sw.step(dcc[0], dout[0], dcost[0], exchange=args.exchange)
 
     def barrier_sync():
         if dist is not None:
@@ -294,55 +453,71 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(step_device, args.steps, args.warmup)
+    ms_dev = timed(step_batch if batch_mode else step_sweeps, args.steps, args.warmup)
     info = ctx.last_launch_info()
-    ms_sweeps = None
-    if batch_mode:   # also measure the north_star layout (sweeps sharded, ordered exchange) in the same run
-        batch_mode = False
-        ms_sweeps = timed(step_device, max(2, args.steps // 2), 2)
-        batch_mode = True
+    launches_per_step = info["kernel_launches"] * (npair if not hasattr(ctx, "aggregate_batch_dev") or npair == 1 else 1)
 
-    # per-kernel split on rank 0 / single GPU: aggregation kernel vs finish kernel (roofline of the dominant one)
+    sweeps_report = None
+    if world > 1:
+        # both exchanges of the north_star layout, measured in the same run, with mismatch counts against the
+        # single-GPU maps of the same pair (computed on this rank by the batch path)
+        ctx.aggregate_dev(dcc[0].data_ptr(), 0, 0, *agg_args, 1, wl["refine"], dout[0].data_ptr(), dcost[0].data_ptr())
+        ctx.synchronize()
+        one_out, one_cost = dout[0].clone(), dcost[0].clone()
+        sweeps_report = {}
+        for ex in ("ordered", "allreduce"):
+            try:
+                ms = timed(lambda: sw.step(dcc[0], dout[0], dcost[0], exchange=ex), max(2, args.steps // 2), 2)
+                torch.cuda.synchronize()
+                neq = lambda a, b: int((~((a == b) | (torch.isnan(a) & torch.isnan(b)))).sum().item())
+                sweeps_report[ex] = {"value": round(updates / (ms * 1e-3) / 1e9, 3), "unit": UNIT, "ms_per_step": round(ms, 4),
+                                     "scaling": "strong", "disparity_mismatch_vs_1gpu": neq(dout[0], one_out),
+                                     "cost_mismatch_vs_1gpu": neq(dcost[0], one_cost), "pixels": W * H,
+                                     "parallelism": sw.describe(ex)}
+            except Exception as e:
+                sweeps_report[ex] = {"error": str(e)[:300]}
+
+    # per-kernel split on a single GPU: aggregation kernel vs finish kernel (explains the fused launch)
     ms_agg = ms_fin = None
-    if world == 1:
+    if world == 1 and NDIR <= 8:
         full_mask = (1 << NDIR) - 1
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         sweeps = None
         tot_a = tot_f = 0.0
-        for i in range(args.steps):
+        nrep = min(args.steps, 3)
+        for i in range(nrep):
             with torch.cuda.stream(stream):
                 ev[0].record(stream)
-                ctx.aggregate_sweeps_dev(dcc.data_ptr(), 0, 0, W, H, dmin, dmax, wl["P1"], wl["P2"], NDIR, K,
-                                         wl["felz"], full_mask)
+                ctx.aggregate_sweeps_dev(dcc[0].data_ptr(), 0, 0, *agg_args, full_mask)
                 ev[1].record(stream)
                 if sweeps is None:
                     sweeps = [ctx.sweep_volume(p)[0] for p in range(NDIR)]
-                ctx.finish_rows_dev(sweeps, dcc.data_ptr(), W, H, dmin, dmax, NDIR, 1, wl["refine"], 0, H,
-                                    dout.data_ptr(), dcost.data_ptr())
+                ctx.finish_rows_dev(sweeps, dcc[0].data_ptr(), W, H, dmin, dmax, NDIR, 1, wl["refine"], 0, H,
+                                    dout[0].data_ptr(), dcost[0].data_ptr())
                 ev[2].record(stream)
             torch.cuda.synchronize()
             tot_a += ev[0].elapsed_time(ev[1]); tot_f += ev[1].elapsed_time(ev[2])
-        ms_agg, ms_fin = tot_a / args.steps, tot_f / args.steps
+        ms_agg, ms_fin = tot_a / nrep, tot_f / nrep
 
-    # end-to-end through the reference-facing C-ABI call with host buffers
+    # end-to-end through the reference-facing C-ABI call with host buffers (pinned): images in, maps out
     ms_e2e = None
-    if world == 1 or batch_mode:
-        # host buffers are pinned (cudaHostAlloc through torch): the two images in, the two maps out
-        pu, pv, pout, pcost = hu.numpy(), hv.numpy(), hout.numpy(), hcost.numpy()
+    if batch_mode:
+        pout, pcost = hout.numpy(), hcost.numpy()
 
         def step_e2e():
-            o, c = ctx.stereo(pu, pv, dmin=dmin, dmax=dmax, P1=wl["P1"], P2=wl["P2"], NDIR=NDIR, MGM=K,
-                              use_felzenszwalb_potentials=wl["felz"], distance="census", census_ncc_win=wl["win"],
-                              refinement=wl["refine"], out=pout, outcost=pcost)
-            return o
-        for _ in range(max(1, args.warmup - 1)):
+            for i in range(npair):
+                ctx.stereo(hu[i].numpy(), hv[i].numpy(), dmin=dmin, dmax=dmax, P1=wl["P1"], P2=wl["P2"], NDIR=NDIR, MGM=K,
+                           use_felzenszwalb_potentials=wl["felz"], distance=wl["dist"], census_ncc_win=wl["win"],
+                           refinement=wl["refine"], out=pout, outcost=pcost)
+        for _ in range(max(1, args.warmup - 1) if npair == 1 else 1):
             step_e2e()
         barrier_sync()
+        nst = args.steps if npair == 1 else max(1, min(args.steps, 2))
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(nst):
             step_e2e()
         torch.cuda.synchronize()
-        ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+        ms_e2e = (time.perf_counter() - t0) * 1e3 / nst
         if dist is not None:
             t = torch.tensor([ms_e2e], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -350,14 +525,14 @@ def main():
     # secondary: the default command-line flow (SURVEY 8(d) "CLI-equivalent"): both directions, median of radius 1,
     # left-right tests, all inside one mgmb200_stereo_lr call with host images in and host maps out
     ms_lr = None
-    if world == 1:
+    if world == 1 and pairs == 1 and NDIR <= 8:
         lr_bufs = {k: torch.empty((H, W), dtype=torch.float32).pin_memory().numpy()
                    for k in ("out", "outcost", "out_nolr", "outR", "outcostR")}
 
         def step_lr():
-            return ctx.stereo_lr(pu, pv, dmin=dmin, dmax=dmax, P1=wl["P1"], P2=wl["P2"], NDIR=NDIR, MGM=K,
-                                 use_felzenszwalb_potentials=wl["felz"], distance="census", census_ncc_win=wl["win"],
-                                 refinement=wl["refine"], testlrrl=1, median=1, buffers=lr_bufs)
+            return ctx.stereo_lr(hu[0].numpy(), hv[0].numpy(), dmin=dmin, dmax=dmax, P1=wl["P1"], P2=wl["P2"], NDIR=NDIR,
+                                 MGM=K, use_felzenszwalb_potentials=wl["felz"], distance=wl["dist"],
+                                 census_ncc_win=wl["win"], refinement=wl["refine"], testlrrl=1, median=1, buffers=lr_bufs)
         step_lr()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -374,76 +549,77 @@ def main():
         return
 
     peak, peak_src = measured_peaks()
-    nunits = world if batch_mode else 1          # stereo pairs processed per step by the whole job
-    value = nunits * updates / (ms_dev * 1e-3) / 1e9
-    line = {"metric": "Gdisp-updates/s (W*H*L*Ndirs)", "value": round(value, 3), "unit": "Gdisp-updates/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev, 4),
-            "higher_is_better": True, "scaling": "weak" if (world == 1 or batch_mode) else "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config,
-            "gpu_launches": info["kernel_launches"] * args.steps * world,
-            "launch_info": info, "clocks": clocks,
-            "mpix_per_s_device": round(nunits * W * H / (ms_dev * 1e-3) / 1e6, 2)}
-    sweeps_desc = "sweeps sharded %d per GPU, ordered peer-memory finish over NVLink + NCCL all_gather of the maps" % (
-        (NDIR + world - 1) // world)
+    units = job_pairs if batch_mode else 1        # stereo pairs processed per step by the whole job
+    value = units * updates / (ms_dev * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_dev, 4), "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "gpu_launches": launches_per_step * args.steps * world, "launch_info": info, "clocks": clocks,
+            "mpix_per_s_device": round(units * W * H / (ms_dev * 1e-3) / 1e6, 2)}
     if world > 1 and batch_mode:
-        config["parallelism"] = "batch: one stereo pair per GPU (%d pairs per step), no data-path collective" % world
-        line["sweep_sharded"] = {"value": round(updates / (ms_sweeps * 1e-3) / 1e9, 3), "unit": "Gdisp-updates/s",
-                                 "ms_per_step": round(ms_sweeps, 4), "scaling": "strong", "parallelism": sweeps_desc,
-                                 "note": "one pair, north_star layout; bit-identical to 1 GPU"}
+        config["parallelism"] = ("batch: %d independent stereo pairs per step over %d GPUs (%d per GPU), no data-path "
+                                 "collective" % (job_pairs, world, npair))
+        line["sweep_sharded"] = sweeps_report
     elif world > 1:
-        config["parallelism"] = sweeps_desc
-    if ms_agg is not None:
-        agg_bytes = 8.0 * updates   # read C + write the sweep's message, fp32, per label update
-        fin_bytes = 4.0 * W * H * L * (NDIR + 1)
-        ach = agg_bytes / (ms_agg * 1e-3) / 1e9
-        traffic = None
-        try:   # DRAM bytes of the same kernel/workload from the committed ncu --set full capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]["mgm_aggregate_kernel"]["traffic"]
-        except Exception:
-            pass
-        split = {"aggregation_only": {"kernel": "mgm_aggregate_kernel (sweeps only)", "ms_per_launch": round(ms_agg, 4),
-                                      "achieved": round(ach, 1), "frac": round(ach / peak, 4),
-                                      "algorithmic_bytes_per_launch": agg_bytes},
-                 "finish_only": {"kernel": "mgm_wta_kernel", "ms_per_launch": round(ms_fin, 4),
-                                 "achieved": round(fin_bytes / (ms_fin * 1e-3) / 1e9, 1),
-                                 "frac": round(fin_bytes / (ms_fin * 1e-3) / 1e9 / peak, 4)}}
-        if info["kernel_launches"] == 1:
-            # the timed step is ONE launch: the aggregation kernel with the finish stage fused in as tile work
-            # (ordered sum + fix + WTA + sub-pixel of tiles whose bands are complete); its algorithmic bytes are the
-            # whole step's: 8 B per label update + 4 B * (NDIR + 1) per cell re-read by the finish
-            step_bytes = agg_bytes + fin_bytes
-            try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]["mgm_aggregate_kernel_fused"]["traffic"]
-            except Exception:
-                traffic = None
-            line["roofline"] = {"bound": "hbm", "kernel": "mgm_aggregate_kernel (sweeps + fused finish tiles)",
-                                "achieved": round(step_bytes / (ms_dev * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
-                                "frac": round(step_bytes / (ms_dev * 1e-3) / 1e9 / peak, 4), "traffic": traffic,
-                                "peak_source": peak_src, "ms_per_launch": round(ms_dev, 4),
-                                "algorithmic_bytes_per_launch": step_bytes, "unfused_split": split}
-        else:
-            line["roofline"] = {"bound": "hbm", "kernel": "mgm_aggregate_kernel", "achieved": round(ach, 1),
-                                "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
-                                "peak_source": peak_src, "ms_per_launch": round(ms_agg, 4),
-                                "algorithmic_bytes_per_launch": agg_bytes, "finish_kernel": split["finish_only"],
-                                "whole_step": {"bytes": 12.0 * updates + 4.0 * W * H * L,
-                                               "frac": round((12.0 * updates + 4.0 * W * H * L) / (ms_dev * 1e-3) / 1e9 / peak, 4)}}
+        config["parallelism"] = sw.describe(args.exchange)
+        line["sweep_sharded"] = sweeps_report
+
+    # roofline of the dominant kernel: the aggregation launch (sweeps + finish tiles fused in).  Algorithmic bytes per
+    # launch: 8 B per label update (read C, write the sweep's message) + 4 B * (NDIR + 1) per cell for the ordered
+    # re-read by the finish; measured peak from MEASURED_PEAKS.json.  With N GPUs in the batch layout every
+    # GPU runs the same launches on its own pairs: bytes and time are per GPU.
+    agg_bytes = 8.0 * updates
+    fin_bytes = 4.0 * W * H * L * (NDIR + 1)
+    if batch_mode:
+        step_bytes = (agg_bytes + fin_bytes) * npair
+        fused = info["kernel_launches"] == 1
+        traffic, traffic_src = recorded_traffic(name, "mgm_aggregate_kernel_fused" if fused else "mgm_aggregate_kernel")
+        roof = {"bound": "hbm", "kernel": "mgm_aggregate_kernel (sweeps + fused finish tiles)" if fused else
+                "mgm_aggregate_kernel + mgm_wta_kernel",
+                "achieved": round(step_bytes / (ms_dev * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(step_bytes / (ms_dev * 1e-3) / 1e9 / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "ms_per_launch": round(ms_dev / max(1, launches_per_step), 4),
+                "launches_per_step": launches_per_step,
+                "algorithmic_bytes_per_launch": step_bytes / max(1, launches_per_step), "per": "GPU"}
+        if ms_agg is not None:
+            ach = agg_bytes / (ms_agg * 1e-3) / 1e9
+            roof["unfused_split"] = {
+                "aggregation_only": {"kernel": "mgm_aggregate_kernel (sweeps only)", "ms_per_launch": round(ms_agg, 4),
+                                     "achieved": round(ach, 1), "frac": round(ach / peak, 4),
+                                     "algorithmic_bytes_per_launch": agg_bytes},
+                "finish_only": {"kernel": "mgm_wta_kernel", "ms_per_launch": round(ms_fin, 4),
+                                "achieved": round(fin_bytes / (ms_fin * 1e-3) / 1e9, 1),
+                                "frac": round(fin_bytes / (ms_fin * 1e-3) / 1e9 / peak, 4)}}
+        line["roofline"] = roof
+    else:
+        # sweeps layout: per GPU NDIR/N sweeps (8 B per update) + the finish of H/N rows
+        per_gpu = agg_bytes / world + fin_bytes / world
+        line["roofline"] = {"bound": "hbm", "kernel": "mgm_aggregate_kernel (this GPU's sweeps) + mgm_wta_kernel (its slab)",
+                            "achieved": round(per_gpu / (ms_dev * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                            "frac": round(per_gpu / (ms_dev * 1e-3) / 1e9 / peak, 4), "traffic": None,
+                            "peak_source": peak_src, "per": "GPU",
+                            "floor": "one axis sweep is a dependency chain of maxii + maxjj pixel steps (DESIGN.md section 5)"}
     if ms_e2e is not None:
-        line["e2e"] = {"value": round(nunits * updates / (ms_e2e * 1e-3) / 1e9, 3), "unit": "Gdisp-updates/s",
-                       "h2d_bytes_per_step": nunits * 2 * W * H * 4, "d2h_bytes_per_step": nunits * 2 * W * H * 4,
-                       "ms_per_step": round(ms_e2e, 3), "mpix_per_s": round(nunits * W * H / (ms_e2e * 1e-3) / 1e6, 2),
-                       "call": "mgmb200_stereo (pinned host images in, pinned host maps out)"}
+        line["e2e"] = {"value": round(units * updates / (ms_e2e * 1e-3) / 1e9, 3), "unit": UNIT,
+                       "h2d_bytes_per_step": units * 2 * W * H * 4, "d2h_bytes_per_step": units * 2 * W * H * 4,
+                       "ms_per_step": round(ms_e2e, 3), "mpix_per_s": round(units * W * H / (ms_e2e * 1e-3) / 1e6, 2),
+                       "call": "mgmb200_stereo per pair (pinned host images in, pinned host maps out)"}
     if ms_lr is not None:
         line["e2e_cli_flow"] = {"ms_per_pair": round(ms_lr, 3), "mpix_per_s": round(W * H / (ms_lr * 1e-3) / 1e6, 2),
-                                "value": round(2 * updates / (ms_lr * 1e-3) / 1e9, 3), "unit": "Gdisp-updates/s",
+                                "value": round(2 * updates / (ms_lr * 1e-3) / 1e9, 3), "unit": UNIT,
                                 "call": "mgmb200_stereo_lr: L->R + R->L runs, median radius 1, left-right tests "
                                         "(TESTLRRL=1 MEDIAN=1, mgm.cc:372-424); host images in, host maps out"}
-    if not args.no_cpu_baseline and world == 1:
+    if not (args.no_cpu_baseline or args.no_parity) and world == 1:
+        # parity gate + CPU baseline: ONE run of the reference on the same pair (full frame when defined)
         try:
-            _, cb = cpu_reference_rate(wl)
-            line["cpu_baseline"] = cb
-        except Exception as e:   # the checker is optional for the measurement itself
-            line["cpu_baseline"] = {"value": None, "error": str(e)}
+            ref = ReferenceRun(wl, seed=0, crop=reference_crop(wl))
+            par, sec = parity_check(ctx, wl, ref, torch)
+            line["parity"] = par
+            line["cpu_baseline"] = {"value": round(ref.rate(sec), 4), "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+                                    "sample": ref.describe(sec)}
+        except Exception as e:   # reported, never hidden
+            line["parity"] = {"ok": False, "error": str(e)[:300]}
+            line["cpu_baseline"] = {"value": None, "error": str(e)[:300]}
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()

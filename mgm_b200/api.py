@@ -126,6 +126,10 @@ class Context:
     def set_rows_per_band(self, rows):
         self._check(self.lib.mgmb200_set_rows_per_band(self._ctx, int(rows)))
 
+    def set_option(self, name, value=None):
+        """Tuning / debugging knob (mgmb200_set_option); name "reset" re-reads the MGMB200_* environment."""
+        self._check(self.lib.mgmb200_set_option(self._ctx, name.encode(), None if value is None else str(value).encode()))
+
     def synchronize(self):
         self._check(self.lib.mgmb200_synchronize(self._ctx))
 

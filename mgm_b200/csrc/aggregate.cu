@@ -36,8 +36,11 @@
 #ifndef MGM_JB
 #define MGM_JB 2   // chunks per lane whose loads are issued together in the gather (measured: 2 < 4 < 8)
 #endif
+#ifndef MGM_CHAIN_PF
+#define MGM_CHAIN_PF 1   // chunks loaded ahead of the min-convolution chain (see minconv_half)
+#endif
 #ifndef MGM_EXP
-#define MGM_EXP 0   // timing experiments only (tests/micro): 1 no message store, 2 no cost load, 3 no gather arithmetic, 4 no min-convolution
+#define MGM_EXP 0   // timing experiments only (tools/micro): 1 no message store, 2 no cost load, 3 no gather arithmetic, 4 no min-convolution
 #endif
 
 namespace mgm {
@@ -88,7 +91,7 @@ __device__ __forceinline__ float4 div3_4(const float4 &e) {
    return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-// Shared-memory vectors are moved as 8-byte halves.  Measured on B200 (tests/micro/smem_bw.cu, smem_pat.cu):
+// Shared-memory vectors are moved as 8-byte halves.  Measured on B200 (tools/micro/smem_bw.cu, smem_pat.cu):
 // LDS.128 delivers 64 B/clk per SM, LDS.64 / STS.64 the full 128 B/clk when the 16 lanes of a half-warp hit 16
 // different 8-byte banks.  With a row stride of 8 bytes modulo 128 (register-cost mode, agg_plan) two adjacent
 // rows read by 8 lanes each -- and 16 consecutive rows read by one lane each (the chains) -- do exactly that;
@@ -144,13 +147,15 @@ __device__ __forceinline__ void sgm_transform_regs(const float4 (&v)[NJR], int n
    for (int j = 0; j < NJR; ++j) {
       if (j < nj) {
          const int q = gl + G * j;
-         // last label of chunk q-1, first label of chunk q+1
-         const float l_same = __shfl_sync(gmask, v[j].w, (gl + G - 1) & (G - 1), G);               // lane gl-1, same j
-         const float l_prev = __shfl_sync(gmask, v[j > 0 ? j - 1 : 0].w, G - 1, G);                // lane 7, j-1
-         const float r_same = __shfl_sync(gmask, v[j].x, (gl + 1) & (G - 1), G);                   // lane gl+1, same j
-         const float r_next = __shfl_sync(gmask, v[j + 1 < NJR ? j + 1 : j].x, 0, G);              // lane 0, j+1
-         const float lft = (q == 0) ? MGM_INF : (gl > 0 ? l_same : l_prev);
-         const float rgt = (q + 1 >= nq) ? MGM_INF : (gl < G - 1 ? r_same : r_next);
+         // last label of chunk q-1, first label of chunk q+1: one rotation of the group each way, the SENDER picks
+         // the value (the last lane hands its chunk j-1 to lane 0, lane 0 its chunk j+1 to the last lane) -- the
+         // shuffles share the LSU pipe with the ring traffic that bounds this kernel
+         const float snd_l = (gl == G - 1) ? v[j > 0 ? j - 1 : 0].w : v[j].w;
+         const float snd_r = (gl == 0) ? v[j + 1 < NJR ? j + 1 : j].x : v[j].x;
+         const float got_l = __shfl_sync(gmask, snd_l, (gl + G - 1) & (G - 1), G);
+         const float got_r = __shfl_sync(gmask, snd_r, (gl + 1) & (G - 1), G);
+         const float lft = (q == 0) ? MGM_INF : got_l;
+         const float rgt = (q + 1 >= nq) ? MGM_INF : got_r;
          float4 a;
          a.x = sgm_x(lft, v[j].x, v[j].y, p1, cap, m) * sc;
          a.y = sgm_x(v[j].x, v[j].y, v[j].z, p1, cap, m) * sc;
@@ -245,7 +250,7 @@ __device__ __forceinline__ RowGroup make_row_group(int tid, int ncomp, int r, in
 //    min(F[o], B[o]) = min(F[o], min(B[o+1]+c, M[o])) = min(F[o], B[o+1]+c)   and   F[o+1]+c >= min(F[o], B[o+1]+c),
 // hence Q[o] = min(Q[o+1]+c, F[o]) (and symmetrically Q[o] = min(Q[o-1]+c, B[o])): each lane continues ITS
 // recurrence over the partner's partial values only -- same additions in the same order as the reference,
-// one shared-memory read per label less (checked bit for bit in tests/micro/chain_bench.cu, form 6).
+// one shared-memory read per label less (checked bit for bit in tools/micro/chain_bench.cu, form 6).
 // MASK: labels outside [mlo,mhi] of the source read as +INF -- the min-convolution of a truncated-linear update
 // with per-pixel ranges runs inside the RECEIVING pixel's range (mgm_core.cc:229-281), which on dense vectors is
 // the convolution of the vector masked to that range.
@@ -260,31 +265,55 @@ __device__ __forceinline__ float4 mask_labels(float4 v, int q, int mlo, int mhi)
 template <int DIR, bool MASK = false>
 __device__ __forceinline__ void minconv_half(bool on, const float2 *src, float2 *dst, int nq, float c, float cap,
                                              float sub, int bar_id, int mlo = 0, int mhi = 0) {
-   const int h = nq >> 1;   // nq is even
+   // D = MGM_CHAIN_PF chunks are loaded ahead of the dependent add/min chain (register ring).  One chunk covers the
+   // shared-memory latency of an otherwise idle LSU; when other warps gather at the same time (row groups) the
+   // queueing delay is longer than one chunk of chain work (~29 cycles) and a deeper ring keeps the chain fed.
+   constexpr int D = MGM_CHAIN_PF;
+   const int h = nq >> 1;   // nq is even (a multiple of 8)
    const int dq = DIR ? -1 : 1;
+   const int qend = DIR ? 0 : (nq - 1);
    int q = DIR ? (nq - 1) : 0;
    float run = MGM_INF;
-   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+   float4 sb[D];
+   auto clampq = [&](int qq) { return DIR ? max(qq, qend) : min(qq, qend); };
+   auto ldm = [&](const float2 *p, int qq, bool msk) {
+      float4 v = ld16<true>(p, qq);
+      if (MASK && msk) v = mask_labels(v, qq, mlo, mhi);
+      return v;
+   };
    if (on) {
-      v = ld16<true>(src, q);
-      if (MASK) v = mask_labels(v, q, mlo, mhi);
-      for (int i = 0; i < h; ++i, q += dq) {
-         float4 vn = ld16<true>(src, q + dq);   // chunk i+1 always exists (h < nq)
-         if (MASK) vn = mask_labels(vn, q + dq, mlo, mhi);
-         if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
-         st16<true>(dst, q, v);
-         v = vn;
+#pragma unroll
+      for (int d = 0; d < D; ++d) sb[d] = ldm(src, clampq(q + d * dq), true);   // own half only needs chunks < h: h >= D or unused
+      for (int i = 0; i < h; i += D) {
+#pragma unroll
+         for (int d = 0; d < D; ++d) {
+            if (i + d < h) {
+               float4 v = sb[d];
+               // never beyond this lane's half: in place, the partner is overwriting the other half
+               if (i + d + D < h) sb[d] = ldm(src, q + D * dq, true);
+               if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
+               st16<true>(dst, q, v);
+               q += dq;
+            }
+         }
       }
    }
    pair_barrier(bar_id);   // partner's partial values are now in dst
    if (on) {
-      v = ld16<true>(dst, q);
-      for (int i = h; i < nq; ++i, q += dq) {
-         const float4 vn = ld16<true>(dst, (i + 1 < nq) ? q + dq : q);
-         if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
-         v = add4s(make_float4(fminf(v.x, cap), fminf(v.y, cap), fminf(v.z, cap), fminf(v.w, cap)), -sub);
-         st16<true>(dst, q, v);
-         v = vn;
+#pragma unroll
+      for (int d = 0; d < D; ++d) sb[d] = ld16<true>(dst, clampq(q + d * dq));
+      for (int i = h; i < nq; i += D) {
+#pragma unroll
+         for (int d = 0; d < D; ++d) {
+            if (i + d < nq) {
+               float4 v = sb[d];
+               sb[d] = ld16<true>(dst, clampq(q + D * dq));   // beyond the end: a redundant re-load, never used
+               if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
+               v = add4s(make_float4(fminf(v.x, cap), fminf(v.y, cap), fminf(v.z, cap), fminf(v.w, cap)), -sub);
+               st16<true>(dst, q, v);
+               q += dq;
+            }
+         }
       }
    }
 }
@@ -414,6 +443,13 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    auto prefetch_cost = [&](int s) {
       const int px = s - SIG * r + 1;   // the pixel my row handles in the NEXT step
       const bool go = rowok && px >= 0 && px < maxii;
+      if (P.cc_pf > 0) {   // short steps (SGM potentials): one step does not cover the HBM latency, warm the L2 further ahead
+         const int pp = px + P.cc_pf;
+         if (rowok && pp >= 0 && pp < maxii) {
+            const float *line = ccv + (size_t)(pix0 + (long long)pp * g.dxs) * VS;
+            for (int l = gl; l < (VS >> 5); l += G) asm volatile("prefetch.global.L2 [%0];" ::"l"(line + l * 32));
+         }
+      }
       if (creg_mode) {
          if (go) {
             const float4 *src = reinterpret_cast<const float4 *>(ccv + (size_t)(pix0 + (long long)px * g.dxs) * VS);
@@ -833,6 +869,13 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
    auto prefetch_cost = [&](int v) {   // costs of position v+1
       const int vn = v + 1;
       const bool go = rowok && vn >= my_lo && vn <= my_hi;
+      if (P.cc_pf > 0) {
+         const int vp = vn + P.cc_pf;
+         if (rowok && vp >= my_lo && vp <= my_hi) {
+            const float *line = ccv + (size_t)(pix_u + (long long)vp * dv) * VS;
+            for (int l = gl; l < (VS >> 5); l += G) asm volatile("prefetch.global.L2 [%0];" ::"l"(line + l * 32));
+         }
+      }
       if (creg_mode) {
          if (go) {
             const float4 *src = reinterpret_cast<const float4 *>(ccv + (size_t)(pix_u + (long long)vn * dv) * VS);
@@ -1218,7 +1261,7 @@ static cudaError_t launch_t(const AggParams &P, const AggPlan &plan, cudaStream_
    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
    int grid = min(P.nbands, plan.num_sms * per_sm);
    if (grid < 1) grid = 1;
-   if (getenv("MGMB200_VERBOSE"))
+   if (plan.verbose)
       fprintf(stderr, "[mgmb200] aggregate: grid=%d block=%d smem=%zu CTAs/SM=%d bands=%d rows=%d/%d groups=%d/%d shear=%d\n", grid,
               plan.block, plan.smem, per_sm, P.nbands, plan.T[0], plan.T[1], plan.ng[0], plan.ng[1], plan.shear);
    kern<<<grid, plan.block, plan.smem, st>>>(P);
@@ -1246,32 +1289,33 @@ static cudaError_t launch_k(int K, const AggParams &P, const AggPlan &plan, cuda
 }
 
 static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
-                         int t_override, int shear) {
+                         int t_override, int shear, const AggTuning &tune) {
+   plan->verbose = tune.verbose;
    const int VS = (L + 31) & ~31;   // 8 lanes x 16 bytes per row and step
    plan->VS = VS;
    const int xtra = (weighted && pot == POT_TRUNC) ? K : 0;
    // lanes per worker: 8; 4 for the unweighted SGM kernels when the label vector is short (<= 128 labels), so that
    // a lane still owns 8 chunks and a band holds twice the workers for the same per-step overhead
    int want_groups = 1;   // row groups per band (RowGroup in the kernel); measured: no gain, the LSU is the shared limit
-   if (const char *e = getenv("MGMB200_GROUPS")) { const int v = atoi(e); if (!weighted && (v == 1 || v == 2 || v == 3)) want_groups = v; }
+   if (!weighted && (tune.groups == 2 || tune.groups == 3)) want_groups = tune.groups;
    plan->lanes = MGM_AGG_GROUP;
-   if (pot == POT_SGM && !weighted && shear && want_groups == 1 && VS <= 16 * MGM_AGG_CREG && !getenv("MGMB200_NO_CREG") &&
-       !getenv("MGMB200_NO_FUSED_SGM") && !getenv("MGMB200_LANES8")) {
+   if (pot == POT_SGM && !weighted && shear && want_groups == 1 && VS <= 16 * MGM_AGG_CREG && !tune.no_creg &&
+       !tune.no_fused_sgm && tune.lanes != 8) {
       // only when the image still yields enough bands of that size to fill the machine twice (measured: with
       // fewer, the longer hand-offs and the idle SMs cost more than the per-step overhead saved)
       const int t4 = (MGM_AGG_MAX_THREADS - 64) / 4;
       const long bands = 2L * ((ny + t4 - 1) / t4 + (nx + t4 - 1) / t4) + 4L * ((nx + ny + t4 - 2) / t4);
-      if (bands >= 2L * num_sms || getenv("MGMB200_LANES4")) plan->lanes = 4;
+      if (bands >= 2L * num_sms || tune.lanes == 4) plan->lanes = 4;
    }
    const int tcap = (MGM_AGG_MAX_THREADS - 64) / plan->lanes;   // rows per CTA allowed by the thread budget
    // costs prefetched into registers when a lane's share fits (one cost buffer per row), else a cp.async ring of two
-   plan->ncb = (VS / (4 * plan->lanes) <= MGM_AGG_CREG && !getenv("MGMB200_NO_CREG")) ? 1 : 2;
+   plan->ncb = (VS / (4 * plan->lanes) <= MGM_AGG_CREG && !tune.no_creg) ? 1 : 2;
    plan->shear = shear;
    const int nvirt = shear ? 2 : 1;   // boundary workers kept per position
    // unweighted truncated-linear kernels with register-resident costs build the message in its ring slot and run
    // the min-convolution in place: no cost buffer
    // ... and the unweighted SGM kernels transform the message straight from registers (one group only)
-   plan->fused_sgm = (!weighted && pot == POT_SGM && plan->ncb == 1 && want_groups == 1 && !getenv("MGMB200_NO_FUSED_SGM")) ? 1 : 0;
+   plan->fused_sgm = (!weighted && pot == POT_SGM && plan->ncb == 1 && want_groups == 1 && !tune.no_fused_sgm) ? 1 : 0;
    const int ncbuf = (!weighted && plan->ncb == 1 && (pot == POT_TRUNC || plan->fused_sgm)) ? 0 : plan->ncb;
    for (int cls = 0; cls < 2; ++cls) {
       int nbuf = ((cls == 1 && shear) ? 2 : ring_slots(cls, K)) + ncbuf + xtra;
@@ -1284,8 +1328,8 @@ static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, b
       int Tc = avail > 0 ? (int)(avail / ((long)TS * 4)) : 0;
       if (Tc > tcap) Tc = tcap;
       {
-         const char *e = getenv(cls == 0 ? "MGMB200_ROWS_AXIS" : "MGMB200_ROWS_DIAG");   // tuning knobs
-         const int ov = e ? atoi(e) : t_override;
+         const int knob = (cls == 0) ? tune.rows_axis : tune.rows_diag;
+         const int ov = knob > 0 ? knob : t_override;
          if (ov > 0 && Tc > ov) Tc = (cls == 1 && shear && ov < 2) ? 2 : ov;
       }
       if (Tc < 1) Tc = 0;
@@ -1313,15 +1357,15 @@ static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, b
 }
 
 void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
-              int t_override) {
+              int t_override, const AggTuning &tune) {
    // diagonal sweeps as sheared wavefronts (run_band_shear): predecessors in the row above only, no image-dependent
    // weights, and room for at least two workers per band (the hand-off carries the last two)
-   const bool want_shear = (K <= 3 && !weighted && !getenv("MGMB200_NO_SHEAR"));
+   const bool want_shear = (K <= 3 && !weighted && !tune.no_shear);
    if (want_shear) {
-      agg_plan_try(plan, nx, ny, L, K, pot, weighted, max_smem, num_sms, t_override, 1);
+      agg_plan_try(plan, nx, ny, L, K, pot, weighted, max_smem, num_sms, t_override, 1, tune);
       if (plan->T[0] >= 1 && plan->T[1] >= 2) return;
    }
-   agg_plan_try(plan, nx, ny, L, K, pot, weighted, max_smem, num_sms, t_override, 0);
+   agg_plan_try(plan, nx, ny, L, K, pot, weighted, max_smem, num_sms, t_override, 0, tune);
 }
 
 cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st) {

@@ -31,6 +31,7 @@ struct AggParams {
    int shear;                  // 1: sweeps 4-7 run as sheared wavefronts (bands of anti-diagonals, run_band_shear)
    int ng[2];                  // row groups per band (axis / diagonal class), each on its own named barrier
    int fused_sgm;              // 1: unweighted SGM kernels transform the message from registers (one barrier per step)
+   int cc_pf;                  // > 0: matching costs of the pixel cc_pf steps ahead are prefetched into L2
    float P1, P2;
    // fused finish (optional): CTAs without a band to run take tiles of pixels whose sweeps are all complete and do
    // the ordered sum + over-count fix + WTA + sub-pixel there (wta_device.cuh), inside the same launch
@@ -45,14 +46,30 @@ struct AggParams {
    unsigned off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };
 
+// Tuning / debugging knobs of the aggregation launch.  They live in the context: read ONCE from the environment
+// (MGMB200_*) by mgmb200_create and changed afterwards only through mgmb200_set_option -- never per call.
+struct AggTuning {
+   int rows_axis = 0, rows_diag = 0;   // rows (workers) per band, 0 = as many as shared memory allows
+   int groups = 1;                     // row groups per band (RowGroup)
+   int no_creg = 0;                    // 1: cp.async cost ring instead of register-resident costs
+   int no_fused_sgm = 0;               // 1: SGM transform through shared memory (two barriers per step)
+   int lanes = 0;                      // 0 auto, 4 or 8 lanes per worker (unweighted SGM kernels)
+   int no_shear = 0;                   // 1: diagonal sweeps row-per-worker
+   int static_order = 0;               // 1: claim bands without the readiness test
+   int no_fused_finish = 0;            // 1: finish stage as a separate launch
+   int fin_tw = 128, fin_th = 16;      // finish tile
+   int cc_pf = 0;                      // L2 prefetch distance (pixels) of the matching costs, 0 = off
+   int verbose = 0;
+};
+
 struct AggPlan {
-   int VS, T[2], TS[2], ncb, shear, ng[2], fused_sgm, lanes, block, num_sms;
+   int VS, T[2], TS[2], ncb, shear, ng[2], fused_sgm, lanes, block, num_sms, verbose;
    size_t smem;
    size_t off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };
 
 void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
-              int t_override);
+              int t_override, const AggTuning &tune);
 cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st);
 
 }  // namespace mgm

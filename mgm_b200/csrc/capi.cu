@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <ctype.h>
 #include <algorithm>
 #include <vector>
 
@@ -59,6 +60,7 @@ struct mgmb200_ctx {
    int device = 0, num_sms = 0, max_smem = 0;
    cudaStream_t own_stream = nullptr, stream = nullptr;
    int rows_override = 0;
+   AggTuning tune;          // MGMB200_* knobs: read once by mgmb200_create, changed only by mgmb200_set_option
    // scratch (grow-only, reused across calls)
    DevBuf u, v, fu, fv, ftmp, cu, cv, w, cc, dense, out, outcost, flags, progress, bnd, bndm, rg[4];
    // per-pixel ranges of the call in flight (device pointers or nullptr): S range, cost-vector range
@@ -107,6 +109,46 @@ extern "C" size_t mgmb200_volume_bytes(int nx, int ny, int L) {
 }
 
 // ------------------------------------------------------------------------------------------ context
+// Tuning / debugging knobs (names = the MGMB200_* environment variables without the prefix, lower case).  A NULL or
+// empty value switches a flag on, like an environment variable that is merely set.
+static bool apply_option(mgmb200_ctx *c, const char *name, const char *value) {
+   AggTuning &t = c->tune;
+   const int iv = (value && *value) ? atoi(value) : 1;
+   if (!strcmp(name, "rows_per_band")) { c->rows_override = iv < 0 ? 0 : iv; return true; }
+   if (!strcmp(name, "rows_axis")) { t.rows_axis = iv; return true; }
+   if (!strcmp(name, "rows_diag")) { t.rows_diag = iv; return true; }
+   if (!strcmp(name, "groups")) { t.groups = iv; return true; }
+   if (!strcmp(name, "no_creg")) { t.no_creg = iv; return true; }
+   if (!strcmp(name, "no_fused_sgm")) { t.no_fused_sgm = iv; return true; }
+   if (!strcmp(name, "lanes4")) { t.lanes = iv ? 4 : 0; return true; }
+   if (!strcmp(name, "lanes8")) { t.lanes = iv ? 8 : 0; return true; }
+   if (!strcmp(name, "no_shear")) { t.no_shear = iv; return true; }
+   if (!strcmp(name, "static_order")) { t.static_order = iv; return true; }
+   if (!strcmp(name, "no_fused_finish")) { t.no_fused_finish = iv; return true; }
+   if (!strcmp(name, "cc_pf")) { t.cc_pf = iv; return true; }
+   if (!strcmp(name, "verbose")) { t.verbose = iv; return true; }
+   if (!strcmp(name, "fin_tile")) {
+      int a = 0, b = 0;
+      if (!value || sscanf(value, "%dx%d", &a, &b) != 2 || a < 1 || b < 1) return false;
+      t.fin_tw = a; t.fin_th = b;
+      return true;
+   }
+   return false;
+}
+static void tuning_from_env(mgmb200_ctx *c) {
+   c->tune = AggTuning();
+   c->rows_override = 0;
+   static const char *const names[] = {"rows_per_band", "rows_axis", "rows_diag", "groups", "no_creg", "no_fused_sgm", "lanes4",
+                                       "lanes8", "no_shear", "static_order", "no_fused_finish", "cc_pf", "verbose", "fin_tile"};
+   for (const char *n : names) {
+      char env[64] = "MGMB200_";
+      size_t k = strlen(env);
+      for (const char *q = n; *q && k + 1 < sizeof(env); ++q) env[k++] = (char)toupper((unsigned char)*q);
+      env[k] = 0;
+      if (const char *e = getenv(env)) apply_option(c, n, e);
+   }
+}
+
 extern "C" int mgmb200_create(int device, mgmb200_ctx **out) {
    if (!out) return fail(MGMB200_EINVAL, "ctx output pointer is NULL");
    *out = nullptr;
@@ -133,9 +175,15 @@ extern "C" int mgmb200_create(int device, mgmb200_ctx **out) {
    }
    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
    c->stream = c->own_stream;
-   const char *env = getenv("MGMB200_ROWS_PER_BAND");
-   if (env) c->rows_override = atoi(env);
+   tuning_from_env(c);
    *out = c;
+   return 0;
+}
+
+extern "C" int mgmb200_set_option(mgmb200_ctx *c, const char *name, const char *value) {
+   if (!c || !name) return fail(MGMB200_EINVAL, "NULL argument");
+   if (!strcmp(name, "reset")) { tuning_from_env(c); return 0; }
+   if (!apply_option(c, name, value)) return fail(MGMB200_EINVAL, "unknown option '%s' or bad value '%s'", name, value ? value : "(null)");
    return 0;
 }
 
@@ -337,8 +385,8 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
    c->sweep_bytes = vol;
 
    AggPlan plan;
-   agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, c->rows_override);
-   if (!c->rows_override && !getenv("MGMB200_ROWS_AXIS") && !getenv("MGMB200_ROWS_DIAG") && plan.T[0] > 40) {
+   agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, c->rows_override, c->tune);
+   if (!c->rows_override && !c->tune.rows_axis && !c->tune.rows_diag && plan.T[0] > 40) {
       // One or two sweeps on this GPU (sweep-sharded layouts): with fewer bands than SMs the launch is bound by the
       // dependency depth alone, and bands of 40 workers step faster than bands of 56 (measured: one axis sweep of
       // the headline shape 15.6 -> 13.9 ms, an axis + a diagonal sweep 15.9 -> 14.9 ms; small images with all
@@ -352,7 +400,7 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
          const int T = plan.T[p < 4 ? 0 : 1];
          bands += (p >= 4 && plan.shear) ? (g.maxii + g.maxjj - 1 + T - 1) / T : (g.maxjj + T - 1) / T;
       }
-      if (nsweeps <= 2 && bands < c->num_sms) agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 40);
+      if (nsweeps <= 2 && bands < c->num_sms) agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 40, c->tune);
    }
    if (plan.T[0] < 1 || plan.T[1] < 1)
       return fail(MGMB200_EUNSUPPORTED, "%d labels do not fit the shared-memory wavefront (max_smem=%d)", L, c->max_smem);
@@ -389,10 +437,9 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
 
    // fused finish: tiles of pixels in the order they are expected to become complete (the axis sweeps decide:
    // band b of a sweep is done after about maxii + (b+1)*T steps)
-   int tw = 128, th = 16;
-   if (const char *e = getenv("MGMB200_FIN_TILE")) { int a = 0, b = 0; if (sscanf(e, "%dx%d", &a, &b) == 2 && a > 0 && b > 0) { tw = a; th = b; } }
+   const int tw = c->tune.fin_tw, th = c->tune.fin_th;
    const size_t rows_region = plan.smem - plan.off_thr;
-   const bool fuse = fin && !getenv("MGMB200_NO_FUSED_FINISH") && (size_t)(plan.block / 32) * VS * 4 <= rows_region;
+   const bool fuse = fin && !c->tune.no_fused_finish && (size_t)(plan.block / 32) * VS * 4 <= rows_region;
    const int tiles_x = (nx + tw - 1) / tw, tiles_y = (ny + th - 1) / th, ntiles = tiles_x * tiles_y;
    if (fuse) {
       const int key[6] = {nx, ny, plan.T[0], tw, th, NDIR};
@@ -442,11 +489,12 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
    }
    for (int p = 0; p < 8; p++) P.nb[p] = nb[p];
    P.nbands = nbands;
-   P.static_order = getenv("MGMB200_STATIC_ORDER") ? 1 : 0;
+   P.static_order = c->tune.static_order;
    P.nx = nx; P.ny = ny; P.L = L; P.VS = VS;
    P.T[0] = plan.T[0]; P.T[1] = plan.T[1];
    P.TS[0] = plan.TS[0]; P.TS[1] = plan.TS[1];
    P.ncb = plan.ncb; P.shear = plan.shear; P.ng[0] = plan.ng[0]; P.ng[1] = plan.ng[1]; P.fused_sgm = plan.fused_sgm;
+   P.cc_pf = c->tune.cc_pf;
    P.P1 = P1; P.P2 = P2;
    P.dbg = nullptr;
    P.off_phase = (unsigned)plan.off_phase; P.off_cbar = (unsigned)plan.off_cbar; P.off_vbar = (unsigned)plan.off_vbar;

@@ -96,23 +96,26 @@ def test_mgm_matches_oracle(ctx, K, felz, weighted):
 
 @pytest.mark.parametrize("knob", ["MGMB200_GROUPS=2", "MGMB200_GROUPS=3", "MGMB200_NO_SHEAR=1", "MGMB200_NO_CREG=1",
                                   "MGMB200_STATIC_ORDER=1", "MGMB200_NO_FUSED_SGM=1", "MGMB200_LANES4=1",
-                                  "MGMB200_NO_FUSED_FINISH=1", "MGMB200_FIN_TILE=7x3", "MGMB200_FIN_TILE=4096x4096"])
-def test_mgm_alternative_kernel_layouts(ctx, knob, monkeypatch):
+                                  "MGMB200_NO_FUSED_FINISH=1", "MGMB200_FIN_TILE=7x3", "MGMB200_FIN_TILE=4096x4096",
+                                  "MGMB200_CC_PF=3"])
+def test_mgm_alternative_kernel_layouts(ctx, knob):
     """The aggregation kernel's alternative layouts (row groups on their own named barriers, row-per-worker diagonal
-    sweeps, cp.async cost ring, static band order, finish stage as a separate launch or fused with other tile sizes) are
-    selected by environment knobs read at every call: each must
-    give the same bits as the default layout, i.e. as the oracle."""
+    sweeps, cp.async cost ring, static band order, finish stage as a separate launch or fused with other tile sizes,
+    L2 prefetch of the costs) are selected by context options (mgmb200_set_option; the MGMB200_* environment is only
+    read when a context is created): each must give the same bits as the default layout, i.e. as the oracle."""
     name, val = knob.split("=")
-    monkeypatch.setenv(name, val)
-    for (nx, ny, L), (K, felz, P1, P2) in itertools.product([(131, 37, 40), (90, 150, 24)],
-                                                            [(3, 1, 2, 20000), (2, 1, 2, 20000), (2, 0, 8, 32), (3, 0, 8, 32)]):
-        cc = synth_volume(nx, ny, L, seed=nx + K, real=True)
-        for rows in (0, 16):
-            ctx.set_rows_per_band(rows)
-            r = ctx.mgm(cc, None, -(L - 1), P1, P2, 8, K, felz, 1)
-            o = O.orc_mgm(cc, None, -(L - 1), P1, P2, 8, K, felz, 1)
-            assert same(r["S"], o["S"]) and same(r["out"], o["out"]), (knob, nx, ny, L, K, felz, rows, mism(r["S"], o["S"]))
-    ctx.set_rows_per_band(0)
+    ctx.set_option(name[len("MGMB200_"):].lower(), val)
+    try:
+        for (nx, ny, L), (K, felz, P1, P2) in itertools.product([(131, 37, 40), (90, 150, 24)],
+                                                                [(3, 1, 2, 20000), (2, 1, 2, 20000), (2, 0, 8, 32), (3, 0, 8, 32)]):
+            cc = synth_volume(nx, ny, L, seed=nx + K, real=True)
+            for rows in (0, 16):
+                ctx.set_rows_per_band(rows)
+                r = ctx.mgm(cc, None, -(L - 1), P1, P2, 8, K, felz, 1)
+                o = O.orc_mgm(cc, None, -(L - 1), P1, P2, 8, K, felz, 1)
+                assert same(r["S"], o["S"]) and same(r["out"], o["out"]), (knob, nx, ny, L, K, felz, rows, mism(r["S"], o["S"]))
+    finally:
+        ctx.set_option("reset")
 
 
 def test_mgm_overcount_flag_and_small_images(ctx):
@@ -299,7 +302,7 @@ def test_stereo_matches_oracle(ctx, kw):
                                  dict(W=1920, H=1080, L=128, dist="census", win=5, K=2, felz=0, P1=8.0, P2=32.0),
                                  dict(W=1242, H=375, L=192, dist="census", win=5, K=4, felz=0, P1=8.0, P2=32.0),
                                  dict(W=4096, H=4096, L=64, dist="ncc", win=5, K=2, felz=0, P1=8.0, P2=32.0)])
-def test_full_size_finish_fused_vs_separate(ctx, cfg, monkeypatch):
+def test_full_size_finish_fused_vs_separate(ctx, cfg):
     """BASELINE.json configs 2-5 shapes: the finish stage run as tiles inside the aggregation launch (completion flags,
     release/acquire across CTAs, thousands of tiles racing with the running bands) gives the bits of the separate
     finish kernel, sub-pixel refinement included, and is reproducible from run to run."""
@@ -310,9 +313,12 @@ def test_full_size_finish_fused_vs_separate(ctx, cfg, monkeypatch):
               use_felzenszwalb_potentials=cfg["felz"], distance=cfg["dist"], census_ncc_win=cfg["win"])
     runs = [ctx.stereo(u, v, **kw) for _ in range(3)]
     assert ctx.last_launch_info()["kernel_launches"] == 1
-    monkeypatch.setenv("MGMB200_NO_FUSED_FINISH", "1")
-    ref = ctx.stereo(u, v, **kw)
-    assert ctx.last_launch_info()["kernel_launches"] == 2
+    ctx.set_option("no_fused_finish", 1)
+    try:
+        ref = ctx.stereo(u, v, **kw)
+        assert ctx.last_launch_info()["kernel_launches"] == 2
+    finally:
+        ctx.set_option("reset")
     for out, cost in runs:
         assert same(out, ref[0]) and same(cost, ref[1]), (mism(out, ref[0]), mism(cost, ref[1]))
     assert (ref[0] != np.round(ref[0])).any()   # sub-pixel offsets present (vfit may give NaN on flat minima, like the reference)
@@ -350,6 +356,40 @@ def test_full_size_properties(ctx, cfg):
     o = O.orc_pipeline(u[:ch, :cw], v[:ch, :cw], -(L - 1), 0, **kk)
     assert same(out1[:ch - 2, :cw - 2], o["out"][:ch - 2, :cw - 2])
     assert same(cost1[:ch - 2, :cw - 2], o["outcost"][:ch - 2, :cw - 2])
+
+
+@pytest.mark.parametrize("cfg", [dict(W=640, H=480, L=256, win=3, K=3, felz=1, P1=2.0, P2=20000.0),      # headline kernel: nj=8 register path
+                                 dict(W=640, H=480, L=128, win=5, K=2, felz=0, P1=8.0, P2=32.0),        # configs[1] kernel
+                                 dict(W=600, H=375, L=192, win=3, K=4, felz=0, P1=8.0, P2=32.0, dist="ad"),   # configs[3] kernel
+                                 dict(W=512, H=512, L=64, win=5, K=2, felz=0, P1=8.0, P2=32.0, dist="ncc")])  # 4 lanes per worker
+def test_midsize_against_the_reference(ctx, cfg):
+    """The label counts and update variants of BASELINE.json's configurations on mid-size frames, DEFAULT bands (several
+    chained bands per sweep, sheared diagonal sweeps, fused finish tiles), all eight sweeps, compared bit for bit with
+    the UNMODIFIED reference run here (oracle/_ref, mgm_core.cc:408-613): cost volume, aggregated volume S, WTA labels,
+    costs, sub-pixel disparities."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built on this box")
+    from bench import synth_pair as bench_pair
+    W, H, L = cfg["W"], cfg["H"], cfg["L"]
+    dist = cfg.get("dist", "census")
+    pf = "census" if dist == "census" else "none"
+    u, v = bench_pair(W, H, L, 3)
+    fl = "_flat" if O.ref_lib("_flat") is not None else ""
+    cc_ref = O.ref_costvolume(u, v, -(L - 1), 0, pf, dist, np.inf, cfg["win"], flavour=fl)
+    cc = ctx.allocate_and_fill_sgm_costvolume(u, v, -(L - 1), 0, pf, dist, np.inf, cfg["win"])
+    assert same(cc, cc_ref), mism(cc, cc_ref)
+    r = O.ref_mgm(cc_ref, None, -(L - 1), cfg["P1"], cfg["P2"], 8, cfg["K"], cfg["felz"], 1, flavour=fl)
+    ro, rc = O.ref_refine(r["S"], -(L - 1), r["out"], r["outcost"], "vfit", flavour=fl)
+    g = ctx.mgm(cc, None, -(L - 1), cfg["P1"], cfg["P2"], 8, cfg["K"], cfg["felz"], 1)
+    assert ctx.last_launch_info()["rows_axis"] >= 40    # default bands
+    assert same(g["out"], r["out"]), mism(g["out"], r["out"])
+    assert same(g["S"], r["S"]), mism(g["S"], r["S"])
+    assert same(g["outcost"], r["outcost"])
+    kw = dict(dmin=-(L - 1), dmax=0, P1=cfg["P1"], P2=cfg["P2"], MGM=cfg["K"], NDIR=8, refinement="vfit",
+              use_felzenszwalb_potentials=cfg["felz"], distance=dist, census_ncc_win=cfg["win"])
+    out, cost = ctx.stereo(u, v, **kw)                  # the fused path: one launch, finish tiles
+    assert ctx.last_launch_info()["kernel_launches"] == 1
+    assert same(out, ro) and same(cost, rc), (mism(out, ro), mism(cost, rc))
 
 
 # ------------------------------------------------------------------------------------------ command lines

@@ -3,7 +3,7 @@ import sys
 sys.path.insert(0, ".")
 import torch
 import mgm_b200
-from tests.gpu_micro import run, ctx
+from tools.gpu_micro import run, ctx
 for felz, K in [(1, 3), (0, 3)]:
     for T in ([int(a) for a in sys.argv[1:]] or [43, 32, 24, 16, 8, 4]):
         for mask, sig in [(0x01, 1), (0x10, 2)]:

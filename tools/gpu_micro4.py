@@ -1,7 +1,7 @@
 """Not a test: incremental cost of chained bands (H = n*T rows, sweep 0; W = n*T for the diagonal sweep 4)."""
 import sys
 sys.path.insert(0, ".")
-from tests.gpu_micro import run
+from tools.gpu_micro import run
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 56
 for mask, name in [(0x01, "sweep0"), (0x10, "sweep4")]:
     base = None

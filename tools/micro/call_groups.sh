@@ -3,6 +3,6 @@ mkdir -p gpurun_out
 cat gpurun_out/pytest.log
 for g in 1 2 3; do
   echo "== MGMB200_GROUPS=$g"
-  MGMB200_GROUPS=$g timeout 300 python tests/micro/rows_sweep.py 56,56 2>&1 | tail -3
-  MGMB200_GROUPS=$g timeout 300 python tests/gpu_micro4.py 56 2>&1 | grep "bands=1:"
+  MGMB200_GROUPS=$g timeout 300 python tools/micro/rows_sweep.py 56,56 2>&1 | tail -3
+  MGMB200_GROUPS=$g timeout 300 python tools/gpu_micro4.py 56 2>&1 | grep "bands=1:"
 done

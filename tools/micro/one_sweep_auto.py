@@ -1,7 +1,7 @@
 """Not a test: the automatic rows-per-band choice for launches with few sweeps."""
 import sys
 sys.path.insert(0, ".")
-from tests.gpu_micro import run
+from tools.gpu_micro import run
 for mask, name in [(0x01, "sweep 0"), (0x10, "sweep 4"), (0x11, "sweeps 0,4"), (0x33, "sweeps 0,1,4,5"), (0xFF, "all")]:
     ms, info = run(2048, 1536, 256, 3, 1, mask, rows=0, reps=2)
     print("%-16s rows=%2d/%2d thr=%3d: %.2f ms" % (name, info["rows_axis"], info["rows_diag"], info["threads_per_cta"], ms), flush=True)

@@ -2,7 +2,7 @@
 import os, sys
 sys.path.insert(0, ".")
 pairs = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]] or [(43, 35), (20, 16), (13, 10), (9, 7)]
-from tests.gpu_micro import run
+from tools.gpu_micro import run
 for (ta, td) in pairs:
     os.environ["MGMB200_ROWS_AXIS"] = str(ta)
     os.environ["MGMB200_ROWS_DIAG"] = str(td)
