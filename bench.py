@@ -250,8 +250,10 @@ def parity_check(ctx, wl, ref, torch):
     par = {"against": ref.kind, "shape": "%dx%dx%d" % (W, H, L), "sweeps": wl["NDIR"], "wta_mismatch": wta_mismatch,
            "cost_max_rel": cost_rel, "subpixel_max_rel": sub_rel, "subpixel_cost_max_rel": subc_rel,
            "nonfinite_mismatch": cost_nf + sub_nf,
-           "disparity_bit_mismatch": int(np.count_nonzero(gro.view(np.int32) != ro.view(np.int32))),
-           "cost_bit_mismatch": int(np.count_nonzero(grc.view(np.int32) != rc.view(np.int32))),
+           # bit comparison of the refined maps; NaNs (vfit on a flat minimum divides 0/0, refine.h:70-92) count as equal
+           # whatever their payload (x86 produces the negative quiet NaN, the GPU the positive one)
+           "disparity_bit_mismatch": int(np.count_nonzero((gro.view(np.int32) != ro.view(np.int32)) & ~(np.isnan(gro) & np.isnan(ro)))),
+           "cost_bit_mismatch": int(np.count_nonzero((grc.view(np.int32) != rc.view(np.int32)) & ~(np.isnan(grc) & np.isnan(rc)))),
            "ref_seconds": round(r["seconds"], 3), "ref_costvolume_seconds": round(ref.t_cc or 0.0, 3)}
     # aggregated volume S (after the over-count fix), compared on the device chunk by chunk
     try:

@@ -217,16 +217,43 @@ int mgmb200_aggregate_dev(mgmb200_ctx *ctx, const float *d_cc, const float *d_w,
                           int use_felzenszwalb_potentials, int sgm_fix_overcount, int refinement_index,
                           float *d_out, float *d_outcost, float *d_S);
 
-/* Multi-GPU direction sharding: the sweeps are split over ranks; every rank
- * aggregates its own sweeps into its own per-sweep volumes, then each rank finishes a slab of
- * image rows reading all NDIR sweep volumes (its own and, through CUDA peer/IPC mappings, the
- * other ranks') in sweep order. */
+/* A batch of npairs stereo pairs of one shape and one parameter set (BASELINE.json configs[3]; the reference
+ * processes one pair per process run, mgm.cc:266-450): the sweeps of several pairs share one launch.  d_w: NULL, or
+ * npairs weight-plane pointers (then the per-edge kernels run, as weights_mode 1).  Equivalent to npairs
+ * mgmb200_aggregate_dev calls. */
+int mgmb200_aggregate_batch_dev(mgmb200_ctx *ctx, int npairs, const float *const *d_cc, const float *const *d_w, int nx,
+                                int ny, int dmin, int dmax, float P1, float P2, int NDIR, int MGM,
+                                int use_felzenszwalb_potentials, int sgm_fix_overcount, int refinement_index,
+                                float *const *d_out, float *const *d_outcost);
+
+/* Multi-GPU direction sharding (the reference's own precedent is mgm_naive_parallelism,
+ * mgm_core.cc:632-831: one thread per sweep, S += Lr at the end).  One process per GPU; sweep p is aggregated by one
+ * rank (sweep_mask), and the sum S = sum_p L_p (mgm_core.cc:582-587) is the only exchange.  Two exchanges are provided:
+ *
+ * (1) ORDERED, bit-exact: the image rows are cut into nslabs slabs of slab_rows rows, slab r is finished by rank r.
+ *     Every rank allocates all NDIR message volumes (mgmb200_sweeps_alloc), exports them (mgmb200_ipc_export) and maps
+ *     the other ranks' (mgmb200_ipc_open).  mgmb200_aggregate_sweeps_slabs_dev then stores the messages of slab r of
+ *     sweep p into d_slab_volumes[p*nslabs + r] -- rank r's volume p, a peer mapping for r != own rank: the stores
+ *     cross NVLink from inside the aggregation kernel while the sweep runs.  After one barrier between the ranks
+ *     every rank holds all sweeps of its slab locally and mgmb200_finish_rows_dev adds them IN SWEEP ORDER.
+ * (2) ALL-REDUCE, as north_star names it: mgmb200_aggregate_sweeps_dev into local volumes, mgmb200_sum_sweeps_dev adds
+ *     the rank's sweeps into one partial volume, the caller all-reduces the partial volumes (NCCL), and
+ *     mgmb200_finish_sum_dev applies fix + WTA + refinement.  The summation order is not the reference's.
+ */
 int mgmb200_aggregate_sweeps_dev(mgmb200_ctx *ctx, const float *d_cc, const float *d_w, int weights_mode,
                                  int nx, int ny, int dmin, int dmax, float P1, float P2, int NDIR, int MGM,
                                  int use_felzenszwalb_potentials, unsigned sweep_mask);
-/* device pointer of the volume this context holds for sweep p after mgmb200_aggregate_sweeps_dev */
+int mgmb200_sweeps_alloc(mgmb200_ctx *ctx, int nx, int ny, int dmin, int dmax, int NDIR);
+/* frees the message volumes (also the exported ones: peers must have closed their mappings) */
+int mgmb200_sweeps_release(mgmb200_ctx *ctx);
+int mgmb200_aggregate_sweeps_slabs_dev(mgmb200_ctx *ctx, const float *d_cc, const float *d_w, int weights_mode, int nx,
+                                       int ny, int dmin, int dmax, float P1, float P2, int NDIR, int MGM,
+                                       int use_felzenszwalb_potentials, unsigned sweep_mask, int nslabs, int slab_rows,
+                                       float *const *d_slab_volumes);
+/* device pointer of the volume this context holds for sweep p (after mgmb200_sweeps_alloc or an aggregation) */
 int mgmb200_sweep_volume(mgmb200_ctx *ctx, int sweep, float **d_ptr, size_t *bytes);
-/* 64-byte CUDA IPC handle of a device allocation / mapping of a peer handle */
+/* 64-byte CUDA IPC handle of a device allocation / mapping of a peer handle.  An exported message volume is never
+ * reallocated: a later call that needs a larger one fails until mgmb200_sweeps_release. */
 int mgmb200_ipc_export(mgmb200_ctx *ctx, const void *d_ptr, unsigned char handle_out[64]);
 int mgmb200_ipc_open(mgmb200_ctx *ctx, const unsigned char handle[64], void **d_ptr);
 int mgmb200_ipc_close(mgmb200_ctx *ctx, void *d_ptr);
@@ -235,6 +262,12 @@ int mgmb200_ipc_close(mgmb200_ctx *ctx, void *d_ptr);
 int mgmb200_finish_rows_dev(mgmb200_ctx *ctx, const float *const *d_sweeps, const float *d_cc, int nx, int ny,
                             int dmin, int dmax, int NDIR, int sgm_fix_overcount, int refinement_index,
                             int row_begin, int row_end, float *d_out, float *d_outcost);
+/* d_sum (padded volume) = sum of this context's sweeps in sweep_mask, in increasing sweep order */
+int mgmb200_sum_sweeps_dev(mgmb200_ctx *ctx, int nx, int ny, int dmin, int dmax, unsigned sweep_mask, float *d_sum);
+/* over-count fix for NDIR sweeps + WTA + sub-pixel on a pre-summed padded volume */
+int mgmb200_finish_sum_dev(mgmb200_ctx *ctx, const float *d_sum, const float *d_cc, int nx, int ny, int dmin, int dmax,
+                           int NDIR, int sgm_fix_overcount, int refinement_index, int row_begin, int row_end,
+                           float *d_out, float *d_outcost);
 
 /* device-pointer forms of the post-processing stages; all out of place except update_dmin_dmax, whose
  * d_minmax is 4 floats of scratch that receive the finite min and max of d_outoff in [0] and [1] */

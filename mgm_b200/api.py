@@ -418,11 +418,49 @@ class Context:
 
     def finish_rows_dev(self, sweep_ptrs, d_cc, nx, ny, dmin, dmax, NDIR, fix, refinement, row_begin, row_end, d_out,
                         d_outcost):
-        arr = (ctypes.c_void_p * 8)(*[ctypes.c_void_p(p) for p in list(sweep_ptrs) + [0] * (8 - len(sweep_ptrs))])
+        arr = (ctypes.c_void_p * 16)(*[ctypes.c_void_p(p) for p in list(sweep_ptrs) + [0] * (16 - len(sweep_ptrs))])
         ri = self.lib.mgmb200_refinement_index(refinement.encode())
         self._check(self.lib.mgmb200_finish_rows_dev(self._ctx, arr, ctypes.c_void_p(d_cc), nx, ny, int(dmin), int(dmax),
                                                      int(NDIR), int(fix), ri, int(row_begin), int(row_end),
                                                      ctypes.c_void_p(d_out), ctypes.c_void_p(d_outcost)))
+
+    def aggregate_batch_dev(self, d_ccs, nx, ny, dmin, dmax, P1, P2, NDIR, MGM, felz, fix, refinement, d_outs, d_outcosts,
+                            d_ws=None):
+        """npairs stereo pairs of one shape in shared launches (mgmb200_aggregate_batch_dev)."""
+        n = len(d_ccs)
+        mk = lambda ps: (ctypes.c_void_p * n)(*[ctypes.c_void_p(p) for p in ps])
+        ri = self.lib.mgmb200_refinement_index(refinement.encode())
+        self._check(self.lib.mgmb200_aggregate_batch_dev(self._ctx, n, mk(d_ccs), mk(d_ws) if d_ws else None, nx, ny,
+                                                         int(dmin), int(dmax), ctypes.c_float(P1), ctypes.c_float(P2),
+                                                         int(NDIR), int(MGM), int(felz), int(fix), ri, mk(d_outs),
+                                                         mk(d_outcosts)))
+
+    def sweeps_alloc(self, nx, ny, dmin, dmax, NDIR):
+        self._check(self.lib.mgmb200_sweeps_alloc(self._ctx, nx, ny, int(dmin), int(dmax), int(NDIR)))
+
+    def sweeps_release(self):
+        self._check(self.lib.mgmb200_sweeps_release(self._ctx))
+
+    def aggregate_sweeps_slabs_dev(self, d_cc, d_w, weights_mode, nx, ny, dmin, dmax, P1, P2, NDIR, MGM, felz, sweep_mask,
+                                   nslabs, slab_rows, slab_volumes):
+        """slab_volumes[p][r]: device pointer of the volume that receives rows [r*slab_rows,(r+1)*slab_rows) of sweep p."""
+        flat = [slab_volumes[p][r] for p in range(NDIR) for r in range(nslabs)]
+        arr = (ctypes.c_void_p * len(flat))(*[ctypes.c_void_p(p) for p in flat])
+        self._check(self.lib.mgmb200_aggregate_sweeps_slabs_dev(self._ctx, ctypes.c_void_p(d_cc), ctypes.c_void_p(d_w or 0),
+                                                                int(weights_mode), nx, ny, int(dmin), int(dmax),
+                                                                ctypes.c_float(P1), ctypes.c_float(P2), int(NDIR), int(MGM),
+                                                                int(felz), ctypes.c_uint(sweep_mask), int(nslabs),
+                                                                int(slab_rows), arr))
+
+    def sum_sweeps_dev(self, nx, ny, dmin, dmax, sweep_mask, d_sum):
+        self._check(self.lib.mgmb200_sum_sweeps_dev(self._ctx, nx, ny, int(dmin), int(dmax), ctypes.c_uint(sweep_mask),
+                                                    ctypes.c_void_p(d_sum)))
+
+    def finish_sum_dev(self, d_sum, d_cc, nx, ny, dmin, dmax, NDIR, fix, refinement, row_begin, row_end, d_out, d_outcost):
+        ri = self.lib.mgmb200_refinement_index(refinement.encode())
+        self._check(self.lib.mgmb200_finish_sum_dev(self._ctx, ctypes.c_void_p(d_sum), ctypes.c_void_p(d_cc), nx, ny,
+                                                    int(dmin), int(dmax), int(NDIR), int(fix), ri, int(row_begin),
+                                                    int(row_end), ctypes.c_void_p(d_out), ctypes.c_void_p(d_outcost)))
 
     def pad_volume_dev(self, d_dense, d_padded, nx, ny, L, label_major=0):
         self._check(self.lib.mgmb200_pad_volume_dev(self._ctx, ctypes.c_void_p(d_dense), ctypes.c_void_p(d_padded), nx,

@@ -49,8 +49,6 @@ static constexpr int RV = 8;   // virtual-row ring (pixels of the previous band'
 static constexpr int PF = 3;   // boundary prefetch distance in pixels
 static constexpr int G = MGM_AGG_GROUP;   // lanes cooperating on one scan row (the band functions shadow it with their GL)
 
-enum PredType { PRED_SAME = 0, PRED_UP = 1, PRED_UPL = 2, PRED_UPR = 3 };
-
 template <bool DIAG>
 __device__ __forceinline__ constexpr int pred_type(int k) {
    return DIAG ? (k == 0 ? PRED_UPR : k == 1 ? PRED_UPL : k == 2 ? PRED_UP : PRED_SAME)
@@ -328,22 +326,34 @@ __device__ __forceinline__ float4 div4_by_k(const float4 &e) {   // e finite (se
 
 // Every message of the band is in memory (all threads have passed the barrier that follows their last store):
 // one thread publishes the completion flag the fused finish tiles wait for.
-__device__ __forceinline__ void band_finished(const AggParams &P, int pass, int band) {
+__device__ __forceinline__ void band_finished(const AggParams &P, const SweepDesc &D, int band) {
    if (P.fin_enabled && threadIdx.x == 0) {
       __threadfence();
-      st_release(P.band_done[pass] + band, 1);
+      st_release(D.band_done + band, 1);
    }
 }
 
-template <int POT, int K, bool WEIGHTED, bool DIAG, int GL>
-__device__ void run_band(const AggParams &P, const int pass, const int band, unsigned char *smem) {
+// Where the message of a pixel in image row y is stored: the sweep's volume, or -- sweep-sharded multi-GPU layout --
+// the volume of the rank that finishes the row slab y belongs to (a peer mapping: the store crosses NVLink while the
+// sweep runs, so the ordered finish later reads local memory only).
+__device__ __forceinline__ float *ldir_of_row(const AggParams &P, const SweepDesc &D, int y) {
+   return (P.nslabs > 1) ? D.ldir[__umulhi((unsigned)y, P.slab_magic)] : D.ldir[0];
+}
+
+// KN: sweeps 8-15 -- the scan of sweep pass-8, lag 2, predecessor ORDER by the parity of the scan coordinates
+// (knight_pred_type, common.cuh); instantiated with DIAG = true for the lag and the ring depth.
+template <int POT, int K, bool WEIGHTED, bool DIAG, int GL, bool KN = false>
+__device__ void run_band(const AggParams &P, const SweepDesc &D, const int band, unsigned char *smem) {
    constexpr int G = GL;   // lanes per worker: 8, or 4 for short label vectors (unweighted SGM kernels, agg_plan)
+   static_assert(!KN || DIAG, "knight sweeps use the lag-2 layout");
+   const int pass = D.pass;
+   const bool kn_diag = (pass & 7) >= 4;
    constexpr int SIG = (DIAG || K == 4) ? 2 : 1;
    constexpr int R = SIG + 2;
    constexpr bool NEEDM = WEIGHTED || (POT == POT_TRUNC && K == 2);
    constexpr bool WTRUNC = WEIGHTED && POT == POT_TRUNC;
    constexpr bool CHAINS = !WEIGHTED && POT == POT_TRUNC;   // phase-2 transform done by lane pairs
-   constexpr int CLS = DIAG ? 1 : 0;
+   constexpr int CLS = KN ? CLS_KNIGHT : (DIAG ? CLS_DIAG : CLS_AXIS);
    constexpr bool A16 = (POT == POT_TRUNC);   // 16-byte aligned rows and accesses (ld16 / st16)
    constexpr int JB = (K <= 3) ? MGM_JB : 2;   // chunks per lane whose loads are issued together in the gather
    constexpr int NJR = MGM_AGG_CREG;      // cost chunks per lane that can be prefetched into registers
@@ -401,27 +411,30 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
       return (rr < 0) ? virt + (px & (RV - 1)) * VS : row_base(rr) + (px % R) * VS;
    };
    auto m_of = [&](int rr, int px) -> float { return (rr < 0) ? vms[px & (RV - 1)] : msr[rr * 4 + (px % R)]; };
-   // predecessor k of pixel (xs) of row rr: which row's slot, which pixel
-   auto pred_of = [&](int rr, int xs, int k, int &prow, int &ppx) {
-      const int pt = pred_type<DIAG>(k);
+   // predecessor k of pixel (xs) of row rr: which row's slot, which pixel; returns the predecessor's type
+   auto pred_of = [&](int rr, int xs, int k, int &prow, int &ppx) -> int {
+      const int pt = KN ? knight_pred_type(kn_diag, k, xs, row0 + rr) : pred_type<DIAG>(k);
       ppx = (pt == PRED_UP) ? xs : (pt == PRED_UPR ? xs + 1 : xs - 1);
       prow = (pt == PRED_SAME) ? rr : rr - 1;   // -1 = virtual row fed from the previous band
+      return pt;
+   };
+   auto plane_of = [&](int k, int pt) -> int {
+      return KN ? pass_weight_plane_of_type(pass & 7, pt) : pass_weight_plane(pass, k);
    };
 
-   const float *ccv = P.cc;
-   float *ldir = P.ldir[pass];
-   float *bnd_out = P.bnd[pass] + (size_t)band * maxii * VS;
-   float *bndm_out = P.bndm[pass] + (size_t)band * maxii;
-   const float *bnd_in = has_prev ? P.bnd[pass] + (size_t)(band - 1) * maxii * VS : nullptr;
-   const float *bndm_in = has_prev ? P.bndm[pass] + (size_t)(band - 1) * maxii : nullptr;
-   int *prog_out = P.progress[pass] + band;
-   const int *prog_in = has_prev ? P.progress[pass] + band - 1 : nullptr;
+   const float *ccv = D.cc;
+   float *bnd_out = D.bnd + (size_t)band * maxii * VS;
+   float *bndm_out = D.bndm + (size_t)band * maxii;
+   const float *bnd_in = has_prev ? D.bnd + (size_t)(band - 1) * maxii * VS : nullptr;
+   const float *bndm_in = has_prev ? D.bndm + (size_t)(band - 1) * maxii : nullptr;
+   int *prog_out = D.progress + band;
+   const int *prog_in = has_prev ? D.progress + band - 1 : nullptr;
    const size_t wplane = (size_t)P.nx * P.ny;
 
    const long long pix0 = g.base0 + (long long)ys * g.dys;   // pixel of (0, ys) for my group's row
 
    uint32_t vph = 0;
-   const int vph_idx = max(P.T[0], P.T[1]);
+   const int vph_idx = max(max(P.T[0], P.T[1]), P.T[2]);
    if (tid < G) vph = phase[vph_idx];
    int next_px = 0;   // producer: next boundary pixel to fetch
 
@@ -514,7 +527,8 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
       float2 *cur = reinterpret_cast<float2 *>(row_base(r) + (act ? (xs % R) : 0) * VS);
       float *Cbf = (CHAINS && creg_mode) ? reinterpret_cast<float *>(cur) : cbuf_of(r, xs);   // where the message is built
       float2 *Cb = reinterpret_cast<float2 *>(Cbf);
-      float4 *gout = reinterpret_cast<float4 *>(ldir + (size_t)(act ? pix : 0) * VS);
+      float4 *gout = reinterpret_cast<float4 *>(ldir_of_row(P, D, act ? g.y0 + xs * g.ydxs + ys * g.ydys : 0) +
+                                                (size_t)(act ? pix : 0) * VS);
       const bool border = (xs == 0) || (ys == 0) || (xs == maxii - 1);
       float m = MGM_INF;
 
@@ -533,12 +547,12 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
             int mlo = 0, mhi = VS;
             if (on) {
                int prow, ppx;
-               pred_of(crow, cxs, ck, prow, ppx);
+               const int cpt = pred_of(crow, cxs, ck, prow, ppx);
                const long long cpix = g.base0 + (long long)(row0 + crow) * g.dys + (long long)cxs * g.dxs;
-               const float wk = P.w ? __ldg(P.w + (size_t)pass_weight_plane(pass, ck) * wplane + cpix) : 1.0f;
-               if (P.win_lo) {   // per-pixel cost ranges: convolve inside the receiving pixel's range
-                  mlo = (int)__ldg(P.win_lo + cpix) - P.win_emin;
-                  mhi = (int)__ldg(P.win_hi + cpix) - P.win_emin;
+               const float wk = D.w ? __ldg(D.w + (size_t)plane_of(ck, cpt) * wplane + cpix) : 1.0f;
+               if (D.win_lo) {   // per-pixel cost ranges: convolve inside the receiving pixel's range
+                  mlo = (int)__ldg(D.win_lo + cpix) - P.win_emin;
+                  mhi = (int)__ldg(D.win_hi + cpix) - P.win_emin;
                }
                mk = m_of(prow, ppx);
                cw1 = P.P1 * wk; capv = mk + P.P2 * wk;
@@ -583,11 +597,11 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                int prow, ppx;
-               pred_of(r, xs, k, prow, ppx);
+               const int pt = pred_of(r, xs, k, prow, ppx);
                S[k] = reinterpret_cast<const float2 *>(WTRUNC ? row_base(r) + (R + ncbuf + k) * VS : slot_of(prow, ppx));
                mk[k] = 0.f; wk[k] = 1.f;
                if (NEEDM) mk[k] = m_of(prow, ppx);
-               if (WEIGHTED && !WTRUNC) wk[k] = __ldg(P.w + (size_t)pass_weight_plane(pass, k) * wplane + pix);
+               if (WEIGHTED && !WTRUNC) wk[k] = __ldg(D.w + (size_t)plane_of(k, pt) * wplane + pix);
             }
             if constexpr (!WEIGHTED || WTRUNC) {
                // slots hold the neighbour-side transform already (producer row, or phase 0 scratch).
@@ -764,7 +778,7 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
    cp_async_wait<0>();
    if (tid == 0) phase[vph_idx] = vph;
    __syncthreads();
-   band_finished(P, pass, band);
+   band_finished(P, D, band);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -779,8 +793,9 @@ __device__ void run_band(const AggParams &P, const int pass, const int band, uns
 // Everything else (register-resident cost prefetch, gather, exact min-convolution chains / SGM transform,
 // boundary lines through TMA stores + release/acquire counters + TMA loads) is as in run_band.
 template <int POT, int K, int GL>
-__device__ void run_band_shear(const AggParams &P, const int pass, const int band, unsigned char *smem) {
+__device__ void run_band_shear(const AggParams &P, const SweepDesc &D, const int band, unsigned char *smem) {
    constexpr int G = GL;
+   const int pass = D.pass;
    static_assert(K <= 3, "the sheared wavefront needs predecessors in the row above only");
    constexpr bool NEEDM = (POT == POT_TRUNC && K == 2);
    constexpr bool CHAINS = (POT == POT_TRUNC);
@@ -844,22 +859,21 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
    auto m_of = [&](int rr, int v) -> float { return (rr < 0) ? vms[(-rr - 1) * RV + (v & (RV - 1))] : msr[rr * 4 + (v & 1)]; };
    auto cbuf_of = [&](int rr, int v) -> float * { return row_base(rr) + (2 + (ncb == 2 ? (v & 1) : 0)) * VS; };
 
-   const float *ccv = P.cc;
-   float *ldir = P.ldir[pass];
+   const float *ccv = D.cc;
    // boundary lines: [band][line][maxjj][VS], line 0 = last worker of the band, line 1 = the one before
-   float *bnd_out = P.bnd[pass] + (size_t)band * 2 * maxjj * VS;
-   float *bndm_out = P.bndm[pass] + (size_t)band * 2 * maxjj;
-   const float *bnd_in = has_prev ? P.bnd[pass] + (size_t)(band - 1) * 2 * maxjj * VS : nullptr;
-   const float *bndm_in = has_prev ? P.bndm[pass] + (size_t)(band - 1) * 2 * maxjj : nullptr;
-   int *prog_out = P.progress[pass] + band;
-   const int *prog_in = has_prev ? P.progress[pass] + band - 1 : nullptr;
+   float *bnd_out = D.bnd + (size_t)band * 2 * maxjj * VS;
+   float *bndm_out = D.bndm + (size_t)band * 2 * maxjj;
+   const float *bnd_in = has_prev ? D.bnd + (size_t)(band - 1) * 2 * maxjj * VS : nullptr;
+   const float *bndm_in = has_prev ? D.bndm + (size_t)(band - 1) * 2 * maxjj : nullptr;
+   int *prog_out = D.progress + band;
+   const int *prog_in = has_prev ? D.progress + band - 1 : nullptr;
 
    // pixel of (u, v): xs = u - v, ys = v
    const long long pix_u = g.base0 + (long long)u * g.dxs;
    const long long dv = g.dys - g.dxs;
 
    uint32_t vph = 0;
-   const int vph_idx = max(P.T[0], P.T[1]);
+   const int vph_idx = max(max(P.T[0], P.T[1]), P.T[2]);
    if (tid < G) vph = phase[vph_idx];
    int next_p = pf_lo;   // producer: next boundary position to fetch
 
@@ -938,7 +952,8 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
       float2 *cur = reinterpret_cast<float2 *>(row_base(r) + (v & 1) * VS);
       float *Cbf = inplace ? reinterpret_cast<float *>(cur) : cbuf_of(r, v);   // where the message is built
       float2 *Cb = reinterpret_cast<float2 *>(Cbf);
-      float4 *gout = reinterpret_cast<float4 *>(ldir + (size_t)(act ? pix : 0) * VS);
+      float4 *gout = reinterpret_cast<float4 *>(ldir_of_row(P, D, act ? g.y0 + xs * g.ydxs + v * g.ydys : 0) +
+                                                (size_t)(act ? pix : 0) * VS);
       const bool border = (xs == 0) || (v == 0) || (xs == maxii - 1);
       float m = MGM_INF;
 
@@ -1092,111 +1107,130 @@ __device__ void run_band_shear(const AggParams &P, const int pass, const int ban
    cp_async_wait<0>();
    if (tid == 0) phase[vph_idx] = vph;
    __syncthreads();
-   band_finished(P, pass, band);
+   band_finished(P, D, band);
 }
 
-// Dynamic band scheduling (one thread per CTA).  Bands of a sweep are claimed strictly in order through a
-// per-sweep counter, so a claimed band's predecessor is always running or finished: any grid size is deadlock
-// free.  An axis band (sweeps 0-3) trails its predecessor by a whole band of steps; claiming it before the
-// predecessor has published anything would park an SM for milliseconds.  Hence:
-//   1. an axis band whose predecessor has started publishing its boundary row (or a first band), longest
-//      remaining chain first -- the axis sweeps are the critical path;
-//   2. else the next band of the diagonal sweep that is least advanced (short hand-off: the filler work);
+// Dynamic band scheduling (warp 0 of every CTA).  A launch holds any number of sweeps (SweepDesc table): the 8 or 16
+// sweeps of a pair, of several pairs, or the few sweeps this GPU owns.  Bands of a sweep are claimed strictly in
+// order through a per-sweep counter, so a claimed band's predecessor is always running or finished: any grid size
+// is deadlock free.  A band of a row-per-worker sweep (axis, knight, unsheared diagonal) trails its predecessor by a
+// whole band of steps; claiming it before the predecessor has published anything would park an SM for
+// milliseconds.  Hence:
+//   1. a row-per-worker band whose predecessor has started publishing its boundary row (or a first band), longest
+//      remaining chain first -- these sweeps are the critical path;
+//   2. else the next band of the sheared diagonal sweep that is least advanced (short hand-off: the filler work);
 //   3. else (fused finish) the finish tile this CTA holds, if the bands that cover it are complete;
-//   4. else any remaining axis band (it waits inside run_band);
+//   4. else any remaining row-per-worker band (it waits inside run_band);
 //   5. else, with a tile still pending, wait for it; without, the CTA is done.
 // Finish tiles never block: they are claimed one per CTA from a host-built order and only run when ready, so the
-// band argument above is unchanged.
+// band argument above is unchanged.  The table is scanned by the 32 lanes in parallel (a batch of 32 pairs holds
+// 256 sweeps).
 
-// A tile can be finished once every band (of every requested sweep) that holds one of its pixels is complete.
+// A tile can be finished once every band (of every sweep of its pair) that holds one of its pixels is complete.
 // Band indices are monotone in the scan coordinates, which are affine in (x,y): the extremes are at the corners.
-__device__ bool tile_ready(const AggParams &P, int tile) {
+// Lane p checks sweep p of the pair.
+__device__ bool tile_ready(const AggParams &P, int gtile, int lane) {
+   const int pair = gtile / P.fin_ntiles, tile = gtile % P.fin_ntiles;
    const int x0 = (tile % P.fin_tiles_x) * P.fin_tw, y0 = (tile / P.fin_tiles_x) * P.fin_th;
    const int x1 = min(x0 + P.fin_tw, P.nx) - 1, y1 = min(y0 + P.fin_th, P.ny) - 1;
    int done = 1;
-   for (int p = 0; p < 8; ++p) {
-      if (!P.nb[p]) continue;
-      const int rm = (0x53 >> p) & 1, incx = (0xC5 >> p) & 1, incy = (0x99 >> p) & 1;   // pass_geometry
-      const int ax0 = incx ? x0 : P.nx - 1 - x1, ax1 = incx ? x1 : P.nx - 1 - x0;       // ascending along the scan
-      const int ay0 = incy ? y0 : P.ny - 1 - y1, ay1 = incy ? y1 : P.ny - 1 - y0;
-      const int xs0 = rm ? ax0 : ay0, xs1 = rm ? ax1 : ay1, ys0 = rm ? ay0 : ax0, ys1 = rm ? ay1 : ax1;
-      int b0, b1;
-      if (p >= 4 && P.shear) { b0 = (xs0 + ys0) / P.T[1]; b1 = (xs1 + ys1) / P.T[1]; }
-      else { const int T = P.T[p < 4 ? 0 : 1]; b0 = ys0 / T; b1 = ys1 / T; }
-      // relaxed loads (they pipeline), ordered before the tile's reads by the fence below
-      for (int b = b1; b >= b0; --b) done &= *reinterpret_cast<volatile const int *>(P.band_done[p] + b);
+   if (lane < P.ndir) {
+      const SweepDesc &d = P.sweeps[pair * P.ndir + lane];
+      if (d.nb) {
+         const int p = d.pass & 7;
+         const int rm = (0x53 >> p) & 1, incx = (0xC5 >> p) & 1, incy = (0x99 >> p) & 1;   // pass_geometry
+         const int ax0 = incx ? x0 : P.nx - 1 - x1, ax1 = incx ? x1 : P.nx - 1 - x0;       // ascending along the scan
+         const int ay0 = incy ? y0 : P.ny - 1 - y1, ay1 = incy ? y1 : P.ny - 1 - y0;
+         const int xs0 = rm ? ax0 : ay0, xs1 = rm ? ax1 : ay1, ys0 = rm ? ay0 : ax0, ys1 = rm ? ay1 : ax1;
+         int b0, b1;
+         if (d.filler) { b0 = (xs0 + ys0) / P.T[CLS_DIAG]; b1 = (xs1 + ys1) / P.T[CLS_DIAG]; }
+         else { const int T = P.T[d.cls]; b0 = ys0 / T; b1 = ys1 / T; }
+         // relaxed loads (they pipeline), ordered before the tile's reads by the fence below
+         for (int b = b1; b >= b0; --b) done &= *reinterpret_cast<volatile const int *>(d.band_done + b);
+      }
    }
-   if (!done) return false;
+   if (!__all_sync(0xffffffffu, done)) return false;
    __threadfence();
    return true;
 }
 
-// `pending`: a finish tile this CTA has claimed but not run yet (-1 none, -2 no tiles left).
-__device__ int2 claim_band(const AggParams &P, int &pending) {
+// Executed by the 32 lanes of warp 0 in lock step; returns (sweep index, band), (-2, global tile) or (-1, 0) = done.
+// `pending`: a finish tile this CTA has claimed but not run yet (-1 none, -2 no tiles left); lane 0's copy counts.
+__device__ int2 claim_band(const AggParams &P, int &pending, int lane) {
    for (;;) {
-      int best = -1, bb = 0, bestrem = 0;
-      for (int p = 0; p < 4; ++p) {
-         const int nbp = P.nb[p];
+      // candidates of this lane: best ready row-per-worker band, best filler band, best not-ready row-per-worker band
+      int rdy_v = -1, rdy_b = 0, rdy_rem = 0, fil_v = -1, fil_b = 0x7fffffff, any_v = -1, any_b = 0, any_rem = 0;
+      for (int v = lane; v < P.nsweeps; v += 32) {
+         const SweepDesc &d = P.sweeps[v];
+         const int nbp = d.nb;
          if (!nbp) continue;
-         const int b = *reinterpret_cast<volatile int *>(P.next_band + p);
+         const int b = *reinterpret_cast<volatile int *>(P.next_band + v);
          if (b >= nbp) continue;
-         const bool ready = P.static_order || b == 0 || ld_acquire(P.progress[p] + b - 1) >= 1;
-         if (ready && nbp - b > bestrem) { best = p; bb = b; bestrem = nbp - b; }
-      }
-      if (best < 0) {
-         int bmin = 0x7fffffff;
-         for (int p = 4; p < 8; ++p) {
-            const int nbp = P.nb[p];
-            if (!nbp) continue;
-            const int b = *reinterpret_cast<volatile int *>(P.next_band + p);
-            if (b < nbp && b < bmin) { best = p; bb = b; bmin = b; }
+         if (d.filler) {
+            if (b < fil_b) { fil_v = v; fil_b = b; }
+         } else {
+            const int rem = nbp - b;
+            const bool ready = P.static_order || b == 0 || ld_acquire(d.progress + b - 1) >= 1;
+            if (ready && rem > rdy_rem) { rdy_v = v; rdy_b = b; rdy_rem = rem; }
+            if (rem > any_rem) { any_v = v; any_b = b; any_rem = rem; }
          }
       }
+      // warp reductions (ties: smaller sweep index)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+         const int orem = __shfl_xor_sync(0xffffffffu, rdy_rem, o), ov = __shfl_xor_sync(0xffffffffu, rdy_v, o),
+                   ob = __shfl_xor_sync(0xffffffffu, rdy_b, o);
+         if (ov >= 0 && (rdy_v < 0 || orem > rdy_rem || (orem == rdy_rem && ov < rdy_v))) { rdy_rem = orem; rdy_v = ov; rdy_b = ob; }
+         const int fb = __shfl_xor_sync(0xffffffffu, fil_b, o), fv = __shfl_xor_sync(0xffffffffu, fil_v, o);
+         if (fv >= 0 && (fil_v < 0 || fb < fil_b || (fb == fil_b && fv < fil_v))) { fil_b = fb; fil_v = fv; }
+         const int arem = __shfl_xor_sync(0xffffffffu, any_rem, o), av = __shfl_xor_sync(0xffffffffu, any_v, o),
+                   ab = __shfl_xor_sync(0xffffffffu, any_b, o);
+         if (av >= 0 && (any_v < 0 || arem > any_rem || (arem == any_rem && av < any_v))) { any_rem = arem; any_v = av; any_b = ab; }
+      }
+      int best = rdy_v, bb = rdy_b;
+      if (best < 0 && fil_v >= 0) { best = fil_v; bb = fil_b; }
       if (best < 0 && P.fin_enabled) {
-         // 3. a finish tile (keeps the SM busy instead of parking on an axis band): tiles are claimed one by one in
+         // 3. a finish tile (keeps the SM busy instead of parking on a not-ready band): tiles are claimed one by one in
          // the expected order of readiness and run once the bands that hold their pixels are complete
          if (pending == -1) {
-            const int t = atomicAdd(P.fin_next, 1);
-            pending = (t < P.fin_ntiles) ? P.fin_order[t] : -2;
+            int t = 0;
+            if (lane == 0) t = atomicAdd(P.fin_next, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            pending = (t < P.fin_total) ? P.fin_order[t] : -2;
          }
-         if (pending >= 0 && tile_ready(P, pending)) {
+         if (pending >= 0 && tile_ready(P, pending, lane)) {
             const int tile = pending;
             pending = -1;
-            return make_int2(8, tile);
+            return make_int2(-2, tile);
          }
       }
-      if (best < 0) {
-         for (int p = 0; p < 4; ++p) {
-            const int nbp = P.nb[p];
-            if (!nbp) continue;
-            const int b = *reinterpret_cast<volatile int *>(P.next_band + p);
-            if (b < nbp && nbp - b > bestrem) { best = p; bb = b; bestrem = nbp - b; }
-         }
-      }
+      if (best < 0 && any_v >= 0) { best = any_v; bb = any_b; }
       if (best < 0) {
          if (!P.fin_enabled || pending < 0) return make_int2(-1, 0);
          __nanosleep(500);   // every band is claimed: wait for the bands that still hold this CTA's tile back
          continue;
       }
-      if (atomicCAS(P.next_band + best, bb, bb + 1) == bb) return make_int2(best, bb);
+      int got = 0;
+      if (lane == 0) got = (atomicCAS(P.next_band + best, bb, bb + 1) == bb);
+      if (__shfl_sync(0xffffffffu, got, 0)) return make_int2(best, bb);
    }
 }
 
 // One finish tile: fin_tw x fin_th pixels, one warp per pixel (wta_device.cuh); the rows region of the shared
-// memory is free between bands and holds one label vector per warp.
-__device__ __forceinline__ void run_finish_tile(const AggParams &P, int tile, unsigned char *smem) {
+// memory is free between bands and holds one label vector per warp.  F: the pair's finish parameters (shared memory).
+__device__ __forceinline__ void run_finish_tile(const AggParams &P, const WtaParams &F, int tile, unsigned char *smem) {
    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
    float *sS = reinterpret_cast<float *>(smem + P.off_thr) + (size_t)warp * P.VS;
    const int x0 = (tile % P.fin_tiles_x) * P.fin_tw, y0 = (tile / P.fin_tiles_x) * P.fin_th;
    const int w = min(P.fin_tw, P.nx - x0), h = min(P.fin_th, P.ny - y0);
    // 128-byte lines of one pixel: (ndir + 1) vectors of VS floats; the warp's next pixel is prefetched into L2
    // while the current one is reduced (16 warps per SM cannot keep enough loads in flight otherwise)
-   const int lpv = P.VS >> 5, nlines = (P.fin.ndir + 1) * lpv;
+   const int lpv = P.VS >> 5, nlines = (F.ndir + 1) * lpv;
    auto prefetch_pixel = [&](int i) {
       const long long pix = (long long)(y0 + i / w) * P.nx + x0 + i % w;
       for (int l = lane; l < nlines; l += 32) {
          const int v = l / lpv;
-         const float *base = (v < P.fin.ndir) ? P.fin.ldir[v] : P.fin.cc;
+         const float *base = (v < F.ndir) ? F.ldir[v] : F.cc;
          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)pix * P.VS + (size_t)(l % lpv) * 32));
       }
    };
@@ -1208,15 +1242,23 @@ __device__ __forceinline__ void run_finish_tile(const AggParams &P, int tile, un
    for (int i = warp; i < w * h; i += nwarps) {
       if (i + MGM_FIN_PF * nwarps < w * h) prefetch_pixel(i + MGM_FIN_PF * nwarps);
       const long long pix = (long long)(y0 + i / w) * P.nx + x0 + i % w;
-      wta_pixel<true>(P.fin, pix, sS, lane);
+      wta_pixel<true>(F, pix, sS, lane);
    }
    __syncthreads();
 }
+
+// the claimed band's sweep (or the claimed tile's pair) staged in shared memory
+union __align__(16) AggStage {
+   SweepDesc d;
+   WtaParams f;
+   __device__ AggStage() {}
+};
 
 template <int POT, int K, bool WEIGHTED, int GL>
 __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(const AggParams P) {
    extern __shared__ __align__(128) unsigned char smem[];
    __shared__ int2 s_ticket;
+   __shared__ AggStage s_stage;
    const int t = threadIdx.x;
    const int ncomp = blockDim.x - 64;   // two service warps follow the row threads
 
@@ -1224,31 +1266,49 @@ __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(c
    {
       uint64_t *vbar = reinterpret_cast<uint64_t *>(smem + P.off_vbar);
       uint32_t *phase = reinterpret_cast<uint32_t *>(smem + P.off_phase);
-      const int tmax = max(P.T[0], P.T[1]);
+      const int tmax = max(max(P.T[0], P.T[1]), P.T[2]);
       if (t == ncomp) { for (int i = 0; i < RV; ++i) mbar_init(&vbar[i], 1); }
       if (t == 0) phase[tmax] = 0;
       mbar_fence_init();
       __syncthreads();
    }
 
-   int pending = -1;   // thread 0: claimed finish tile
+   int pending = -1;   // warp 0: claimed finish tile
    for (;;) {
-      if (t == 0) s_ticket = claim_band(P, pending);
+      if (t < 32) {
+         const int2 tk = claim_band(P, pending, t);
+         if (t == 0) s_ticket = tk;
+         // stage the descriptor (16-byte words, warp 0)
+         if (tk.x >= 0) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.sweeps + tk.x);
+            uint4 *dst = reinterpret_cast<uint4 *>(&s_stage.d);
+            for (int i = t; i < (int)(sizeof(SweepDesc) / 16); i += 32) dst[i] = src[i];
+         } else if (tk.x == -2) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(P.fins + tk.y / P.fin_ntiles);
+            uint4 *dst = reinterpret_cast<uint4 *>(&s_stage.f);
+            for (int i = t; i < (int)(sizeof(WtaParams) / 16); i += 32) dst[i] = src[i];
+         }
+      }
       __syncthreads();
       const int2 pb = s_ticket;
-      __syncthreads();
-      if (pb.x < 0) break;
-      if (pb.x == 8) run_finish_tile(P, pb.y, smem);
-      else if (pb.x < 4) run_band<POT, K, WEIGHTED, false, GL>(P, pb.x, pb.y, smem);
-      else if constexpr (!WEIGHTED && K <= 3) {
-         if (P.shear) run_band_shear<POT, K, GL>(P, pb.x, pb.y, smem);
-         else run_band<POT, K, WEIGHTED, true, GL>(P, pb.x, pb.y, smem);
-      } else run_band<POT, K, WEIGHTED, true, GL>(P, pb.x, pb.y, smem);
+      if (pb.x == -1) break;
+      if (pb.x == -2) run_finish_tile(P, s_stage.f, pb.y % P.fin_ntiles, smem);
+      else {
+         const SweepDesc &D = s_stage.d;
+         const int pass = D.pass;
+         if (pass >= 8) run_band<POT, K, WEIGHTED, true, GL, true>(P, D, pb.y, smem);
+         else if (pass < 4) run_band<POT, K, WEIGHTED, false, GL>(P, D, pb.y, smem);
+         else if constexpr (!WEIGHTED && K <= 3) {
+            if (P.shear) run_band_shear<POT, K, GL>(P, D, pb.y, smem);
+            else run_band<POT, K, WEIGHTED, true, GL>(P, D, pb.y, smem);
+         } else run_band<POT, K, WEIGHTED, true, GL>(P, D, pb.y, smem);
+      }
+      __syncthreads();   // the staged descriptor and the ticket are rewritten by the next claim
    }
 }
 
 // ---------------------------------------------------------------- host side
-static int ring_slots(int cls, int K) { return ((cls == 1 || K == 4) ? 2 : 1) + 2; }
+static int ring_slots(int cls, int K) { return ((cls != CLS_AXIS || K == 4) ? 2 : 1) + 2; }
 
 template <int POT, int K, bool WEIGHTED, int GL = MGM_AGG_GROUP>
 static cudaError_t launch_t(const AggParams &P, const AggPlan &plan, cudaStream_t st) {
@@ -1262,8 +1322,9 @@ static cudaError_t launch_t(const AggParams &P, const AggPlan &plan, cudaStream_
    int grid = min(P.nbands, plan.num_sms * per_sm);
    if (grid < 1) grid = 1;
    if (plan.verbose)
-      fprintf(stderr, "[mgmb200] aggregate: grid=%d block=%d smem=%zu CTAs/SM=%d bands=%d rows=%d/%d groups=%d/%d shear=%d\n", grid,
-              plan.block, plan.smem, per_sm, P.nbands, plan.T[0], plan.T[1], plan.ng[0], plan.ng[1], plan.shear);
+      fprintf(stderr, "[mgmb200] aggregate: grid=%d block=%d smem=%zu CTAs/SM=%d sweeps=%d bands=%d rows=%d/%d/%d groups=%d/%d shear=%d\n",
+              grid, plan.block, plan.smem, per_sm, P.nsweeps, P.nbands, plan.T[0], plan.T[1], plan.T[2], plan.ng[0], plan.ng[1],
+              plan.shear);
    kern<<<grid, plan.block, plan.smem, st>>>(P);
    return cudaGetLastError();
 }
@@ -1317,8 +1378,8 @@ static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, b
    // ... and the unweighted SGM kernels transform the message straight from registers (one group only)
    plan->fused_sgm = (!weighted && pot == POT_SGM && plan->ncb == 1 && want_groups == 1 && !tune.no_fused_sgm) ? 1 : 0;
    const int ncbuf = (!weighted && plan->ncb == 1 && (pot == POT_TRUNC || plan->fused_sgm)) ? 0 : plan->ncb;
-   for (int cls = 0; cls < 2; ++cls) {
-      int nbuf = ((cls == 1 && shear) ? 2 : ring_slots(cls, K)) + ncbuf + xtra;
+   for (int cls = 0; cls < 3; ++cls) {
+      int nbuf = ((cls == CLS_DIAG && shear) ? 2 : ring_slots(cls, K)) + ncbuf + xtra;
       int TS = nbuf * VS;
       if (plan->ncb == 1 && pot == POT_SGM) TS += 2;   // 8 bytes modulo 128: 64-bit accesses of adjacent rows tile the banks
       else if (((TS >> 2) & 1) == 0) TS += 4;          // 16-byte aligned rows (truncated linear, cp.async mode): odd number of 16-byte units
@@ -1328,9 +1389,9 @@ static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, b
       int Tc = avail > 0 ? (int)(avail / ((long)TS * 4)) : 0;
       if (Tc > tcap) Tc = tcap;
       {
-         const int knob = (cls == 0) ? tune.rows_axis : tune.rows_diag;
+         const int knob = (cls == CLS_AXIS) ? tune.rows_axis : tune.rows_diag;
          const int ov = knob > 0 ? knob : t_override;
-         if (ov > 0 && Tc > ov) Tc = (cls == 1 && shear && ov < 2) ? 2 : ov;
+         if (ov > 0 && Tc > ov) Tc = (cls == CLS_DIAG && shear && ov < 2) ? 2 : ov;
       }
       if (Tc < 1) Tc = 0;
       // groups need whole warps (4 rows) and at least two warps each for their chain pair
@@ -1340,7 +1401,7 @@ static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, b
       plan->ng[cls] = ng;
       plan->T[cls] = Tc;
    }
-   const int tm = max(plan->T[0], plan->T[1]);
+   const int tm = max(max(plan->T[0], plan->T[1]), plan->T[2]);
    const int ncomp = (tm * plan->lanes + 31) & ~31;
    plan->block = ncomp + 64;   // + boundary-consumer warp + boundary-publisher warp
    size_t off = 0;
@@ -1351,7 +1412,8 @@ static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, b
    plan->off_vms = off; off += (size_t)nvirt * RV * 4; off = (off + 127) & ~(size_t)127;
    plan->off_virt = off; off += (size_t)nvirt * RV * VS * 4; off = (off + 127) & ~(size_t)127;
    plan->off_thr = off;
-   size_t per_thr = (size_t)max(plan->TS[0] * plan->T[0], plan->TS[1] * plan->T[1]) * 4;
+   size_t per_thr = 0;
+   for (int cls = 0; cls < 3; ++cls) per_thr = max(per_thr, (size_t)plan->TS[cls] * plan->T[cls] * 4);
    plan->smem = off + per_thr;
    plan->num_sms = num_sms;
 }
@@ -1363,9 +1425,30 @@ void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighte
    const bool want_shear = (K <= 3 && !weighted && !tune.no_shear);
    if (want_shear) {
       agg_plan_try(plan, nx, ny, L, K, pot, weighted, max_smem, num_sms, t_override, 1, tune);
-      if (plan->T[0] >= 1 && plan->T[1] >= 2) return;
+      if (plan->T[0] >= 1 && plan->T[1] >= 2 && plan->T[2] >= 1) return;
    }
    agg_plan_try(plan, nx, ny, L, K, pot, weighted, max_smem, num_sms, t_override, 0, tune);
+}
+
+int agg_sweep_class(const AggPlan &plan, int pass) {
+   (void)plan;
+   return pass >= 8 ? CLS_KNIGHT : (pass >= 4 ? CLS_DIAG : CLS_AXIS);
+}
+
+void agg_sweep_bands(const AggPlan &plan, int pass, int nx, int ny, int *nb, size_t *bnd_floats, size_t *bndm_floats) {
+   const PassGeom g = pass_geometry(pass, nx, ny);
+   const int cls = agg_sweep_class(plan, pass);
+   const int T = plan.T[cls];
+   if (cls == CLS_DIAG && plan.shear) {
+      // sheared wavefront: bands of T anti-diagonals, two boundary lines of maxjj positions per band
+      *nb = (g.maxii + g.maxjj - 1 + T - 1) / T;
+      *bnd_floats = (size_t)*nb * 2 * g.maxjj * plan.VS;
+      *bndm_floats = (size_t)*nb * 2 * g.maxjj;
+   } else {
+      *nb = (g.maxjj + T - 1) / T;
+      *bnd_floats = (size_t)*nb * g.maxii * plan.VS;
+      *bndm_floats = (size_t)*nb * g.maxii;
+   }
 }
 
 cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st) {

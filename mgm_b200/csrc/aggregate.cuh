@@ -6,42 +6,68 @@
 #define MGM_AGG_GROUP 8           // lanes cooperating on one scan row
 #define MGM_AGG_MAX_THREADS 512   // 56 rows x 8 lanes + two service warps (boundary consumer / publisher); 128 registers per thread
 #define MGM_AGG_CREG 8            // 16-byte cost chunks per lane prefetched into registers (covers 256 labels)
+#define MGM_MAX_SLABS 8           // row slabs of a message volume (multi-GPU: one per rank, peer mappings)
+#define MGM_MAX_NDIR 16           // sweeps per stereo pair (8 of the reference + 8 defined here, common.cuh)
 
 namespace mgm {
 
 enum PotKind { POT_SGM = 0, POT_TRUNC = 1 };
+enum SweepClass { CLS_AXIS = 0, CLS_DIAG = 1, CLS_KNIGHT = 2 };
+
+// One sweep of one stereo pair ("virtual sweep").  A launch runs any number of them concurrently: the 8 or 16
+// sweeps of a pair, of several pairs (batches, both directions of a left-right run), or the few sweeps a GPU owns
+// in the sweep-sharded multi-GPU layout.  The table lives in device memory; a CTA copies the entry of the band it
+// has claimed into shared memory.
+struct SweepDesc {
+   const float *cc;                  // matching costs [ny][nx][VS] of the sweep's pair, labels >= L hold +INF
+   const float *w;                   // 8 weight planes [8][ny][nx] (weighted kernels only; nullptr = all ones)
+   const float *win_lo, *win_hi;     // per-pixel cost ranges (float images, truncated) or nullptr: the weighted
+                                     // truncated-linear kernels convolve inside the receiving pixel's range
+   float *ldir[MGM_MAX_SLABS];       // message volume [ny][nx][VS]; with nslabs > 1 entry r is the volume that holds
+                                     // image rows [r*slab_rows, (r+1)*slab_rows) -- on another GPU for r != own rank
+   float *bnd;                       // boundary lines [nb][maxii][VS] (sheared: [nb][2][maxjj][VS])
+   float *bndm;                      // boundary minima
+   int *progress;                    // [nb] finished pixels of each band's last row
+   int *band_done;                   // [nb] 1 once every message of the band is in memory (fused finish)
+   int nb;                           // bands (0 = sweep not requested)
+   int pass;                         // 0..15: scan geometry and predecessor order (common.cuh)
+   int cls;                          // SweepClass: which band layout (T, TS) the sweep uses
+   int filler;                       // 1: sheared diagonal sweep (short hand-off): claimed without the readiness test
+   int pair;                         // index of the sweep's pair in the finish table
+   int pad_[3];
+};
+static_assert(sizeof(SweepDesc) % 16 == 0, "staged into shared memory in 16-byte words");
+static_assert(sizeof(WtaParams) % 16 == 0, "staged into shared memory in 16-byte words");
 
 struct AggParams {
-   const float *cc;            // matching costs [ny][nx][VS], labels >= L hold +INF
-   const float *w;             // 8 weight planes [8][ny][nx] (weighted kernels only; nullptr = all ones)
-   const float *win_lo, *win_hi;   // per-pixel cost ranges (float images, truncated) or nullptr: the weighted
-   int win_emin;                   // truncated-linear kernels convolve inside the receiving pixel's range
-   float *ldir[8];             // per-sweep message volumes [ny][nx][VS], indexed by sweep id
-   float *bnd[8];              // per-sweep boundary lines [nbands][maxii][VS]
-   float *bndm[8];             // per-sweep boundary minima [nbands][maxii]
-   int *progress[8];           // per-sweep [nbands]: finished pixels of each band's last row
-   int *next_band;             // per-sweep claim counters [8]: bands of a sweep are claimed in order
-   int nb[8];                  // bands per sweep (0 = sweep not requested)
+   const SweepDesc *sweeps;    // [nsweeps] device memory
+   int nsweeps;
+   int *next_band;             // [nsweeps] claim counters: bands of a sweep are claimed in order
    int nbands;                 // total
    int static_order;           // debugging knob: claim without the readiness test
+   int win_emin;               // label origin of win_lo / win_hi
    int nx, ny, L, VS;
-   int T[2];                   // rows per band: [0] axis sweeps 0-3, [1] diagonal sweeps 4-7
-   int TS[2];                  // per-row shared-memory stride in floats
+   int ndir;                   // sweeps per pair (the pairs' sweeps are consecutive table entries)
+   int nslabs, slab_rows;      // row slabs of the message volumes (1 = whole volume in ldir[0])
+   unsigned slab_magic;        // ceil(2^32 / slab_rows): y / slab_rows = umulhi(y, magic) for y < 2^16
+   int T[3];                   // rows per band by SweepClass
+   int TS[3];                  // per-row shared-memory stride in floats by SweepClass
    int ncb;                    // cost buffers per row (1: costs prefetched into registers, 2: cp.async ring)
    int shear;                  // 1: sweeps 4-7 run as sheared wavefronts (bands of anti-diagonals, run_band_shear)
-   int ng[2];                  // row groups per band (axis / diagonal class), each on its own named barrier
+   int ng[3];                  // row groups per band by SweepClass, each on its own named barrier
    int fused_sgm;              // 1: unweighted SGM kernels transform the message from registers (one barrier per step)
    int cc_pf;                  // > 0: matching costs of the pixel cc_pf steps ahead are prefetched into L2
    float P1, P2;
    // fused finish (optional): CTAs without a band to run take tiles of pixels whose sweeps are all complete and do
    // the ordered sum + over-count fix + WTA + sub-pixel there (wta_device.cuh), inside the same launch
    int fin_enabled;
-   int fin_ntiles, fin_tw, fin_th, fin_tiles_x;   // tiles of fin_tw x fin_th pixels, fin_tiles_x per image row of tiles
-   const int *fin_order;       // tile ids in the expected order of readiness
+   int fin_ntiles;             // tiles per pair; global tile id = pair * fin_ntiles + tile
+   int fin_total;              // npairs * fin_ntiles
+   int fin_tw, fin_th, fin_tiles_x;   // tiles of fin_tw x fin_th pixels, fin_tiles_x per image row of tiles
+   const int *fin_order;       // global tile ids in the expected order of readiness
    int *fin_next;              // claim counter into fin_order
-   int *band_done[8];          // per-sweep [nbands]: 1 once every message of the band is in memory
-   WtaParams fin;
-   unsigned long long *dbg;    // optional 24-word phase-timing accumulator (profiling aid), or nullptr
+   const WtaParams *fins;      // [npairs] device memory
+   int npairs;
    // dynamic shared memory carve-up (bytes)
    unsigned off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };
@@ -58,15 +84,21 @@ struct AggTuning {
    int static_order = 0;               // 1: claim bands without the readiness test
    int no_fused_finish = 0;            // 1: finish stage as a separate launch
    int fin_tw = 128, fin_th = 16;      // finish tile
-   int cc_pf = 0;                      // L2 prefetch distance (pixels) of the matching costs, 0 = off
+   int cc_pf = -1;                     // L2 prefetch distance (pixels) of the matching costs; 0 = off, -1 = auto (3 for
+                                       // the SGM-potential kernels, whose steps are shorter than the HBM latency)
+   int batch = 8;                      // stereo pairs in flight per launch (batch entry points)
    int verbose = 0;
 };
 
 struct AggPlan {
-   int VS, T[2], TS[2], ncb, shear, ng[2], fused_sgm, lanes, block, num_sms, verbose;
+   int VS, T[3], TS[3], ncb, shear, ng[3], fused_sgm, lanes, block, num_sms, verbose;
    size_t smem;
    size_t off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };
+
+// bands of one sweep under a plan, and the floats of boundary lines / minima it needs
+int agg_sweep_class(const AggPlan &plan, int pass);
+void agg_sweep_bands(const AggPlan &plan, int pass, int nx, int ny, int *nb, size_t *bnd_floats, size_t *bndm_floats);
 
 void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
               int t_override, const AggTuning &tune);

@@ -40,8 +40,12 @@ static int fail(int code, const char *fmt, ...) {
 struct DevBuf {
    void *p = nullptr;
    size_t cap = 0;
+   bool exported = false;   // a CUDA IPC handle of this allocation is in other processes' hands: never reallocate it
    int reserve(size_t bytes) {
       if (bytes <= cap) return 0;
+      if (exported)
+         return fail(MGMB200_EINVAL, "a message volume exported to other processes (mgmb200_ipc_export) would have to grow "
+                     "from %zu to %zu bytes: call mgmb200_sweeps_release and exchange the handles again", cap, bytes);
       if (p) cudaFree(p);
       p = nullptr; cap = 0;
       cudaError_t e = cudaMalloc(&p, bytes);
@@ -56,6 +60,43 @@ struct DevBuf {
    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Small host->device tables (sweep descriptors, finish parameters, tile order) go through a ring of pinned staging
+// slots: a plain cudaMemcpyAsync from pageable memory would synchronise the stream before every aggregation launch.
+struct PinnedRing {
+   static constexpr int NSLOT = 4;
+   void *slot[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+   size_t cap[NSLOT] = {0, 0, 0, 0};
+   cudaEvent_t ev[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+   int next = 0;
+   // copies `bytes` from h to device memory d on stream st without blocking on earlier work of the stream
+   cudaError_t push(void *d, const void *h, size_t bytes, cudaStream_t st) {
+      const int i = next;
+      next = (next + 1) % NSLOT;
+      cudaError_t e;
+      if (!ev[i]) { e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+      else { e = cudaEventSynchronize(ev[i]); if (e != cudaSuccess) return e; }   // the slot's previous copy has been consumed
+      if (cap[i] < bytes) {
+         if (slot[i]) cudaFreeHost(slot[i]);
+         slot[i] = nullptr; cap[i] = 0;
+         const size_t want = std::max(bytes, (size_t)65536);
+         e = cudaMallocHost(&slot[i], want);
+         if (e != cudaSuccess) return e;
+         cap[i] = want;
+      }
+      memcpy(slot[i], h, bytes);
+      e = cudaMemcpyAsync(d, slot[i], bytes, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return e;
+      return cudaEventRecord(ev[i], st);
+   }
+   void release() {
+      for (int i = 0; i < NSLOT; i++) {
+         if (ev[i]) cudaEventDestroy(ev[i]);
+         if (slot[i]) cudaFreeHost(slot[i]);
+         ev[i] = nullptr; slot[i] = nullptr; cap[i] = 0;
+      }
+   }
+};
+
 struct mgmb200_ctx {
    int device = 0, num_sms = 0, max_smem = 0;
    cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -67,12 +108,14 @@ struct mgmb200_ctx {
    const float *r_smin = nullptr, *r_smax = nullptr, *r_ccmin = nullptr, *r_ccmax = nullptr;
    bool r_window = false;   // truncated-linear update inside the receiving pixel's cost range (consumer-side kernels)
    int r_emin = 0;
-   DevBuf sweep[8];
+   std::vector<DevBuf> sweepv;   // per-sweep message volumes, slot pair*MGM_MAX_NDIR + sweep
+   DevBuf desc, fins;            // device tables of the launch in flight (SweepDesc, WtaParams per pair)
+   PinnedRing staging;
    DevBuf post[10];   // maps of the post-processing stages (N1/N2)
    // fused finish: tile order (expected readiness) cached per geometry
    DevBuf tiles;
    std::vector<int> tile_order;
-   int tile_key[6] = {0, 0, 0, 0, 0, 0};
+   int tile_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
    bool fin_done = false;   // the last run_sweeps finished the maps inside the aggregation launch
    DevBuf dbgbuf;
    size_t sweep_bytes = 0;
@@ -195,7 +238,8 @@ extern "C" void mgmb200_destroy(mgmb200_ctx *c) {
                      &c->outcost, &c->flags, &c->ftmp, &c->progress, &c->bnd, &c->bndm, &c->rg[0], &c->rg[1],
                      &c->rg[2], &c->rg[3]};
    for (DevBuf *b : bufs) b->release();
-   for (int i = 0; i < 8; i++) c->sweep[i].release();
+   for (DevBuf &b : c->sweepv) b.release();
+   c->desc.release(); c->fins.release(); c->staging.release();
    for (DevBuf &b : c->post) b.release();
    c->tiles.release();
    if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -346,157 +390,203 @@ extern "C" int mgmb200_unpad_volume_dev(mgmb200_ctx *c, const float *d_padded, f
    return 0;
 }
 
-// Runs the sweeps in `mask` into c->sweep[p]; fills `weighted`.  d_cc padded.
-// fin != nullptr: all sweeps are requested and the finish stage (ordered sum, fix, WTA, sub-pixel) may run inside the
-// same launch on tiles whose bands are complete (c->fin_done tells whether it did).
-static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int weights_mode, int nx, int ny,
-                      int L, float P1, float P2, int NDIR, int K, int felz, unsigned mask, const WtaParams *fin = nullptr) {
+// One aggregation launch: the sweeps in `mask` of `npairs` stereo pairs of the same shape and parameters.
+struct SweepRun {
+   int npairs = 1;
+   const float *const *cc = nullptr;     // [npairs] padded cost volumes
+   const float *const *w = nullptr;      // [npairs] weight planes, or nullptr
+   WtaParams *fin = nullptr;             // [npairs] finish parameters (sweep pointers are filled in here), or nullptr:
+                                         // with it, all sweeps are requested and the finish stage (ordered sum, fix,
+                                         // WTA, sub-pixel) may run inside the same launch on tiles whose bands are
+                                         // complete (c->fin_done tells whether it did)
+   unsigned mask = 0;
+   int nslabs = 1, slab_rows = 0;        // sweep-sharded multi-GPU layout (npairs == 1): image rows
+   float *const *slab_ptrs = nullptr;    // [r*slab_rows, (r+1)*slab_rows) of sweep p are stored to slab_ptrs[p*nslabs+r]
+};
+
+static int sweep_slot(int pair, int p) { return pair * MGM_MAX_NDIR + p; }
+
+static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode, int nx, int ny, int L, float P1,
+                            float P2, int NDIR, int K, int felz) {
    c->fin_done = false;
-   if (NDIR < 1 || NDIR > 8)
-      return fail(MGMB200_EUNSUPPORTED, "NDIR=%d: the reference defines 8 sweeps (mgm_core.cc:463-471); "
-                  "-O 16 indexes past its table", NDIR);
+   if (NDIR < 1 || NDIR > MGM_MAX_NDIR)
+      return fail(MGMB200_EUNSUPPORTED, "NDIR=%d: 1..8 sweeps of the reference (mgm_core.cc:463-471) or up to 16 with the "
+                  "sweeps 8-15 defined by this library (include/mgmb200.h)", NDIR);
    if (K < 1 || K > 4) return fail(MGMB200_EINVAL, "MGM/TSGM=%d not in 1..4", K);
    if (!(P1 >= 0.f) || !(P2 >= 0.f)) return fail(MGMB200_EUNSUPPORTED, "P1=%g P2=%g must be >= 0", P1, P2);
    if (!(P1 < INFINITY)) return fail(MGMB200_EUNSUPPORTED, "P1 must be finite");
    const int pot = felz > 0 ? POT_TRUNC : POT_SGM;
    if (pot == POT_SGM && !(P2 < INFINITY)) return fail(MGMB200_EUNSUPPORTED, "P2 must be finite with SGM potentials");
+   if (R.npairs < 1) return 0;
+   if (R.nslabs > 1 && (R.npairs != 1 || R.nslabs > MGM_MAX_SLABS || R.slab_rows < 2 || !R.slab_ptrs || R.fin ||
+                        (long long)R.slab_rows * R.nslabs < ny || ny > 65535))
+      return fail(MGMB200_EINVAL, "row slabs: one pair, at most %d slabs that cover the image, no fused finish", MGM_MAX_SLABS);
    const int VS = mgmb200_padded_labels(L);
    const size_t vol = (size_t)nx * ny * VS * sizeof(float);
+   const unsigned mask = R.mask & ((NDIR >= 32) ? ~0u : ((1u << NDIR) - 1u));
    c->n_launches = 0;
 
    bool weighted = false;
    if (weights_mode == 1) weighted = true;
-   if (weights_mode == 2 && d_w) {
+   if (weights_mode == 2 && R.w && R.w[0]) {
+      if (R.npairs != 1) return fail(MGMB200_EINVAL, "weights_mode 2 (scan) is a single-pair mode");
       RET(clear_flags(c));
-      CU(scan_weights_launch(d_w, (long long)nx * ny * 8, c->flags.as<int>(), c->stream));
+      CU(scan_weights_launch(R.w[0], (long long)nx * ny * 8, c->flags.as<int>(), c->stream));
       c->n_launches++;
       int fl = 0;
       RET(read_flags(c, &fl));
       weighted = fl & 1;
       if (fl & 2) return fail(MGMB200_EUNSUPPORTED, "edge weights must be finite and >= 0");
    }
-   if (weighted && !d_w) return fail(MGMB200_EINVAL, "weighted aggregation without weights");
+   if (weighted && !(R.w && R.w[0])) return fail(MGMB200_EINVAL, "weighted aggregation without weights");
    // windowed truncated-linear updates need the consumer-side (per-edge) kernels, with or without weights
    const bool window = c->r_window && pot == POT_TRUNC;
-   if (window) { if (!weighted) d_w = nullptr; weighted = true; }
+   bool use_w = weighted;
+   if (window) { weighted = true; }
 
-   for (int p = 0; p < NDIR; p++)
-      if (mask & (1u << p)) RET(c->sweep[p].reserve(vol));
+   if ((int)c->sweepv.size() < R.npairs * MGM_MAX_NDIR) c->sweepv.resize((size_t)R.npairs * MGM_MAX_NDIR);
+   if (R.nslabs == 1)
+      for (int b = 0; b < R.npairs; b++)
+         for (int p = 0; p < NDIR; p++)
+            if (mask & (1u << p)) RET(c->sweepv[sweep_slot(b, p)].reserve(vol));
    c->sweep_bytes = vol;
 
+   int nsw = 0;
+   for (int p = 0; p < NDIR; p++) nsw += (mask >> p) & 1;
    AggPlan plan;
    agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, c->rows_override, c->tune);
-   if (!c->rows_override && !c->tune.rows_axis && !c->tune.rows_diag && plan.T[0] > 40) {
+   if (!c->rows_override && !c->tune.rows_axis && !c->tune.rows_diag && plan.T[0] > 40 && R.npairs == 1 && nsw <= 2) {
       // One or two sweeps on this GPU (sweep-sharded layouts): with fewer bands than SMs the launch is bound by the
       // dependency depth alone, and bands of 40 workers step faster than bands of 56 (measured: one axis sweep of
-      // the headline shape 15.6 -> 13.9 ms, an axis + a diagonal sweep 15.9 -> 14.9 ms; small images with all
+      // the headline shape 15.7 -> 14.2 ms, an axis + a diagonal sweep 16.2 -> 15.3 ms; small images with all
       // eight sweeps do not gain)
       long bands = 0;
-      int nsweeps = 0;
-      for (int p = 0; p < NDIR; p++) nsweeps += (mask >> p) & 1;
-      for (int p = 0; p < NDIR && nsweeps <= 2; p++) {
+      for (int p = 0; p < NDIR; p++) {
          if (!(mask & (1u << p))) continue;
-         const PassGeom g = pass_geometry(p, nx, ny);
-         const int T = plan.T[p < 4 ? 0 : 1];
-         bands += (p >= 4 && plan.shear) ? (g.maxii + g.maxjj - 1 + T - 1) / T : (g.maxjj + T - 1) / T;
+         int nb = 0; size_t a = 0, bq = 0;
+         agg_sweep_bands(plan, p, nx, ny, &nb, &a, &bq);
+         bands += nb;
       }
-      if (nsweeps <= 2 && bands < c->num_sms) agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 40, c->tune);
+      if (bands < c->num_sms) agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 40, c->tune);
    }
-   if (plan.T[0] < 1 || plan.T[1] < 1)
+   if (plan.T[0] < 1 || plan.T[1] < 1 || plan.T[2] < 1)
       return fail(MGMB200_EUNSUPPORTED, "%d labels do not fit the shared-memory wavefront (max_smem=%d)", L, c->max_smem);
    c->rows_axis = plan.T[0]; c->rows_diag = plan.T[1]; c->block = plan.block; c->smem = plan.smem;
 
-   // bands per sweep; the kernel claims them dynamically, in order within a sweep (aggregate.cu claim_band)
-   int nb[8] = {0}, nbands = 0;
-   size_t bnd_off[8] = {0}, bndm_off[8] = {0}, prog_off[8] = {0};
+   // the sweep table; the kernel claims bands dynamically, in order within a sweep (aggregate.cu claim_band)
+   const int nsweeps = R.npairs * NDIR;
+   std::vector<SweepDesc> desc((size_t)nsweeps);
+   std::vector<size_t> bnd_off((size_t)nsweeps), bndm_off((size_t)nsweeps), prog_off((size_t)nsweeps);
    size_t bnd_total = 0, bndm_total = 0, prog_total = 0;
-   for (int p = 0; p < NDIR; p++) {
-      if (!(mask & (1u << p))) continue;
-      PassGeom g = pass_geometry(p, nx, ny);
-      const int T = plan.T[p < 4 ? 0 : 1];
-      if (p >= 4 && plan.shear) {
-         // sheared wavefront: bands of T anti-diagonals, two boundary lines of maxjj positions per band
-         nb[p] = (g.maxii + g.maxjj - 1 + T - 1) / T;
-         bnd_off[p] = bnd_total; bnd_total += (size_t)nb[p] * 2 * g.maxjj * VS;
-         bndm_off[p] = bndm_total; bndm_total += (size_t)nb[p] * 2 * g.maxjj;
-      } else {
-         nb[p] = (g.maxjj + T - 1) / T;
-         bnd_off[p] = bnd_total; bnd_total += (size_t)nb[p] * g.maxii * VS;
-         bndm_off[p] = bndm_total; bndm_total += (size_t)nb[p] * g.maxii;
+   int nbands = 0;
+   memset(desc.data(), 0, sizeof(SweepDesc) * desc.size());
+   for (int b = 0; b < R.npairs; b++)
+      for (int p = 0; p < NDIR; p++) {
+         SweepDesc &d = desc[(size_t)b * NDIR + p];
+         d.pass = p; d.pair = b;
+         d.cls = agg_sweep_class(plan, p);
+         d.filler = (d.cls == CLS_DIAG && plan.shear) ? 1 : 0;
+         if (!(mask & (1u << p))) continue;
+         size_t bf = 0, bmf = 0;
+         agg_sweep_bands(plan, p, nx, ny, &d.nb, &bf, &bmf);
+         const size_t v = (size_t)b * NDIR + p;
+         bnd_off[v] = bnd_total; bnd_total += bf;
+         bndm_off[v] = bndm_total; bndm_total += bmf;
+         prog_off[v] = prog_total; prog_total += d.nb;
+         nbands += d.nb;
       }
-      nbands += nb[p];
-      prog_off[p] = prog_total; prog_total += nb[p];
-   }
    if (nbands == 0) return 0;
 
-   // layout of the counters: [prog_total] progress, [16] claim counters (8 sweeps + the finish tiles), [prog_total] done flags
-   RET(c->progress.reserve((2 * prog_total + 16) * sizeof(int)));
+   // layout of the counters: [prog_total] progress | [nsweeps] claim counters | [4] finish-tile claim counter | [prog_total] done flags
+   const size_t ncount = 2 * prog_total + nsweeps + 4;
+   RET(c->progress.reserve(ncount * sizeof(int)));
    RET(c->bnd.reserve(bnd_total * sizeof(float)));
    RET(c->bndm.reserve(bndm_total * sizeof(float)));
-   CU(cudaMemsetAsync(c->progress.p, 0, (2 * prog_total + 16) * sizeof(int), c->stream));
+   CU(cudaMemsetAsync(c->progress.p, 0, ncount * sizeof(int), c->stream));
+   int *d_prog = c->progress.as<int>(), *d_next = d_prog + prog_total, *d_fin_next = d_next + nsweeps,
+       *d_done = d_fin_next + 4;
 
-   // fused finish: tiles of pixels in the order they are expected to become complete (the axis sweeps decide:
-   // band b of a sweep is done after about maxii + (b+1)*T steps)
+   for (int b = 0; b < R.npairs; b++)
+      for (int p = 0; p < NDIR; p++) {
+         const size_t v = (size_t)b * NDIR + p;
+         SweepDesc &d = desc[v];
+         d.cc = R.cc[b];
+         d.w = (use_w && R.w) ? R.w[b] : nullptr;
+         if (window) { d.win_lo = c->r_ccmin; d.win_hi = c->r_ccmax; }
+         if (R.nslabs > 1) { for (int r = 0; r < R.nslabs; r++) d.ldir[r] = R.slab_ptrs[(size_t)p * R.nslabs + r]; }
+         else d.ldir[0] = c->sweepv[sweep_slot(b, p)].as<float>();
+         d.bnd = c->bnd.as<float>() + bnd_off[v];
+         d.bndm = c->bndm.as<float>() + bndm_off[v];
+         d.progress = d_prog + prog_off[v];
+         d.band_done = d_done + prog_off[v];
+      }
+   RET(c->desc.reserve(sizeof(SweepDesc) * desc.size()));
+   CU(c->staging.push(c->desc.p, desc.data(), sizeof(SweepDesc) * desc.size(), c->stream));
+
+   // fused finish: tiles of pixels in the order they are expected to become complete (the row-per-worker sweeps
+   // decide: band b of such a sweep is done after about maxii + (b+1)*T steps), pairs interleaved
    const int tw = c->tune.fin_tw, th = c->tune.fin_th;
    const size_t rows_region = plan.smem - plan.off_thr;
-   const bool fuse = fin && !c->tune.no_fused_finish && (size_t)(plan.block / 32) * VS * 4 <= rows_region;
+   const bool fuse = R.fin && !c->tune.no_fused_finish && (size_t)(plan.block / 32) * VS * 4 <= rows_region;
    const int tiles_x = (nx + tw - 1) / tw, tiles_y = (ny + th - 1) / th, ntiles = tiles_x * tiles_y;
+   if (R.fin)
+      for (int b = 0; b < R.npairs; b++)
+         for (int p = 0; p < MGM_MAX_NDIR; p++) R.fin[b].ldir[p] = p < NDIR ? c->sweepv[sweep_slot(b, p)].as<float>() : nullptr;
    if (fuse) {
-      const int key[6] = {nx, ny, plan.T[0], tw, th, NDIR};
-      if (memcmp(key, c->tile_key, sizeof(key)) != 0 || (int)c->tile_order.size() != ntiles) {
-         std::vector<std::pair<long long, int>> when(ntiles);
+      const int key[8] = {nx, ny, plan.T[0], plan.T[2], tw, th, NDIR, R.npairs};
+      if (memcmp(key, c->tile_key, sizeof(key)) != 0 || (int)c->tile_order.size() != ntiles * R.npairs) {
+         std::vector<std::pair<long long, int>> when((size_t)ntiles);
          for (int t = 0; t < ntiles; t++) {
             const int x0 = (t % tiles_x) * tw, y0 = (t / tiles_x) * th;
             const int x1 = std::min(x0 + tw, nx) - 1, y1 = std::min(y0 + th, ny) - 1;
             long long ready = 0;
-            for (int p = 0; p < 4 && p < NDIR; p++) {
+            for (int p = 0; p < NDIR; p++) {
+               const int cls = agg_sweep_class(plan, p);
+               if (cls == CLS_DIAG && plan.shear) continue;
                const PassGeom g = pass_geometry(p, nx, ny);
-               const int rm = (0x53 >> p) & 1, incx = (0xC5 >> p) & 1, incy = (0x99 >> p) & 1;
+               const int q = p & 7;
+               const int rm = (0x53 >> q) & 1, incx = (0xC5 >> q) & 1, incy = (0x99 >> q) & 1;
                const int ax1 = incx ? x1 : nx - 1 - x0, ay1 = incy ? y1 : ny - 1 - y0;
                const int ys1 = rm ? ay1 : ax1;
-               ready = std::max(ready, (long long)g.maxii + (long long)(ys1 / plan.T[0] + 1) * plan.T[0]);
+               const int T = plan.T[cls], sig = (cls != CLS_AXIS || K == 4) ? 2 : 1;
+               ready = std::max(ready, (long long)g.maxii + (long long)(ys1 / T + 1) * T * sig);
             }
             when[t] = std::make_pair(ready, t);
          }
          std::stable_sort(when.begin(), when.end());
-         c->tile_order.resize(ntiles);
-         for (int t = 0; t < ntiles; t++) c->tile_order[t] = when[t].second;
+         c->tile_order.resize((size_t)ntiles * R.npairs);
+         for (int t = 0; t < ntiles; t++)
+            for (int b = 0; b < R.npairs; b++) c->tile_order[(size_t)t * R.npairs + b] = b * ntiles + when[t].second;
          memcpy(c->tile_key, key, sizeof(key));
-         RET(c->tiles.reserve((size_t)ntiles * sizeof(int)));
-         CU(cudaMemcpyAsync(c->tiles.p, c->tile_order.data(), (size_t)ntiles * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-         CU(cudaStreamSynchronize(c->stream));   // the host vector may be rebuilt by the next call
+         RET(c->tiles.reserve(c->tile_order.size() * sizeof(int)));
+         CU(c->staging.push(c->tiles.p, c->tile_order.data(), c->tile_order.size() * sizeof(int), c->stream));
       }
+      RET(c->fins.reserve(sizeof(WtaParams) * (size_t)R.npairs));
+      CU(c->staging.push(c->fins.p, R.fin, sizeof(WtaParams) * (size_t)R.npairs, c->stream));
    }
 
    AggParams P;
    memset(&P, 0, sizeof(P));
-   P.cc = d_cc; P.w = d_w;
-   if (window) { P.win_lo = c->r_ccmin; P.win_hi = c->r_ccmax; P.win_emin = c->r_emin; }
-   for (int p = 0; p < 8; p++) {
-      P.ldir[p] = c->sweep[p].as<float>();
-      P.bnd[p] = c->bnd.as<float>() + bnd_off[p];
-      P.bndm[p] = c->bndm.as<float>() + bndm_off[p];
-      P.progress[p] = c->progress.as<int>() + prog_off[p];
-   }
-   P.next_band = c->progress.as<int>() + prog_total;   // 8 per-sweep claim counters (zeroed above)
-   if (fuse) {
-      P.fin_enabled = 1;
-      P.fin_ntiles = ntiles; P.fin_tw = tw; P.fin_th = th; P.fin_tiles_x = tiles_x;
-      P.fin_order = c->tiles.as<int>();
-      P.fin_next = P.next_band + 8;
-      for (int p = 0; p < 8; p++) P.band_done[p] = c->progress.as<int>() + prog_total + 16 + prog_off[p];
-      P.fin = *fin;
-   }
-   for (int p = 0; p < 8; p++) P.nb[p] = nb[p];
+   P.sweeps = c->desc.as<SweepDesc>(); P.nsweeps = nsweeps;
+   P.next_band = d_next;
    P.nbands = nbands;
    P.static_order = c->tune.static_order;
-   P.nx = nx; P.ny = ny; P.L = L; P.VS = VS;
-   P.T[0] = plan.T[0]; P.T[1] = plan.T[1];
-   P.TS[0] = plan.TS[0]; P.TS[1] = plan.TS[1];
-   P.ncb = plan.ncb; P.shear = plan.shear; P.ng[0] = plan.ng[0]; P.ng[1] = plan.ng[1]; P.fused_sgm = plan.fused_sgm;
-   P.cc_pf = c->tune.cc_pf;
+   P.win_emin = c->r_emin;
+   P.nx = nx; P.ny = ny; P.L = L; P.VS = VS; P.ndir = NDIR;
+   P.nslabs = R.nslabs; P.slab_rows = R.slab_rows;
+   P.slab_magic = R.nslabs > 1 ? (unsigned)((0x100000000ull + (unsigned)R.slab_rows - 1) / (unsigned)R.slab_rows) : 0u;
+   for (int i = 0; i < 3; i++) { P.T[i] = plan.T[i]; P.TS[i] = plan.TS[i]; P.ng[i] = plan.ng[i]; }
+   P.ncb = plan.ncb; P.shear = plan.shear; P.fused_sgm = plan.fused_sgm;
+   // measured (profiles/r02_experiments.md): 1920x1080x128 TSGM=2 8.37 -> 6.96 ms, 4096x4096x64 25.8 -> 22.8 ms
+   P.cc_pf = c->tune.cc_pf >= 0 ? c->tune.cc_pf : (pot == POT_SGM ? 3 : 0);
    P.P1 = P1; P.P2 = P2;
-   P.dbg = nullptr;
+   if (fuse) {
+      P.fin_enabled = 1;
+      P.fin_ntiles = ntiles; P.fin_total = ntiles * R.npairs; P.fin_tw = tw; P.fin_th = th; P.fin_tiles_x = tiles_x;
+      P.fin_order = c->tiles.as<int>();
+      P.fin_next = d_fin_next;
+      P.fins = c->fins.as<WtaParams>(); P.npairs = R.npairs;
+   }
    P.off_phase = (unsigned)plan.off_phase; P.off_cbar = (unsigned)plan.off_cbar; P.off_vbar = (unsigned)plan.off_vbar;
    P.off_ms = (unsigned)plan.off_ms; P.off_vms = (unsigned)plan.off_vms; P.off_virt = (unsigned)plan.off_virt;
    P.off_thr = (unsigned)plan.off_thr;
@@ -504,6 +594,15 @@ static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int w
    c->n_launches++;
    c->fin_done = fuse;
    return 0;
+}
+
+// single pair (the reference's mgm() shape)
+static int run_sweeps(mgmb200_ctx *c, const float *d_cc, const float *d_w, int weights_mode, int nx, int ny,
+                      int L, float P1, float P2, int NDIR, int K, int felz, unsigned mask, WtaParams *fin = nullptr) {
+   SweepRun R;
+   const float *ccs[1] = {d_cc}, *ws[1] = {d_w};
+   R.cc = ccs; R.w = ws; R.fin = fin; R.mask = mask;
+   return run_sweeps_multi(c, R, weights_mode, nx, ny, L, P1, P2, NDIR, K, felz);
 }
 
 static WtaParams finish_params(mgmb200_ctx *c, const float *const *d_sweeps, const float *d_cc, int nx, int dmin, int L,
@@ -535,14 +634,92 @@ extern "C" int mgmb200_aggregate_sweeps_dev(mgmb200_ctx *c, const float *d_cc, c
    if (!c || !d_cc) return fail(MGMB200_EINVAL, "NULL argument");
    RET(check_dims(nx, ny, dmin, dmax));
    CU(cudaSetDevice(c->device));
-   if (NDIR >= 1 && NDIR <= 8) sweep_mask &= (1u << NDIR) - 1u;
    return run_sweeps(c, d_cc, d_w, weights_mode, nx, ny, dmax - dmin + 1, P1, P2, NDIR, K, felz, sweep_mask);
 }
 
 extern "C" int mgmb200_sweep_volume(mgmb200_ctx *c, int sweep, float **d_ptr, size_t *bytes) {
-   if (!c || sweep < 0 || sweep > 7 || !d_ptr) return fail(MGMB200_EINVAL, "bad argument");
-   *d_ptr = c->sweep[sweep].as<float>();
-   if (bytes) *bytes = c->sweep[sweep].p ? c->sweep_bytes : 0;
+   if (!c || sweep < 0 || sweep >= MGM_MAX_NDIR || !d_ptr) return fail(MGMB200_EINVAL, "bad argument");
+   if ((int)c->sweepv.size() < MGM_MAX_NDIR) c->sweepv.resize(MGM_MAX_NDIR);
+   *d_ptr = c->sweepv[sweep].as<float>();
+   if (bytes) *bytes = c->sweepv[sweep].p ? c->sweepv[sweep].cap : 0;
+   return 0;
+}
+
+// Sweep-sharded multi-GPU layout.  Every rank allocates all NDIR message volumes and exports them
+// (mgmb200_ipc_export marks them: they are never reallocated while exported); the rank that aggregates sweep p
+// stores the messages of image rows [r*slab_rows, (r+1)*slab_rows) straight into rank r's volume p -- peer stores
+// over NVLink issued by the aggregation kernel itself, overlapped with the sweep -- so that after one barrier every
+// rank finds all sweeps of its own slab in LOCAL memory and finishes it in sweep order (mgmb200_finish_rows_dev).
+extern "C" int mgmb200_sweeps_alloc(mgmb200_ctx *c, int nx, int ny, int dmin, int dmax, int NDIR) {
+   if (!c) return fail(MGMB200_EINVAL, "ctx is NULL");
+   RET(check_dims(nx, ny, dmin, dmax));
+   if (NDIR < 1 || NDIR > MGM_MAX_NDIR) return fail(MGMB200_EINVAL, "NDIR=%d", NDIR);
+   CU(cudaSetDevice(c->device));
+   if ((int)c->sweepv.size() < MGM_MAX_NDIR) c->sweepv.resize(MGM_MAX_NDIR);
+   const size_t vol = mgmb200_volume_bytes(nx, ny, dmax - dmin + 1);
+   for (int p = 0; p < NDIR; p++) RET(c->sweepv[p].reserve(vol));
+   c->sweep_bytes = vol;
+   return 0;
+}
+extern "C" int mgmb200_sweeps_release(mgmb200_ctx *c) {
+   if (!c) return fail(MGMB200_EINVAL, "ctx is NULL");
+   CU(cudaSetDevice(c->device));
+   CU(cudaStreamSynchronize(c->stream));
+   for (DevBuf &b : c->sweepv) { b.exported = false; b.release(); }
+   return 0;
+}
+extern "C" int mgmb200_aggregate_sweeps_slabs_dev(mgmb200_ctx *c, const float *d_cc, const float *d_w, int weights_mode,
+                                                  int nx, int ny, int dmin, int dmax, float P1, float P2, int NDIR, int K,
+                                                  int felz, unsigned sweep_mask, int nslabs, int slab_rows,
+                                                  float *const *d_slab_volumes) {
+   if (!c || !d_cc || !d_slab_volumes) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, dmin, dmax));
+   CU(cudaSetDevice(c->device));
+   SweepRun R;
+   const float *ccs[1] = {d_cc}, *ws[1] = {d_w};
+   R.cc = ccs; R.w = ws; R.mask = sweep_mask;
+   R.nslabs = nslabs; R.slab_rows = slab_rows; R.slab_ptrs = d_slab_volumes;
+   if (nslabs == 1) {   // degenerate: one slab = the plain layout with caller-provided volumes is not needed; use own volumes
+      R.slab_ptrs = nullptr; R.slab_rows = 0;
+   }
+   return run_sweeps_multi(c, R, weights_mode, nx, ny, dmax - dmin + 1, P1, P2, NDIR, K, felz);
+}
+
+// The exchange north_star names: every rank adds ITS sweeps (in increasing sweep order) into one partial
+// volume, the partial volumes are summed by an NCCL all-reduce (the caller's collective), and mgmb200_finish_sum_dev
+// applies the over-count fix for all NDIR sweeps, WTA and refinement.  The floating-point summation order differs
+// from the reference's (mgm_core.cc:582-587), so the bits may: bench.py counts the differences.
+extern "C" int mgmb200_sum_sweeps_dev(mgmb200_ctx *c, int nx, int ny, int dmin, int dmax, unsigned sweep_mask,
+                                      float *d_sum) {
+   if (!c || !d_sum) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, dmin, dmax));
+   CU(cudaSetDevice(c->device));
+   const float *src[MGM_MAX_NDIR];
+   int n = 0;
+   for (int p = 0; p < MGM_MAX_NDIR; p++)
+      if (sweep_mask & (1u << p)) {
+         if (p >= (int)c->sweepv.size() || !c->sweepv[p].p) return fail(MGMB200_EINVAL, "sweep %d has not been aggregated", p);
+         src[n++] = c->sweepv[p].as<float>();
+      }
+   CU(sum_volumes_launch(src, n, d_sum, (long long)nx * ny * mgmb200_padded_labels(dmax - dmin + 1), c->num_sms, c->stream));
+   c->n_launches++;
+   return 0;
+}
+extern "C" int mgmb200_finish_sum_dev(mgmb200_ctx *c, const float *d_sum, const float *d_cc, int nx, int ny, int dmin,
+                                      int dmax, int NDIR, int fix, int refine, int row_begin, int row_end, float *d_out,
+                                      float *d_outcost) {
+   if (!c || !d_sum || !d_cc || !d_out || !d_outcost) return fail(MGMB200_EINVAL, "NULL argument");
+   RET(check_dims(nx, ny, dmin, dmax));
+   if (NDIR < 1 || NDIR > MGM_MAX_NDIR) return fail(MGMB200_EUNSUPPORTED, "NDIR=%d", NDIR);
+   if (row_begin < 0 || row_end > ny || row_begin > row_end) return fail(MGMB200_EINVAL, "rows [%d,%d)", row_begin, row_end);
+   if (refine < 0 || refine > 4) return fail(MGMB200_EINVAL, "refinement index %d", refine);
+   CU(cudaSetDevice(c->device));
+   if (row_begin == row_end) return 0;
+   const float *one[1] = {d_sum};
+   WtaParams W = finish_params(c, one, d_cc, nx, dmin, dmax - dmin + 1, 1, fix, refine, row_begin, row_end, d_out, d_outcost, nullptr);
+   W.fix_count = NDIR;   // S - (NDIR-1)*C although a single (pre-summed) volume is read
+   CU(wta_launch(W, c->num_sms, c->stream));
+   c->n_launches++;
    return 0;
 }
 
@@ -551,7 +728,7 @@ extern "C" int mgmb200_finish_rows_dev(mgmb200_ctx *c, const float *const *d_swe
                                        int row_end, float *d_out, float *d_outcost) {
    if (!c || !d_sweeps || !d_cc || !d_out || !d_outcost) return fail(MGMB200_EINVAL, "NULL argument");
    RET(check_dims(nx, ny, dmin, dmax));
-   if (NDIR < 1 || NDIR > 8) return fail(MGMB200_EUNSUPPORTED, "NDIR=%d", NDIR);
+   if (NDIR < 1 || NDIR > MGM_MAX_NDIR) return fail(MGMB200_EUNSUPPORTED, "NDIR=%d", NDIR);
    if (row_begin < 0 || row_end > ny || row_begin > row_end) return fail(MGMB200_EINVAL, "rows [%d,%d)", row_begin, row_end);
    if (refine < 0 || refine > 4) return fail(MGMB200_EINVAL, "refinement index %d", refine);
    CU(cudaSetDevice(c->device));
@@ -568,17 +745,50 @@ extern "C" int mgmb200_aggregate_dev(mgmb200_ctx *c, const float *d_cc, const fl
    if (refine < 0 || refine > 4) return fail(MGMB200_EINVAL, "refinement index %d", refine);
    CU(cudaSetDevice(c->device));
    const int L = dmax - dmin + 1;
-   unsigned mask = (NDIR >= 1 && NDIR <= 8) ? ((1u << NDIR) - 1u) : 0u;
-   if (NDIR < 1 || NDIR > 8) return run_sweeps(c, d_cc, d_w, weights_mode, nx, ny, L, P1, P2, NDIR, K, felz, mask);   // fails with the message
-   // the sweep volumes must exist before their addresses go into the finish parameters
-   const size_t vol = (size_t)nx * ny * mgmb200_padded_labels(L) * sizeof(float);
-   for (int p = 0; p < NDIR; p++) RET(c->sweep[p].reserve(vol));
-   const float *sw[8];
-   for (int p = 0; p < 8; p++) sw[p] = c->sweep[p].as<float>();
-   const WtaParams W = finish_params(c, sw, d_cc, nx, dmin, L, NDIR, fix, refine, 0, ny, d_out, d_outcost, d_S);
-   RET(run_sweeps(c, d_cc, d_w, weights_mode, nx, ny, L, P1, P2, NDIR, K, felz, mask, &W));
+   const unsigned mask = (NDIR >= 1 && NDIR <= MGM_MAX_NDIR) ? ((NDIR == 32 ? 0u : (1u << NDIR)) - 1u) : 0u;
+   if (NDIR < 1 || NDIR > MGM_MAX_NDIR) return run_sweeps(c, d_cc, d_w, weights_mode, nx, ny, L, P1, P2, NDIR, K, felz, mask);   // fails with the message
+   const float *none[MGM_MAX_NDIR] = {nullptr};
+   WtaParams W = finish_params(c, none, d_cc, nx, dmin, L, NDIR, fix, refine, 0, ny, d_out, d_outcost, d_S);
+   RET(run_sweeps(c, d_cc, d_w, weights_mode, nx, ny, L, P1, P2, NDIR, K, felz, mask, &W));   // fills W.ldir
    if (c->fin_done) return 0;   // finished tile by tile inside the aggregation launch
-   return finish_rows(c, sw, d_cc, nx, ny, dmin, L, NDIR, fix, refine, 0, ny, d_out, d_outcost, d_S);
+   CU(wta_launch(W, c->num_sms, c->stream));
+   c->n_launches++;
+   return 0;
+}
+
+// A batch of stereo pairs of one shape (BASELINE.json configs[3]: 32 KITTI-shape pairs): the sweeps of up to
+// `batch` (mgmb200_set_option, default 8) pairs share one launch, so that the machine stays full although one small
+// pair alone is bound by the dependency depth of its sweeps.  Results are those of npairs mgmb200_aggregate_dev calls.
+extern "C" int mgmb200_aggregate_batch_dev(mgmb200_ctx *c, int npairs, const float *const *d_cc, const float *const *d_w,
+                                           int nx, int ny, int dmin, int dmax, float P1, float P2, int NDIR, int K,
+                                           int felz, int fix, int refine, float *const *d_out, float *const *d_outcost) {
+   if (!c || !d_cc || !d_out || !d_outcost || npairs < 0) return fail(MGMB200_EINVAL, "bad argument");
+   RET(check_dims(nx, ny, dmin, dmax));
+   if (refine < 0 || refine > 4) return fail(MGMB200_EINVAL, "refinement index %d", refine);
+   if (NDIR < 1 || NDIR > MGM_MAX_NDIR) return fail(MGMB200_EUNSUPPORTED, "NDIR=%d", NDIR);
+   if (c->r_smin || c->r_ccmin) return fail(MGMB200_EINVAL, "per-pixel ranges are a single-pair mode");
+   CU(cudaSetDevice(c->device));
+   const int L = dmax - dmin + 1;
+   const unsigned mask = (1u << NDIR) - 1u;
+   const int chunk = std::max(1, c->tune.batch);
+   int launches = 0;
+   for (int b0 = 0; b0 < npairs; b0 += chunk) {
+      const int nb = std::min(chunk, npairs - b0);
+      std::vector<WtaParams> W((size_t)nb);
+      const float *none[MGM_MAX_NDIR] = {nullptr};
+      for (int b = 0; b < nb; b++) {
+         if (!d_cc[b0 + b] || !d_out[b0 + b] || !d_outcost[b0 + b]) return fail(MGMB200_EINVAL, "NULL pointer for pair %d", b0 + b);
+         W[b] = finish_params(c, none, d_cc[b0 + b], nx, dmin, L, NDIR, fix, refine, 0, ny, d_out[b0 + b], d_outcost[b0 + b], nullptr);
+      }
+      SweepRun R;
+      R.npairs = nb; R.cc = d_cc + b0; R.w = d_w ? d_w + b0 : nullptr; R.fin = W.data(); R.mask = mask;
+      RET(run_sweeps_multi(c, R, d_w ? 1 : 0, nx, ny, L, P1, P2, NDIR, K, felz));
+      launches += c->n_launches;
+      if (!c->fin_done)
+         for (int b = 0; b < nb; b++) { CU(wta_launch(W[b], c->num_sms, c->stream)); launches++; }
+   }
+   c->n_launches = launches;
+   return 0;
 }
 
 // ------------------------------------------------------------------------------------------ IPC (multi-GPU)
@@ -587,6 +797,7 @@ extern "C" int mgmb200_ipc_export(mgmb200_ctx *c, const void *d_ptr, unsigned ch
    CU(cudaSetDevice(c->device));
    cudaIpcMemHandle_t h;
    CU(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+   for (DevBuf &b : c->sweepv) if (b.p == d_ptr) b.exported = true;
    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
    memcpy(handle_out, &h, 64);
    return 0;

@@ -131,13 +131,16 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 // Scan space: xs in [0,maxii) fast, ys in [0,maxjj) slow.  Image pixel of (xs,ys):
 //   p0 (xs,ys)  p1 (W-1-xs,H-1-ys)  p2 (ys,H-1-xs)  p3 (W-1-ys,xs)
 //   p4 (W-1-xs,ys)  p5 (W-1-ys,H-1-xs)  p6 (xs,H-1-ys)  p7 (ys,xs)
+// Sweeps 8-15 (-O 16) scan like sweeps 0-7 and differ in the ORDER of the predecessors only (knight_pred_type).
 struct PassGeom {
    int maxii, maxjj;
    long long base0;   // pixel index of (xs=0, ys=0)
    long long dxs;     // pixel index increment per xs
    long long dys;     // pixel index increment per ys
+   int y0, ydxs, ydys;   // image row of (xs,ys) = y0 + xs*ydxs + ys*ydys
 };
 __host__ __device__ inline PassGeom pass_geometry(int pass, int nx, int ny) {
+   pass &= 7;
    // row_major / inc_x / inc_y per sweep, restated from the reference table
    const int rm = (0x53 >> pass) & 1;     // passes 0,1,4,6 scan image rows
    const int incx = (0xC5 >> pass) & 1;   // passes 0,2,6,7 ascend in x
@@ -148,15 +151,58 @@ __host__ __device__ inline PassGeom pass_geometry(int pass, int nx, int ny) {
    long long x0 = incx ? 0 : nx - 1, y0 = incy ? 0 : ny - 1;
    long long sx = incx ? 1 : -1, sy = incy ? 1 : -1;
    g.base0 = x0 + y0 * nx;
-   if (rm) { g.dxs = sx; g.dys = sy * nx; }
-   else    { g.dxs = sy * nx; g.dys = sx; }
+   g.y0 = (int)y0;
+   if (rm) { g.dxs = sx; g.dys = sy * nx; g.ydxs = 0; g.ydys = (int)sy; }
+   else    { g.dxs = sy * nx; g.dys = sx; g.ydxs = (int)sy; g.ydys = 0; }
    return g;
 }
 
-// weight plane of neighbour k (0..3) for each sweep, read AT the pixel (mgm_core.cc:481-484,550-554)
+// Scan-space predecessors {(-1,0),(0,-1),(-1,-1),(+1,-1)} of every sweep
+enum PredType { PRED_SAME = 0, PRED_UP = 1, PRED_UPL = 2, PRED_UPR = 3 };
+
+// Sweeps 8-15 (NDIR = 16).  The reference advertises -O 16 (mgm.cc:223) but its table ends after the eight sweeps
+// above with the stub comment "// 22.5 deg" (mgm_core.cc:472-473), and Pass_setup carries the note "use dir1 if y odd
+// dir2 otherwise" (mgm_core.cc:386): running it reads past the table (undefined).  DEFINED HERE:
+// sweep 8+b scans exactly like sweep b and visits the same four predecessors, but takes them in an order that
+// depends on the parity of the scan coordinates, so that the k-th neighbour chains follow the eight knight-move
+// (22.5 degree) directions -- the first neighbour alternates between the axis direction and the adjacent diagonal:
+//   base sweeps 0-3:  k0 = xs odd ? (-1,-1) : (-1,0)    net (-2,-1) per two pixels
+//                     k1 = ys odd ? (+1,-1) : (0,-1)    net (+1,-2), perpendicular to k0
+//                     k2, k3 = the other member of {(-1,0),(-1,-1)} resp. {(0,-1),(+1,-1)}
+//   base sweeps 4-7:  k0 = ys odd ? (0,-1) : (+1,-1)    net (+1,-2)
+//                     k1 = xs odd ? (-1,0) : (-1,-1)    net (-2,-1)
+//                     k2, k3 = the other member of {(+1,-1),(0,-1)} resp. {(-1,-1),(-1,0)}
+// In image space the first-neighbour chains of sweeps 8..15 run along (-2,-1) (2,1) (-1,2) (1,-2) (-1,-2) (2,-1)
+// (1,2) (-2,1).  Border rule, weights (the plane of the neighbour's offset, read at the pixel) and everything else
+// are as for sweeps 0-7.  oracle/mgm_oracle.c restates the same definition; parity against the reference is
+// necessarily unpinned for these sweeps.
+__host__ __device__ inline int knight_pred_type(bool diag_base, int k, int xs, int ys) {
+   const int xo = xs & 1, yo = ys & 1;
+   if (!diag_base) {
+      switch (k) {
+      case 0: return xo ? PRED_UPL : PRED_SAME;
+      case 1: return yo ? PRED_UPR : PRED_UP;
+      case 2: return xo ? PRED_SAME : PRED_UPL;
+      default: return yo ? PRED_UP : PRED_UPR;
+      }
+   }
+   switch (k) {
+   case 0: return yo ? PRED_UP : PRED_UPR;
+   case 1: return xo ? PRED_SAME : PRED_UPL;
+   case 2: return yo ? PRED_UPR : PRED_UP;
+   default: return xo ? PRED_UPL : PRED_SAME;
+   }
+}
+
+// weight plane of neighbour k (0..3) for each sweep 0-7, read AT the pixel (mgm_core.cc:481-484,550-554)
 __host__ __device__ inline int pass_weight_plane(int pass, int k) {
    const unsigned tab[4] = {0x76543210u, 0x47651023u, 0x02135764u, 0x30216475u};
    return (tab[k] >> (4 * pass)) & 0xF;
+}
+// weight plane of the predecessor of scan-space type `pt` for base sweep 0-7: sweeps 0-3 list their neighbours in the
+// order SAME, UP, UPL, UPR (k = pt), sweeps 4-7 in the order UPR, UPL, UP, SAME (k = 3 - pt)
+__host__ __device__ inline int pass_weight_plane_of_type(int base_pass, int pt) {
+   return pass_weight_plane(base_pass, base_pass < 4 ? pt : 3 - pt);
 }
 
 }  // namespace mgm

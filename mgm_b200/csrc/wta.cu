@@ -54,6 +54,25 @@ cudaError_t refine_launch(const float *d_S, long long npix, int L, int dmin, int
    return cudaGetLastError();
 }
 
+struct SumSrc { const float *p[16]; };
+__global__ void __launch_bounds__(256) mgm_sum_volumes_kernel(const SumSrc S, int n, float4 *__restrict__ out, long long n4) {
+   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < n; ++k) {
+         const float4 l = __ldcs(reinterpret_cast<const float4 *>(S.p[k]) + i);
+         s.x += l.x; s.y += l.y; s.z += l.z; s.w += l.w;
+      }
+      out[i] = s;
+   }
+}
+cudaError_t sum_volumes_launch(const float *const *src, int n, float *out, long long nelem, int num_sms, cudaStream_t st) {
+   if (n < 0 || n > 16 || (nelem & 3)) return cudaErrorInvalidValue;
+   SumSrc S;
+   for (int k = 0; k < 16; ++k) S.p[k] = k < n ? src[k] : nullptr;
+   mgm_sum_volumes_kernel<<<num_sms * 8, 256, 0, st>>>(S, n, reinterpret_cast<float4 *>(out), nelem / 4);
+   return cudaGetLastError();
+}
+
 cudaError_t wta_launch(const WtaParams &P, int num_sms, cudaStream_t st) {
    const int block = 256;
    const size_t smem = (size_t)(block / 32) * P.VS * sizeof(float);

@@ -16,10 +16,13 @@ struct WtaParams {
    long long pix_begin, pix_end;
    int ndir, L, VS, dmin;
    int fix;                 // SGM_FIX_OVERCOUNT
+   int fix_count;           // sweeps the over-count fix refers to; 0 = ndir (differs when ldir[0] is a pre-summed volume)
    int refine;              // 0 none, 1 vfit, 2 parabola, 3 cubic, 4 parabolaOCV (mgm_refine.h:14-27)
 };
 
 cudaError_t wta_launch(const WtaParams &P, int num_sms, cudaStream_t st);
+// out = ((0 + src[0]) + src[1]) + ...  element-wise over n volumes (partial sums of the all-reduce exchange)
+cudaError_t sum_volumes_launch(const float *const *src, int n, float *out, long long nelem, int num_sms, cudaStream_t st);
 cudaError_t refine_launch(const float *d_S, long long npix, int L, int dmin, int method, const float *d_smin,
                           const float *d_smax, float *d_out, float *d_outcost, cudaStream_t st);
 

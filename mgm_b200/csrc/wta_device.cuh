@@ -81,7 +81,7 @@ __device__ __forceinline__ float4 ld_stream(const float4 *p) {
 template <bool COHERENT>
 __device__ __forceinline__ void wta_pixel(const WtaParams &P, const long long pix, float *sS, const int lane) {
    const int nq = P.VS >> 2;
-   const float fixmul = (float)(P.ndir - 1);
+   const float fixmul = (float)((P.fix_count ? P.fix_count : P.ndir) - 1);
    {
       float best = MGM_INF;
       int besto = -1;

@@ -5,8 +5,9 @@
 // GPU.  The default flow is one mgmb200_stereo_lr call: the images go up once and the maps come back once.
 // -m/-M range images and TSGM_ITER > 1 take mgmb200_stereo_ranges per direction (mgm.cc:372-395 on the device: cost
 // volume once, then mgm + refinement + range update per iteration); MGMB200_STEPWISE=1 runs the same sequence call
-// by call through the mirror functions of mgmb200_host.hpp (volumes cross the host between the calls).  Not supported
-// (exit code 2 or 3 with a message, never a silent fallback): -O 16, MEDIAN > 7.
+// by call through the mirror functions of mgmb200_host.hpp (volumes cross the host between the calls).  -O 9..16 run the
+// sweeps 8-15 DEFINED by this build (include/mgmb200.h; the reference reads past its 8-entry table there).  Not
+// supported (exit code 2 or 3 with a message, never a silent fallback): -O > 16, MEDIAN > 7.
 #include <algorithm>
 #include <cmath>
 
@@ -14,7 +15,10 @@
 
 using namespace mgmb200;
 
-// pick_option (mgm.cc:165-179): "-name value" anywhere on the line, removed in place; with d == NULL a flag
+// The command-line SURFACE is kept verbatim from the reference, as north_star asks: pick_option below is taken from
+// mgm.cc:165-179 ("-name value" anywhere on the line, removed in place; with d == NULL a flag) and the option block in
+// main from mgm.cc:303-325 -- same names, defaults and order, because the order of extraction is observable (an
+// option value that looks like an option name).  About 40 lines of glue; everything behind them is this build's.
 static char *pick_option(int *c, char ***v, const char *o, const char *d) {
    int argc = *c;
    char **argv = *v;
@@ -63,6 +67,7 @@ int main(int argc, char *argv[]) {
       return 1;
    }
    try {
+      // option extraction: names, defaults and order of mgm.cc:303-318
       char *in_min_disp_file = pick_option(&argc, &argv, "m", "");
       char *in_max_disp_file = pick_option(&argc, &argv, "M", "");
       int dmin = atoi(pick_option(&argc, &argv, "r", "-30"));

@@ -197,6 +197,114 @@ def test_sweep_sharding_api_single_gpu(ctx):
     assert same(dout.cpu().numpy(), ro) and same(dcost.cpu().numpy(), rc)
 
 
+def test_sweep_slab_stores_single_gpu(ctx):
+    """The ordered multi-GPU exchange on one device: the aggregation kernel stores the messages of the lower row slab
+    into a second set of volumes (what a peer mapping would be), every slab is finished from "its" volumes in sweep
+    order -> identical to the one-call path, for row-major and column-major sweeps, sheared and knight sweeps."""
+    import torch
+    for (nx, ny, L, NDIR, K, felz, P1, P2, nslabs) in [(83, 47, 24, 8, 3, 1, 2.0, 20000.0, 2), (61, 90, 40, 16, 2, 0, 8.0, 32.0, 3),
+                                                       (50, 33, 12, 8, 4, 0, 8.0, 32.0, 2)]:
+        cc = synth_volume(nx, ny, L, seed=nx, real=True)
+        VS = ctx.padded_labels(L)
+        dense = torch.from_numpy(cc).cuda()
+        dcc = torch.empty((ny, nx, VS), device="cuda")
+        dout = torch.full((ny, nx), -777.0, device="cuda")
+        dcost = torch.empty((ny, nx), device="cuda")
+        ctx.pad_volume_dev(dense.data_ptr(), dcc.data_ptr(), nx, ny, L)
+        ctx.sweeps_alloc(nx, ny, -(L - 1), 0, NDIR)
+        rps = max(2, -(-ny // nslabs))
+        own = [ctx.sweep_volume(p)[0] for p in range(NDIR)]
+        other = [[torch.full((ny, nx, VS), float("nan"), device="cuda") for p in range(NDIR)] for r in range(nslabs - 1)]
+        table = [[own[p]] + [other[r][p].data_ptr() for r in range(nslabs - 1)] for p in range(NDIR)]
+        for rows in (0, 7):
+            ctx.set_rows_per_band(rows)
+            for mask in ((0x5555, 0xAAAA) if rows else (0xFFFF,)):
+                ctx.aggregate_sweeps_slabs_dev(dcc.data_ptr(), 0, 0, nx, ny, -(L - 1), 0, P1, P2, NDIR, K, felz, mask, nslabs,
+                                               rps, table)
+            for r in range(nslabs):
+                r0, r1 = min(ny, r * rps), min(ny, (r + 1) * rps)
+                ctx.finish_rows_dev([table[p][r] for p in range(NDIR)], dcc.data_ptr(), nx, ny, -(L - 1), 0, NDIR, 1, "vfit",
+                                    r0, r1, dout.data_ptr(), dcost.data_ptr())
+            ctx.synchronize()
+            o = O.orc_mgm(cc, None, -(L - 1), P1, P2, NDIR, K, felz, 1)
+            ro, rc = O.orc_refine(o["S"], -(L - 1), o["out"], o["outcost"], "vfit")
+            assert same(dout.cpu().numpy(), ro) and same(dcost.cpu().numpy(), rc), (nx, ny, L, NDIR, K, felz, rows)
+        ctx.set_rows_per_band(0)
+        # the all-reduce exchange on one device: partial sums of two "ranks", added, finished from the sum
+        part = [torch.empty((ny, nx, VS), device="cuda") for _ in range(2)]
+        ctx.aggregate_sweeps_dev(dcc.data_ptr(), 0, 0, nx, ny, -(L - 1), 0, P1, P2, NDIR, K, felz, (1 << NDIR) - 1)
+        for i, mask in enumerate((0x5555, 0xAAAA)):
+            ctx.sum_sweeps_dev(nx, ny, -(L - 1), 0, mask & ((1 << NDIR) - 1), part[i].data_ptr())
+        tot = part[0] + part[1]
+        ctx.finish_sum_dev(tot.data_ptr(), dcc.data_ptr(), nx, ny, -(L - 1), 0, NDIR, 1, "none", 0, ny, dout.data_ptr(),
+                           dcost.data_ptr())
+        ctx.synchronize()
+        # another summation order: equal up to rounding (labels may flip at near-ties; costs within 1e-5 relative)
+        o = O.orc_mgm(cc, None, -(L - 1), P1, P2, NDIR, K, felz, 1)
+        fin = np.isfinite(o["outcost"])
+        assert np.allclose(dcost.cpu().numpy()[fin], o["outcost"][fin], rtol=1e-5)
+        assert np.mean(dout.cpu().numpy() != o["out"]) < 0.02
+        ctx.sweeps_release()
+
+
+@pytest.mark.parametrize("felz", [0, 1])
+@pytest.mark.parametrize("weighted", [0, 1])
+def test_mgm_16_sweeps(ctx, felz, weighted):
+    """-O 16: sweeps 8-15 as defined by this build (knight-move neighbour chains; the reference is
+    undefined there) against the oracle port's restatement of the same definition: every update variant, chained bands."""
+    for K in [1, 2, 3, 4]:
+        for (nx, ny, L) in [(41, 29, 12), (30, 52, 35)]:
+            cc = synth_volume(nx, ny, L, seed=K + nx, real=True)
+            w = synth_weights(nx, ny, seed=K) if weighted else None
+            P1, P2 = ((8, 32) if K % 2 else (3.5, 21.25)) if not felz else ((2, 20000) if K != 4 else (1.5, 11))
+            for rows in (0, 5):
+                ctx.set_rows_per_band(rows)
+                for NDIR in (16, 11):
+                    r = ctx.mgm(cc, w, -(L - 1), P1, P2, NDIR, K, felz, 1)
+                    o = O.orc_mgm(cc, w, -(L - 1), P1, P2, NDIR, K, felz, 1)
+                    assert same(r["out"], o["out"]) and same(r["S"], o["S"]) and same(r["outcost"], o["outcost"]), \
+                        (K, felz, weighted, nx, ny, L, rows, NDIR, mism(r["S"], o["S"]))
+    ctx.set_rows_per_band(0)
+    # the whole path with 16 sweeps
+    u, v = synth_pair(97, 61, 20, seed=5)
+    kw = dict(P1=8.0, P2=32.0, NDIR=16, distance="ncc", refinement="parabola")
+    out, cost = ctx.stereo(u, v, dmin=-19, dmax=0, MGM=4 - felz, use_felzenszwalb_potentials=felz, census_ncc_win=3,
+                           aP=4.0 if weighted else 1.0, aThresh=12.0, **kw)
+    ref = O.orc_pipeline(u, v, -19, 0, K=4 - felz, felz=felz, win=3, aP=4.0 if weighted else 1.0, aThresh=12.0, **kw)
+    assert same(out, ref["out"]) and same(cost, ref["outcost"])
+
+
+def test_aggregate_batch(ctx):
+    """mgmb200_aggregate_batch_dev: several pairs per launch (more pairs than the in-flight limit, so several launches)
+    give the bits of one mgmb200_aggregate_dev call per pair."""
+    import torch
+    nx, ny, L, npairs = 70, 45, 24, 5
+    VS = ctx.padded_labels(L)
+    ctx.set_option("batch", 2)
+    try:
+        for (K, felz, P1, P2, NDIR) in [(4, 0, 8.0, 32.0, 8), (3, 1, 2.0, 20000.0, 8), (2, 0, 8.0, 32.0, 16)]:
+            ccs = [synth_volume(nx, ny, L, seed=100 + b, real=True) for b in range(npairs)]
+            dccs = []
+            for cc in ccs:
+                d = torch.empty((ny, nx, VS), device="cuda")
+                ctx.pad_volume_dev(torch.from_numpy(cc).cuda().data_ptr(), d.data_ptr(), nx, ny, L)
+                dccs.append(d)
+            outs = [torch.empty((ny, nx), device="cuda") for _ in range(npairs)]
+            costs = [torch.empty((ny, nx), device="cuda") for _ in range(npairs)]
+            for rows in (0, 9):
+                ctx.set_rows_per_band(rows)
+                ctx.aggregate_batch_dev([d.data_ptr() for d in dccs], nx, ny, -(L - 1), 0, P1, P2, NDIR, K, felz, 1, "vfit",
+                                        [o.data_ptr() for o in outs], [c.data_ptr() for c in costs])
+                ctx.synchronize()
+                for b in range(npairs):
+                    o = O.orc_mgm(ccs[b], None, -(L - 1), P1, P2, NDIR, K, felz, 1)
+                    ro, rc = O.orc_refine(o["S"], -(L - 1), o["out"], o["outcost"], "vfit")
+                    assert same(outs[b].cpu().numpy(), ro) and same(costs[b].cpu().numpy(), rc), (K, felz, NDIR, rows, b)
+    finally:
+        ctx.set_option("reset")
+        ctx.set_rows_per_band(0)
+
+
 # ------------------------------------------------------------------------------------------ per-pixel ranges
 def _ragged(nx, ny, emin, emax, seed):
     rng = np.random.default_rng(seed)

@@ -325,3 +325,44 @@ def test_golden_flow_lr_oracle(path):
 def test_golden_flow_ranges_oracle(path):
     from tests.flow_checks import OracleImpl, check_flow_ranges
     check_flow_ranges(load_golden(path), OracleImpl())
+
+
+# ------------------------------------------------------------------------------------------ sweeps 8-15 (-O 16)
+def test_knight_sweeps_definition():
+    """Sweeps 8-15 are defined by this build (the reference's table ends at 8, mgm_core.cc:463-473).  The definition
+    (mgm_b200/csrc/common.cuh, oracle/mgm_oracle.c orc_pass_order): same scan and same four neighbours as sweep b = p-8,
+    order by coordinate parity such that the first-neighbour chain advances by a knight move every two pixels and the
+    second-neighbour chain by the perpendicular knight move."""
+    import ctypes
+    lib = O.orc_lib()
+    def nb(p, xs, ys, k):
+        dx, dy = ctypes.c_int(), ctypes.c_int()
+        lib.orc_pass_neighbour(p, xs, ys, k, ctypes.byref(dx), ctypes.byref(dy))
+        return dx.value, dy.value
+    nx, ny = 9, 7
+    expect_k0 = {8: (-2, -1), 9: (2, 1), 10: (-1, 2), 11: (1, -2), 12: (-1, -2), 13: (2, -1), 14: (1, 2), 15: (-2, 1)}
+    for p in range(8, 16):
+        base = [nb(p - 8, 3, 3, k) for k in range(4)]
+        for xs in range(2, 6):
+            for ys in range(2, 6):
+                cur = [nb(p, xs, ys, k) for k in range(4)]
+                assert sorted(cur) == sorted(base)          # the same four neighbours, reordered
+                # two steps along neighbour k: scan coordinates of the neighbour (from the base table in scan space)
+                pre = O.orc_scan_preds(p - 8, nx, ny)       # scan-space offsets of the base order
+                for k in (0, 1):
+                    d1 = cur[k]
+                    s1 = pre[base.index(d1)]                # scan offset of that neighbour
+                    d2 = nb(p, xs + s1[0], ys + s1[1], k)
+                    step2 = (d1[0] + d2[0], d1[1] + d2[1])
+                    assert abs(step2[0]) + abs(step2[1]) == 3 and 0 not in step2, (p, xs, ys, k, step2)
+                    if k == 0:
+                        assert step2 == expect_k0[p], (p, step2)
+                    else:
+                        assert step2[0] * expect_k0[p][0] + step2[1] * expect_k0[p][1] == 0   # perpendicular
+    # with all four neighbours the sweeps 8+b and b differ by the order of one float sum only; with fewer they differ
+    cc = synth_volume(23, 17, 9, seed=4, inf_border=False)
+    r = O.orc_mgm(cc, None, 0, 8, 32, 16, 4, 0, 1, want_passes=True)
+    for b in range(8):
+        assert np.allclose(r["passes"][8 + b], r["passes"][b], rtol=1e-5)
+    r = O.orc_mgm(cc, None, 0, 8, 32, 16, 2, 0, 1, want_passes=True)
+    assert all(not np.allclose(r["passes"][8 + b], r["passes"][b], rtol=1e-3) for b in range(8))

@@ -15,15 +15,21 @@ from mgm_b200 import sharding
 
 
 def test_partitions():
-    for ndir in [1, 2, 4, 8]:
+    for ndir in [1, 2, 4, 8, 16]:
         for world in [1, 2, 3, 4, 8]:
             masks = [sharding.sweep_mask(ndir, world, r) for r in range(world)]
             assert sum(masks) == (1 << ndir) - 1 and all(a & b == 0 for i, a in enumerate(masks) for b in masks[i + 1:])
-    for ny in [1, 7, 375, 1536]:
+    for ny in [1, 7, 375, 1536, 4096]:
         for world in [1, 2, 3, 8]:
             s = sharding.row_slabs(ny, world)
+            rps = sharding.slab_rows(ny, world)
             assert s[0][0] == 0 and s[-1][1] == ny and all(s[i][1] == s[i + 1][0] for i in range(world - 1))
-            assert max(b - a for a, b in s) - min(b - a for a, b in s) <= 1
+            # uniform slabs: the aggregation kernel finds the slab of an image row by one division
+            assert all((a, b) == (min(ny, r * rps), min(ny, (r + 1) * rps)) for r, (a, b) in enumerate(s))
+            assert rps * world >= ny and rps >= 2
+            # the kernel's magic-number division (capi.cu: slab_magic) is exact for every row
+            magic = ((1 << 32) + rps - 1) // rps
+            assert all((y * magic) >> 32 == y // rps for y in range(ny))
 
 
 def _free_port():
