@@ -339,6 +339,11 @@ __device__ __forceinline__ void band_finished(const AggParams &P, const SweepDes
 __device__ __forceinline__ float *ldir_of_row(const AggParams &P, const SweepDesc &D, int y) {
    return (P.nslabs > 1) ? D.ldir[__umulhi((unsigned)y, P.slab_magic)] : D.ldir[0];
 }
+// the same from the pixel index: the row is only computed in the slab layout (nothing extra stays live otherwise)
+__device__ __forceinline__ float *ldir_of_pix(const AggParams &P, const SweepDesc &D, long long pix) {
+   if (P.nslabs > 1) return D.ldir[__umulhi((unsigned)pix / (unsigned)P.nx, P.slab_magic)];
+   return D.ldir[0];
+}
 
 // KN: sweeps 8-15 -- the scan of sweep pass-8, lag 2, predecessor ORDER by the parity of the scan coordinates
 // (knight_pred_type, common.cuh); instantiated with DIAG = true for the lag and the ring depth.
@@ -527,8 +532,12 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
       float2 *cur = reinterpret_cast<float2 *>(row_base(r) + (act ? (xs % R) : 0) * VS);
       float *Cbf = (CHAINS && creg_mode) ? reinterpret_cast<float *>(cur) : cbuf_of(r, xs);   // where the message is built
       float2 *Cb = reinterpret_cast<float2 *>(Cbf);
+#ifdef MGM_Y_FROM_PIX
+      float4 *gout = reinterpret_cast<float4 *>(ldir_of_pix(P, D, act ? pix : 0) + (size_t)(act ? pix : 0) * VS);
+#else
       float4 *gout = reinterpret_cast<float4 *>(ldir_of_row(P, D, act ? g.y0 + xs * g.ydxs + ys * g.ydys : 0) +
                                                 (size_t)(act ? pix : 0) * VS);
+#endif
       const bool border = (xs == 0) || (ys == 0) || (xs == maxii - 1);
       float m = MGM_INF;
 
@@ -952,8 +961,12 @@ __device__ void run_band_shear(const AggParams &P, const SweepDesc &D, const int
       float2 *cur = reinterpret_cast<float2 *>(row_base(r) + (v & 1) * VS);
       float *Cbf = inplace ? reinterpret_cast<float *>(cur) : cbuf_of(r, v);   // where the message is built
       float2 *Cb = reinterpret_cast<float2 *>(Cbf);
+#ifdef MGM_Y_FROM_PIX
+      float4 *gout = reinterpret_cast<float4 *>(ldir_of_pix(P, D, act ? pix : 0) + (size_t)(act ? pix : 0) * VS);
+#else
       float4 *gout = reinterpret_cast<float4 *>(ldir_of_row(P, D, act ? g.y0 + xs * g.ydxs + v * g.ydys : 0) +
                                                 (size_t)(act ? pix : 0) * VS);
+#endif
       const bool border = (xs == 0) || (v == 0) || (xs == maxii - 1);
       float m = MGM_INF;
 
@@ -1283,7 +1296,7 @@ __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(c
             const uint4 *src = reinterpret_cast<const uint4 *>(P.sweeps + tk.x);
             uint4 *dst = reinterpret_cast<uint4 *>(&s_stage.d);
             for (int i = t; i < (int)(sizeof(SweepDesc) / 16); i += 32) dst[i] = src[i];
-         } else if (tk.x == -2) {
+         } else if (tk.x == -2 && P.npairs > 1) {
             const uint4 *src = reinterpret_cast<const uint4 *>(P.fins + tk.y / P.fin_ntiles);
             uint4 *dst = reinterpret_cast<uint4 *>(&s_stage.f);
             for (int i = t; i < (int)(sizeof(WtaParams) / 16); i += 32) dst[i] = src[i];
@@ -1292,12 +1305,18 @@ __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(c
       __syncthreads();
       const int2 pb = s_ticket;
       if (pb.x == -1) break;
-      if (pb.x == -2) run_finish_tile(P, s_stage.f, pb.y % P.fin_ntiles, smem);
+      if (pb.x == -2) {
+         if (P.npairs == 1) run_finish_tile(P, P.fin0, pb.y, smem);
+         else run_finish_tile(P, s_stage.f, pb.y % P.fin_ntiles, smem);
+      }
       else {
          const SweepDesc &D = s_stage.d;
          const int pass = D.pass;
+#ifndef MGM_NO_KNIGHT
          if (pass >= 8) run_band<POT, K, WEIGHTED, true, GL, true>(P, D, pb.y, smem);
-         else if (pass < 4) run_band<POT, K, WEIGHTED, false, GL>(P, D, pb.y, smem);
+         else
+#endif
+         if (pass < 4) run_band<POT, K, WEIGHTED, false, GL>(P, D, pb.y, smem);
          else if constexpr (!WEIGHTED && K <= 3) {
             if (P.shear) run_band_shear<POT, K, GL>(P, D, pb.y, smem);
             else run_band<POT, K, WEIGHTED, true, GL>(P, D, pb.y, smem);
@@ -1350,7 +1369,7 @@ static cudaError_t launch_k(int K, const AggParams &P, const AggPlan &plan, cuda
 }
 
 static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
-                         int t_override, int shear, const AggTuning &tune) {
+                         int t_override, int shear, bool knight, const AggTuning &tune) {
    plan->verbose = tune.verbose;
    const int VS = (L + 31) & ~31;   // 8 lanes x 16 bytes per row and step
    plan->VS = VS;
@@ -1401,6 +1420,7 @@ static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, b
       plan->ng[cls] = ng;
       plan->T[cls] = Tc;
    }
+   if (!knight) plan->T[CLS_KNIGHT] = min(plan->T[CLS_KNIGHT], max(plan->T[0], plan->T[1]));   // unused: keep max() below unchanged
    const int tm = max(max(plan->T[0], plan->T[1]), plan->T[2]);
    const int ncomp = (tm * plan->lanes + 31) & ~31;
    plan->block = ncomp + 64;   // + boundary-consumer warp + boundary-publisher warp
@@ -1412,22 +1432,25 @@ static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, b
    plan->off_vms = off; off += (size_t)nvirt * RV * 4; off = (off + 127) & ~(size_t)127;
    plan->off_virt = off; off += (size_t)nvirt * RV * VS * 4; off = (off + 127) & ~(size_t)127;
    plan->off_thr = off;
+   // the rows region is sized for the classes this launch runs: the knight class (ring of 4 slots) only with more than
+   // 8 sweeps -- shared memory the kernel does not need stays L1 (measured: 228 KB instead of 191 KB of shared memory
+   // made the headline launch 13 % slower)
    size_t per_thr = 0;
-   for (int cls = 0; cls < 3; ++cls) per_thr = max(per_thr, (size_t)plan->TS[cls] * plan->T[cls] * 4);
+   for (int cls = 0; cls < (knight ? 3 : 2); ++cls) per_thr = max(per_thr, (size_t)plan->TS[cls] * plan->T[cls] * 4);
    plan->smem = off + per_thr;
    plan->num_sms = num_sms;
 }
 
 void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
-              int t_override, const AggTuning &tune) {
+              int t_override, bool knight, const AggTuning &tune) {
    // diagonal sweeps as sheared wavefronts (run_band_shear): predecessors in the row above only, no image-dependent
    // weights, and room for at least two workers per band (the hand-off carries the last two)
    const bool want_shear = (K <= 3 && !weighted && !tune.no_shear);
    if (want_shear) {
-      agg_plan_try(plan, nx, ny, L, K, pot, weighted, max_smem, num_sms, t_override, 1, tune);
+      agg_plan_try(plan, nx, ny, L, K, pot, weighted, max_smem, num_sms, t_override, 1, knight, tune);
       if (plan->T[0] >= 1 && plan->T[1] >= 2 && plan->T[2] >= 1) return;
    }
-   agg_plan_try(plan, nx, ny, L, K, pot, weighted, max_smem, num_sms, t_override, 0, tune);
+   agg_plan_try(plan, nx, ny, L, K, pot, weighted, max_smem, num_sms, t_override, 0, knight, tune);
 }
 
 int agg_sweep_class(const AggPlan &plan, int pass) {

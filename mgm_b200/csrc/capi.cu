@@ -169,6 +169,7 @@ static bool apply_option(mgmb200_ctx *c, const char *name, const char *value) {
    if (!strcmp(name, "static_order")) { t.static_order = iv; return true; }
    if (!strcmp(name, "no_fused_finish")) { t.no_fused_finish = iv; return true; }
    if (!strcmp(name, "cc_pf")) { t.cc_pf = iv; return true; }
+   if (!strcmp(name, "batch")) { t.batch = iv < 1 ? 1 : iv; return true; }
    if (!strcmp(name, "verbose")) { t.verbose = iv; return true; }
    if (!strcmp(name, "fin_tile")) {
       int a = 0, b = 0;
@@ -182,7 +183,7 @@ static void tuning_from_env(mgmb200_ctx *c) {
    c->tune = AggTuning();
    c->rows_override = 0;
    static const char *const names[] = {"rows_per_band", "rows_axis", "rows_diag", "groups", "no_creg", "no_fused_sgm", "lanes4",
-                                       "lanes8", "no_shear", "static_order", "no_fused_finish", "cc_pf", "verbose", "fin_tile"};
+                                       "lanes8", "no_shear", "static_order", "no_fused_finish", "cc_pf", "batch", "verbose", "fin_tile"};
    for (const char *n : names) {
       char env[64] = "MGMB200_";
       size_t k = strlen(env);
@@ -454,7 +455,8 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
    int nsw = 0;
    for (int p = 0; p < NDIR; p++) nsw += (mask >> p) & 1;
    AggPlan plan;
-   agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, c->rows_override, c->tune);
+   const bool knight = (mask >> 8) != 0;
+   agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, c->rows_override, knight, c->tune);
    if (!c->rows_override && !c->tune.rows_axis && !c->tune.rows_diag && plan.T[0] > 40 && R.npairs == 1 && nsw <= 2) {
       // One or two sweeps on this GPU (sweep-sharded layouts): with fewer bands than SMs the launch is bound by the
       // dependency depth alone, and bands of 40 workers step faster than bands of 56 (measured: one axis sweep of
@@ -467,7 +469,7 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
          agg_sweep_bands(plan, p, nx, ny, &nb, &a, &bq);
          bands += nb;
       }
-      if (bands < c->num_sms) agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 40, c->tune);
+      if (bands < c->num_sms) agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 40, knight, c->tune);
    }
    if (plan.T[0] < 1 || plan.T[1] < 1 || plan.T[2] < 1)
       return fail(MGMB200_EUNSUPPORTED, "%d labels do not fit the shared-memory wavefront (max_smem=%d)", L, c->max_smem);
@@ -586,6 +588,7 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
       P.fin_order = c->tiles.as<int>();
       P.fin_next = d_fin_next;
       P.fins = c->fins.as<WtaParams>(); P.npairs = R.npairs;
+      P.fin0 = R.fin[0];
    }
    P.off_phase = (unsigned)plan.off_phase; P.off_cbar = (unsigned)plan.off_cbar; P.off_vbar = (unsigned)plan.off_vbar;
    P.off_ms = (unsigned)plan.off_ms; P.off_vms = (unsigned)plan.off_vms; P.off_virt = (unsigned)plan.off_virt;

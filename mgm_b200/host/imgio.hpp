@@ -4,6 +4,8 @@
 // (8/16-bit integer, 32-bit float, chunky, strips).  Writes NPY, PFM and uncompressed float32 TIFF, chosen by
 // the file extension.  Images are returned planar: data[x + y*nx + c*nx*ny] (iio_read_image_float_split).
 // Row order follows iio: rows are stored top-down in every format, including PFM (iio.c:2561-2579,4112-4125).
+// Every offset and length taken from a file is validated against the file size before it is used: a truncated or
+// malformed input ends in a runtime_error (the CLI prints it and exits with code 3), never in an out-of-bounds read.
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
@@ -28,6 +30,16 @@ inline std::vector<uint8_t> slurp(const char *path) {
    while ((n = fread(tmp, 1, sizeof tmp, f)) > 0) b.insert(b.end(), tmp, tmp + n);
    fclose(f);
    return b;
+}
+
+// [off, off+len) must lie inside a buffer of `size` bytes
+inline void need(size_t size, size_t off, size_t len, const char *what) {
+   if (off > size || len > size - off) throw std::runtime_error(std::string("truncated or malformed ") + what);
+}
+// image dimensions from a header: positive, and small enough that nx*ny*nch floats can be indexed and allocated
+inline void check_dims(long long nx, long long ny, long long nch, const char *what) {
+   if (nx < 1 || ny < 1 || nch < 1 || nx > (1 << 24) || ny > (1 << 24) || nch > 64 || nx * ny * nch > (1LL << 33))
+      throw std::runtime_error(std::string("implausible image size in ") + what);
 }
 
 // interleaved (x,y,c) -> planar Img
@@ -62,8 +74,9 @@ inline Img read_pnm(const std::vector<uint8_t> &b) {
       pnm_token(b, p, t); const int ny = atoi(t.c_str());
       pnm_token(b, p, t); const double scale = atof(t.c_str());
       p++;   // single whitespace after the scale
+      check_dims(nx, ny, nch, "PFM header");
+      need(b.size(), p, (size_t)nx * ny * nch * 4, "PFM");
       std::vector<float> v((size_t)nx * ny * nch);
-      if (p + v.size() * 4 > b.size()) throw std::runtime_error("truncated PFM");
       memcpy(v.data(), &b[p], v.size() * 4);
       if (scale > 0)   // big endian payload
          for (float &f : v) { uint32_t u; memcpy(&u, &f, 4); u = __builtin_bswap32(u); memcpy(&f, &u, 4); }
@@ -76,13 +89,16 @@ inline Img read_pnm(const std::vector<uint8_t> &b) {
    pnm_token(b, p, t); const int nx = atoi(t.c_str());
    pnm_token(b, p, t); const int ny = atoi(t.c_str());
    pnm_token(b, p, t); const int maxval = atoi(t.c_str());
+   check_dims(nx, ny, nch, "PNM header");
+   if (maxval < 1 || maxval > 65535) throw std::runtime_error("bad PNM maxval");
+   if (kind == 2 || kind == 3) need(b.size(), p, (size_t)nx * ny * nch, "PNM");   // at least one byte per sample
    std::vector<float> v((size_t)nx * ny * nch);
    if (kind == 2 || kind == 3) {
-      for (float &f : v) { pnm_token(b, p, t); f = (float)atoi(t.c_str()); }
+      for (float &f : v) { if (!pnm_token(b, p, t)) throw std::runtime_error("truncated PNM"); f = (float)atoi(t.c_str()); }
    } else {
       p++;
       const int bps = maxval > 255 ? 2 : 1;
-      if (p + v.size() * bps > b.size()) throw std::runtime_error("truncated PNM");
+      need(b.size(), p, v.size() * bps, "PNM");
       for (size_t i = 0; i < v.size(); i++)
          v[i] = bps == 1 ? (float)b[p + i] : (float)((b[p + 2 * i] << 8) | b[p + 2 * i + 1]);
    }
@@ -95,14 +111,17 @@ inline Img read_npy(const std::vector<uint8_t> &b) {
    const int major = b[6];
    size_t hlen = major == 1 ? (b[8] | (b[9] << 8)) : (b[8] | (b[9] << 8) | (b[10] << 16) | ((size_t)b[11] << 24));
    const size_t hoff = major == 1 ? 10 : 12;
+   need(b.size(), hoff, hlen, "NPY header");
    const std::string h((const char *)&b[hoff], hlen);
    auto field = [&](const char *key) { size_t k = h.find(key); if (k == std::string::npos) throw std::runtime_error("bad NPY header"); return k; };
    size_t k = field("'descr'");
    k = h.find('\'', k + 7);
+   if (k == std::string::npos || h.find('\'', k + 1) == std::string::npos) throw std::runtime_error("bad NPY header");
    const std::string descr = h.substr(k + 1, h.find('\'', k + 1) - k - 1);
    if (h.find("'fortran_order': True") != std::string::npos) throw std::runtime_error("fortran-order NPY not supported");
    k = field("'shape'");
    k = h.find('(', k);
+   if (k == std::string::npos || h.find(')', k) == std::string::npos) throw std::runtime_error("bad NPY header");
    std::vector<int> shape;
    const std::string sh = h.substr(k + 1, h.find(')', k) - k - 1);
    for (size_t i = 0; i < sh.size();) {
@@ -113,7 +132,11 @@ inline Img read_npy(const std::vector<uint8_t> &b) {
    }
    if (shape.size() < 2 || shape.size() > 3) throw std::runtime_error("NPY image must be (H,W) or (H,W,C)");
    const int ny = shape[0], nx = shape[1], nch = shape.size() == 3 ? shape[2] : 1;
-   const uint8_t *d = &b[hoff + hlen];
+   check_dims(nx, ny, nch, "NPY header");
+   const size_t esz = (descr == "<f4" || descr == "<i4") ? 4 : descr == "<f8" ? 8 : descr == "|u1" ? 1 : descr == "<u2" ? 2 : 0;
+   if (!esz) throw std::runtime_error("unsupported NPY dtype " + descr);
+   need(b.size(), hoff + hlen, (size_t)nx * ny * nch * esz, "NPY payload");
+   const uint8_t *d = b.data() + hoff + hlen;
    std::vector<float> v((size_t)nx * ny * nch);
    for (size_t i = 0; i < v.size(); i++) {
       if (descr == "<f4") { memcpy(&v[i], d + 4 * i, 4); }
@@ -137,7 +160,11 @@ inline Img read_png(const std::vector<uint8_t> &b) {
       const uint32_t len = be32(p);
       const std::string type((const char *)&b[p + 4], 4);
       const size_t d = p + 8;
-      if (type == "IHDR") { w = be32(d); h = be32(d + 4); depth = b[d + 8]; ctype = b[d + 9]; interlace = b[d + 12]; }
+      need(b.size(), d, (size_t)len + 4, "PNG chunk");   // data + CRC
+      if (type == "IHDR") {
+         if (len < 13) throw std::runtime_error("bad PNG header");
+         w = be32(d); h = be32(d + 4); depth = b[d + 8]; ctype = b[d + 9]; interlace = b[d + 12];
+      }
       else if (type == "PLTE") plte.assign(b.begin() + d, b.begin() + d + len);
       else if (type == "IDAT") idat.insert(idat.end(), b.begin() + d, b.begin() + d + len);
       else if (type == "IEND") break;
@@ -145,12 +172,16 @@ inline Img read_png(const std::vector<uint8_t> &b) {
    }
    if (interlace) throw std::runtime_error("interlaced PNG not supported");
    if (depth != 8 && depth != 16) throw std::runtime_error("PNG bit depth must be 8 or 16");
+   if (ctype != 0 && ctype != 2 && ctype != 3 && ctype != 4 && ctype != 6) throw std::runtime_error("bad PNG colour type");
+   if (ctype == 3 && depth != 8) throw std::runtime_error("palette PNG must be 8 bit");
+   check_dims(w, h, 4, "PNG header");
    const int chans = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : 4;
    const int bpp = chans * depth / 8;
    const size_t stride = (size_t)w * bpp;
    std::vector<uint8_t> raw((stride + 1) * h);
    uLongf rawlen = raw.size();
-   if (uncompress(raw.data(), &rawlen, idat.data(), idat.size()) != Z_OK) throw std::runtime_error("PNG inflate failed");
+   if (idat.empty() || uncompress(raw.data(), &rawlen, idat.data(), idat.size()) != Z_OK) throw std::runtime_error("PNG inflate failed");
+   if (rawlen != raw.size()) throw std::runtime_error("PNG pixel data shorter than the header says");
    std::vector<uint8_t> img(stride * h);
    for (uint32_t y = 0; y < h; y++) {
       const uint8_t *src = &raw[(stride + 1) * y];
@@ -184,18 +215,22 @@ inline Img read_png(const std::vector<uint8_t> &b) {
 // ---------------------------------------------------------------- TIFF (uncompressed strips)
 inline Img read_tiff(const std::vector<uint8_t> &b) {
    const bool le = b[0] == 'I';
-   auto u16 = [&](size_t p) -> uint32_t { return le ? (b[p] | (b[p + 1] << 8)) : ((b[p] << 8) | b[p + 1]); };
-   auto u32 = [&](size_t p) -> uint32_t { return le ? (b[p] | (b[p + 1] << 8) | (b[p + 2] << 16) | ((uint32_t)b[p + 3] << 24))
+   auto u16 = [&](size_t p) -> uint32_t { need(b.size(), p, 2, "TIFF"); return le ? (b[p] | (b[p + 1] << 8)) : ((b[p] << 8) | b[p + 1]); };
+   auto u32 = [&](size_t p) -> uint32_t { need(b.size(), p, 4, "TIFF");
+                                          return le ? (b[p] | (b[p + 1] << 8) | (b[p + 2] << 16) | ((uint32_t)b[p + 3] << 24))
                                                     : (((uint32_t)b[p] << 24) | (b[p + 1] << 16) | (b[p + 2] << 8) | b[p + 3]); };
    if (u16(2) != 42) throw std::runtime_error("not a classic TIFF");
    size_t ifd = u32(4);
    const int n = u16(ifd);
+   need(b.size(), ifd + 2, (size_t)12 * n, "TIFF directory");
    uint32_t w = 0, h = 0, bps = 8, comp = 1, spp = 1, fmt = 1, planar = 1;
    std::vector<uint32_t> offs, counts;
    for (int i = 0; i < n; i++) {
       const size_t e = ifd + 2 + 12 * i;
       const uint32_t tag = u16(e), type = u16(e + 2), cnt = u32(e + 4);
       const size_t tsz = type == 3 ? 2 : 4;
+      if ((tag == 273 || tag == 279) && (type != 3 && type != 4)) throw std::runtime_error("unsupported TIFF strip table type");
+      if ((tag == 273 || tag == 279) && cnt > b.size()) throw std::runtime_error("malformed TIFF strip table");
       auto value = [&](uint32_t j) -> uint32_t {
          const size_t base = (cnt * tsz <= 4) ? e + 8 : u32(e + 8);
          return type == 3 ? u16(base + 2 * j) : u32(base + 4 * j);
@@ -208,9 +243,15 @@ inline Img read_tiff(const std::vector<uint8_t> &b) {
    }
    if (comp != 1) throw std::runtime_error("compressed TIFF is not supported by this reader (convert to uncompressed TIFF, PFM or NPY)");
    if (planar != 1 && spp > 1) throw std::runtime_error("planar TIFF not supported");
+   check_dims(w, h, spp, "TIFF directory");
+   if (offs.size() != counts.size()) throw std::runtime_error("malformed TIFF strip table");
    std::vector<uint8_t> pix;
-   for (size_t s = 0; s < offs.size(); s++) pix.insert(pix.end(), b.begin() + offs[s], b.begin() + offs[s] + counts[s]);
+   for (size_t s = 0; s < offs.size(); s++) {
+      need(b.size(), offs[s], counts[s], "TIFF strip");
+      pix.insert(pix.end(), b.begin() + offs[s], b.begin() + offs[s] + counts[s]);
+   }
    std::vector<float> v((size_t)w * h * spp);
+   if (bps != 8 && bps != 16 && bps != 32) throw std::runtime_error("unsupported TIFF sample size");
    const size_t by = bps / 8;
    if (pix.size() < v.size() * by) throw std::runtime_error("truncated TIFF");
    for (size_t i = 0; i < v.size(); i++) {
@@ -225,6 +266,7 @@ inline Img read_tiff(const std::vector<uint8_t> &b) {
 
 inline Img read_image(const char *path) {
    const std::vector<uint8_t> b = slurp(path);
+   if (b.size() < 8) throw std::runtime_error(std::string("empty or truncated image file: ") + path);
    if (b.size() >= 8 && !memcmp(b.data(), "\x89PNG\r\n\x1a\n", 8)) return read_png(b);
    if (b.size() >= 6 && !memcmp(b.data(), "\x93NUMPY", 6)) return read_npy(b);
    if (b.size() >= 4 && ((b[0] == 'I' && b[1] == 'I') || (b[0] == 'M' && b[1] == 'M'))) return read_tiff(b);
@@ -245,6 +287,12 @@ inline void write_image(const char *path, const Img &im) {
    const std::string p(path);
    const std::string ext = p.rfind('.') == std::string::npos ? "" : p.substr(p.rfind('.') + 1);
    const std::vector<float> v = to_interleaved(im);
+   // formats are chosen by the extension like iio does; the ones this build cannot encode are refused instead of
+   // writing other bytes under that name (no extension = PFM, what the reference built without image libraries writes)
+   const bool pfm = ext == "pfm" || ext == "PFM" || ext.empty() || p.rfind('.') < p.rfind('/') + 1;
+   if (!(ext == "npy" || ext == "tif" || ext == "tiff" || pfm))
+      throw std::runtime_error("cannot write " + p + ": supported output formats are .npy, .tif/.tiff (float32) and .pfm");
+   if (pfm && im.nch != 1 && im.nch != 3) throw std::runtime_error("cannot write " + p + ": PFM holds 1 or 3 channels, use .npy or .tif");
    FILE *f = fopen(path, "wb");
    if (!f) throw std::runtime_error("cannot write " + p);
    if (ext == "npy") {
@@ -274,11 +322,9 @@ inline void write_image(const char *path, const Img &im) {
       const uint32_t zero = 0;
       fwrite(&zero, 4, 1, f);
    } else {
-      // PFM the way iio writes it: top-down rows, little endian (negative scale); 2 or >3 channels fall back to NPY-less raw PFM of the first plane
-      const int nch = (im.nch == 3) ? 3 : 1;
-      fprintf(f, "%s\n%d %d\n-1\n", nch == 3 ? "PF" : "Pf", im.nx, im.ny);
-      if (nch == im.nch) fwrite(v.data(), 4, v.size(), f);
-      else fwrite(im.data.data(), 4, (size_t)im.nx * im.ny, f);
+      // PFM the way iio writes it: top-down rows, little endian (negative scale)
+      fprintf(f, "%s\n%d %d\n-1\n", im.nch == 3 ? "PF" : "Pf", im.nx, im.ny);
+      fwrite(v.data(), 4, v.size(), f);
    }
    fclose(f);
 }

@@ -57,6 +57,8 @@ int main(int argc, char *argv[]) {
            " -r {-30} -R {30} -O {4} -P1 {8} -P2 {32} -p {none|census|sobelx|gblur} -t {ad|sd|census|ncc|btad|btsd}\n"
            " -truncDist {inf} -s {none|vfit|parabola|cubic|parabolaOCV} -aP1 {1} -aP2 {1} -aThresh {5}\n"
            " -m FILE -M FILE -l FILE\n"
+           "Images: PNM, PFM, NPY, PNG (non-interlaced), uncompressed TIFF in; .npy, .tif/.tiff (float32), .pfm out.\n"
+           "-O 9..16 add the knight-move sweeps defined by this build (the reference is undefined beyond 8).\n"
            "Environment: CENSUS_NCC_WIN=3 TESTLRRL=1 TESTLRRL_TAU=1.0 MEDIAN=0 TSGM=4 TSGM_ITER=1\n"
            "             TSGM_FIX_OVERCOUNT=1 USE_TRUNCATED_LINEAR_POTENTIALS=0 MGMB200_DEVICE=<gpu>\n"
            "Same surface as gfacciol/mgm; the hot path runs on the GPU (libmgmb200).");

@@ -160,7 +160,7 @@ def test_unsupported_inputs_fail_loudly(ctx):
     with pytest.raises(mgm_b200.MgmError):
         ctx.mgm(bad, None, 0, 8, 32, 4, 2)
     with pytest.raises(mgm_b200.MgmError):
-        ctx.mgm(cc, None, 0, 8, 32, 16, 2)             # -O 16 indexes past the reference's table
+        ctx.mgm(cc, None, 0, 8, 32, 17, 2)             # 16 sweeps are defined (8 of the reference + 8 of this build), not more
     with pytest.raises(mgm_b200.MgmError):
         ctx.mgm(cc, None, 0, 8, 32, 4, 5)
 
@@ -216,6 +216,7 @@ def test_sweep_slab_stores_single_gpu(ctx):
         own = [ctx.sweep_volume(p)[0] for p in range(NDIR)]
         other = [[torch.full((ny, nx, VS), float("nan"), device="cuda") for p in range(NDIR)] for r in range(nslabs - 1)]
         table = [[own[p]] + [other[r][p].data_ptr() for r in range(nslabs - 1)] for p in range(NDIR)]
+        torch.cuda.synchronize()   # torch's stream and the context's are not ordered with each other
         for rows in (0, 7):
             ctx.set_rows_per_band(rows)
             for mask in ((0x5555, 0xAAAA) if rows else (0xFFFF,)):
@@ -235,7 +236,9 @@ def test_sweep_slab_stores_single_gpu(ctx):
         ctx.aggregate_sweeps_dev(dcc.data_ptr(), 0, 0, nx, ny, -(L - 1), 0, P1, P2, NDIR, K, felz, (1 << NDIR) - 1)
         for i, mask in enumerate((0x5555, 0xAAAA)):
             ctx.sum_sweeps_dev(nx, ny, -(L - 1), 0, mask & ((1 << NDIR) - 1), part[i].data_ptr())
+        ctx.synchronize()
         tot = part[0] + part[1]
+        torch.cuda.synchronize()
         ctx.finish_sum_dev(tot.data_ptr(), dcc.data_ptr(), nx, ny, -(L - 1), 0, NDIR, 1, "none", 0, ny, dout.data_ptr(),
                            dcost.data_ptr())
         ctx.synchronize()

@@ -132,3 +132,74 @@ def test_finish_tile_band_bounds():
             assert min(brute) == b0 and max(brute) == b1, (p, nx, ny, shear)
             nb = (maxii + maxjj - 1 + T1 - 1) // T1 if (p >= 4 and shear) else (maxjj + (T0 if p < 4 else T1) - 1) // (T0 if p < 4 else T1)
             assert 0 <= b0 <= b1 < nb
+
+
+# ------------------------------------------------------------------------------------------ image files of the CLI
+def test_image_reader_rejects_malformed_files(tmp_path):
+    """mgm_b200/host/imgio.hpp validates every offset and length it takes from a file: truncated and malformed inputs
+    end in an error message (exit code 3 of the CLI), never in an out-of-bounds read.  Built with -fsanitize=address
+    so that a missed check fails the test."""
+    import os, struct, subprocess, zlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "imgio_probe")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address", "-I", os.path.join(root, "mgm_b200", "host"),
+                           "-I", os.path.join(root, "include"), "-o", exe, os.path.join(root, "tests", "imgio_probe.cc"),
+                           "-L", os.path.join(root, "mgm_b200"), "-lmgmb200", "-Wl,-rpath," + os.path.join(root, "mgm_b200"), "-lz"])
+
+    def probe(data, name="f", out=None):
+        path = str(tmp_path / name)
+        open(path, "wb").write(data)
+        r = subprocess.run([exe, path] + ([out] if out else []), capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+        assert "AddressSanitizer" not in r.stderr, r.stderr[-2000:]
+        assert r.returncode in (0, 3), (r.returncode, r.stderr[-500:])
+        return r.stdout.strip()
+
+    img = (np.arange(6 * 5 * 3) % 251).astype(np.uint8).reshape(5, 6, 3)
+    # good files of every format
+    pnm = b"P6\n6 5\n255\n" + img.tobytes()
+    assert probe(pnm) == "ok 6 5 3"
+    pfm = b"Pf\n6 5\n-1\n" + np.arange(30, dtype="<f4").tobytes()
+    assert probe(pfm) == "ok 6 5 1"
+    import io as _io
+    bio = _io.BytesIO(); np.save(bio, img.astype(np.float32)); npy = bio.getvalue()
+    assert probe(npy) == "ok 6 5 3"
+    def png_bytes(w, h, raw, ctype=2, depth=8):
+        def chunk(t, d): return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+        return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+    raw = b"".join(b"\x00" + img[y].tobytes() for y in range(5))
+    png = png_bytes(6, 5, raw)
+    assert probe(png) == "ok 6 5 3"
+    def tiff_bytes(w, h, data, strip_off=None, strip_cnt=None, nent_extra=0):
+        ents = [(256, 4, 1, w), (257, 4, 1, h), (258, 3, 1, 32), (259, 3, 1, 1), (273, 4, 1, 8 if strip_off is None else strip_off),
+                (277, 3, 1, 1), (279, 4, 1, len(data) if strip_cnt is None else strip_cnt), (339, 3, 1, 3)]
+        ifd = 8 + len(data)
+        b = b"II*\x00" + struct.pack("<I", ifd) + data + struct.pack("<H", len(ents) + nent_extra)
+        for t, ty, c, v in ents:
+            b += struct.pack("<HHII", t, ty, c, v)
+        return b + struct.pack("<I", 0)
+    tif = tiff_bytes(6, 5, np.arange(30, dtype="<f4").tobytes())
+    assert probe(tif) == "ok 6 5 1"
+    # truncations of every format at every few bytes
+    for good, okline in ((pnm, "ok 6 5 3"), (pfm, "ok 6 5 1"), (npy, "ok 6 5 3"), (png, "ok 6 5 3"), (tif, "ok 6 5 1")):
+        for cut in list(range(0, min(len(good), 160), 3)) + [len(good) - 1, len(good) - 7]:
+            r = probe(good[:cut])
+            # an error, or -- when only trailing bytes that carry no pixels are missing (PNG IEND) -- the right image
+            assert r.startswith("error") or (r == okline and cut > len(good) - 16), (cut, r)
+    # malformed headers
+    assert probe(b"P6\n60000 50000\n255\n" + img.tobytes()).startswith("error")
+    assert probe(b"Pf\n-6 5\n-1\n" + pfm[10:]).startswith("error")
+    assert probe(npy.replace(b"(5, 6, 3)", b"(5, 6, 9)")).startswith("error")
+    assert probe(png_bytes(6, 50, raw)).startswith("error")                       # fewer scanlines than the header says
+    assert probe(png_bytes(6, 5, raw, ctype=5)).startswith("error")
+    assert probe(png[:33] + struct.pack(">I", 0x7fffffff) + png[37:]).startswith("error")   # chunk length beyond the file
+    assert probe(tiff_bytes(6, 5, np.arange(30, dtype="<f4").tobytes(), strip_off=1 << 30)).startswith("error")
+    assert probe(tiff_bytes(6, 5, np.arange(30, dtype="<f4").tobytes(), strip_cnt=1 << 30)).startswith("error")
+    assert probe(tiff_bytes(6, 5, np.arange(30, dtype="<f4").tobytes(), nent_extra=4000)).startswith("error")
+    assert probe(tif[:4] + struct.pack("<I", 1 << 31) + tif[8:]).startswith("error")   # directory offset beyond the file
+    # writers: extensions this build cannot encode are refused, PFM only with 1 or 3 channels
+    assert probe(pnm, out=str(tmp_path / "o.png")).startswith("error")
+    assert probe(pnm, out=str(tmp_path / "o.npy")) == "ok 6 5 3" and np.load(str(tmp_path / "o.npy")).shape == (5, 6, 3)
+    assert probe(pnm, out=str(tmp_path / "o.pfm")) == "ok 6 5 3"
+    two = _io.BytesIO(); np.save(two, img[:, :, :2].astype(np.float32))
+    assert probe(two.getvalue(), out=str(tmp_path / "o2.pfm")).startswith("error")
+    assert probe(two.getvalue(), out=str(tmp_path / "o2.tif")) == "ok 6 5 2"
