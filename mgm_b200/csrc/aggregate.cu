@@ -99,17 +99,27 @@ __device__ __forceinline__ float4 div3_4(const float4 &e) {
 // A16: the rows are 16-byte aligned and the chunk moves as one 16-byte access (truncated-linear kernels: their
 // chain lanes read one chunk per ROW, a pattern that gains little from 8-byte halves and pays for the extra
 // instructions in its dependent stream -- measured).
-template <bool A16>
+// LAY: 0 = 8-byte halves (SGM kernels), 1 = 16-byte aligned rows and accesses (truncated-linear kernels with lane-pair
+// chains), 2 = 8-byte halves in the PADDED layout of the register-chain kernels: 16 bytes of padding after every 8
+// chunks (128 bytes), i.e. chunk q sits at float offset 4q + 4(q >> 3).  With a row stride of 8 bytes modulo 128 this
+// layout is conflict-free at the LSU's full 128 B/clk for BOTH ways the 8 lanes of a worker walk a vector: interleaved
+// (lane g takes chunks g, g+8, ...: the gather, coalesced with the global accesses) and contiguous (lane g takes chunks
+// g*nj .. g*nj+nj-1: the min-convolution chain, nj = 1, 2, 4, 8) -- the transposition between the two costs nothing.
+template <int LAY>
+__device__ __forceinline__ int chunk_pos(int q) { return LAY == 2 ? 2 * q + 2 * (q >> 3) : 2 * q; }   // in float2 units
+template <int LAY>
 __device__ __forceinline__ float4 ld16(const float2 *p, int q) {
-   if (A16) return *reinterpret_cast<const float4 *>(p + 2 * q);
-   const float2 a = p[2 * q], b = p[2 * q + 1];
+   if (LAY == 1) return *reinterpret_cast<const float4 *>(p + 2 * q);
+   const int u = chunk_pos<LAY>(q);
+   const float2 a = p[u], b = p[u + 1];
    return make_float4(a.x, a.y, b.x, b.y);
 }
-template <bool A16>
+template <int LAY>
 __device__ __forceinline__ void st16(float2 *p, int q, const float4 &v) {
-   if (A16) { *reinterpret_cast<float4 *>(p + 2 * q) = v; return; }
-   p[2 * q] = make_float2(v.x, v.y);
-   p[2 * q + 1] = make_float2(v.z, v.w);
+   if (LAY == 1) { *reinterpret_cast<float4 *>(p + 2 * q) = v; return; }
+   const int u = chunk_pos<LAY>(q);
+   p[u] = make_float2(v.x, v.y);
+   p[u + 1] = make_float2(v.z, v.w);
 }
 
 // The publisher warp copies a boundary vector from its ring slot to the global boundary line (rows may be only
@@ -135,7 +145,7 @@ __device__ __forceinline__ float sgm_x(float l, float c, float r, float p1, floa
 // 8-lane group holds the chunks gl + 8j in v[j]; the labels next to a chunk live in the neighbouring lanes (same
 // j) or, at the ends of the group, in lane 7 / lane 0 of the previous / next j.  The message never goes through
 // shared memory and the step needs one barrier instead of two.
-template <int K, int NJR, bool A16, int GL>
+template <int K, int NJR, int A16, int GL>
 __device__ __forceinline__ void sgm_transform_regs(const float4 (&v)[NJR], int nj, int nq, int gl, unsigned gmask, float m,
                                                    float p1, float p2, float2 *cur) {
    constexpr int G = GL;
@@ -316,6 +326,76 @@ __device__ __forceinline__ void minconv_half(bool on, const float2 *src, float2 
    }
 }
 
+// Register-resident min-convolution by the 8 lanes of a worker (unweighted truncated-linear kernels, register-chain
+// mode).  Lane gl owns the CONTIGUOUS labels of chunks gl*nj .. gl*nj+nj-1 (padded layout LAY 2: conflict-free).  The
+// forward recurrence F[o] = min(F[o-1]+c, M[o]) and the backward recurrence B on the ORIGINAL values (identity 2:
+// the reference's backward pass over F equals min(F, B)) run as segmented scans:
+//   1. every lane scans its own labels from +INF (local F, local B);
+//   2. the value at the end of a lane's segment hops to the next lane, which adds c once per label of its segment --
+//      4*nj separately rounded additions, the reference's own sequence -- and takes the minimum with its local end
+//      value; 7 hops per direction, both directions interleaved in one instruction stream;
+//   3. every lane folds its carry into its labels: F[o] = min(local F[o], carry + c + ... + c).
+// x -> RN(x+c) is monotone, so min distributes over it: each F[o] is the minimum over the same candidates, each built
+// by the same chain of rounded additions, as in the sequential loop (mgm_core.cc:152-163).  Result written in place:
+// min(F, B, cap) - sub.  No barrier: a worker's 8 lanes sit in one warp (the caller's __syncwarp orders the slot).
+// __noinline__ on purpose: inlined into the band loops the compiler schedules the surrounding loads and address
+// arithmetic across the chain and spills 2.5 KB per thread; as a call it is a scheduling barrier (87 registers of its own).
+template <int NJR>
+__device__ __noinline__ void chain_regs(float2 *slot, const int nj, const int gl, const unsigned gmask, const float c,
+                                           const float cap, const float sub) {
+   float4 f[NJR], b[NJR];
+   const int q0 = gl * nj;
+#pragma unroll
+   for (int j = 0; j < NJR; ++j)
+      if (j < nj) f[j] = b[j] = ld16<2>(slot, q0 + j);
+   float runf = MGM_INF, runb = MGM_INF;
+#pragma unroll
+   for (int j = 0; j < NJR; ++j) {   // local scans: forward ascending, backward descending (independent: they interleave)
+      if (j < nj) chain4(runf, f[j].x, f[j].y, f[j].z, f[j].w, c);
+      const int jb = NJR - 1 - j;
+      if (jb < nj) chain4(runb, b[jb].w, b[jb].z, b[jb].y, b[jb].x, c);
+   }
+   const float lastf = runf, lastb = runb;
+   float ef = lastf, eb = lastb, cf = MGM_INF, cb = MGM_INF;
+   const int nadd = 4 * nj;
+#pragma unroll
+   for (int r = 1; r < 8; ++r) {
+      const float tf = __shfl_up_sync(gmask, ef, 1, 8);      // end value of the segment below
+      const float tb = __shfl_down_sync(gmask, eb, 1, 8);    // start value of the segment above
+      float uf = tf, ub = tb;
+      for (int k = 0; k < nadd; k += 4) {
+         uf = ((((uf + c) + c) + c) + c);
+         ub = ((((ub + c) + c) + c) + c);
+      }
+      if (gl == r) { cf = tf; ef = fminf(lastf, uf); }
+      if (gl == 7 - r) { cb = tb; eb = fminf(lastb, ub); }
+   }
+#pragma unroll
+   for (int j = 0; j < NJR; ++j) {   // fold the carries in
+      if (j < nj) {
+         cf += c; f[j].x = fminf(f[j].x, cf);
+         cf += c; f[j].y = fminf(f[j].y, cf);
+         cf += c; f[j].z = fminf(f[j].z, cf);
+         cf += c; f[j].w = fminf(f[j].w, cf);
+      }
+      const int jb = NJR - 1 - j;
+      if (jb < nj) {
+         cb += c; b[jb].w = fminf(b[jb].w, cb);
+         cb += c; b[jb].z = fminf(b[jb].z, cb);
+         cb += c; b[jb].y = fminf(b[jb].y, cb);
+         cb += c; b[jb].x = fminf(b[jb].x, cb);
+      }
+   }
+#pragma unroll
+   for (int j = 0; j < NJR; ++j) {
+      if (j < nj) {
+         const float4 o = make_float4(fminf(fminf(f[j].x, b[j].x), cap), fminf(fminf(f[j].y, b[j].y), cap),
+                                      fminf(fminf(f[j].z, b[j].z), cap), fminf(fminf(f[j].w, b[j].w), cap));
+         st16<2>(slot, q0 + j, add4s(o, -sub));
+      }
+   }
+}
+
 template <int K>
 __device__ __forceinline__ float4 div4_by_k(const float4 &e) {   // e finite (see div3_4)
    if (K == 1) return e;
@@ -347,10 +427,13 @@ __device__ __forceinline__ float *ldir_of_pix(const AggParams &P, const SweepDes
 
 // KN: sweeps 8-15 -- the scan of sweep pass-8, lag 2, predecessor ORDER by the parity of the scan coordinates
 // (knight_pred_type, common.cuh); instantiated with DIAG = true for the lag and the ring depth.
-template <int POT, int K, bool WEIGHTED, bool DIAG, int GL, bool KN = false>
+// RC: register-chain mode of the unweighted truncated-linear kernels (chain_regs): padded slots, costs in registers,
+// gather -> __syncwarp -> chain by the same 8 lanes -> ONE block barrier per step.
+template <int POT, int K, bool WEIGHTED, bool DIAG, int GL, bool KN = false, bool RC = false>
 __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band, unsigned char *smem) {
    constexpr int G = GL;   // lanes per worker: 8, or 4 for short label vectors (unweighted SGM kernels, agg_plan)
    static_assert(!KN || DIAG, "knight sweeps use the lag-2 layout");
+   static_assert(!RC || (!WEIGHTED && POT == POT_TRUNC && GL == 8), "register chains: unweighted truncated linear, 8 lanes");
    const int pass = D.pass;
    const bool kn_diag = (pass & 7) >= 4;
    constexpr int SIG = (DIAG || K == 4) ? 2 : 1;
@@ -359,7 +442,7 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
    constexpr bool WTRUNC = WEIGHTED && POT == POT_TRUNC;
    constexpr bool CHAINS = !WEIGHTED && POT == POT_TRUNC;   // phase-2 transform done by lane pairs
    constexpr int CLS = KN ? CLS_KNIGHT : (DIAG ? CLS_DIAG : CLS_AXIS);
-   constexpr bool A16 = (POT == POT_TRUNC);   // 16-byte aligned rows and accesses (ld16 / st16)
+   constexpr int A16 = RC ? 2 : (POT == POT_TRUNC ? 1 : 0);   // shared-memory vector layout (ld16 / st16)
    constexpr int JB = (K <= 3) ? MGM_JB : 2;   // chunks per lane whose loads are issued together in the gather
    constexpr int NJR = MGM_AGG_CREG;      // cost chunks per lane that can be prefetched into registers
 
@@ -368,11 +451,12 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
    const int T = P.T[CLS];
    const int TS = P.TS[CLS];
    const int VS = P.VS;
+   const int VSP = RC ? VS + (VS >> 3) : VS;   // floats per vector in shared memory and in the boundary lines
    const int nq = VS >> 2;
    const int nj = nq / G;   // chunks per lane (VS is a multiple of 4*G)
-   const int ncb = P.ncb;   // cost buffers per row: 1 = costs prefetched into registers (nj <= NJR), 2 = cp.async ring
+   const int ncb = RC ? 1 : P.ncb;   // cost buffers per row: 1 = costs prefetched into registers (nj <= NJR), 2 = cp.async ring
    const bool creg_mode = (ncb == 1);
-   const uint32_t vbytes = (uint32_t)VS * 4u;
+   const uint32_t vbytes = (uint32_t)VSP * 4u;
    const int tid = threadIdx.x;
    const int ncomp = blockDim.x - 64;   // two service warps follow the row threads
    const bool is_prod = (tid == ncomp);        // fetches the previous band's boundary row
@@ -413,7 +497,7 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
    // per-row shared memory: ring slots [R][VS] | cost buffers [ncbuf][VS] | scratch [K][VS] (weighted trunc)
    auto row_base = [&](int rr) -> float * { return thr + (size_t)rr * TS; };
    auto slot_of = [&](int rr, int px) -> float * {
-      return (rr < 0) ? virt + (px & (RV - 1)) * VS : row_base(rr) + (px % R) * VS;
+      return (rr < 0) ? virt + (px & (RV - 1)) * VSP : row_base(rr) + (px % R) * VSP;
    };
    auto m_of = [&](int rr, int px) -> float { return (rr < 0) ? vms[px & (RV - 1)] : msr[rr * 4 + (px % R)]; };
    // predecessor k of pixel (xs) of row rr: which row's slot, which pixel; returns the predecessor's type
@@ -428,9 +512,9 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
    };
 
    const float *ccv = D.cc;
-   float *bnd_out = D.bnd + (size_t)band * maxii * VS;
+   float *bnd_out = D.bnd + (size_t)band * maxii * VSP;
    float *bndm_out = D.bndm + (size_t)band * maxii;
-   const float *bnd_in = has_prev ? D.bnd + (size_t)(band - 1) * maxii * VS : nullptr;
+   const float *bnd_in = has_prev ? D.bnd + (size_t)(band - 1) * maxii * VSP : nullptr;
    const float *bndm_in = has_prev ? D.bndm + (size_t)(band - 1) * maxii : nullptr;
    int *prog_out = D.progress + band;
    const int *prog_in = has_prev ? D.progress + band - 1 : nullptr;
@@ -457,7 +541,7 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
    // sgm_transform_regs); one barrier per step, no cost buffer either
    const bool fused = !WEIGHTED && POT == POT_SGM && P.fused_sgm != 0;
    const int ncbuf = ((CHAINS && creg_mode) || fused) ? 0 : ncb;
-   auto cbuf_of = [&](int rr, int px) -> float * { return row_base(rr) + (R + (ncb == 2 ? (px & 1) : 0)) * VS; };
+   auto cbuf_of = [&](int rr, int px) -> float * { return row_base(rr) + (R + (ncb == 2 ? (px & 1) : 0)) * VSP; };
    auto prefetch_cost = [&](int s) {
       const int px = s - SIG * r + 1;   // the pixel my row handles in the NEXT step
       const bool go = rowok && px >= 0 && px < maxii;
@@ -473,7 +557,7 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
             const float4 *src = reinterpret_cast<const float4 *>(ccv + (size_t)(pix0 + (long long)px * g.dxs) * VS);
 #pragma unroll
             for (int j = 0; j < NJR; ++j)
-               if (j < nj) creg[j] = (MGM_EXP == 2) ? make_float4((float)j, 1.f, 2.f, 3.f) : __ldcs(src + gl + G * j);
+               if (j < nj) creg[j] = (MGM_EXP == 2) ? make_float4((float)j, 1.f, 2.f, 3.f) : (RC ? __ldg(src + gl + G * j) : __ldcs(src + gl + G * j));
          }
          return;
       }
@@ -484,12 +568,24 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
       }
       cp_async_commit();   // one (possibly empty) group per step keeps the wait count uniform
    };
+   auto prefetch_cost_l1 = [&](int s) {
+      const int px = s - SIG * r + 1;
+      if (rowok && px >= 0 && px < maxii) {
+         const float *line = ccv + (size_t)(pix0 + (long long)px * g.dxs) * VS;
+         for (int l = gl; l < (VS >> 5); l += G) asm volatile("prefetch.global.L1 [%0];" ::"l"(line + l * 32));
+      }
+   };
    prefetch_cost(-1);   // pixel 0 of row 0 (the other rows start later)
    // cp.async mode: lanes of warps that run min-convolution chains in phase 2 issue their prefetch at the top of
    // the step; all other warps are idle in phase 2 and issue it there (the LSU is less busy then).
    // Register mode: every lane issues its loads right after its gather (they complete during phase 2).
    const bool late_prefetch = !creg_mode && CHAINS && (warp_id - gw0 >= 2 * ncw);
 
+   // optional phase timing (option "dbg"): thread 0 of the block adds the clock cycles of each phase of its steps
+   const bool timing = P.dbg != nullptr && tid == 0;
+   long long tacc[6] = {0, 0, 0, 0, 0, 0}, tl = 0;
+   auto tick = [&](int i) { if (timing) { const long long t = clock64(); tacc[i] += t - tl; tl = t; } };
+   if (timing) tl = clock64();
    for (int s = 0; s < nsteps; ++s) {
       if (!late_prefetch && !creg_mode) prefetch_cost(s);
       if (is_prod && has_prev) {
@@ -507,7 +603,7 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
             const int slot = next_px & (RV - 1);
             if (NEEDM) vms[slot] = __ldcg(bndm_in + next_px);
             mbar_expect_tx(&vbar[slot], vbytes);
-            tma_load_1d(virt + slot * VS, bnd_in + (size_t)next_px * VS, vbytes, &vbar[slot]);
+            tma_load_1d(virt + slot * VSP, bnd_in + (size_t)next_px * VSP, vbytes, &vbar[slot]);
             ++next_px;
          }
       }
@@ -526,10 +622,11 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
          }
       }
       grp.begin_step(s == 0);   // group ordering (RowGroup): token from the group above, slot reuse below
+      tick(0);
       const int xs = s - SIG * r;
       const bool act = rowok && xs >= 0 && xs < maxii;
       const long long pix = pix0 + (long long)xs * g.dxs;
-      float2 *cur = reinterpret_cast<float2 *>(row_base(r) + (act ? (xs % R) : 0) * VS);
+      float2 *cur = reinterpret_cast<float2 *>(row_base(r) + (act ? (xs % R) : 0) * VSP);
       float *Cbf = (CHAINS && creg_mode) ? reinterpret_cast<float *>(cur) : cbuf_of(r, xs);   // where the message is built
       float2 *Cb = reinterpret_cast<float2 *>(Cbf);
 #ifdef MGM_Y_FROM_PIX
@@ -712,15 +809,29 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
             if (fused) sgm_transform_regs<K, NJR, A16, G>(creg, nj, nq, gl, gmask, m, P.P1, P.P2, cur);
          }
       }
-      if (creg_mode) prefetch_cost(s);   // costs of the next pixel -> registers, in flight during phase 2
-      if (!fused) {
+      if (creg_mode && !RC) prefetch_cost(s);   // costs of the next pixel -> registers, in flight during phase 2
+      if constexpr (RC) {
+         // phase 2 by the worker's own 8 lanes, from registers (chain_regs): the slot only has to be ordered within the warp.
+         // The chain needs the registers the prefetched costs would occupy: the next pixel's costs are pulled into L1
+         // before the chain and loaded after it (an L1 hit by then).
+         tick(1);
+         prefetch_cost_l1(s);
+         __syncwarp();
+         tick(2);
+         if (act) chain_regs<NJR>(cur, nj, gl, gmask, P.P1, m + P.P2, (K == 2) ? 0.0f : m);
+         tick(3);
+         prefetch_cost(s);
+      } else if (!fused) {
+         tick(1);
          grp.gather_done(s == nsteps - 1);
          grp.sync();
-      }
+         tick(2);
+      } else { tick(1); tick(2); }
 
       // ---------------- phase 2: build the neighbour-side transform of the message in the ring slot
       if (late_prefetch) prefetch_cost(s);
-      if constexpr (CHAINS) {
+      if constexpr (RC) {
+      } else if constexpr (CHAINS) {
          // minConvTruncatedLinear of the finished message, one lane pair per row (the first 2*ncw warps of the group)
          const int wg = warp_id - gw0;
          if (tid < ncomp + 64 && wg >= 0 && wg < 2 * ncw) {
@@ -769,7 +880,10 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
             for (int j = 0; j < nj; ++j) st16<A16>(cur, gl + G * j, ld16<A16>(Cb, gl + G * j));   // weighted paths keep the raw message
          }
       }
+      if constexpr (!RC) tick(3);
+      tick(4);
       grp.sync();
+      tick(5);
 
       // ---------------- hand the boundary row to the next band: the publisher warp copies the transformed vector
       // of the last row to the boundary line and releases the counter right away (pixels [0,xl] are in memory)
@@ -777,12 +891,16 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
          const int xl = s - SIG * (nrows - 1);
          if (xl >= 0 && xl < maxii) {
             if (NEEDM && lane_id == 0) bndm_out[xl] = msr[(nrows - 1) * 4 + (xl % R)];
-            warp_copy_vector(bnd_out + (size_t)xl * VS, slot_of(nrows - 1, xl), VS, lane_id);
+            warp_copy_vector(bnd_out + (size_t)xl * VSP, slot_of(nrows - 1, xl), VSP, lane_id);
             warp_publish(prog_out, xl + 1, lane_id);
          }
       }
    }
 
+   if (timing) {
+      for (int i = 0; i < 6; ++i) atomicAdd(P.dbg + i, (unsigned long long)tacc[i]);
+      atomicAdd(P.dbg + 6, (unsigned long long)nsteps);
+   }
    // epilogue: save mbarrier parities
    cp_async_wait<0>();
    if (tid == 0) phase[vph_idx] = vph;
@@ -801,14 +919,15 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
 // maxii + 2*maxjj steps (row-per-worker, lag 2) to maxjj + (band hand-off) * #bands.
 // Everything else (register-resident cost prefetch, gather, exact min-convolution chains / SGM transform,
 // boundary lines through TMA stores + release/acquire counters + TMA loads) is as in run_band.
-template <int POT, int K, int GL>
+template <int POT, int K, int GL, bool RC = false>
 __device__ void run_band_shear(const AggParams &P, const SweepDesc &D, const int band, unsigned char *smem) {
    constexpr int G = GL;
+   static_assert(!RC || (POT == POT_TRUNC && GL == 8), "register chains: unweighted truncated linear, 8 lanes");
    const int pass = D.pass;
    static_assert(K <= 3, "the sheared wavefront needs predecessors in the row above only");
    constexpr bool NEEDM = (POT == POT_TRUNC && K == 2);
    constexpr bool CHAINS = (POT == POT_TRUNC);
-   constexpr bool A16 = (POT == POT_TRUNC);   // 16-byte aligned rows and accesses (ld16 / st16)
+   constexpr int A16 = RC ? 2 : (POT == POT_TRUNC ? 1 : 0);   // shared-memory vector layout (ld16 / st16)
    constexpr int JB = MGM_JB;
    constexpr int NJR = MGM_AGG_CREG;
 
@@ -818,11 +937,12 @@ __device__ void run_band_shear(const AggParams &P, const SweepDesc &D, const int
    const int T = P.T[1];
    const int TS = P.TS[1];
    const int VS = P.VS;
+   const int VSP = RC ? VS + (VS >> 3) : VS;   // floats per vector in shared memory and in the boundary lines
    const int nq = VS >> 2;
    const int nj = nq / G;
-   const int ncb = P.ncb;
+   const int ncb = RC ? 1 : P.ncb;
    const bool creg_mode = (ncb == 1);
-   const uint32_t vbytes = (uint32_t)VS * 4u;
+   const uint32_t vbytes = (uint32_t)VSP * 4u;
    const int tid = threadIdx.x;
    const int ncomp = blockDim.x - 64;
    const bool is_prod = (tid == ncomp);
@@ -863,16 +983,16 @@ __device__ void run_band_shear(const AggParams &P, const SweepDesc &D, const int
    // per-worker shared memory: ring slots [2][VS] (position v&1) | cost buffers [ncb][VS] (none when in place)
    auto row_base = [&](int rr) -> float * { return thr + (size_t)rr * TS; };
    auto slot_of = [&](int rr, int v) -> float * {
-      return (rr < 0) ? virt + ((-rr - 1) * RV + (v & (RV - 1))) * VS : row_base(rr) + (v & 1) * VS;
+      return (rr < 0) ? virt + ((-rr - 1) * RV + (v & (RV - 1))) * VSP : row_base(rr) + (v & 1) * VSP;
    };
    auto m_of = [&](int rr, int v) -> float { return (rr < 0) ? vms[(-rr - 1) * RV + (v & (RV - 1))] : msr[rr * 4 + (v & 1)]; };
-   auto cbuf_of = [&](int rr, int v) -> float * { return row_base(rr) + (2 + (ncb == 2 ? (v & 1) : 0)) * VS; };
+   auto cbuf_of = [&](int rr, int v) -> float * { return row_base(rr) + (2 + (ncb == 2 ? (v & 1) : 0)) * VSP; };
 
    const float *ccv = D.cc;
    // boundary lines: [band][line][maxjj][VS], line 0 = last worker of the band, line 1 = the one before
-   float *bnd_out = D.bnd + (size_t)band * 2 * maxjj * VS;
+   float *bnd_out = D.bnd + (size_t)band * 2 * maxjj * VSP;
    float *bndm_out = D.bndm + (size_t)band * 2 * maxjj;
-   const float *bnd_in = has_prev ? D.bnd + (size_t)(band - 1) * 2 * maxjj * VS : nullptr;
+   const float *bnd_in = has_prev ? D.bnd + (size_t)(band - 1) * 2 * maxjj * VSP : nullptr;
    const float *bndm_in = has_prev ? D.bndm + (size_t)(band - 1) * 2 * maxjj : nullptr;
    int *prog_out = D.progress + band;
    const int *prog_in = has_prev ? D.progress + band - 1 : nullptr;
@@ -904,7 +1024,7 @@ __device__ void run_band_shear(const AggParams &P, const SweepDesc &D, const int
             const float4 *src = reinterpret_cast<const float4 *>(ccv + (size_t)(pix_u + (long long)vn * dv) * VS);
 #pragma unroll
             for (int j = 0; j < NJR; ++j)
-               if (j < nj) creg[j] = __ldcs(src + gl + G * j);
+               if (j < nj) creg[j] = RC ? __ldg(src + gl + G * j) : __ldcs(src + gl + G * j);
          }
          return;
       }
@@ -914,6 +1034,13 @@ __device__ void run_band_shear(const AggParams &P, const SweepDesc &D, const int
          for (int j = 0; j < nj; ++j) cp_async16(dst + 4 * (gl + G * j), src + gl + G * j);
       }
       cp_async_commit();
+   };
+   auto prefetch_cost_l1 = [&](int v) {
+      const int vn = v + 1;
+      if (rowok && vn >= my_lo && vn <= my_hi) {
+         const float *line = ccv + (size_t)(pix_u + (long long)vn * dv) * VS;
+         for (int l = gl; l < (VS >> 5); l += G) asm volatile("prefetch.global.L1 [%0];" ::"l"(line + l * 32));
+      }
    };
    prefetch_cost(sb - 1);
    const bool late_prefetch = !creg_mode && CHAINS && (warp_id - gw0 >= 2 * ncw);
@@ -937,8 +1064,8 @@ __device__ void run_band_shear(const AggParams &P, const SweepDesc &D, const int
                vms[RV + slot] = __ldcg(bndm_in + maxjj + next_p);
             }
             mbar_expect_tx(&vbar[slot], 2 * vbytes);
-            tma_load_1d(virt + slot * VS, bnd_in + (size_t)next_p * VS, vbytes, &vbar[slot]);
-            tma_load_1d(virt + (RV + slot) * VS, bnd_in + ((size_t)maxjj + next_p) * VS, vbytes, &vbar[slot]);
+            tma_load_1d(virt + slot * VSP, bnd_in + (size_t)next_p * VSP, vbytes, &vbar[slot]);
+            tma_load_1d(virt + (RV + slot) * VSP, bnd_in + ((size_t)maxjj + next_p) * VSP, vbytes, &vbar[slot]);
             ++next_p;
          }
       }
@@ -958,7 +1085,7 @@ __device__ void run_band_shear(const AggParams &P, const SweepDesc &D, const int
       const bool act = rowok && v >= my_lo && v <= my_hi;
       const int xs = u - v;
       const long long pix = pix_u + (long long)v * dv;
-      float2 *cur = reinterpret_cast<float2 *>(row_base(r) + (v & 1) * VS);
+      float2 *cur = reinterpret_cast<float2 *>(row_base(r) + (v & 1) * VSP);
       float *Cbf = inplace ? reinterpret_cast<float *>(cur) : cbuf_of(r, v);   // where the message is built
       float2 *Cb = reinterpret_cast<float2 *>(Cbf);
 #ifdef MGM_Y_FROM_PIX
@@ -1063,15 +1190,21 @@ __device__ void run_band_shear(const AggParams &P, const SweepDesc &D, const int
             if (fused) sgm_transform_regs<K, NJR, A16, G>(creg, nj, nq, gl, gmask, m, P.P1, P.P2, cur);
          }
       }
-      if (creg_mode) prefetch_cost(v);
-      if (!fused) {
+      if (creg_mode && !RC) prefetch_cost(v);
+      if constexpr (RC) {
+         prefetch_cost_l1(v);   // see run_band
+         __syncwarp();
+         if (act) chain_regs<NJR>(cur, nj, gl, gmask, P.P1, m + P.P2, (K == 2) ? 0.0f : m);
+         prefetch_cost(v);
+      } else if (!fused) {
          grp.gather_done(v == se);
          grp.sync();
       }
 
       // ---------------- phase 2: neighbour-side transform of the message into ring slot v&1
       if (late_prefetch) prefetch_cost(v);
-      if constexpr (CHAINS) {
+      if constexpr (RC) {
+      } else if constexpr (CHAINS) {
          const int wg = warp_id - gw0;
          if (wg >= 0 && wg < 2 * ncw) {
             const int cw = wg % ncw, cdir = wg / ncw;
@@ -1109,7 +1242,7 @@ __device__ void run_band_shear(const AggParams &P, const SweepDesc &D, const int
             const int br = nrows - 1 - line;
             if (v >= vlo(u0 + br) && v <= vhi(u0 + br)) {
                if (NEEDM && lane_id == 0) bndm_out[(size_t)line * maxjj + v] = msr[br * 4 + (v & 1)];
-               warp_copy_vector(bnd_out + ((size_t)line * maxjj + v) * VS, slot_of(br, v), VS, lane_id);
+               warp_copy_vector(bnd_out + ((size_t)line * maxjj + v) * VSP, slot_of(br, v), VSP, lane_id);
             }
          }
          warp_publish(prog_out, v + 1, lane_id);   // positions <= v of both boundary workers are in global memory
@@ -1267,8 +1400,10 @@ union __align__(16) AggStage {
    __device__ AggStage() {}
 };
 
-template <int POT, int K, bool WEIGHTED, int GL>
-__global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(const AggParams P) {
+// RC: the register-chain kernels (unweighted truncated linear, 8 lanes per worker) are separate entry points with a
+// smaller block (48 workers) so that a thread can hold two label segments and the prefetched costs (144 registers)
+template <int POT, int K, bool WEIGHTED, int GL, bool RC = false>
+__global__ void __launch_bounds__(RC ? MGM_AGG_MAX_THREADS_RC : MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(const AggParams P) {
    extern __shared__ __align__(128) unsigned char smem[];
    __shared__ int2 s_ticket;
    __shared__ AggStage s_stage;
@@ -1312,15 +1447,14 @@ __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(c
       else {
          const SweepDesc &D = s_stage.d;
          const int pass = D.pass;
-#ifndef MGM_NO_KNIGHT
-         if (pass >= 8) run_band<POT, K, WEIGHTED, true, GL, true>(P, D, pb.y, smem);
-         else
-#endif
-         if (pass < 4) run_band<POT, K, WEIGHTED, false, GL>(P, D, pb.y, smem);
-         else if constexpr (!WEIGHTED && K <= 3) {
-            if (P.shear) run_band_shear<POT, K, GL>(P, D, pb.y, smem);
-            else run_band<POT, K, WEIGHTED, true, GL>(P, D, pb.y, smem);
-         } else run_band<POT, K, WEIGHTED, true, GL>(P, D, pb.y, smem);
+         {
+            if (pass >= 8) run_band<POT, K, WEIGHTED, true, GL, true, RC>(P, D, pb.y, smem);
+            else if (pass < 4) run_band<POT, K, WEIGHTED, false, GL, false, RC>(P, D, pb.y, smem);
+            else if constexpr (!WEIGHTED && K <= 3) {
+               if (P.shear) run_band_shear<POT, K, GL, RC>(P, D, pb.y, smem);
+               else run_band<POT, K, WEIGHTED, true, GL, false, RC>(P, D, pb.y, smem);
+            } else run_band<POT, K, WEIGHTED, true, GL, false, RC>(P, D, pb.y, smem);
+         }
       }
       __syncthreads();   // the staged descriptor and the ticket are rewritten by the next claim
    }
@@ -1329,9 +1463,9 @@ __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_kernel(c
 // ---------------------------------------------------------------- host side
 static int ring_slots(int cls, int K) { return ((cls != CLS_AXIS || K == 4) ? 2 : 1) + 2; }
 
-template <int POT, int K, bool WEIGHTED, int GL = MGM_AGG_GROUP>
+template <int POT, int K, bool WEIGHTED, int GL = MGM_AGG_GROUP, bool RC = false>
 static cudaError_t launch_t(const AggParams &P, const AggPlan &plan, cudaStream_t st) {
-   auto kern = mgm_aggregate_kernel<POT, K, WEIGHTED, GL>;
+   auto kern = mgm_aggregate_kernel<POT, K, WEIGHTED, GL, RC>;
    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
    if (e != cudaSuccess) return e;
    int per_sm = 0;
@@ -1357,6 +1491,16 @@ static cudaError_t launch_k(int K, const AggParams &P, const AggPlan &plan, cuda
          case 2: return launch_t<POT, 2, WEIGHTED, 4>(P, plan, st);
          case 3: return launch_t<POT, 3, WEIGHTED, 4>(P, plan, st);
          default: return launch_t<POT, 4, WEIGHTED, 4>(P, plan, st);
+         }
+      }
+   }
+   if constexpr (POT == POT_TRUNC && !WEIGHTED) {
+      if (plan.regchain) {
+         switch (K) {
+         case 1: return launch_t<POT, 1, WEIGHTED, 8, true>(P, plan, st);
+         case 2: return launch_t<POT, 2, WEIGHTED, 8, true>(P, plan, st);
+         case 3: return launch_t<POT, 3, WEIGHTED, 8, true>(P, plan, st);
+         default: return launch_t<POT, 4, WEIGHTED, 8, true>(P, plan, st);
          }
       }
    }
@@ -1387,23 +1531,28 @@ static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, b
       const long bands = 2L * ((ny + t4 - 1) / t4 + (nx + t4 - 1) / t4) + 4L * ((nx + ny + t4 - 2) / t4);
       if (bands >= 2L * num_sms || tune.lanes == 4) plan->lanes = 4;
    }
-   const int tcap = (MGM_AGG_MAX_THREADS - 64) / plan->lanes;   // rows per CTA allowed by the thread budget
    // costs prefetched into registers when a lane's share fits (one cost buffer per row), else a cp.async ring of two
    plan->ncb = (VS / (4 * plan->lanes) <= MGM_AGG_CREG && !tune.no_creg) ? 1 : 2;
+   // unweighted truncated-linear kernels with register-resident costs: min-convolution chains in registers by the
+   // worker's own lanes (chain_regs), vectors in the padded layout (VSP floats per vector), smaller block
+   plan->regchain = (!weighted && pot == POT_TRUNC && plan->ncb == 1 && plan->lanes == 8 && want_groups == 1 && tune.reg_chains) ? 1 : 0;
+   const int tcap = ((plan->regchain ? MGM_AGG_MAX_THREADS_RC : MGM_AGG_MAX_THREADS) - 64) / plan->lanes;   // rows per CTA allowed by the thread budget
    plan->shear = shear;
    const int nvirt = shear ? 2 : 1;   // boundary workers kept per position
    // unweighted truncated-linear kernels with register-resident costs build the message in its ring slot and run
    // the min-convolution in place: no cost buffer
    // ... and the unweighted SGM kernels transform the message straight from registers (one group only)
    plan->fused_sgm = (!weighted && pot == POT_SGM && plan->ncb == 1 && want_groups == 1 && !tune.no_fused_sgm) ? 1 : 0;
+   const int VSP = plan->regchain ? VS + (VS >> 3) : VS;
+   plan->VSP = VSP;
    const int ncbuf = (!weighted && plan->ncb == 1 && (pot == POT_TRUNC || plan->fused_sgm)) ? 0 : plan->ncb;
    for (int cls = 0; cls < 3; ++cls) {
       int nbuf = ((cls == CLS_DIAG && shear) ? 2 : ring_slots(cls, K)) + ncbuf + xtra;
-      int TS = nbuf * VS;
-      if (plan->ncb == 1 && pot == POT_SGM) TS += 2;   // 8 bytes modulo 128: 64-bit accesses of adjacent rows tile the banks
+      int TS = nbuf * VSP;
+      if ((plan->ncb == 1 && pot == POT_SGM) || plan->regchain) TS += 2;   // 8 bytes modulo 128: 64-bit accesses of adjacent rows tile the banks
       else if (((TS >> 2) & 1) == 0) TS += 4;          // 16-byte aligned rows (truncated linear, cp.async mode): odd number of 16-byte units
       plan->TS[cls] = TS;
-      size_t fixed = 1024 + (size_t)nvirt * RV * VS * 4 + (size_t)tcap * (16 + 16 + 4) + RV * 16;
+      size_t fixed = 1024 + (size_t)nvirt * RV * VSP * 4 + (size_t)tcap * (16 + 16 + 4) + RV * 16;
       long avail = (long)max_smem - (long)fixed;
       int Tc = avail > 0 ? (int)(avail / ((long)TS * 4)) : 0;
       if (Tc > tcap) Tc = tcap;
@@ -1430,7 +1579,7 @@ static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, b
    plan->off_vbar = off; off += RV * 8;
    plan->off_ms = off; off += (size_t)tm * 16;
    plan->off_vms = off; off += (size_t)nvirt * RV * 4; off = (off + 127) & ~(size_t)127;
-   plan->off_virt = off; off += (size_t)nvirt * RV * VS * 4; off = (off + 127) & ~(size_t)127;
+   plan->off_virt = off; off += (size_t)nvirt * RV * VSP * 4; off = (off + 127) & ~(size_t)127;
    plan->off_thr = off;
    // the rows region is sized for the classes this launch runs: the knight class (ring of 4 slots) only with more than
    // 8 sweeps -- shared memory the kernel does not need stays L1 (measured: 228 KB instead of 191 KB of shared memory
@@ -1465,11 +1614,11 @@ void agg_sweep_bands(const AggPlan &plan, int pass, int nx, int ny, int *nb, siz
    if (cls == CLS_DIAG && plan.shear) {
       // sheared wavefront: bands of T anti-diagonals, two boundary lines of maxjj positions per band
       *nb = (g.maxii + g.maxjj - 1 + T - 1) / T;
-      *bnd_floats = (size_t)*nb * 2 * g.maxjj * plan.VS;
+      *bnd_floats = (size_t)*nb * 2 * g.maxjj * plan.VSP;
       *bndm_floats = (size_t)*nb * 2 * g.maxjj;
    } else {
       *nb = (g.maxjj + T - 1) / T;
-      *bnd_floats = (size_t)*nb * g.maxii * plan.VS;
+      *bnd_floats = (size_t)*nb * g.maxii * plan.VSP;
       *bndm_floats = (size_t)*nb * g.maxii;
    }
 }

@@ -5,6 +5,7 @@
 
 #define MGM_AGG_GROUP 8           // lanes cooperating on one scan row
 #define MGM_AGG_MAX_THREADS 512   // 56 rows x 8 lanes + two service warps (boundary consumer / publisher); 128 registers per thread
+#define MGM_AGG_MAX_THREADS_RC 384   // register-chain kernels: 40 rows x 8 lanes + two service warps = 3 warps per SM sub-partition: 168 registers per thread
 #define MGM_AGG_CREG 8            // 16-byte cost chunks per lane prefetched into registers (covers 256 labels)
 #define MGM_MAX_SLABS 8           // row slabs of a message volume (multi-GPU: one per rank, peer mappings)
 #define MGM_MAX_NDIR 16           // sweeps per stereo pair (8 of the reference + 8 defined here, common.cuh)
@@ -56,6 +57,7 @@ struct AggParams {
    int shear;                  // 1: sweeps 4-7 run as sheared wavefronts (bands of anti-diagonals, run_band_shear)
    int ng[3];                  // row groups per band by SweepClass, each on its own named barrier
    int fused_sgm;              // 1: unweighted SGM kernels transform the message from registers (one barrier per step)
+   int regchain;               // 1: unweighted truncated-linear kernels run the min-convolution from registers (chain_regs)
    int cc_pf;                  // > 0: matching costs of the pixel cc_pf steps ahead are prefetched into L2
    float P1, P2;
    // fused finish (optional): CTAs without a band to run take tiles of pixels whose sweeps are all complete and do
@@ -70,6 +72,7 @@ struct AggParams {
    int npairs;
    WtaParams fin0;             // npairs == 1: the pair's finish parameters as kernel parameters (constant bank operands
                                // in the per-pixel loop instead of shared-memory loads: 25.1 -> 19.9 ms on the headline step)
+   unsigned long long *dbg;    // optional 8-word phase-timing accumulator (option "dbg"), or nullptr
    // dynamic shared memory carve-up (bytes)
    unsigned off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };
@@ -81,6 +84,9 @@ struct AggTuning {
    int groups = 1;                     // row groups per band (RowGroup)
    int no_creg = 0;                    // 1: cp.async cost ring instead of register-resident costs
    int no_fused_sgm = 0;               // 1: SGM transform through shared memory (two barriers per step)
+   int reg_chains = 0;                 // 1: truncated-linear min-convolution from registers by the worker's own 8 lanes
+                                       // (chain_regs; parity-tested, measured SLOWER than the lane-pair chains: the
+                                       // hops between lanes repeat the additions in every lane)
    int lanes = 0;                      // 0 auto, 4 or 8 lanes per worker (unweighted SGM kernels)
    int no_shear = 0;                   // 1: diagonal sweeps row-per-worker
    int static_order = 0;               // 1: claim bands without the readiness test
@@ -90,10 +96,11 @@ struct AggTuning {
                                        // the SGM-potential kernels, whose steps are shorter than the HBM latency)
    int batch = 8;                      // stereo pairs in flight per launch (batch entry points)
    int verbose = 0;
+   int dbg = 0;                        // 1: print the per-phase clock cycles of the register-chain band steps (axis sweeps)
 };
 
 struct AggPlan {
-   int VS, T[3], TS[3], ncb, shear, ng[3], fused_sgm, lanes, block, num_sms, verbose;
+   int VS, VSP, T[3], TS[3], ncb, shear, ng[3], fused_sgm, regchain, lanes, block, num_sms, verbose;
    size_t smem;
    size_t off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };

@@ -163,6 +163,7 @@ static bool apply_option(mgmb200_ctx *c, const char *name, const char *value) {
    if (!strcmp(name, "groups")) { t.groups = iv; return true; }
    if (!strcmp(name, "no_creg")) { t.no_creg = iv; return true; }
    if (!strcmp(name, "no_fused_sgm")) { t.no_fused_sgm = iv; return true; }
+   if (!strcmp(name, "reg_chains")) { t.reg_chains = iv; return true; }
    if (!strcmp(name, "lanes4")) { t.lanes = iv ? 4 : 0; return true; }
    if (!strcmp(name, "lanes8")) { t.lanes = iv ? 8 : 0; return true; }
    if (!strcmp(name, "no_shear")) { t.no_shear = iv; return true; }
@@ -171,6 +172,7 @@ static bool apply_option(mgmb200_ctx *c, const char *name, const char *value) {
    if (!strcmp(name, "cc_pf")) { t.cc_pf = iv; return true; }
    if (!strcmp(name, "batch")) { t.batch = iv < 1 ? 1 : iv; return true; }
    if (!strcmp(name, "verbose")) { t.verbose = iv; return true; }
+   if (!strcmp(name, "dbg")) { t.dbg = iv; return true; }
    if (!strcmp(name, "fin_tile")) {
       int a = 0, b = 0;
       if (!value || sscanf(value, "%dx%d", &a, &b) != 2 || a < 1 || b < 1) return false;
@@ -182,8 +184,8 @@ static bool apply_option(mgmb200_ctx *c, const char *name, const char *value) {
 static void tuning_from_env(mgmb200_ctx *c) {
    c->tune = AggTuning();
    c->rows_override = 0;
-   static const char *const names[] = {"rows_per_band", "rows_axis", "rows_diag", "groups", "no_creg", "no_fused_sgm", "lanes4",
-                                       "lanes8", "no_shear", "static_order", "no_fused_finish", "cc_pf", "batch", "verbose", "fin_tile"};
+   static const char *const names[] = {"rows_per_band", "rows_axis", "rows_diag", "groups", "no_creg", "no_fused_sgm", "reg_chains", "lanes4",
+                                       "lanes8", "no_shear", "static_order", "no_fused_finish", "cc_pf", "batch", "verbose", "dbg", "fin_tile"};
    for (const char *n : names) {
       char env[64] = "MGMB200_";
       size_t k = strlen(env);
@@ -578,7 +580,7 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
    P.nslabs = R.nslabs; P.slab_rows = R.slab_rows;
    P.slab_magic = R.nslabs > 1 ? (unsigned)((0x100000000ull + (unsigned)R.slab_rows - 1) / (unsigned)R.slab_rows) : 0u;
    for (int i = 0; i < 3; i++) { P.T[i] = plan.T[i]; P.TS[i] = plan.TS[i]; P.ng[i] = plan.ng[i]; }
-   P.ncb = plan.ncb; P.shear = plan.shear; P.fused_sgm = plan.fused_sgm;
+   P.ncb = plan.ncb; P.shear = plan.shear; P.fused_sgm = plan.fused_sgm; P.regchain = plan.regchain;
    // measured (profiles/r02_experiments.md): 1920x1080x128 TSGM=2 8.37 -> 6.96 ms, 4096x4096x64 25.8 -> 22.8 ms
    P.cc_pf = c->tune.cc_pf >= 0 ? c->tune.cc_pf : (pot == POT_SGM ? 3 : 0);
    P.P1 = P1; P.P2 = P2;
@@ -593,9 +595,22 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
    P.off_phase = (unsigned)plan.off_phase; P.off_cbar = (unsigned)plan.off_cbar; P.off_vbar = (unsigned)plan.off_vbar;
    P.off_ms = (unsigned)plan.off_ms; P.off_vms = (unsigned)plan.off_vms; P.off_virt = (unsigned)plan.off_virt;
    P.off_thr = (unsigned)plan.off_thr;
+   if (c->tune.dbg) {
+      RET(c->dbgbuf.reserve(64));
+      CU(cudaMemsetAsync(c->dbgbuf.p, 0, 64, c->stream));
+      P.dbg = c->dbgbuf.as<unsigned long long>();
+   }
    CU(agg_launch(P, plan, pot, K, weighted, c->stream));
    c->n_launches++;
    c->fin_done = fuse;
+   if (c->tune.dbg) {   // profiling aid: synchronises
+      unsigned long long h[8];
+      CU(cudaMemcpyAsync(h, c->dbgbuf.p, 64, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      if (h[6])
+         fprintf(stderr, "[mgmb200 phase timing] steps=%llu cycles/step: top=%.0f gather=%.0f sync1=%.0f transform=%.0f rest=%.0f barrier=%.0f\n",
+                 h[6], (double)h[0] / h[6], (double)h[1] / h[6], (double)h[2] / h[6], (double)h[3] / h[6], (double)h[4] / h[6], (double)h[5] / h[6]);
+   }
    return 0;
 }
 

@@ -97,7 +97,7 @@ def test_mgm_matches_oracle(ctx, K, felz, weighted):
 @pytest.mark.parametrize("knob", ["MGMB200_GROUPS=2", "MGMB200_GROUPS=3", "MGMB200_NO_SHEAR=1", "MGMB200_NO_CREG=1",
                                   "MGMB200_STATIC_ORDER=1", "MGMB200_NO_FUSED_SGM=1", "MGMB200_LANES4=1",
                                   "MGMB200_NO_FUSED_FINISH=1", "MGMB200_FIN_TILE=7x3", "MGMB200_FIN_TILE=4096x4096",
-                                  "MGMB200_CC_PF=3"])
+                                  "MGMB200_CC_PF=3", "MGMB200_REG_CHAINS=1"])
 def test_mgm_alternative_kernel_layouts(ctx, knob):
     """The aggregation kernel's alternative layouts (row groups on their own named barriers, row-per-worker diagonal
     sweeps, cp.async cost ring, static band order, finish stage as a separate launch or fused with other tile sizes,
