@@ -343,14 +343,10 @@ static int costvolume_dev_impl(mgmb200_ctx *c, const float *d_u, const float *d_
    if (win < 1) return fail(MGMB200_EINVAL, "CENSUS_NCC_WIN=%d", win);
    CU(cudaSetDevice(c->device));
    const int L = dmax - dmin + 1, VS = mgmb200_padded_labels(L);
-   // the reference picks the cost function before forcing census/census (mgm_costvolume.h:355-362);
-   // "-p census" with another distance would run it on bit patterns reinterpreted as floats.
-   if (pf == PF_CENSUS && dist != DIST_CENSUS)
-      return fail(MGMB200_EUNSUPPORTED, "prefilter census with a non-census distance is not supported");
    const float *uu = d_u, *vv = d_v;
    const uint32_t *cu = nullptr, *cv = nullptr;
    int cnch = nch;
-   if (dist == DIST_CENSUS) {
+   if (dist == DIST_CENSUS || pf == PF_CENSUS) {
       cnch = census_nwords(nch, win);
       if (cnch < 1 || cnch > 32) return fail(MGMB200_EUNSUPPORTED, "census window %d with %d channels", win, nch);
       RET(c->cu.reserve((size_t)nx * ny * cnch * 4));
@@ -358,6 +354,13 @@ static int costvolume_dev_impl(mgmb200_ctx *c, const float *d_u, const float *d_
       CU(census_launch(d_u, nx, ny, nch, win, c->cu.as<uint32_t>(), c->stream));
       CU(census_launch(d_v, vnx, vny, nch, win, c->cv.as<uint32_t>(), c->stream));
       cu = c->cu.as<uint32_t>(); cv = c->cv.as<uint32_t>();
+      if (dist != DIST_CENSUS) {
+         // "-p census -t ad|sd|ncc|bt*": the reference picks the cost function before it forces census/census
+         // (mgm_costvolume.h:355 vs :358-362), so the distance runs on the census bit strings held in float channels
+         // (census_tools.cc:76-99) -- reproduced: the words are the same bits, read as floats, one channel per word
+         uu = reinterpret_cast<const float *>(cu); vv = reinterpret_cast<const float *>(cv);
+         cu = cv = nullptr;
+      }
    } else if (pf == PF_SOBELX) {
       RET(c->fu.reserve((size_t)nx * ny * nch * 4));
       RET(c->fv.reserve((size_t)vnx * vny * nch * 4));
@@ -897,9 +900,10 @@ extern "C" int mgmb200_costvolume(mgmb200_ctx *c, const float *u, const float *v
    return 0;
 }
 
-// uploads a host volume (pixel-major or label-major) into the padded c->cc and validates the
-// fast-path preconditions
-static int upload_volume(mgmb200_ctx *c, const float *cc, int nx, int ny, int L, int label_major) {
+// uploads a host volume (pixel-major or label-major) into the padded c->cc and scans it for values outside the fast
+// path's envelope (*flags: bit0 a vector without any finite entry, bit1 NaN, bit2 -INF); with flags == nullptr such a
+// volume is rejected
+static int upload_volume(mgmb200_ctx *c, const float *cc, int nx, int ny, int L, int label_major, int *flags = nullptr) {
    const int VS = mgmb200_padded_labels(L);
    const size_t np = (size_t)nx * ny;
    RET(c->cc.reserve(np * VS * 4));
@@ -913,11 +917,51 @@ static int upload_volume(mgmb200_ctx *c, const float *cc, int nx, int ny, int L,
    CU(validate_volume_launch(c->cc.as<float>(), (long long)np, L, VS, c->flags.as<int>(), c->num_sms, c->stream));
    int fl = 0;
    RET(read_flags(c, &fl));
+   if (flags) { *flags = fl; return 0; }
    if (fl)
       return fail(MGMB200_EUNSUPPORTED, "cost volume outside the supported envelope:%s%s%s",
                   (fl & 1) ? " a pixel without any finite cost" : "", (fl & 2) ? " NaN cost" : "",
                   (fl & 4) ? " -INF cost" : "");
    return 0;
+}
+
+namespace mgm {
+cudaError_t agg_generic_launch(const float *cc, const float *w, int nx, int ny, int L, int VS, float P1, float P2, int NDIR,
+                               int K, int variant, unsigned mask, float *const *ldir, int *d_counters, float *d_scratch,
+                               int nwarps, cudaStream_t st);
+}
+// mgm() for inputs outside the fast path's envelope (non-finite costs, weights or penalties): the compare-select
+// kernel of aggregate_generic.cu, then the ordinary finish kernel (whose sums, isfinite test and '>' argmin are the
+// reference's own, mgm_core.cc:582-609).  Uniform ranges only.
+static int aggregate_generic(mgmb200_ctx *c, const float *d_cc, const float *d_w, int nx, int ny, int dmin, int L, float P1,
+                             float P2, int NDIR, int K, int felz, int fix, int refine, float *d_out, float *d_outcost,
+                             float *d_S) {
+   if (NDIR < 1 || NDIR > MGM_MAX_NDIR) return fail(MGMB200_EUNSUPPORTED, "NDIR=%d", NDIR);
+   if (K < 1 || K > 4) return fail(MGMB200_EINVAL, "MGM/TSGM=%d not in 1..4", K);
+   const int VS = mgmb200_padded_labels(L);
+   const size_t vol = (size_t)nx * ny * VS * sizeof(float);
+   bool weighted = false;
+   if (d_w) {   // mgm_core.cc:420-422: any weight != 1 selects the W variants
+      RET(clear_flags(c));
+      CU(scan_weights_launch(d_w, (long long)nx * ny * 8, c->flags.as<int>(), c->stream));
+      int fl = 0;
+      RET(read_flags(c, &fl));
+      weighted = fl & 1;
+   }
+   const int variant = weighted ? (felz > 0 ? 3 : 1) : (felz > 0 ? (K == 2 ? 2 : 3) : (K == 2 ? 0 : 1));   // :543-576
+   if ((int)c->sweepv.size() < MGM_MAX_NDIR) c->sweepv.resize(MGM_MAX_NDIR);
+   float *ldir[MGM_MAX_NDIR] = {nullptr};
+   for (int p = 0; p < NDIR; p++) { RET(c->sweepv[p].reserve(vol)); ldir[p] = c->sweepv[p].as<float>(); }
+   const int maxrows = std::max(nx, ny);
+   const size_t ncount = 4 + (size_t)NDIR * maxrows;
+   RET(c->progress.reserve(ncount * sizeof(int)));
+   CU(cudaMemsetAsync(c->progress.p, 0, ncount * sizeof(int), c->stream));
+   const int nwarps = (int)std::min<long long>((long long)NDIR * maxrows, (long long)c->num_sms * 32);
+   RET(c->bnd.reserve((size_t)(nwarps + 4) * 4 * L * sizeof(float)));
+   CU(agg_generic_launch(d_cc, weighted ? d_w : nullptr, nx, ny, L, VS, P1, P2, NDIR, K, variant, (1u << NDIR) - 1u, ldir,
+                         c->progress.as<int>(), c->bnd.as<float>(), nwarps, c->stream));
+   c->n_launches = 1;
+   return finish_rows(c, ldir, d_cc, nx, ny, dmin, L, NDIR, fix, refine, 0, ny, d_out, d_outcost, d_S);
 }
 
 static int mgm_host(mgmb200_ctx *c, const float *cc, const float *w, int nx, int ny, int dmin, int dmax, float P1,
@@ -928,14 +972,30 @@ static int mgm_host(mgmb200_ctx *c, const float *cc, const float *w, int nx, int
    CU(cudaSetDevice(c->device));
    const int L = dmax - dmin + 1;
    const size_t np = (size_t)nx * ny;
-   RET(upload_volume(c, cc, nx, ny, L, label_major));
+   int vflags = 0;
+   RET(upload_volume(c, cc, nx, ny, L, label_major, &vflags));
    if (w) RET(upload(c, c->w, w, np * 8 * 4));
    RET(c->out.reserve(np * 4));
    RET(c->outcost.reserve(np * 4));
    float *dS = nullptr;
    if (S_out) { RET(c->dense.reserve(np * L * 4)); dS = c->dense.as<float>(); }
-   RET(mgmb200_aggregate_dev(c, c->cc.as<float>(), w ? c->w.as<float>() : nullptr, w ? 2 : 0, nx, ny, dmin, dmax, P1,
-                             P2, NDIR, K, felz, fix, 0, c->out.as<float>(), c->outcost.as<float>(), dS));
+   // the fast kernels assume finite vectors, penalties and weights (hardware minima = the reference's compare-select
+   // forms only then); anything else takes the compare-select kernel, which propagates non-finite values like the
+   // reference
+   bool generic = vflags != 0 || !(P1 >= 0.f) || !(P2 >= 0.f) || !(P1 < INFINITY) || (felz <= 0 && !(P2 < INFINITY));
+   if (w && !generic) {
+      RET(clear_flags(c));
+      CU(scan_weights_launch(c->w.as<float>(), (long long)np * 8, c->flags.as<int>(), c->stream));
+      int fl = 0;
+      RET(read_flags(c, &fl));
+      generic = (fl & 2) != 0;   // a negative, NaN or infinite weight
+   }
+   if (generic)
+      RET(aggregate_generic(c, c->cc.as<float>(), w ? c->w.as<float>() : nullptr, nx, ny, dmin, L, P1, P2, NDIR, K, felz, fix, 0,
+                            c->out.as<float>(), c->outcost.as<float>(), dS));
+   else
+      RET(mgmb200_aggregate_dev(c, c->cc.as<float>(), w ? c->w.as<float>() : nullptr, w ? 2 : 0, nx, ny, dmin, dmax, P1,
+                                P2, NDIR, K, felz, fix, 0, c->out.as<float>(), c->outcost.as<float>(), dS));
    RET(download(c, out, c->out.p, np * 4));
    RET(download(c, outcost, c->outcost.p, np * 4));
    if (S_out) RET(download(c, S_out, dS, np * L * 4));

@@ -136,11 +136,15 @@ __device__ __forceinline__ float bt_channel(const float *__restrict__ ur, const 
    float IRp = IR, IRm = IR;
    if (qx < vnx - 1) IRp = (IR + vr[qx + 1]) * 0.5f;
    if (qx >= 1) IRm = (IR + vr[qx - 1]) * 0.5f;
-   const float IminR = fminf(fminf(IRm, IRp), IR), ImaxR = fmaxf(fmaxf(IRm, IRp), IR);
-   const float IminL = fminf(fminf(ILm, ILp), IL), ImaxL = fmaxf(fmaxf(ILm, ILp), IL);
-   const float dLR = fmaxf(0.f, fmaxf(IL - ImaxR, IminR - IL));
-   const float dRL = fmaxf(0.f, fmaxf(IR - ImaxL, IminL - IR));
-   return fabsf(fminf(dLR, dRL));
+   // the reference's min3 / max3 / __min are compare-and-select macros (:85-86, mgm_core.cc:48): restated as such, so
+   // that NaN samples (census bit strings read as floats, "-p census -t btad") select the same operand
+   auto min3 = [](float a, float b, float c) { return (a < b) ? ((a < c) ? a : c) : ((c < b) ? c : b); };
+   auto max3 = [](float a, float b, float c) { return (a > b) ? ((a > c) ? a : c) : ((c > b) ? c : b); };
+   const float IminR = min3(IRm, IRp, IR), ImaxR = max3(IRm, IRp, IR);
+   const float IminL = min3(ILm, ILp, IL), ImaxL = max3(ILm, ILp, IL);
+   const float dLR = max3(0.f, IL - ImaxR, IminR - IL);
+   const float dRL = max3(0.f, IR - ImaxL, IminL - IR);
+   return fabsf(sel_min(dLR, dRL));
 }
 
 template <int DIST>

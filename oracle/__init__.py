@@ -101,11 +101,10 @@ def orc_costvolume(u, v, dmin, dmax, prefilter="none", distance="ad", truncDist=
     lib = orc_lib()
     pf = lib.orc_prefilter_index(prefilter.encode())
     di = lib.orc_distance_index(distance.encode())
-    # consistency fix of mgm_costvolume.h:358-362
-    if pf == 1 or di == 2:
-        if di != 2:
-            raise ValueError("-p census with a non-census distance is not modelled")
-        pf, di = 1, 2
+    # consistency fix of mgm_costvolume.h:358-362: either one selects the census prefilter; the cost FUNCTION was picked
+    # before (:355), so "-p census -t ad" runs AD on the census bit strings (modelled by the C port)
+    if di == 2:
+        pf = 1
     L = dmax - dmin + 1
     cc = np.empty((ny, nx, L), np.float32)
     rc = lib.orc_costvolume(_fp(u), _fp(v), nx, ny, nch, vnx, vny, dmin, dmax, pf, di,
@@ -168,10 +167,8 @@ def orc_costvolume_ranges(u, v, dminI, dmaxI, emin, emax, prefilter="none", dist
     lib = orc_lib()
     pf = lib.orc_prefilter_index(prefilter.encode())
     di = lib.orc_distance_index(distance.encode())
-    if pf == 1 or di == 2:
-        if di != 2:
-            raise ValueError("-p census with a non-census distance is not modelled")
-        pf, di = 1, 2
+    if di == 2:
+        pf = 1
     lo, hi = _ranges(dminI, dmaxI, ny, nx)
     cc = np.empty((ny, nx, emax - emin + 1), np.float32)
     rc = lib.orc_costvolume_ranges(_fp(u), _fp(v), nx, ny, nch, vnx, vny, _fp(lo), _fp(hi), emin, emax, pf, di,

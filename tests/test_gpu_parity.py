@@ -46,6 +46,19 @@ def test_costvolume(ctx, dist, win, nch):
     assert same(a, O.orc_costvolume(u, v[:, :, :33], -13, 3, "none", dist, np.inf, win))
 
 
+def test_costvolume_census_prefilter_quirk(ctx):
+    """-p census with a non-census distance (mgm_costvolume.h:355 vs :358-362): the distance runs on the census bit
+    strings read as floats (denormals; NaN / INF patterns with 7x7 windows) -- like the reference, bit for bit."""
+    for nch in (1, 3):
+        u, v = synth_pair(45, 29, 14, seed=4, nch=nch)
+        for win in (3, 5, 7):
+            for dist in ("ad", "sd", "ncc", "btad", "btsd"):
+                for trunc in (np.inf, 1e-38):
+                    a = ctx.allocate_and_fill_sgm_costvolume(u, v, -13, 3, "census", dist, trunc, win)
+                    b = O.orc_costvolume(u, v, -13, 3, "census", dist, trunc, win)
+                    assert same(a, b), (nch, win, dist, trunc, mism(a, b))
+
+
 def test_costvolume_edge_cases(ctx):
     u, v = synth_pair(40, 9, 60, seed=1)
     # range entirely outside the right image for most pixels -> the all-invalid rule (mgm_costvolume.h:414-421)
@@ -150,19 +163,65 @@ def test_mgm_labelmajor_protocol(ctx):
     assert same(lab, o["out"])
 
 
+def _nonfinite_volume(nx, ny, L, kind, seed):
+    rng = np.random.default_rng(seed)
+    cc = synth_volume(nx, ny, L, seed=seed, real=True)
+    if kind in ("allinf", "mix"):
+        for _ in range(6):
+            cc[rng.integers(ny), rng.integers(nx), :] = np.inf      # a pixel without any finite cost
+    if kind in ("nan", "mix"):
+        for _ in range(8):
+            cc[rng.integers(ny), rng.integers(nx), rng.integers(L)] = np.nan
+    if kind in ("neginf", "mix"):
+        for _ in range(4):
+            cc[rng.integers(ny), rng.integers(nx), rng.integers(L)] = -np.inf
+    return cc
+
+
+@pytest.mark.parametrize("kind", ["allinf", "nan", "neginf", "mix"])
+def test_mgm_nonfinite_volumes(ctx, kind):
+    """User-supplied volumes with all-INF vectors, NaN or -INF costs (the mgm(CC, ...) / mgm_o boundary): the reference
+    propagates them by its compare-select minima and '<' scans (mgm_core.cc:47-60, dvec.cc:81-88).  The
+    host-pointer entry points detect such inputs and run the compare-select kernel (aggregate_generic.cu): same bits as
+    the oracle port, which tests/test_oracle.py pins against the reference on the same kind of volumes.  Pixels without
+    a finite label are NaN here (uninitialised in the reference, mgm_core.cc:594)."""
+    for (nx, ny, L) in [(23, 17, 9), (45, 31, 40)]:
+        cc = _nonfinite_volume(nx, ny, L, kind, 3)
+        for K, felz, wt, NDIR in itertools.product((1, 2, 3, 4), (0, 1), (0, 1), (8, 16)):
+            if NDIR == 16 and (K, wt) not in ((2, 0), (3, 1)):
+                continue
+            w = synth_weights(nx, ny, seed=K) if wt else None
+            P1, P2 = (8, 32) if not felz else (2, 20000)
+            r = ctx.mgm(cc, w, -(L - 1), P1, P2, NDIR, K, felz, 1)
+            o = O.orc_mgm(cc, w, -(L - 1), P1, P2, NDIR, K, felz, 1)
+            assert same(r["S"], o["S"]) and same(r["out"], o["out"]) and same(r["outcost"], o["outcost"]), \
+                (kind, nx, K, felz, wt, NDIR, mism(r["S"], o["S"]))
+    # non-finite penalties and weights take the same path
+    cc = synth_volume(31, 22, 12, seed=8, real=True)
+    w = synth_weights(31, 22, seed=2)
+    w[3, 5, 7] = -2.0
+    w[1, 9, 9] = np.inf
+    for K, felz, P1, P2 in [(2, 0, 8, np.inf), (3, 0, np.inf, 32), (2, 1, -1.0, 20), (4, 1, 2, 20000)]:
+        for ww in (None, w):
+            r = ctx.mgm(cc, ww, -11, P1, P2, 8, K, felz, 1)
+            o = O.orc_mgm(cc, ww, -11, P1, P2, 8, K, felz, 1)
+            assert same(r["S"], o["S"]) and same(r["out"], o["out"]), (K, felz, P1, P2, ww is not None)
+    # the matlab/mgm_o.cc protocol entry
+    cc = _nonfinite_volume(41, 23, 16, "mix", 9)
+    lab, _ = ctx.mgm_labelmajor(np.ascontiguousarray(np.transpose(cc, (2, 0, 1))), None, 8, 32, 8, 2, 0)
+    assert same(lab, O.orc_mgm(cc, None, 0, 8, 32, 8, 2, 0, 1)["out"])
+
+
 def test_unsupported_inputs_fail_loudly(ctx):
     import mgm_b200
     cc = synth_volume(9, 9, 5, seed=1, inf_border=False)
-    bad = cc.copy(); bad[4, 4, :] = np.inf          # a pixel without any finite cost
-    with pytest.raises(mgm_b200.MgmError):
-        ctx.mgm(bad, None, 0, 8, 32, 4, 2)
-    bad = cc.copy(); bad[2, 3, 1] = np.nan
-    with pytest.raises(mgm_b200.MgmError):
-        ctx.mgm(bad, None, 0, 8, 32, 4, 2)
     with pytest.raises(mgm_b200.MgmError):
         ctx.mgm(cc, None, 0, 8, 32, 17, 2)             # 16 sweeps are defined (8 of the reference + 8 of this build), not more
     with pytest.raises(mgm_b200.MgmError):
         ctx.mgm(cc, None, 0, 8, 32, 4, 5)
+    bad = cc.copy(); bad[2, 3, 1] = np.nan              # per-pixel ranges stay on the fast kernels: non-finite costs are refused
+    with pytest.raises(mgm_b200.MgmError):
+        ctx.mgm_ranges(bad, 0, 4, None, 0, 0, 4, 8, 32, 4, 2)
 
 
 @pytest.mark.parametrize("method", ["none", "vfit", "parabola", "cubic", "parabolaOCV", "bogus"])

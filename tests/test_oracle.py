@@ -366,3 +366,60 @@ def test_knight_sweeps_definition():
         assert np.allclose(r["passes"][8 + b], r["passes"][b], rtol=1e-5)
     r = O.orc_mgm(cc, None, 0, 8, 32, 16, 2, 0, 1, want_passes=True)
     assert all(not np.allclose(r["passes"][8 + b], r["passes"][b], rtol=1e-3) for b in range(8))
+
+
+def test_census_prefilter_with_another_distance():
+    """"-p census -t ad|sd|ncc|btad|btsd": the reference picks the cost function before it forces census/census
+    (mgm_costvolume.h:355 vs :358-362), so the distance runs on the census bit strings held in float channels
+    (denormals, and with 7x7 windows NaN / INF bit patterns).  The port reproduces it bit for bit."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built")
+    for nch in (1, 3):
+        u, v = synth_pair(45, 29, 14, seed=4, nch=nch)
+        for win in (3, 5, 7):
+            for dist in ("ad", "sd", "ncc", "btad", "btsd"):
+                for trunc in (np.inf, 1e-38):
+                    a = O.orc_costvolume(u, v, -13, 3, "census", dist, trunc, win)
+                    b = O.ref_costvolume(u, v, -13, 3, "census", dist, trunc, win)
+                    assert np.array_equal(a, b, equal_nan=True), (nch, win, dist, trunc)
+
+
+def test_nonfinite_volumes_port_vs_reference():
+    """The port against the reference on volumes with all-INF vectors, NaN and -INF costs, every update variant: this pins
+    the checker used by the GPU test of the compare-select kernel (tests/test_gpu_parity.py::test_mgm_nonfinite_volumes).
+    Where no label is finite the reference's disparity is uninitialised (mgm_core.cc:594): compared where the cost is."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(5)
+    for (nx, ny, L) in [(23, 17, 9), (31, 22, 12)]:
+        for kind in ("allinf", "nan", "neginf", "mix"):
+            cc = synth_volume(nx, ny, L, seed=3, real=True)
+            if kind in ("allinf", "mix"):
+                for _ in range(6):
+                    cc[rng.integers(ny), rng.integers(nx), :] = np.inf
+            if kind in ("nan", "mix"):
+                for _ in range(8):
+                    cc[rng.integers(ny), rng.integers(nx), rng.integers(L)] = np.nan
+            if kind in ("neginf", "mix"):
+                for _ in range(4):
+                    cc[rng.integers(ny), rng.integers(nx), rng.integers(L)] = -np.inf
+            for K, felz, wt in itertools.product((1, 2, 3, 4), (0, 1), (0, 1)):
+                w = synth_weights(nx, ny, seed=K) if wt else None
+                P1, P2 = (8, 32) if not felz else (2, 20000)
+                a = O.orc_mgm(cc, w, -(L - 1), P1, P2, 8, K, felz, 1)
+                b = O.ref_mgm(cc, w, -(L - 1), P1, P2, 8, K, felz, 1)
+                fin = np.isfinite(b["outcost"])
+                assert np.array_equal(a["S"], b["S"], equal_nan=True), (kind, K, felz, wt)
+                assert np.array_equal(a["out"][fin], b["out"][fin]) and np.array_equal(a["outcost"], b["outcost"], equal_nan=True)
+                assert np.isnan(a["out"][~fin]).all()
+    # non-finite / negative penalties and weights
+    cc = synth_volume(31, 22, 12, seed=8, real=True)
+    w = synth_weights(31, 22, seed=2)
+    w[3, 5, 7] = -2.0
+    w[1, 9, 9] = np.inf
+    for K, felz, P1, P2 in [(2, 0, 8, np.inf), (3, 0, np.inf, 32), (2, 1, -1.0, 20), (4, 1, 2, 20000)]:
+        for ww in (None, w):
+            a = O.orc_mgm(cc, ww, -11, P1, P2, 8, K, felz, 1)
+            b = O.ref_mgm(cc, ww, -11, P1, P2, 8, K, felz, 1)
+            fin = np.isfinite(b["outcost"])
+            assert np.array_equal(a["S"], b["S"], equal_nan=True) and np.array_equal(a["out"][fin], b["out"][fin])
