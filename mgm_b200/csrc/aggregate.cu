@@ -453,7 +453,11 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
    const int VS = P.VS;
    const int VSP = RC ? VS + (VS >> 3) : VS;   // floats per vector in shared memory and in the boundary lines
    const int nq = VS >> 2;
+#ifdef MGM_FORCE_NJ
+   constexpr int nj = MGM_FORCE_NJ;   // experiment: compile-time chunks per lane
+#else
    const int nj = nq / G;   // chunks per lane (VS is a multiple of 4*G)
+#endif
    const int ncb = RC ? 1 : P.ncb;   // cost buffers per row: 1 = costs prefetched into registers (nj <= NJR), 2 = cp.async ring
    const bool creg_mode = (ncb == 1);
    const uint32_t vbytes = (uint32_t)VSP * 4u;
@@ -900,6 +904,14 @@ __device__ void run_band(const AggParams &P, const SweepDesc &D, const int band,
    if (timing) {
       for (int i = 0; i < 6; ++i) atomicAdd(P.dbg + i, (unsigned long long)tacc[i]);
       atomicAdd(P.dbg + 6, (unsigned long long)nsteps);
+      if (D.pass == 0 && band < 60) {   // per band of sweep 0: phases, steps, start and end time stamps
+         unsigned long long *b = P.dbg + 8 + band * 10;
+         for (int i = 0; i < 6; ++i) b[i] = (unsigned long long)tacc[i];
+         b[6] = (unsigned long long)nsteps;
+         unsigned long long gt;
+         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+         b[7] = gt;
+      }
    }
    // epilogue: save mbarrier parities
    cp_async_wait<0>();
@@ -939,7 +951,11 @@ __device__ void run_band_shear(const AggParams &P, const SweepDesc &D, const int
    const int VS = P.VS;
    const int VSP = RC ? VS + (VS >> 3) : VS;   // floats per vector in shared memory and in the boundary lines
    const int nq = VS >> 2;
+#ifdef MGM_FORCE_NJ
+   constexpr int nj = MGM_FORCE_NJ;
+#else
    const int nj = nq / G;
+#endif
    const int ncb = RC ? 1 : P.ncb;
    const bool creg_mode = (ncb == 1);
    const uint32_t vbytes = (uint32_t)VSP * 4u;

@@ -91,10 +91,12 @@ struct AggTuning {
    int no_shear = 0;                   // 1: diagonal sweeps row-per-worker
    int static_order = 0;               // 1: claim bands without the readiness test
    int no_fused_finish = 0;            // 1: finish stage as a separate launch
+   int fused_finish = -1;              // 1: finish tiles inside the launch whenever possible, -1: where measured to gain
    int fin_tw = 128, fin_th = 16;      // finish tile
    int cc_pf = -1;                     // L2 prefetch distance (pixels) of the matching costs; 0 = off, -1 = auto (3 for
                                        // the SGM-potential kernels, whose steps are shorter than the HBM latency)
-   int batch = 8;                      // stereo pairs in flight per launch (batch entry points)
+   int batch = 16;                     // stereo pairs in flight per launch (batch entry points; measured 32 KITTI-size
+                                       // pairs: 88 / 74 / 69 / 68 ms with 4 / 8 / 16 / 32 pairs per launch)
    int verbose = 0;
    int dbg = 0;                        // 1: print the per-phase clock cycles of the register-chain band steps (axis sweeps)
 };

@@ -169,6 +169,7 @@ static bool apply_option(mgmb200_ctx *c, const char *name, const char *value) {
    if (!strcmp(name, "no_shear")) { t.no_shear = iv; return true; }
    if (!strcmp(name, "static_order")) { t.static_order = iv; return true; }
    if (!strcmp(name, "no_fused_finish")) { t.no_fused_finish = iv; return true; }
+   if (!strcmp(name, "fused_finish")) { t.fused_finish = iv; return true; }
    if (!strcmp(name, "cc_pf")) { t.cc_pf = iv; return true; }
    if (!strcmp(name, "batch")) { t.batch = iv < 1 ? 1 : iv; return true; }
    if (!strcmp(name, "verbose")) { t.verbose = iv; return true; }
@@ -185,7 +186,7 @@ static void tuning_from_env(mgmb200_ctx *c) {
    c->tune = AggTuning();
    c->rows_override = 0;
    static const char *const names[] = {"rows_per_band", "rows_axis", "rows_diag", "groups", "no_creg", "no_fused_sgm", "reg_chains", "lanes4",
-                                       "lanes8", "no_shear", "static_order", "no_fused_finish", "cc_pf", "batch", "verbose", "dbg", "fin_tile"};
+                                       "lanes8", "no_shear", "static_order", "no_fused_finish", "fused_finish", "cc_pf", "batch", "verbose", "dbg", "fin_tile"};
    for (const char *n : names) {
       char env[64] = "MGMB200_";
       size_t k = strlen(env);
@@ -475,6 +476,21 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
          bands += nb;
       }
       if (bands < c->num_sms) agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 40, knight, c->tune);
+   } else if (!c->rows_override && !c->tune.rows_axis && !c->tune.rows_diag && pot == POT_SGM && R.npairs == 1) {
+      // One small pair with SGM potentials (a KITTI-size frame yields fewer bands than 1.5 x the SMs): the launch is bound
+      // by the dependency depth of its sweeps and the step of a band shortens with its rows (no label chain): 40, then
+      // 28 rows per band (measured 1242x375x192 TSGM=4: 7.83 / 6.62 / 6.08 ms with 56 / 40 / 28 rows)
+      for (int t : {40, 28}) {
+         long bands = 0;
+         for (int p = 0; p < NDIR; p++) {
+            if (!(mask & (1u << p))) continue;
+            int nb = 0; size_t a = 0, bq = 0;
+            agg_sweep_bands(plan, p, nx, ny, &nb, &a, &bq);
+            bands += nb;
+         }
+         if (2 * bands >= 3L * c->num_sms || plan.T[0] <= t) break;
+         agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, t, knight, c->tune);
+      }
    }
    if (plan.T[0] < 1 || plan.T[1] < 1 || plan.T[2] < 1)
       return fail(MGMB200_EUNSUPPORTED, "%d labels do not fit the shared-memory wavefront (max_smem=%d)", L, c->max_smem);
@@ -534,7 +550,12 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
    // decide: band b of such a sweep is done after about maxii + (b+1)*T steps), pairs interleaved
    const int tw = c->tune.fin_tw, th = c->tune.fin_th;
    const size_t rows_region = plan.smem - plan.off_thr;
-   const bool fuse = R.fin && !c->tune.no_fused_finish && (size_t)(plan.block / 32) * VS * 4 <= rows_region;
+   // The finish stage runs as tile work inside the launch where that is a gain: one pair (its parameters are kernel
+   // arguments) and label vectors of at least 128 floats (a warp per pixel is then fully used).  Measured otherwise
+   // (profiles/r02_experiments.md): 32 x 1242x375x192 TSGM=4 in launches of 8 pairs 95.7 ms fused vs 74.5 ms with
+   // separate finish launches, 4096x4096x64 -O 16 113.2 vs 97.4 ms; 2048x1536x256 20.0 vs 22.2 ms, 1920x1080x128 8.4 vs 9.4.
+   const bool fuse_gain = c->tune.fused_finish > 0 || (c->tune.fused_finish < 0 && R.npairs == 1 && VS >= 128);
+   const bool fuse = R.fin && !c->tune.no_fused_finish && fuse_gain && (size_t)(plan.block / 32) * VS * 4 <= rows_region;
    const int tiles_x = (nx + tw - 1) / tw, tiles_y = (ny + th - 1) / th, ntiles = tiles_x * tiles_y;
    if (R.fin)
       for (int b = 0; b < R.npairs; b++)
@@ -599,17 +620,24 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
    P.off_ms = (unsigned)plan.off_ms; P.off_vms = (unsigned)plan.off_vms; P.off_virt = (unsigned)plan.off_virt;
    P.off_thr = (unsigned)plan.off_thr;
    if (c->tune.dbg) {
-      RET(c->dbgbuf.reserve(64));
-      CU(cudaMemsetAsync(c->dbgbuf.p, 0, 64, c->stream));
+      RET(c->dbgbuf.reserve(8 * (8 + 600)));
+      CU(cudaMemsetAsync(c->dbgbuf.p, 0, 8 * (8 + 600), c->stream));
       P.dbg = c->dbgbuf.as<unsigned long long>();
    }
    CU(agg_launch(P, plan, pot, K, weighted, c->stream));
    c->n_launches++;
    c->fin_done = fuse;
    if (c->tune.dbg) {   // profiling aid: synchronises
-      unsigned long long h[8];
-      CU(cudaMemcpyAsync(h, c->dbgbuf.p, 64, cudaMemcpyDeviceToHost, c->stream));
+      static unsigned long long h[8 + 600];
+      CU(cudaMemcpyAsync(h, c->dbgbuf.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
       CU(cudaStreamSynchronize(c->stream));
+      if (c->tune.dbg > 1)
+         for (int b = 0; b < 60 && h[8 + b * 10 + 6]; b++) {
+            const unsigned long long *q = h + 8 + b * 10;
+            fprintf(stderr, "[mgmb200 band %2d of sweep 0] steps=%llu cycles/step: top=%.0f gather=%.0f sync1=%.0f transform=%.0f rest=%.0f "
+                    "barrier=%.0f end=%.3f ms\n", b, q[6], (double)q[0] / q[6], (double)q[1] / q[6], (double)q[2] / q[6],
+                    (double)q[3] / q[6], (double)q[4] / q[6], (double)q[5] / q[6], (double)(q[7] - h[8 + 7]) * 1e-6);
+         }
       if (h[6])
          fprintf(stderr, "[mgmb200 phase timing] steps=%llu cycles/step: top=%.0f gather=%.0f sync1=%.0f transform=%.0f rest=%.0f barrier=%.0f\n",
                  h[6], (double)h[0] / h[6], (double)h[1] / h[6], (double)h[2] / h[6], (double)h[3] / h[6], (double)h[4] / h[6], (double)h[5] / h[6]);

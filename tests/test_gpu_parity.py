@@ -109,7 +109,7 @@ def test_mgm_matches_oracle(ctx, K, felz, weighted):
 
 @pytest.mark.parametrize("knob", ["MGMB200_GROUPS=2", "MGMB200_GROUPS=3", "MGMB200_NO_SHEAR=1", "MGMB200_NO_CREG=1",
                                   "MGMB200_STATIC_ORDER=1", "MGMB200_NO_FUSED_SGM=1", "MGMB200_LANES4=1",
-                                  "MGMB200_NO_FUSED_FINISH=1", "MGMB200_FIN_TILE=7x3", "MGMB200_FIN_TILE=4096x4096",
+                                  "MGMB200_NO_FUSED_FINISH=1", "MGMB200_FUSED_FINISH=1", "MGMB200_FIN_TILE=7x3", "MGMB200_FIN_TILE=4096x4096",
                                   "MGMB200_CC_PF=3", "MGMB200_REG_CHAINS=1"])
 def test_mgm_alternative_kernel_layouts(ctx, knob):
     """The aggregation kernel's alternative layouts (row groups on their own named barriers, row-per-worker diagonal
@@ -117,6 +117,7 @@ def test_mgm_alternative_kernel_layouts(ctx, knob):
     L2 prefetch of the costs) are selected by context options (mgmb200_set_option; the MGMB200_* environment is only
     read when a context is created): each must give the same bits as the default layout, i.e. as the oracle."""
     name, val = knob.split("=")
+    ctx.set_option("fused_finish", 1)   # these small label counts would not take the finish tiles by default
     ctx.set_option(name[len("MGMB200_"):].lower(), val)
     try:
         for (nx, ny, L), (K, felz, P1, P2) in itertools.product([(131, 37, 40), (90, 150, 24)],
@@ -481,6 +482,7 @@ def test_full_size_finish_fused_vs_separate(ctx, cfg):
     u, v = bench_pair(W, H, L, 1)
     kw = dict(dmin=-(L - 1), dmax=0, P1=cfg["P1"], P2=cfg["P2"], MGM=cfg["K"], NDIR=8, refinement="vfit",
               use_felzenszwalb_potentials=cfg["felz"], distance=cfg["dist"], census_ncc_win=cfg["win"])
+    ctx.set_option("fused_finish", 1)   # also where the default would not fuse (short label vectors)
     runs = [ctx.stereo(u, v, **kw) for _ in range(3)]
     assert ctx.last_launch_info()["kernel_launches"] == 1
     ctx.set_option("no_fused_finish", 1)
@@ -557,8 +559,12 @@ def test_midsize_against_the_reference(ctx, cfg):
     assert same(g["outcost"], r["outcost"])
     kw = dict(dmin=-(L - 1), dmax=0, P1=cfg["P1"], P2=cfg["P2"], MGM=cfg["K"], NDIR=8, refinement="vfit",
               use_felzenszwalb_potentials=cfg["felz"], distance=dist, census_ncc_win=cfg["win"])
-    out, cost = ctx.stereo(u, v, **kw)                  # the fused path: one launch, finish tiles
-    assert ctx.last_launch_info()["kernel_launches"] == 1
+    ctx.set_option("fused_finish", 1)
+    try:
+        out, cost = ctx.stereo(u, v, **kw)                  # the fused path: one launch, finish tiles
+        assert ctx.last_launch_info()["kernel_launches"] == 1
+    finally:
+        ctx.set_option("reset")
     assert same(out, ro) and same(cost, rc), (mism(out, ro), mism(cost, rc))
 
 
