@@ -1380,33 +1380,47 @@ __device__ int2 claim_band(const AggParams &P, int &pending, int lane) {
 
 // One finish tile: fin_tw x fin_th pixels, one warp per pixel (wta_device.cuh); the rows region of the shared
 // memory is free between bands and holds one label vector per warp.  F: the pair's finish parameters (shared memory).
-__device__ __forceinline__ void run_finish_tile(const AggParams &P, const WtaParams &F, int tile, unsigned char *smem) {
-   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-   float *sS = reinterpret_cast<float *>(smem + P.off_thr) + (size_t)warp * P.VS;
+template <int LP>
+__device__ __forceinline__ void run_finish_tile_lp(const AggParams &P, const WtaParams &F, int tile, unsigned char *smem) {
+   constexpr int NP = 32 / LP;   // pixels per warp (wta_pixel)
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5, sub = lane / LP;
+   float *sS = reinterpret_cast<float *>(smem + P.off_thr) + ((size_t)warp * NP + sub) * P.VS;
    const int x0 = (tile % P.fin_tiles_x) * P.fin_tw, y0 = (tile / P.fin_tiles_x) * P.fin_th;
    const int w = min(P.fin_tw, P.nx - x0), h = min(P.fin_th, P.ny - y0);
-   // 128-byte lines of one pixel: (ndir + 1) vectors of VS floats; the warp's next pixel is prefetched into L2
-   // while the current one is reduced (16 warps per SM cannot keep enough loads in flight otherwise)
-   const int lpv = P.VS >> 5, nlines = (F.ndir + 1) * lpv;
-   auto prefetch_pixel = [&](int i) {
-      const long long pix = (long long)(y0 + i / w) * P.nx + x0 + i % w;
-      for (int l = lane; l < nlines; l += 32) {
-         const int v = l / lpv;
-         const float *base = (v < F.ndir) ? F.ldir[v] : F.cc;
-         asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)pix * P.VS + (size_t)(l % lpv) * 32));
+   // 128-byte lines of one pixel: (ndir + 1) vectors of VS floats; the warp's next pixels are prefetched into L2
+   // while the current ones are reduced (16 warps per SM cannot keep enough loads in flight otherwise)
+   const int lpv = max(1, P.VS >> 5), nlines = (F.ndir + 1) * lpv;
+   auto prefetch_pixels = [&](int i0) {   // pixels i0 .. i0+NP-1 of the tile
+      for (int k = 0; k < NP; ++k) {
+         const int i = i0 + k;
+         if (i >= w * h) break;
+         const long long pix = (long long)(y0 + i / w) * P.nx + x0 + i % w;
+         for (int l = lane; l < nlines; l += 32) {
+            const int v = l / lpv;
+            const float *base = (v < F.ndir) ? F.ldir[v] : F.cc;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)pix * P.VS + (size_t)(l % lpv) * 32));
+         }
       }
    };
 #ifndef MGM_FIN_PF
-#define MGM_FIN_PF 1   // prefetch distance in pixels of the warp
+#define MGM_FIN_PF 1   // prefetch distance in pixel groups of the warp
 #endif
    for (int d = 0; d < MGM_FIN_PF; ++d)
-      if (warp + d * nwarps < w * h) prefetch_pixel(warp + d * nwarps);
-   for (int i = warp; i < w * h; i += nwarps) {
-      if (i + MGM_FIN_PF * nwarps < w * h) prefetch_pixel(i + MGM_FIN_PF * nwarps);
-      const long long pix = (long long)(y0 + i / w) * P.nx + x0 + i % w;
-      wta_pixel<true>(F, pix, sS, lane);
+      if ((warp + d * nwarps) * NP < w * h) prefetch_pixels((warp + d * nwarps) * NP);
+   for (int i0 = warp * NP; i0 < w * h; i0 += nwarps * NP) {
+      if (i0 + MGM_FIN_PF * nwarps * NP < w * h) prefetch_pixels(i0 + MGM_FIN_PF * nwarps * NP);
+      const int i = i0 + sub;
+      const bool valid = i < w * h;
+      const long long pix = valid ? (long long)(y0 + i / w) * P.nx + x0 + i % w : 0;
+      wta_pixel<true, LP>(F, pix, sS, lane, valid);
    }
    __syncthreads();
+}
+__device__ __forceinline__ void run_finish_tile(const AggParams &P, const WtaParams &F, int tile, unsigned char *smem) {
+   const int lp = wta_lanes_per_pixel(P.VS);
+   if (lp == 32) run_finish_tile_lp<32>(P, F, tile, smem);
+   else if (lp == 16) run_finish_tile_lp<16>(P, F, tile, smem);
+   else run_finish_tile_lp<8>(P, F, tile, smem);
 }
 
 // the claimed band's sweep (or the claimed tile's pair) staged in shared memory

@@ -555,7 +555,8 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
    // (profiles/r02_experiments.md): 32 x 1242x375x192 TSGM=4 in launches of 8 pairs 95.7 ms fused vs 74.5 ms with
    // separate finish launches, 4096x4096x64 -O 16 113.2 vs 97.4 ms; 2048x1536x256 20.0 vs 22.2 ms, 1920x1080x128 8.4 vs 9.4.
    const bool fuse_gain = c->tune.fused_finish > 0 || (c->tune.fused_finish < 0 && R.npairs == 1 && VS >= 128);
-   const bool fuse = R.fin && !c->tune.no_fused_finish && fuse_gain && (size_t)(plan.block / 32) * VS * 4 <= rows_region;
+   const bool fuse = R.fin && !c->tune.no_fused_finish && fuse_gain &&
+                     (size_t)(plan.block / 32) * (32 / wta_lanes_per_pixel(VS)) * VS * 4 <= rows_region;
    const int tiles_x = (nx + tw - 1) / tw, tiles_y = (ny + th - 1) / th, ntiles = tiles_x * tiles_y;
    if (R.fin)
       for (int b = 0; b < R.npairs; b++)

@@ -11,14 +11,23 @@
 
 namespace mgm {
 
+template <int LP>
+__device__ __forceinline__ void wta_loop(const WtaParams &P, float *s_all) {
+   constexpr int NP = 32 / LP;   // pixels per warp
+   const int warps_per_cta = blockDim.x >> 5;
+   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / LP;
+   float *sS = s_all + ((size_t)wid * NP + sub) * P.VS;
+   for (long long p0 = ((long long)blockIdx.x * warps_per_cta + wid) * NP + P.pix_begin; p0 < P.pix_end;
+        p0 += (long long)gridDim.x * warps_per_cta * NP)
+      wta_pixel<false, LP>(P, p0 + sub, sS, lane, p0 + sub < P.pix_end);
+}
+
 __global__ void __launch_bounds__(256) mgm_wta_kernel(const WtaParams P) {
    extern __shared__ float s_all[];
-   const int warps_per_cta = blockDim.x >> 5;
-   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-   float *sS = s_all + (size_t)wid * P.VS;
-   for (long long pix = (long long)blockIdx.x * warps_per_cta + wid + P.pix_begin; pix < P.pix_end;
-        pix += (long long)gridDim.x * warps_per_cta)
-      wta_pixel<false>(P, pix, sS, lane);
+   const int lp = wta_lanes_per_pixel(P.VS);
+   if (lp == 32) wta_loop<32>(P, s_all);
+   else if (lp == 16) wta_loop<16>(P, s_all);
+   else wta_loop<8>(P, s_all);
 }
 
 // Stand-alone sub-pixel refinement of given labels on a dense volume S [npix][L]
@@ -75,7 +84,7 @@ cudaError_t sum_volumes_launch(const float *const *src, int n, float *out, long 
 
 cudaError_t wta_launch(const WtaParams &P, int num_sms, cudaStream_t st) {
    const int block = 256;
-   const size_t smem = (size_t)(block / 32) * P.VS * sizeof(float);
+   const size_t smem = (size_t)(block / 32) * (32 / wta_lanes_per_pixel(P.VS)) * P.VS * sizeof(float);
    cudaError_t e = cudaFuncSetAttribute(mgm_wta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
    if (e != cudaSuccess) return e;
    int per_sm = 0;
@@ -83,7 +92,8 @@ cudaError_t wta_launch(const WtaParams &P, int num_sms, cudaStream_t st) {
    if (e != cudaSuccess) return e;
    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
    const long long npix = P.pix_end - P.pix_begin;
-   long long want = (npix + block / 32 - 1) / (block / 32);
+   const long long ppb = (long long)(block / 32) * (32 / wta_lanes_per_pixel(P.VS));   // pixels per block and pass
+   long long want = (npix + ppb - 1) / ppb;
    long long grid = (long long)num_sms * per_sm;
    if (grid > want) grid = want;
    if (grid < 1) grid = 1;

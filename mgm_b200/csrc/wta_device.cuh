@@ -77,10 +77,15 @@ __device__ __forceinline__ float4 ld_stream(const float4 *p) {
    return COHERENT ? __ldcg(p) : __ldcs(p);
 }
 
-// One pixel by one warp: lanes over labels with 16-byte accesses; sS = VS floats of shared memory owned by the warp.
-template <bool COHERENT>
-__device__ __forceinline__ void wta_pixel(const WtaParams &P, const long long pix, float *sS, const int lane) {
-   const int nq = P.VS >> 2;
+// One pixel by LP lanes of a warp (LP = 32: one pixel per warp; 16 or 8 for short label vectors, so that 64 or 32
+// padded labels still use every lane: the warp then finishes 2 or 4 pixels at once): lanes over labels with 16-byte
+// accesses; sS = VS floats of shared memory owned by the pixel's lane group; `valid` = the group has a pixel (all
+// lanes take part in the shuffles either way).
+template <bool COHERENT, int LP = 32>
+__device__ __forceinline__ void wta_pixel(const WtaParams &P, const long long pix, float *sS, const int lane_in_warp,
+                                          const bool valid = true) {
+   const int lane = lane_in_warp & (LP - 1);
+   const int nq = valid ? (P.VS >> 2) : 0;
    const float fixmul = (float)((P.fix_count ? P.fix_count : P.ndir) - 1);
    {
       float best = MGM_INF;
@@ -88,10 +93,10 @@ __device__ __forceinline__ void wta_pixel(const WtaParams &P, const long long pi
       const size_t base = (size_t)pix * P.VS;
       // per-pixel ranges as label indices (defaults: the whole envelope)
       int slo = 0, shi = P.L - 1, clo = 0, chi = P.L - 1;
-      if (P.smin) { slo = (int)P.smin[pix] - P.dmin; shi = (int)P.smax[pix] - P.dmin; }
-      if (P.ccmin) { clo = (int)P.ccmin[pix] - P.dmin; chi = (int)P.ccmax[pix] - P.dmin; }
+      if (P.smin && valid) { slo = (int)P.smin[pix] - P.dmin; shi = (int)P.smax[pix] - P.dmin; }
+      if (P.ccmin && valid) { clo = (int)P.ccmin[pix] - P.dmin; chi = (int)P.ccmax[pix] - P.dmin; }
       const bool ranged = (P.smin != nullptr) || (P.ccmin != nullptr);
-      for (int q = lane; q < nq; q += 32) {
+      for (int q = lane; q < nq; q += LP) {
          const size_t off = base + (size_t)q * 4;
          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
@@ -136,14 +141,14 @@ __device__ __forceinline__ void wta_pixel(const WtaParams &P, const long long pi
       }
       // first minimum wins: smaller value, then smaller label
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
+      for (int d = LP / 2; d > 0; d >>= 1) {
          const float ob = __shfl_xor_sync(0xffffffffu, best, d);
          const int oo = __shfl_xor_sync(0xffffffffu, besto, d);
          const bool take = (oo >= 0) && (besto < 0 || ob < best || (ob == best && oo < besto));
          if (take) { best = ob; besto = oo; }
       }
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && valid) {
          float minP, minL = best;
          if (besto < 0) {
             minP = __int_as_float(0x7fc00000);   // reference leaves it uninitialised (mgm_core.cc:594)

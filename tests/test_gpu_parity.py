@@ -553,7 +553,7 @@ def test_midsize_against_the_reference(ctx, cfg):
     r = O.ref_mgm(cc_ref, None, -(L - 1), cfg["P1"], cfg["P2"], 8, cfg["K"], cfg["felz"], 1, flavour=fl)
     ro, rc = O.ref_refine(r["S"], -(L - 1), r["out"], r["outcost"], "vfit", flavour=fl)
     g = ctx.mgm(cc, None, -(L - 1), cfg["P1"], cfg["P2"], 8, cfg["K"], cfg["felz"], 1)
-    assert ctx.last_launch_info()["rows_axis"] >= 40    # default bands
+    assert ctx.last_launch_info()["rows_axis"] >= 28    # default bands (small SGM frames take 40 or 28 rows per band)
     assert same(g["out"], r["out"]), mism(g["out"], r["out"])
     assert same(g["S"], r["S"]), mism(g["S"], r["S"])
     assert same(g["outcost"], r["outcost"])
