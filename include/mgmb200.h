@@ -90,7 +90,15 @@ int mgmb200_costvolume(mgmb200_ctx *ctx, const float *u, const float *v, int nx,
  *        Img *out, Img *outcost, float P1, float P2, int NDIR, int MGM,
  *        int USE_FELZENSZWALB_POTENTIALS, int SGM_FIX_OVERCOUNT)                 mgm_core.cc:408
  * cc: nx*ny*L floats; w: 8*nx*ny floats or NULL (all ones); out/outcost: nx*ny floats;
- * S_out: NULL or nx*ny*L floats receiving the returned (over-count corrected) volume. */
+ * S_out: NULL or nx*ny*L floats receiving the returned (over-count corrected) volume.
+ * NDIR 1..8 are the reference's sweeps; 9..16 add the sweeps 8-15 DEFINED by this library (the reference advertises
+ * -O 16, mgm.cc:223, but reads past its 8-entry table, mgm_core.cc:463-473): sweep 8+b scans like sweep b and takes the
+ * same four neighbours in an order given by the parity of the scan coordinates, so that the neighbour chains follow the
+ * knight-move (22.5 degree) directions (mgm_b200/csrc/common.cuh knight_pred_type).
+ * Inputs are scanned: volumes with NaN / -INF costs or vectors without a finite entry, negative or non-finite weights
+ * or penalties run on a slower compare-select kernel that propagates them like the reference's macros
+ * (mgm_core.cc:47-60, dvec.cc:81-88); a pixel without any finite label gets a NaN disparity (uninitialised in the
+ * reference, mgm_core.cc:594). */
 int mgmb200_mgm(mgmb200_ctx *ctx, const float *cc, const float *w, int nx, int ny, int dmin, int dmax,
                 float P1, float P2, int NDIR, int MGM, int use_felzenszwalb_potentials,
                 int sgm_fix_overcount, float *out, float *outcost, float *S_out);
@@ -157,6 +165,13 @@ typedef struct mgmb200_stereo_params {
    const char *refinement;        /* -s */
 } mgmb200_stereo_params;
 void mgmb200_stereo_params_default(mgmb200_stereo_params *p);   /* defaults of mgm.cc:186-196,303-318 */
+/* Boundary limitations of the fused mgmb200_stereo* calls (all fail with a message, none silently):
+ *  - u and v must have the same size (the reference lets them differ: outoffR then has v's size, mgm.cc:404-424;
+ *    the stage-by-stage calls mgmb200_costvolume / _dev take vnx, vny and do support it);
+ *  - at most 65535 image rows, 4096 labels, 16 sweeps, median radius 7.
+ * Limitations of mgmb200_mgm_ranges (per-pixel ranges): costs must be finite where present, weights finite and >= 0,
+ * penalties >= 0 -- the compare-select kernel that reproduces the reference on non-finite inputs (mgmb200_mgm,
+ * mgmb200_mgm_labelmajor) covers uniform ranges only. */
 int mgmb200_stereo(mgmb200_ctx *ctx, const float *u, const float *v, int nx, int ny, int nch,
                    const mgmb200_stereo_params *p, float *out, float *outcost);
 

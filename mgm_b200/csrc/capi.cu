@@ -301,6 +301,8 @@ static int check_dims(int nx, int ny, int dmin, int dmax) {
    if (dmax <= dmin) return fail(MGMB200_EINVAL, "empty disparity range [%d,%d] (the reference asserts min<max, dvec.cc:57)", dmin, dmax);
    long long L = (long long)dmax - dmin + 1;
    if (L > 4096) return fail(MGMB200_EUNSUPPORTED, "%lld labels: at most 4096 are supported", L);
+   if (ny > 65535) return fail(MGMB200_EUNSUPPORTED, "%d image rows: at most 65535 are supported (one grid row per image row in the "
+                               "O(W*H) kernels)", ny);
    return 0;
 }
 

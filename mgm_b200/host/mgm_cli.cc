@@ -59,6 +59,7 @@ int main(int argc, char *argv[]) {
            " -m FILE -M FILE -l FILE\n"
            "Images: PNM, PFM, NPY, PNG (non-interlaced), uncompressed TIFF in; .npy, .tif/.tiff (float32), .pfm out.\n"
            "-O 9..16 add the knight-move sweeps defined by this build (the reference is undefined beyond 8).\n"
+           "u and v must have the same size and channels; at most 65535 rows, 4096 disparities, MEDIAN <= 7.\n"
            "Environment: CENSUS_NCC_WIN=3 TESTLRRL=1 TESTLRRL_TAU=1.0 MEDIAN=0 TSGM=4 TSGM_ITER=1\n"
            "             TSGM_FIX_OVERCOUNT=1 USE_TRUNCATED_LINEAR_POTENTIALS=0 MGMB200_DEVICE=<gpu>\n"
            "Same surface as gfacciol/mgm; the hot path runs on the GPU (libmgmb200).");
