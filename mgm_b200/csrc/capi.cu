@@ -103,7 +103,7 @@ struct mgmb200_ctx {
    int rows_override = 0;
    AggTuning tune;          // MGMB200_* knobs: read once by mgmb200_create, changed only by mgmb200_set_option
    // scratch (grow-only, reused across calls)
-   DevBuf u, v, fu, fv, ftmp, cu, cv, w, cc, dense, out, outcost, flags, progress, bnd, bndm, rg[4];
+   DevBuf u, v, fu, fv, ftmp, cu, cv, w, cc, dense, out, outcost, flags, progress, bnd, bndm, rg[4], ncc;
    // per-pixel ranges of the call in flight (device pointers or nullptr): S range, cost-vector range
    const float *r_smin = nullptr, *r_smax = nullptr, *r_ccmin = nullptr, *r_ccmax = nullptr;
    bool r_window = false;   // truncated-linear update inside the receiving pixel's cost range (consumer-side kernels)
@@ -239,7 +239,7 @@ extern "C" void mgmb200_destroy(mgmb200_ctx *c) {
    cudaSetDevice(c->device);
    cudaStreamSynchronize(c->stream);
    DevBuf *bufs[] = {&c->u, &c->v, &c->fu, &c->fv, &c->cu, &c->cv, &c->w, &c->cc, &c->dense, &c->out,
-                     &c->outcost, &c->flags, &c->ftmp, &c->progress, &c->bnd, &c->bndm, &c->rg[0], &c->rg[1],
+                     &c->outcost, &c->flags, &c->ftmp, &c->progress, &c->bnd, &c->bndm, &c->ncc, &c->rg[0], &c->rg[1],
                      &c->rg[2], &c->rg[3]};
    for (DevBuf *b : bufs) b->release();
    for (DevBuf &b : c->sweepv) b.release();
@@ -379,8 +379,13 @@ static int costvolume_dev_impl(mgmb200_ctx *c, const float *d_u, const float *d_
       CU(gblur_launch(d_v, vnx, vny, nch, 1.0f, c->ftmp.as<float>(), c->fv.as<float>(), c->stream));
       uu = c->fu.as<float>(); vv = c->fv.as<float>();
    }
+   float *scratch = nullptr;
+   if (dist == DIST_NCC) {
+      RET(c->ncc.reserve(costvolume_ncc_scratch_floats(nx, ny, vnx, vny, cnch) * sizeof(float)));
+      scratch = c->ncc.as<float>();
+   }
    CU(costvolume_launch(dist, uu, vv, cu, cv, nx, ny, vnx, vny, cnch, win, dmin, L, VS, truncDist, d_rlo, d_rhi, d_cc,
-                        c->num_sms, c->stream));
+                        c->num_sms, c->stream, scratch));
    return 0;
 }
 

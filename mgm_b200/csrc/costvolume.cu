@@ -340,6 +340,111 @@ __global__ void __launch_bounds__(256) mgm_costvolume_kernel(const CostArgs A, i
    }
 }
 
+// ------------------------------------------------------------------ clipped NCC, fast path
+// computeC_clippedNCC (mgm_costvolume.h:137-165) spends most of its additions on quantities that do not depend on the
+// label: the window sums of v1, v1^2 (left pixel) and v2, v2^2 (right pixel).  They are computed ONCE per pixel of each
+// image, with the reference's own loop order (dx outer, dy inner) and float operations, so every value is the one
+// the reference forms: mean = (sum v)/n and dev = (sum v^2)/n - mean*mean per channel, valid = the whole window is
+// inside the image and holds no NaN in any channel (otherwise the cost is +INF whatever the other image holds).
+// Only sum v1*v2 is left per (pixel, label): 1/3 of the loads and additions of the direct form.
+__global__ void mgm_ncc_stats_kernel(const float *__restrict__ img, int nx, int ny, int nch, int h,
+                                     float *__restrict__ mean, float *__restrict__ dev, float *__restrict__ valid) {
+   const long long np = (long long)nx * ny;
+   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (p >= np) return;
+   const int x = (int)(p % nx), y = (int)(p / nx);
+   bool ok = true;
+   for (int c = 0; c < nch && ok; ++c) {
+      float mu = 0.f, s = 0.f;
+      int n = 0;
+      for (int i = -h; i <= h && ok; ++i)
+         for (int j = -h; j <= h; ++j) {
+            const int ax = x + i, ay = y + j;
+            if (ax < 0 || ay < 0 || ax >= nx || ay >= ny) { ok = false; break; }
+            const float v = __ldg(img + ax + (long long)ay * nx + c * np);
+            if (v != v) { ok = false; break; }
+            mu += v; s += v * v;
+            ++n;
+         }
+      if (!ok) break;
+      const float fn = (float)n;
+      mu = __fdiv_rn(mu, fn);
+      s = __fdiv_rn(s, fn);
+      mean[p + c * np] = mu;
+      dev[p + c * np] = s - mu * mu;
+   }
+   valid[p] = ok ? 1.f : 0.f;
+}
+
+#define MGM_NCC_MAXWIN 512   // floats of the left window a warp stages (channels x window samples)
+__global__ void __launch_bounds__(256) mgm_costvolume_ncc_kernel(const CostArgs A, int dmin, int L, int VS, float cap,
+                                                                 const float *__restrict__ rlo, const float *__restrict__ rhi,
+                                                                 const float *__restrict__ um, const float *__restrict__ ud,
+                                                                 const float *__restrict__ uok, const float *__restrict__ vm,
+                                                                 const float *__restrict__ vd, const float *__restrict__ vok,
+                                                                 float *__restrict__ cc) {
+   __shared__ float s_win[8][MGM_NCC_MAXWIN];
+   const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const long long np = (long long)A.nx * A.ny, vnp = (long long)A.vnx * A.vny;
+   const int h = A.win / 2, w = 2 * h + 1, w2 = w * w;
+   const float fn = (float)w2, fnch = (float)A.nch;
+   float *uw = s_win[wid];
+   for (long long p = (long long)blockIdx.x * warps + wid; p < np; p += (long long)gridDim.x * warps) {
+      const int x = (int)(p % A.nx), y = (int)(p / A.nx);
+      float *dst = cc + (size_t)p * VS;
+      int klo = 0, khi = L - 1;
+      if (rlo) {
+         klo = max((int)rlo[p] - dmin, 0);
+         khi = min((int)rhi[p] - dmin, L - 1);
+      }
+      const bool pok = __ldg(uok + p) != 0.f;
+      __syncwarp();
+      if (pok)
+         for (int t = lane; t < A.nch * w2; t += 32) {
+            const int c = t / w2, r = t - c * w2, i = r / w - h, j = r % w - h;   // dx outer, dy inner
+            uw[t] = __ldg(A.u + (x + i) + (long long)(y + j) * A.nx + c * np);
+         }
+      __syncwarp();
+      bool anyfinite = false;
+      for (int k = lane; k < VS; k += 32) {
+         float e = MGM_INF;   // padding labels, labels outside the pixel's range
+         if (k >= klo && k <= khi) {
+            const int qx = x + dmin + k;
+            e = cap;   // the match falls outside v (mgm_costvolume.h:398-400)
+            if (qx >= 0 && qx < A.vnx && y < A.vny) {
+               const long long q = qx + (long long)y * A.vnx;
+               e = MGM_INF;   // a window sample outside an image or NaN (:150-154)
+               if (pok && __ldg(vok + q) != 0.f) {
+                  float NCC = 0.f;
+                  for (int c = 0; c < A.nch; ++c) {
+                     const float *vb = A.v + q + c * vnp;
+                     const float *uc = uw + c * w2;
+                     float prod = 0.f;
+                     int t = 0;
+                     for (int i = -h; i <= h; ++i)
+                        for (int j = -h; j <= h; ++j, ++t) prod += uc[t] * __ldg(vb + i + (long long)j * A.vnx);
+                     prod = __fdiv_rn(prod, fn);
+                     const float mu1 = __ldg(um + p + c * np), mu2 = __ldg(vm + q + c * vnp);
+                     const float num = prod - mu1 * mu2;
+                     const float var = __ldg(ud + p + c * np) * __ldg(vd + q + c * vnp);
+                     const double den = (0.0000001 > (double)var) ? 0.0000001 : (double)var;
+                     NCC = (float)((double)NCC + (double)num / sqrt(den));
+                  }
+                  float t2 = (NCC < fnch) ? NCC : fnch;
+                  t2 = (0.f > t2) ? 0.f : t2;
+                  e = (fnch - t2) * 64.f;
+               }
+            }
+            e = sel_min(e, cap);   // :403
+            anyfinite |= (fabsf(e) < MGM_INF);
+         }
+         dst[k] = e;
+      }
+      if (!__any_sync(0xffffffffu, anyfinite))   // no valid hypothesis: all costs become 0 (:414-421)
+         for (int k = lane; k < VS; k += 32) dst[k] = (k >= klo && k <= khi) ? 0.f : MGM_INF;
+   }
+}
+
 // ------------------------------------------------------------------ layout helpers
 // dense [npix][L] (the flat Dvec layout of mgm_costvolume.h:276-299) <-> padded [npix][VS]
 __global__ void mgm_pad_volume_kernel(const float *__restrict__ src, float *__restrict__ dst, long long npix, int L,
@@ -452,10 +557,11 @@ cudaError_t gblur_launch(const float *d_u, int nx, int ny, int nch, float sigma,
    return cudaGetLastError();
 }
 
+static inline unsigned blocks_for(long long n, int b);
 cudaError_t costvolume_launch(int dist, const float *d_u, const float *d_v, const uint32_t *d_cu,
                               const uint32_t *d_cv, int nx, int ny, int vnx, int vny, int nch, int win, int dmin,
                               int L, int VS, float truncDist, const float *d_rlo, const float *d_rhi, float *d_cc,
-                              int num_sms, cudaStream_t st) {
+                              int num_sms, cudaStream_t st, float *d_scratch) {
    CostArgs A;
    A.u = d_u; A.v = d_v; A.cu = d_cu; A.cv = d_cv;
    A.nx = nx; A.ny = ny; A.vnx = vnx; A.vny = vny; A.nch = nch; A.win = win;
@@ -472,6 +578,16 @@ cudaError_t costvolume_launch(int dist, const float *d_u, const float *d_v, cons
    case 3: MGM_CV_LAUNCH(D, 3); break;                  \
    case 4: MGM_CV_LAUNCH(D, 4); break;                  \
    default: MGM_CV_LAUNCH(D, 0); break;                 \
+   }
+   if (dist == DIST_NCC && d_scratch && nch * (2 * (win / 2) + 1) * (2 * (win / 2) + 1) <= MGM_NCC_MAXWIN) {
+      // label-independent window statistics once per pixel of each image, then one product sum per cell
+      const long long vnp = (long long)vnx * vny;
+      float *um = d_scratch, *ud = um + np * nch, *uok = ud + np * nch;
+      float *vm = uok + np, *vd = vm + vnp * nch, *vok = vd + vnp * nch;
+      mgm_ncc_stats_kernel<<<blocks_for(np, 128), 128, 0, st>>>(d_u, nx, ny, nch, win / 2, um, ud, uok);
+      mgm_ncc_stats_kernel<<<blocks_for(vnp, 128), 128, 0, st>>>(d_v, vnx, vny, nch, win / 2, vm, vd, vok);
+      mgm_costvolume_ncc_kernel<<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, um, ud, uok, vm, vd, vok, d_cc);
+      return cudaGetLastError();
    }
    switch (dist) {
    case DIST_AD: MGM_CV_FAST(DIST_AD); break;

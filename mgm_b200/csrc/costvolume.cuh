@@ -24,7 +24,11 @@ cudaError_t gblur_launch(const float *d_u, int nx, int ny, int nch, float sigma,
 cudaError_t costvolume_launch(int dist, const float *d_u, const float *d_v, const uint32_t *d_cu,
                               const uint32_t *d_cv, int nx, int ny, int vnx, int vny, int nch, int win, int dmin,
                               int L, int VS, float truncDist, const float *d_rlo, const float *d_rhi, float *d_cc,
-                              int num_sms, cudaStream_t st);
+                              int num_sms, cudaStream_t st, float *d_scratch = nullptr);
+// floats of scratch the NCC fast path needs (window statistics of both images); without scratch the direct form runs
+inline size_t costvolume_ncc_scratch_floats(int nx, int ny, int vnx, int vny, int nch) {
+   return ((size_t)nx * ny + (size_t)vnx * vny) * (2 * (size_t)nch + 1);
+}
 cudaError_t mask_volume_launch(float *d_cc, long long npix, int L, int VS, int dmin, const float *d_rlo,
                                const float *d_rhi, cudaStream_t st);
 cudaError_t pad_volume_launch(const float *d_src, float *d_dst, long long npix, int L, int VS, int label_major,
