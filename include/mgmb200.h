@@ -174,6 +174,11 @@ void mgmb200_stereo_params_default(mgmb200_stereo_params *p);   /* defaults of m
  * mgmb200_mgm_labelmajor) covers uniform ranges only. */
 int mgmb200_stereo(mgmb200_ctx *ctx, const float *u, const float *v, int nx, int ny, int nch,
                    const mgmb200_stereo_params *p, float *out, float *outcost);
+/* The same for npairs pairs of one shape (a driver looping over frames or tiles): images up, weights + cost volume per
+ * pair, the aggregation of several pairs per launch (mgmb200_aggregate_batch_dev), maps down.  u, v, out, outcost are
+ * arrays of npairs host pointers.  Results are those of npairs mgmb200_stereo calls. */
+int mgmb200_stereo_batch(mgmb200_ctx *ctx, int npairs, const float *const *u, const float *const *v, int nx, int ny,
+                         int nch, const mgmb200_stereo_params *params, float *const *out, float *const *outcost);
 
 /* ---- the O(W*H) stages around the hot path in the CLI flow (mgm.cc:396-443), as small kernels so that the two
  * directions, the median, the left-right tests and the back-projection stay on the device. */

@@ -275,6 +275,26 @@ class Context:
                                             _fp(outcost)))
         return out, outcost
 
+    def stereo_batch(self, us, vs, dmin=-30, dmax=30, P1=8.0, P2=32.0, NDIR=4, MGM=4, use_felzenszwalb_potentials=0,
+                     sgm_fix_overcount=1, aP=1.0, aThresh=5.0, prefilter="none", distance="ad", truncDist=np.inf,
+                     census_ncc_win=3, refinement="none", outs=None, outcosts=None):
+        """mgmb200_stereo_batch: lists of images of one shape in, lists of (disparity, cost) maps out."""
+        n = len(us)
+        imgs = [(_img(a), _img(b)) for a, b in zip(us, vs)]
+        (u0, nx, ny, nch) = imgs[0][0]
+        for (a, ax, ay, ac), (b, bx, by, bc) in imgs:
+            if (ax, ay, ac) != (nx, ny, nch) or (bx, by, bc) != (nx, ny, nch):
+                raise ValueError("all images of a batch must have the same shape")
+        p = StereoParams(int(dmin), int(dmax), P1, P2, int(NDIR), int(MGM), int(use_felzenszwalb_potentials),
+                         int(sgm_fix_overcount), aP, aThresh, prefilter.encode(), distance.encode(), truncDist,
+                         int(census_ncc_win), refinement.encode())
+        outs = [np.empty((ny, nx), np.float32) for _ in range(n)] if outs is None else outs
+        outcosts = [np.empty((ny, nx), np.float32) for _ in range(n)] if outcosts is None else outcosts
+        arr = lambda xs: (c_float_p * n)(*[_fp(x) for x in xs])
+        self._check(self.lib.mgmb200_stereo_batch(self._ctx, n, arr([i[0][0] for i in imgs]), arr([i[1][0] for i in imgs]), nx, ny,
+                                                  nch, ctypes.byref(p), arr(outs), arr(outcosts)))
+        return outs, outcosts
+
     # ------------------------------------------------------------------ post-processing of the CLI flow
     def leftright_test(self, dx, Rdx, threshold=1.0):
         """leftright_test (mgm.cc:68-91): returns the tested copy of dx."""

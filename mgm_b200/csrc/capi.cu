@@ -110,6 +110,7 @@ struct mgmb200_ctx {
    int r_emin = 0;
    std::vector<DevBuf> sweepv;   // per-sweep message volumes, slot pair*MGM_MAX_NDIR + sweep
    DevBuf desc, fins;            // device tables of the launch in flight (SweepDesc, WtaParams per pair)
+   std::vector<DevBuf> bcc, bw, bout;   // per-pair cost volumes, weights and maps of mgmb200_stereo_batch
    PinnedRing staging;
    DevBuf post[10];   // maps of the post-processing stages (N1/N2)
    // fused finish: tile order (expected readiness) cached per geometry
@@ -243,6 +244,9 @@ extern "C" void mgmb200_destroy(mgmb200_ctx *c) {
                      &c->rg[2], &c->rg[3]};
    for (DevBuf *b : bufs) b->release();
    for (DevBuf &b : c->sweepv) b.release();
+   for (DevBuf &b : c->bcc) b.release();
+   for (DevBuf &b : c->bw) b.release();
+   for (DevBuf &b : c->bout) b.release();
    c->desc.release(); c->fins.release(); c->staging.release();
    for (DevBuf &b : c->post) b.release();
    c->tiles.release();
@@ -1419,6 +1423,70 @@ extern "C" int mgmb200_stereo_lr(mgmb200_ctx *c, const float *u, const float *v,
       RET(download(c, backproj, c->post[6].p, np * nch * 4));
    }
    CU(cudaStreamSynchronize(c->stream));
+   return 0;
+}
+
+// The hot path of mgm.cc:372-385 for a batch of pairs of one shape (BASELINE.json configs[3]: 32 KITTI-size frames):
+// every pair's images go up, weights and cost volume are built, then the aggregation runs for several pairs per launch
+// (mgmb200_aggregate_batch_dev) and the maps come back.  Same results as npairs mgmb200_stereo calls.
+extern "C" int mgmb200_stereo_batch(mgmb200_ctx *c, int npairs, const float *const *u, const float *const *v, int nx, int ny,
+                                    int nch, const mgmb200_stereo_params *p, float *const *out, float *const *outcost) {
+   if (!c || !u || !v || !p || !out || !outcost || npairs < 0) return fail(MGMB200_EINVAL, "bad argument");
+   RET(check_dims(nx, ny, p->dmin, p->dmax));
+   CU(cudaSetDevice(c->device));
+   const int L = p->dmax - p->dmin + 1, VS = mgmb200_padded_labels(L);
+   const size_t np = (size_t)nx * ny, vol = np * VS * 4;
+   int pf = mgmb200_prefilter_index(p->prefilter), di = mgmb200_distance_index(p->distance);
+   if (di == DIST_CENSUS) pf = PF_CENSUS;
+   const float P1 = p->P1 * nch, P2 = p->P2 * nch;   // mgm.cc:356-357
+   const int refine = mgmb200_refinement_index(p->refinement);
+   const int chunk = std::max(1, c->tune.batch);
+   if ((int)c->bcc.size() < chunk) { c->bcc.resize(chunk); c->bw.resize(chunk); c->bout.resize(2 * (size_t)chunk); }
+   int launches = 0;
+   for (int b0 = 0; b0 < npairs; b0 += chunk) {
+      const int nb = std::min(chunk, npairs - b0);
+      int weighted_any = 0, weighted_all = 1;
+      std::vector<const float *> ccs((size_t)nb), ws((size_t)nb);
+      std::vector<float *> outs((size_t)nb), costs((size_t)nb);
+      for (int b = 0; b < nb; b++) {
+         if (!u[b0 + b] || !v[b0 + b] || !out[b0 + b] || !outcost[b0 + b]) return fail(MGMB200_EINVAL, "NULL pointer for pair %d", b0 + b);
+         RET(upload(c, c->u, u[b0 + b], np * nch * 4));
+         RET(upload(c, c->v, v[b0 + b], np * nch * 4));
+         RET(c->bcc[b].reserve(vol));
+         RET(c->bw[b].reserve(np * 8 * 4));
+         RET(c->bout[2 * b].reserve(np * 4));
+         RET(c->bout[2 * b + 1].reserve(np * 4));
+         RET(clear_flags(c));
+         CU(weights_launch(c->u.as<float>(), nx, ny, nch, p->aP, p->aThresh, c->bw[b].as<float>(), c->flags.as<int>(), c->stream));
+         RET(mgmb200_costvolume_dev(c, c->u.as<float>(), c->v.as<float>(), nx, ny, nch, nx, ny, p->dmin, p->dmax, pf, di,
+                                    p->truncDist, p->census_ncc_win, c->bcc[b].as<float>()));
+         int fl = 0;
+         RET(read_flags(c, &fl));
+         if ((fl & 1) && !(p->aP >= 0.f && p->aP < INFINITY)) return fail(MGMB200_EUNSUPPORTED, "aP must be finite and >= 0");
+         weighted_any |= (fl & 1);
+         weighted_all &= (fl & 1);
+         ccs[b] = c->bcc[b].as<float>(); ws[b] = c->bw[b].as<float>();
+         outs[b] = c->bout[2 * b].as<float>(); costs[b] = c->bout[2 * b + 1].as<float>();
+      }
+      if (weighted_any == weighted_all) {   // all pairs take the same kernels (mgm_core.cc:420-423 decides per pair)
+         RET(mgmb200_aggregate_batch_dev(c, nb, ccs.data(), weighted_any ? ws.data() : nullptr, nx, ny, p->dmin, p->dmax, P1, P2,
+                                         p->NDIR, p->MGM, p->use_felzenszwalb_potentials, p->sgm_fix_overcount, refine,
+                                         outs.data(), costs.data()));
+         launches += c->n_launches;
+      } else {
+         for (int b = 0; b < nb; b++) {
+            RET(mgmb200_aggregate_dev(c, ccs[b], ws[b], 2, nx, ny, p->dmin, p->dmax, P1, P2, p->NDIR, p->MGM,
+                                      p->use_felzenszwalb_potentials, p->sgm_fix_overcount, refine, outs[b], costs[b], nullptr));
+            launches += c->n_launches;
+         }
+      }
+      for (int b = 0; b < nb; b++) {
+         RET(download(c, out[b0 + b], outs[b], np * 4));
+         RET(download(c, outcost[b0 + b], costs[b], np * 4));
+      }
+   }
+   CU(cudaStreamSynchronize(c->stream));
+   c->n_launches = launches;
    return 0;
 }
 

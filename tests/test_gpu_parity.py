@@ -337,6 +337,24 @@ def test_mgm_16_sweeps(ctx, felz, weighted):
     assert same(out, ref["out"]) and same(cost, ref["outcost"])
 
 
+def test_stereo_batch(ctx):
+    """mgmb200_stereo_batch (images in, maps out, several pairs per aggregation launch) = one mgmb200_stereo per pair;
+    pairs with and without image-dependent weights in one batch fall back to per-pair launches."""
+    pairs = [synth_pair(83, 47, 20, seed=30 + i) for i in range(5)]
+    us, vs = [p[0] for p in pairs], [p[1] for p in pairs]
+    ctx.set_option("batch", 3)
+    try:
+        for kw in (dict(P1=8.0, P2=32.0, NDIR=8, MGM=4, distance="ad", refinement="vfit"),
+                   dict(P1=2.0, P2=20000.0, NDIR=16, MGM=3, use_felzenszwalb_potentials=1, distance="census", refinement="cubic"),
+                   dict(P1=8.0, P2=32.0, NDIR=8, MGM=2, distance="sd", aP=4.0, aThresh=12.0)):
+            outs, costs = ctx.stereo_batch(us, vs, dmin=-19, dmax=0, **kw)
+            for i in range(len(us)):
+                o, c = ctx.stereo(us[i], vs[i], dmin=-19, dmax=0, **kw)
+                assert same(outs[i], o) and same(costs[i], c), (kw, i)
+    finally:
+        ctx.set_option("reset")
+
+
 def test_aggregate_batch(ctx):
     """mgmb200_aggregate_batch_dev: several pairs per launch (more pairs than the in-flight limit, so several launches)
     give the bits of one mgmb200_aggregate_dev call per pair."""
