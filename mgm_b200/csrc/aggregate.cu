@@ -1291,13 +1291,13 @@ __device__ void run_band_shear(const AggParams &P, const SweepDesc &D, const int
 // A tile can be finished once every band (of every sweep of its pair) that holds one of its pixels is complete.
 // Band indices are monotone in the scan coordinates, which are affine in (x,y): the extremes are at the corners.
 // Lane p checks sweep p of the pair.
-__device__ bool tile_ready(const AggParams &P, int gtile, int lane) {
+__device__ bool tile_ready(const AggParams &P, const SweepDesc *tab, int gtile, int lane) {
    const int pair = gtile / P.fin_ntiles, tile = gtile % P.fin_ntiles;
    const int x0 = (tile % P.fin_tiles_x) * P.fin_tw, y0 = (tile / P.fin_tiles_x) * P.fin_th;
    const int x1 = min(x0 + P.fin_tw, P.nx) - 1, y1 = min(y0 + P.fin_th, P.ny) - 1;
    int done = 1;
    if (lane < P.ndir) {
-      const SweepDesc &d = P.sweeps[pair * P.ndir + lane];
+      const SweepDesc &d = tab[pair * P.ndir + lane];
       if (d.nb) {
          const int p = d.pass & 7;
          const int rm = (0x53 >> p) & 1, incx = (0xC5 >> p) & 1, incy = (0x99 >> p) & 1;   // pass_geometry
@@ -1318,12 +1318,12 @@ __device__ bool tile_ready(const AggParams &P, int gtile, int lane) {
 
 // Executed by the 32 lanes of warp 0 in lock step; returns (sweep index, band), (-2, global tile) or (-1, 0) = done.
 // `pending`: a finish tile this CTA has claimed but not run yet (-1 none, -2 no tiles left); lane 0's copy counts.
-__device__ int2 claim_band(const AggParams &P, int &pending, int lane) {
+__device__ int2 claim_band(const AggParams &P, const SweepDesc *tab, int &pending, int lane) {
    for (;;) {
       // candidates of this lane: best ready row-per-worker band, best filler band, best not-ready row-per-worker band
       int rdy_v = -1, rdy_b = 0, rdy_rem = 0, fil_v = -1, fil_b = 0x7fffffff, any_v = -1, any_b = 0, any_rem = 0;
       for (int v = lane; v < P.nsweeps; v += 32) {
-         const SweepDesc &d = P.sweeps[v];
+         const SweepDesc &d = tab[v];
          const int nbp = d.nb;
          if (!nbp) continue;
          const int b = *reinterpret_cast<volatile int *>(P.next_band + v);
@@ -1360,7 +1360,7 @@ __device__ int2 claim_band(const AggParams &P, int &pending, int lane) {
             t = __shfl_sync(0xffffffffu, t, 0);
             pending = (t < P.fin_total) ? P.fin_order[t] : -2;
          }
-         if (pending >= 0 && tile_ready(P, pending, lane)) {
+         if (pending >= 0 && tile_ready(P, tab, pending, lane)) {
             const int tile = pending;
             pending = -1;
             return make_int2(-2, tile);
@@ -1437,8 +1437,19 @@ __global__ void __launch_bounds__(RC ? MGM_AGG_MAX_THREADS_RC : MGM_AGG_MAX_THRE
    extern __shared__ __align__(128) unsigned char smem[];
    __shared__ int2 s_ticket;
    __shared__ AggStage s_stage;
+   __shared__ __align__(16) unsigned char s_tab_raw[MGM_MAX_NDIR * sizeof(SweepDesc)];
    const int t = threadIdx.x;
    const int ncomp = blockDim.x - 64;   // two service warps follow the row threads
+   // the sweep table of a single pair (up to 16 entries) is kept in shared memory: band claims and tile readiness
+   // tests read it at every poll
+   SweepDesc *s_tab = reinterpret_cast<SweepDesc *>(s_tab_raw);
+   const bool small_tab = P.nsweeps <= MGM_MAX_NDIR;
+   if (small_tab) {
+      const uint4 *src = reinterpret_cast<const uint4 *>(P.sweeps);
+      uint4 *dst = reinterpret_cast<uint4 *>(s_tab_raw);
+      for (int i = t; i < P.nsweeps * (int)(sizeof(SweepDesc) / 16); i += blockDim.x) dst[i] = src[i];
+   }
+   const SweepDesc *tab = small_tab ? s_tab : P.sweeps;
 
    // one-time barrier setup: RV boundary barriers
    {
@@ -1454,11 +1465,11 @@ __global__ void __launch_bounds__(RC ? MGM_AGG_MAX_THREADS_RC : MGM_AGG_MAX_THRE
    int pending = -1;   // warp 0: claimed finish tile
    for (;;) {
       if (t < 32) {
-         const int2 tk = claim_band(P, pending, t);
+         const int2 tk = claim_band(P, tab, pending, t);
          if (t == 0) s_ticket = tk;
          // stage the descriptor (16-byte words, warp 0)
          if (tk.x >= 0) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(P.sweeps + tk.x);
+            const uint4 *src = reinterpret_cast<const uint4 *>(tab + tk.x);
             uint4 *dst = reinterpret_cast<uint4 *>(&s_stage.d);
             for (int i = t; i < (int)(sizeof(SweepDesc) / 16); i += 32) dst[i] = src[i];
          } else if (tk.x == -2 && P.npairs > 1) {
