@@ -97,6 +97,7 @@ struct AggTuning {
                                        // the SGM-potential kernels, whose steps are shorter than the HBM latency)
    int batch = 16;                     // stereo pairs in flight per launch (batch entry points; measured 32 KITTI-size
                                        // pairs: 88 / 74 / 69 / 68 ms with 4 / 8 / 16 / 32 pairs per launch)
+   int lr_sequential = 0;              // 1: mgmb200_stereo_lr runs its two directions in two launches
    int verbose = 0;
    int dbg = 0;                        // 1: print the per-phase clock cycles of the register-chain band steps (axis sweeps)
 };

@@ -173,6 +173,7 @@ static bool apply_option(mgmb200_ctx *c, const char *name, const char *value) {
    if (!strcmp(name, "fused_finish")) { t.fused_finish = iv; return true; }
    if (!strcmp(name, "cc_pf")) { t.cc_pf = iv; return true; }
    if (!strcmp(name, "batch")) { t.batch = iv < 1 ? 1 : iv; return true; }
+   if (!strcmp(name, "lr_sequential")) { t.lr_sequential = iv; return true; }
    if (!strcmp(name, "verbose")) { t.verbose = iv; return true; }
    if (!strcmp(name, "dbg")) { t.dbg = iv; return true; }
    if (!strcmp(name, "fin_tile")) {
@@ -187,7 +188,7 @@ static void tuning_from_env(mgmb200_ctx *c) {
    c->tune = AggTuning();
    c->rows_override = 0;
    static const char *const names[] = {"rows_per_band", "rows_axis", "rows_diag", "groups", "no_creg", "no_fused_sgm", "reg_chains", "lanes4",
-                                       "lanes8", "no_shear", "static_order", "no_fused_finish", "fused_finish", "cc_pf", "batch", "verbose", "dbg", "fin_tile"};
+                                       "lanes8", "no_shear", "static_order", "no_fused_finish", "fused_finish", "cc_pf", "batch", "lr_sequential", "verbose", "dbg", "fin_tile"};
    for (const char *n : names) {
       char env[64] = "MGMB200_";
       size_t k = strlen(env);
@@ -820,16 +821,11 @@ extern "C" int mgmb200_aggregate_dev(mgmb200_ctx *c, const float *d_cc, const fl
 // A batch of stereo pairs of one shape (BASELINE.json configs[3]: 32 KITTI-shape pairs): the sweeps of up to
 // `batch` (mgmb200_set_option, default 8) pairs share one launch, so that the machine stays full although one small
 // pair alone is bound by the dependency depth of its sweeps.  Results are those of npairs mgmb200_aggregate_dev calls.
-extern "C" int mgmb200_aggregate_batch_dev(mgmb200_ctx *c, int npairs, const float *const *d_cc, const float *const *d_w,
-                                           int nx, int ny, int dmin, int dmax, float P1, float P2, int NDIR, int K,
-                                           int felz, int fix, int refine, float *const *d_out, float *const *d_outcost) {
-   if (!c || !d_cc || !d_out || !d_outcost || npairs < 0) return fail(MGMB200_EINVAL, "bad argument");
-   RET(check_dims(nx, ny, dmin, dmax));
-   if (refine < 0 || refine > 4) return fail(MGMB200_EINVAL, "refinement index %d", refine);
-   if (NDIR < 1 || NDIR > MGM_MAX_NDIR) return fail(MGMB200_EUNSUPPORTED, "NDIR=%d", NDIR);
-   if (c->r_smin || c->r_ccmin) return fail(MGMB200_EINVAL, "per-pixel ranges are a single-pair mode");
-   CU(cudaSetDevice(c->device));
-   const int L = dmax - dmin + 1;
+// npairs pairs of one shape, each with its own label origin dmins[b] (the two directions of a left-right run have
+// mirrored ranges): several pairs per aggregation launch
+static int aggregate_pairs(mgmb200_ctx *c, int npairs, const float *const *d_cc, const float *const *d_w, int nx, int ny,
+                           const int *dmins, int L, float P1, float P2, int NDIR, int K, int felz, int fix, int refine,
+                           float *const *d_out, float *const *d_outcost) {
    const unsigned mask = (1u << NDIR) - 1u;
    const int chunk = std::max(1, c->tune.batch);
    int launches = 0;
@@ -839,7 +835,7 @@ extern "C" int mgmb200_aggregate_batch_dev(mgmb200_ctx *c, int npairs, const flo
       const float *none[MGM_MAX_NDIR] = {nullptr};
       for (int b = 0; b < nb; b++) {
          if (!d_cc[b0 + b] || !d_out[b0 + b] || !d_outcost[b0 + b]) return fail(MGMB200_EINVAL, "NULL pointer for pair %d", b0 + b);
-         W[b] = finish_params(c, none, d_cc[b0 + b], nx, dmin, L, NDIR, fix, refine, 0, ny, d_out[b0 + b], d_outcost[b0 + b], nullptr);
+         W[b] = finish_params(c, none, d_cc[b0 + b], nx, dmins[b0 + b], L, NDIR, fix, refine, 0, ny, d_out[b0 + b], d_outcost[b0 + b], nullptr);
       }
       SweepRun R;
       R.npairs = nb; R.cc = d_cc + b0; R.w = d_w ? d_w + b0 : nullptr; R.fin = W.data(); R.mask = mask;
@@ -850,6 +846,20 @@ extern "C" int mgmb200_aggregate_batch_dev(mgmb200_ctx *c, int npairs, const flo
    }
    c->n_launches = launches;
    return 0;
+}
+
+extern "C" int mgmb200_aggregate_batch_dev(mgmb200_ctx *c, int npairs, const float *const *d_cc, const float *const *d_w,
+                                           int nx, int ny, int dmin, int dmax, float P1, float P2, int NDIR, int K,
+                                           int felz, int fix, int refine, float *const *d_out, float *const *d_outcost) {
+   if (!c || !d_cc || !d_out || !d_outcost || npairs < 0) return fail(MGMB200_EINVAL, "bad argument");
+   RET(check_dims(nx, ny, dmin, dmax));
+   if (refine < 0 || refine > 4) return fail(MGMB200_EINVAL, "refinement index %d", refine);
+   if (NDIR < 1 || NDIR > MGM_MAX_NDIR) return fail(MGMB200_EUNSUPPORTED, "NDIR=%d", NDIR);
+   if (c->r_smin || c->r_ccmin) return fail(MGMB200_EINVAL, "per-pixel ranges are a single-pair mode");
+   CU(cudaSetDevice(c->device));
+   std::vector<int> dmins((size_t)std::max(npairs, 1), dmin);
+   return aggregate_pairs(c, npairs, d_cc, d_w, nx, ny, dmins.data(), dmax - dmin + 1, P1, P2, NDIR, K, felz, fix, refine, d_out,
+                          d_outcost);
 }
 
 // ------------------------------------------------------------------------------------------ IPC (multi-GPU)
@@ -1220,20 +1230,30 @@ extern "C" void mgmb200_stereo_params_default(mgmb200_stereo_params *p) {
 }
 
 // one direction of mgm.cc:372-385 on device-resident images: weights, cost volume, aggregation, WTA + refinement
-static int stereo_dev(mgmb200_ctx *c, const float *d_u, const float *d_v, int nx, int ny, int nch,
-                      const mgmb200_stereo_params *p, int dmin, int dmax, int pf, int di, float *d_out, float *d_outcost) {
+// weights + cost volume of one direction into (wbuf, ccbuf); *weighted = the image has weights != 1 (mgm_core.cc:420-422)
+static int stereo_build(mgmb200_ctx *c, const float *d_u, const float *d_v, int nx, int ny, int nch,
+                        const mgmb200_stereo_params *p, int dmin, int dmax, int pf, int di, DevBuf &wbuf, DevBuf &ccbuf,
+                        int *weighted) {
    const int L = dmax - dmin + 1, VS = mgmb200_padded_labels(L);
    const size_t np = (size_t)nx * ny;
-   RET(c->w.reserve(np * 8 * 4));
-   RET(c->cc.reserve(np * VS * 4));
+   RET(wbuf.reserve(np * 8 * 4));
+   RET(ccbuf.reserve(np * VS * 4));
    RET(clear_flags(c));
    // weights + the "all ones?" scan of mgm_core.cc:420-422 in one kernel
-   CU(weights_launch(d_u, nx, ny, nch, p->aP, p->aThresh, c->w.as<float>(), c->flags.as<int>(), c->stream));
+   CU(weights_launch(d_u, nx, ny, nch, p->aP, p->aThresh, wbuf.as<float>(), c->flags.as<int>(), c->stream));
    RET(mgmb200_costvolume_dev(c, d_u, d_v, nx, ny, nch, nx, ny, dmin, dmax, pf, di, p->truncDist, p->census_ncc_win,
-                              c->cc.as<float>()));
+                              ccbuf.as<float>()));
    int fl = 0;
    RET(read_flags(c, &fl));
    if ((fl & 1) && !(p->aP >= 0.f && p->aP < INFINITY)) return fail(MGMB200_EUNSUPPORTED, "aP must be finite and >= 0");
+   *weighted = fl & 1;
+   return 0;
+}
+
+static int stereo_dev(mgmb200_ctx *c, const float *d_u, const float *d_v, int nx, int ny, int nch,
+                      const mgmb200_stereo_params *p, int dmin, int dmax, int pf, int di, float *d_out, float *d_outcost) {
+   int fl = 0;
+   RET(stereo_build(c, d_u, d_v, nx, ny, nch, p, dmin, dmax, pf, di, c->w, c->cc, &fl));
    const float P1 = p->P1 * nch, P2 = p->P2 * nch;   // mgm.cc:356-357
    return mgmb200_aggregate_dev(c, c->cc.as<float>(), c->w.as<float>(), (fl & 1) ? 1 : 0, nx, ny, dmin, dmax, P1, P2, p->NDIR,
                                 p->MGM, p->use_felzenszwalb_potentials, p->sgm_fix_overcount,
@@ -1394,6 +1414,31 @@ extern "C" int mgmb200_stereo_lr(mgmb200_ctx *c, const float *u, const float *v,
    for (int i = 0; i < 6; i++) RET(c->post[i].reserve(np * 4));
    float *offL = c->post[0].as<float>(), *costL = c->post[1].as<float>(), *offR = c->post[2].as<float>(),
          *costR = c->post[3].as<float>(), *t0 = c->post[4].as<float>(), *t1 = c->post[5].as<float>();
+   // Both directions (mgm.cc:372-385 and :405-414) are independent until the left-right test: when they take the same
+   // kernels (both images with or both without image-dependent weights) their 2 x NDIR sweeps share one launch -- the
+   // tail of one direction is filled with bands of the other -- instead of two launches back to back.
+   bool both_done = false;
+   if (q->testlrrl && !c->tune.lr_sequential) {
+      int wl = 0, wr = 0;
+      if (c->bcc.empty()) { c->bcc.resize(1); c->bw.resize(1); }
+      RET(stereo_build(c, c->u.as<float>(), c->v.as<float>(), nx, ny, nch, p, p->dmin, p->dmax, pf, di, c->w, c->cc, &wl));
+      RET(stereo_build(c, c->v.as<float>(), c->u.as<float>(), nx, ny, nch, p, -p->dmax, -p->dmin, pf, di, c->bw[0], c->bcc[0], &wr));
+      const float P1 = p->P1 * nch, P2 = p->P2 * nch;   // mgm.cc:356-357
+      const int refine = mgmb200_refinement_index(p->refinement);
+      if (wl == wr) {
+         const float *ccs[2] = {c->cc.as<float>(), c->bcc[0].as<float>()}, *ws[2] = {c->w.as<float>(), c->bw[0].as<float>()};
+         float *outs[2] = {offL, offR}, *costs[2] = {costL, costR};
+         const int dmins[2] = {p->dmin, -p->dmax};
+         RET(aggregate_pairs(c, 2, ccs, wl ? ws : nullptr, nx, ny, dmins, p->dmax - p->dmin + 1, P1, P2, p->NDIR, p->MGM,
+                             p->use_felzenszwalb_potentials, p->sgm_fix_overcount, refine, outs, costs));
+      } else {
+         RET(mgmb200_aggregate_dev(c, c->cc.as<float>(), c->w.as<float>(), wl, nx, ny, p->dmin, p->dmax, P1, P2, p->NDIR, p->MGM,
+                                   p->use_felzenszwalb_potentials, p->sgm_fix_overcount, refine, offL, costL, nullptr));
+         RET(mgmb200_aggregate_dev(c, c->bcc[0].as<float>(), c->bw[0].as<float>(), wr, nx, ny, -p->dmax, -p->dmin, P1, P2, p->NDIR,
+                                   p->MGM, p->use_felzenszwalb_potentials, p->sgm_fix_overcount, refine, offR, costR, nullptr));
+      }
+      both_done = true;
+   } else
    RET(stereo_dev(c, c->u.as<float>(), c->v.as<float>(), nx, ny, nch, p, p->dmin, p->dmax, pf, di, offL, costL));
    if (q->median) {   // mgm.cc:396
       CU(median_launch(offL, nx, ny, 1, q->median, t0, c->stream));
@@ -1402,7 +1447,8 @@ extern "C" int mgmb200_stereo_lr(mgmb200_ctx *c, const float *u, const float *v,
    if (out_nolr) RET(download(c, out_nolr, offL, np * 4));   // mgm.cc:399-401
    if (q->testlrrl) {
       // mgm.cc:404-419: the other direction with the mirrored range
-      RET(stereo_dev(c, c->v.as<float>(), c->u.as<float>(), nx, ny, nch, p, -p->dmax, -p->dmin, pf, di, offR, costR));
+      if (!both_done)
+         RET(stereo_dev(c, c->v.as<float>(), c->u.as<float>(), nx, ny, nch, p, -p->dmax, -p->dmin, pf, di, offR, costR));
       if (q->median) {
          CU(median_launch(offR, nx, ny, 1, q->median, t0, c->stream));
          std::swap(offR, t0);
