@@ -97,6 +97,8 @@ struct AggTuning {
                                        // the SGM-potential kernels, whose steps are shorter than the HBM latency)
    int batch = 16;                     // stereo pairs in flight per launch (batch entry points; measured 32 KITTI-size
                                        // pairs: 88 / 74 / 69 / 68 ms with 4 / 8 / 16 / 32 pairs per launch)
+   int no_lean_sgm = 0;                // 1: unweighted SGM launches take the generic kernel (aggregate.cu) instead of the lean
+                                       // one (aggregate_sgm.cu); parity tests run both
    int lr_sequential = 0;              // 1: mgmb200_stereo_lr runs its two directions in two launches
    int verbose = 0;
    int dbg = 0;                        // 1: print the per-phase clock cycles of the register-chain band steps (axis sweeps)
@@ -104,6 +106,7 @@ struct AggTuning {
 
 struct AggPlan {
    int VS, VSP, T[3], TS[3], ncb, shear, ng[3], fused_sgm, regchain, lanes, block, num_sms, verbose;
+   int lean_sgm;   // 1: the launch qualifies for the lean unweighted-SGM kernels (aggregate_sgm.cu)
    size_t smem;
    size_t off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };
@@ -116,5 +119,8 @@ void agg_sweep_bands(const AggPlan &plan, int pass, int nx, int ny, int *nb, siz
 void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
               int t_override, bool knight, const AggTuning &tune);
 cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st);
+// lean unweighted-SGM kernels (aggregate_sgm.cu): label layouts they are built for, and their launch
+bool agg_sgm_lean_supported(int VS, int lanes);
+cudaError_t agg_launch_sgm_lean(const AggParams &P, const AggPlan &plan, int K, cudaStream_t st);
 
 }  // namespace mgm

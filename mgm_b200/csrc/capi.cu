@@ -164,6 +164,7 @@ static bool apply_option(mgmb200_ctx *c, const char *name, const char *value) {
    if (!strcmp(name, "groups")) { t.groups = iv; return true; }
    if (!strcmp(name, "no_creg")) { t.no_creg = iv; return true; }
    if (!strcmp(name, "no_fused_sgm")) { t.no_fused_sgm = iv; return true; }
+   if (!strcmp(name, "no_lean_sgm")) { t.no_lean_sgm = iv; return true; }
    if (!strcmp(name, "reg_chains")) { t.reg_chains = iv; return true; }
    if (!strcmp(name, "lanes4")) { t.lanes = iv ? 4 : 0; return true; }
    if (!strcmp(name, "lanes8")) { t.lanes = iv ? 8 : 0; return true; }
@@ -187,7 +188,7 @@ static bool apply_option(mgmb200_ctx *c, const char *name, const char *value) {
 static void tuning_from_env(mgmb200_ctx *c) {
    c->tune = AggTuning();
    c->rows_override = 0;
-   static const char *const names[] = {"rows_per_band", "rows_axis", "rows_diag", "groups", "no_creg", "no_fused_sgm", "reg_chains", "lanes4",
+   static const char *const names[] = {"rows_per_band", "rows_axis", "rows_diag", "groups", "no_creg", "no_fused_sgm", "no_lean_sgm", "reg_chains", "lanes4",
                                        "lanes8", "no_shear", "static_order", "no_fused_finish", "fused_finish", "cc_pf", "batch", "lr_sequential", "verbose", "dbg", "fin_tile"};
    for (const char *n : names) {
       char env[64] = "MGMB200_";
@@ -652,8 +653,8 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
                     (double)q[3] / q[6], (double)q[4] / q[6], (double)q[5] / q[6], (double)(q[7] - h[8 + 7]) * 1e-6);
          }
       if (h[6])
-         fprintf(stderr, "[mgmb200 phase timing] steps=%llu cycles/step: top=%.0f gather=%.0f sync1=%.0f transform=%.0f rest=%.0f barrier=%.0f\n",
-                 h[6], (double)h[0] / h[6], (double)h[1] / h[6], (double)h[2] / h[6], (double)h[3] / h[6], (double)h[4] / h[6], (double)h[5] / h[6]);
+         fprintf(stderr, "[mgmb200 phase timing] steps=%llu cycles/step: top=%.0f gather=%.0f sync1=%.0f transform=%.0f rest=%.0f barrier=%.0f x7=%.0f\n",
+                 h[6], (double)h[0] / h[6], (double)h[1] / h[6], (double)h[2] / h[6], (double)h[3] / h[6], (double)h[4] / h[6], (double)h[5] / h[6], (double)h[7] / h[6]);
    }
    return 0;
 }

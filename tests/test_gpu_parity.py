@@ -110,7 +110,7 @@ def test_mgm_matches_oracle(ctx, K, felz, weighted):
 @pytest.mark.parametrize("knob", ["MGMB200_GROUPS=2", "MGMB200_GROUPS=3", "MGMB200_NO_SHEAR=1", "MGMB200_NO_CREG=1",
                                   "MGMB200_STATIC_ORDER=1", "MGMB200_NO_FUSED_SGM=1", "MGMB200_LANES4=1",
                                   "MGMB200_NO_FUSED_FINISH=1", "MGMB200_FUSED_FINISH=1", "MGMB200_FIN_TILE=7x3", "MGMB200_FIN_TILE=4096x4096",
-                                  "MGMB200_CC_PF=3", "MGMB200_REG_CHAINS=1"])
+                                  "MGMB200_CC_PF=3", "MGMB200_REG_CHAINS=1", "MGMB200_NO_LEAN_SGM=1"])
 def test_mgm_alternative_kernel_layouts(ctx, knob):
     """The aggregation kernel's alternative layouts (row groups on their own named barriers, row-per-worker diagonal
     sweeps, cp.async cost ring, static band order, finish stage as a separate launch or fused with other tile sizes,
@@ -129,6 +129,32 @@ def test_mgm_alternative_kernel_layouts(ctx, knob):
                 o = O.orc_mgm(cc, None, -(L - 1), P1, P2, 8, K, felz, 1)
                 assert same(r["S"], o["S"]) and same(r["out"], o["out"]), (knob, nx, ny, L, K, felz, rows, mism(r["S"], o["S"]))
     finally:
+        ctx.set_option("reset")
+
+
+@pytest.mark.parametrize("lanes", [0, 4])
+def test_mgm_lean_sgm_kernels(ctx, lanes):
+    """The lean unweighted-SGM kernels (aggregate_sgm.cu: compile-time label layout, split warp roles, double-buffered
+    costs) against the oracle for every chunk count per lane they are built for (2, 4, 6, 8 with 8 lanes per worker;
+    4, 8 with 4 lanes), TSGM 1-4, chained bands (16 rows) and default bands, with and without the L2 cost prefetch;
+    the generic kernel runs the same cases under MGMB200_NO_LEAN_SGM=1 and must give the same bits."""
+    labels = [40, 100, 180, 250] if lanes == 0 else [50, 120]
+    try:
+        if lanes:
+            ctx.set_option("lanes4", 1)
+        for L, K in itertools.product(labels, (1, 2, 3, 4)):
+            nx, ny = (75, 44) if L > 150 else (101, 58)
+            cc = synth_volume(nx, ny, L, seed=L + K, real=True)
+            o = O.orc_mgm(cc, None, -(L - 1), 8, 32, 8, K, 0, 1)
+            for rows, pf, lean in ((16, 3, 1), (0, 0, 1), (16, 3, 0)):
+                ctx.set_rows_per_band(rows)
+                ctx.set_option("cc_pf", pf)
+                ctx.set_option("no_lean_sgm", 0 if lean else 1)
+                r = ctx.mgm(cc, None, -(L - 1), 8, 32, 8, K, 0, 1)
+                tag = (lanes, L, K, rows, pf, lean, mism(r["S"], o["S"]), mism(r["out"], o["out"]))
+                assert same(r["S"], o["S"]) and same(r["out"], o["out"]) and same(r["outcost"], o["outcost"]), tag
+    finally:
+        ctx.set_rows_per_band(0)
         ctx.set_option("reset")
 
 
