@@ -598,8 +598,10 @@ def main():
         step_bytes = (agg_bytes + fin_bytes) * npair
         fused = info["kernel_launches"] == 1
         traffic, traffic_src = recorded_traffic(name, "mgm_aggregate_kernel_fused" if fused else "mgm_aggregate_kernel")
-        roof = {"bound": "hbm", "kernel": "mgm_aggregate_kernel (sweeps + fused finish tiles)" if fused else
-                "mgm_aggregate_kernel + mgm_wta_kernel",
+        # which aggregation kernel the library launches for this workload (csrc/aggregate.cu agg_launch)
+        kname = "mgm_aggregate_kernel" if NDIR > 8 else ("mgm_aggregate_trunc_kernel" if wl["felz"] else "mgm_aggregate_sgm_kernel")
+        roof = {"bound": "hbm", "kernel": kname + " (sweeps + fused finish tiles)" if fused else
+                kname + " + mgm_wta_kernel",
                 "achieved": round(step_bytes / (ms_dev * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(step_bytes / (ms_dev * 1e-3) / 1e9 / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "ms_per_launch": round(ms_dev / max(1, launches_per_step), 4),
@@ -608,7 +610,7 @@ def main():
         if ms_agg is not None:
             ach = agg_bytes / (ms_agg * 1e-3) / 1e9
             roof["unfused_split"] = {
-                "aggregation_only": {"kernel": "mgm_aggregate_kernel (sweeps only)", "ms_per_launch": round(ms_agg, 4),
+                "aggregation_only": {"kernel": kname + " (sweeps only)", "ms_per_launch": round(ms_agg, 4),
                                      "achieved": round(ach, 1), "frac": round(ach / peak, 4),
                                      "algorithmic_bytes_per_launch": agg_bytes},
                 "finish_only": {"kernel": "mgm_wta_kernel", "ms_per_launch": round(ms_fin, 4),

@@ -30,36 +30,6 @@
 namespace mgm {
 
 
-// Truncated-linear min-convolution (minConvTruncatedLinear, mgm_core.cc:152-163) of src into dst by a PAIR
-// of adjacent lanes: lane dir=0 runs the forward recurrence F[o] = min(F[o-1]+c, M[o]) upwards, lane dir=1
-// the same recurrence downwards on the ORIGINAL values (Bp).  Because x -> RN(x+c) is monotone and
-// inflationary (c >= 0) the reference's backward pass over F equals min(F, Bp) bit for bit, so the two
-// sequential chains can run concurrently and meet in the middle: each lane writes its partial values for
-// its first half of the labels, then finishes the other half with the partner's partials.  Every addition
-// is performed in the same order as the reference's sequential loops.  The result written to dst is
-// min(minconv, cap) - sub.  Loads are issued one chunk ahead of the dependent add/min chain.
-// One chunk of four labels of the recurrence F[o] = min(F[o-1]+c, a[o]), two labels per dependent step.  By
-// monotonicity of x -> RN(x+c):  F1 = min(r+c, a0),  F2 = min((r+c)+c, a0+c, a1)  with every "+c" a separately
-// rounded addition -- bit-identical to the step-by-step form.  The loop-carried dependency per pair is two
-// additions and one 3-input minimum (~13 cycles) instead of two add->min pairs (~20) for five instructions
-// instead of four; the kernel is issue-bound in this phase, so the cheaper two-label form beats deeper unrolling.
-__device__ __forceinline__ void chain4(float &run, float &a0, float &a1, float &a2, float &a3, const float c) {
-   {
-      const float u1 = run + c, u2 = u1 + c, a0p = a0 + c;
-      a0 = fminf(u1, a0);
-      a1 = fminf(fminf(u2, a0p), a1);
-   }
-   {
-      const float u1 = a1 + c, u2 = u1 + c, a2p = a2 + c;
-      a2 = fminf(u1, a2);
-      a3 = fminf(fminf(u2, a2p), a3);
-   }
-   run = a3;
-}
-
-// named barrier shared by one forward warp and its backward partner warp (ids 1..15; 0 is __syncthreads)
-__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-
 // Row groups.  The rows of a band are split into NG <= 3 groups of TG rows that run the two phases of a step on
 // their OWN named barrier, out of phase with each other: while one group gathers (LSU-bound) the others run their
 // min-convolution chains (latency-bound).  Adjacent groups are ordered by two producer/consumer named barriers
@@ -102,84 +72,6 @@ __device__ __forceinline__ RowGroup make_row_group(int tid, int ncomp, int r, in
    g.cnt_next = g.gi < NG - 1 ? count(g.gi + 1) : 0;
    g.first_tid = g.gi * TG * G;
    return g;
-}
-
-// Half of the meet-in-the-middle min-convolution of `src` into `dst`, executed by a whole WARP whose lanes
-// hold the same direction (DIR=0 upwards, DIR=1 downwards) of 32 different vectors; the partner warp runs
-// the other direction of the same vectors.  Warp-uniform direction: no divergence, no lane swizzles.
-// `on` = this lane has a vector to process (the barrier is executed by every lane regardless).
-//
-// Second half without re-reading the source: with F the upward recurrence and B the downward one, both on the
-// original values M, the result is Q[o] = min(F[o], B[o]).  Since F[o] <= M[o] and x -> RN(x+c) is monotone,
-//    min(F[o], B[o]) = min(F[o], min(B[o+1]+c, M[o])) = min(F[o], B[o+1]+c)   and   F[o+1]+c >= min(F[o], B[o+1]+c),
-// hence Q[o] = min(Q[o+1]+c, F[o]) (and symmetrically Q[o] = min(Q[o-1]+c, B[o])): each lane continues ITS
-// recurrence over the partner's partial values only -- same additions in the same order as the reference,
-// one shared-memory read per label less (checked bit for bit in tools/micro/chain_bench.cu, form 6).
-// MASK: labels outside [mlo,mhi] of the source read as +INF -- the min-convolution of a truncated-linear update
-// with per-pixel ranges runs inside the RECEIVING pixel's range (mgm_core.cc:229-281), which on dense vectors is
-// the convolution of the vector masked to that range.
-__device__ __forceinline__ float4 mask_labels(float4 v, int q, int mlo, int mhi) {
-   const int o = 4 * q;
-   v.x = (o >= mlo && o <= mhi) ? v.x : MGM_INF;
-   v.y = (o + 1 >= mlo && o + 1 <= mhi) ? v.y : MGM_INF;
-   v.z = (o + 2 >= mlo && o + 2 <= mhi) ? v.z : MGM_INF;
-   v.w = (o + 3 >= mlo && o + 3 <= mhi) ? v.w : MGM_INF;
-   return v;
-}
-template <int DIR, bool MASK = false>
-__device__ __forceinline__ void minconv_half(bool on, const float2 *src, float2 *dst, int nq, float c, float cap,
-                                             float sub, int bar_id, int mlo = 0, int mhi = 0) {
-   // D = MGM_CHAIN_PF chunks are loaded ahead of the dependent add/min chain (register ring).  One chunk covers the
-   // shared-memory latency of an otherwise idle LSU; when other warps gather at the same time (row groups) the
-   // queueing delay is longer than one chunk of chain work (~29 cycles) and a deeper ring keeps the chain fed.
-   constexpr int D = MGM_CHAIN_PF;
-   const int h = nq >> 1;   // nq is even (a multiple of 8)
-   const int dq = DIR ? -1 : 1;
-   const int qend = DIR ? 0 : (nq - 1);
-   int q = DIR ? (nq - 1) : 0;
-   float run = MGM_INF;
-   float4 sb[D];
-   auto clampq = [&](int qq) { return DIR ? max(qq, qend) : min(qq, qend); };
-   auto ldm = [&](const float2 *p, int qq, bool msk) {
-      float4 v = ld16<true>(p, qq);
-      if (MASK && msk) v = mask_labels(v, qq, mlo, mhi);
-      return v;
-   };
-   if (on) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) sb[d] = ldm(src, clampq(q + d * dq), true);   // own half only needs chunks < h: h >= D or unused
-      for (int i = 0; i < h; i += D) {
-#pragma unroll
-         for (int d = 0; d < D; ++d) {
-            if (i + d < h) {
-               float4 v = sb[d];
-               // never beyond this lane's half: in place, the partner is overwriting the other half
-               if (i + d + D < h) sb[d] = ldm(src, q + D * dq, true);
-               if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
-               st16<true>(dst, q, v);
-               q += dq;
-            }
-         }
-      }
-   }
-   pair_barrier(bar_id);   // partner's partial values are now in dst
-   if (on) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) sb[d] = ld16<true>(dst, clampq(q + d * dq));
-      for (int i = h; i < nq; i += D) {
-#pragma unroll
-         for (int d = 0; d < D; ++d) {
-            if (i + d < nq) {
-               float4 v = sb[d];
-               sb[d] = ld16<true>(dst, clampq(q + D * dq));   // beyond the end: a redundant re-load, never used
-               if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
-               v = add4s(make_float4(fminf(v.x, cap), fminf(v.y, cap), fminf(v.z, cap), fminf(v.w, cap)), -sub);
-               st16<true>(dst, q, v);
-               q += dq;
-            }
-         }
-      }
-   }
 }
 
 // Register-resident min-convolution by the 8 lanes of a worker (unweighted truncated-linear kernels, register-chain
@@ -1256,9 +1148,11 @@ static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, b
    // the min-convolution in place: no cost buffer
    // ... and the unweighted SGM kernels transform the message straight from registers (one group only)
    plan->fused_sgm = (!weighted && pot == POT_SGM && plan->ncb == 1 && want_groups == 1 && !tune.no_fused_sgm) ? 1 : 0;
-   // ... through the lean kernels of aggregate_sgm.cu when the launch holds sweeps 0-7 only, the diagonal ones sheared
+   // ... through the lean kernels of aggregate_sgm.cu when the diagonal sweeps 4-7 run sheared
    // (TSGM <= 3) or row-per-worker (TSGM = 4), and the label layout is one they are built for
-   plan->lean_sgm = (plan->fused_sgm && !knight && !tune.no_lean_sgm && (K == 4 || shear) && agg_sgm_lean_supported(VS, plan->lanes)) ? 1 : 0;
+   plan->lean_trunc = (!weighted && pot == POT_TRUNC && plan->ncb == 1 && !plan->regchain && want_groups == 1 && plan->lanes == 8 && !knight &&
+                       !tune.no_lean_trunc && (K == 4 || shear) && agg_trunc_lean_supported(VS)) ? 1 : 0;
+   plan->lean_sgm = (plan->fused_sgm && !tune.no_lean_sgm && (K == 4 || shear) && agg_sgm_lean_supported(VS, plan->lanes)) ? 1 : 0;
    const int VSP = plan->regchain ? VS + (VS >> 3) : VS;
    plan->VSP = VSP;
    const int ncbuf = (!weighted && plan->ncb == 1 && (pot == POT_TRUNC || plan->fused_sgm)) ? 0 : plan->ncb;
@@ -1342,6 +1236,8 @@ void agg_sweep_bands(const AggPlan &plan, int pass, int nx, int ny, int *nb, siz
 cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st) {
    if (pot == POT_SGM && !weighted && plan.lean_sgm && P.nslabs == 1 && plan.ng[0] == 1 && plan.ng[1] == 1)
       return agg_launch_sgm_lean(P, plan, K, st);
+   if (pot == POT_TRUNC && !weighted && plan.lean_trunc && P.nslabs == 1 && plan.ng[0] == 1 && plan.ng[1] == 1)
+      return agg_launch_trunc_lean(P, plan, K, st);
    if (pot == POT_SGM)
       return weighted ? launch_k<POT_SGM, true>(K, P, plan, st) : launch_k<POT_SGM, false>(K, P, plan, st);
    return weighted ? launch_k<POT_TRUNC, true>(K, P, plan, st) : launch_k<POT_TRUNC, false>(K, P, plan, st);

@@ -99,6 +99,7 @@ struct AggTuning {
                                        // pairs: 88 / 74 / 69 / 68 ms with 4 / 8 / 16 / 32 pairs per launch)
    int no_lean_sgm = 0;                // 1: unweighted SGM launches take the generic kernel (aggregate.cu) instead of the lean
                                        // one (aggregate_sgm.cu); parity tests run both
+   int no_lean_trunc = 0;              // 1: unweighted truncated-linear launches take the generic kernel instead of aggregate_trunc.cu
    int lr_sequential = 0;              // 1: mgmb200_stereo_lr runs its two directions in two launches
    int verbose = 0;
    int dbg = 0;                        // 1: print the per-phase clock cycles of the register-chain band steps (axis sweeps)
@@ -107,6 +108,7 @@ struct AggTuning {
 struct AggPlan {
    int VS, VSP, T[3], TS[3], ncb, shear, ng[3], fused_sgm, regchain, lanes, block, num_sms, verbose;
    int lean_sgm;   // 1: the launch qualifies for the lean unweighted-SGM kernels (aggregate_sgm.cu)
+   int lean_trunc; // 1: ... for the lean unweighted truncated-linear kernels (aggregate_trunc.cu)
    size_t smem;
    size_t off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };
@@ -122,5 +124,7 @@ cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, 
 // lean unweighted-SGM kernels (aggregate_sgm.cu): label layouts they are built for, and their launch
 bool agg_sgm_lean_supported(int VS, int lanes);
 cudaError_t agg_launch_sgm_lean(const AggParams &P, const AggPlan &plan, int K, cudaStream_t st);
+bool agg_trunc_lean_supported(int VS);
+cudaError_t agg_launch_trunc_lean(const AggParams &P, const AggPlan &plan, int K, cudaStream_t st);
 
 }  // namespace mgm

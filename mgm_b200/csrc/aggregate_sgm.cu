@@ -25,7 +25,7 @@
 //         vectors into the 8-deep virtual-row ring as soon as they are published and their slot is free (step counter),
 //         and the lanes that read the virtual row wait on the slot's mbarrier themselves.
 // Arithmetic and its order are those of the generic path (bit-identical results; tests/test_gpu_parity.py runs every
-// SGM case through both).  Not covered here (the generic kernel runs them): image-dependent weights, sweeps 8-15,
+// SGM case through both).  Not covered here (the generic kernel runs them): image-dependent weights,
 // row slabs on peer GPUs, label counts whose chunk count per lane is odd, diagonal sweeps without the sheared wavefront.
 #include "aggregate_dev.cuh"
 
@@ -113,14 +113,17 @@ __device__ __forceinline__ void finish_pixel(float4 (&v)[NJ], float m, float4 *g
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Row-per-worker bands: axis sweeps 0-3 (lag 1; lag 2 with TSGM = 4) and, DIAG, sweeps 4-7 with TSGM = 4 (lag 2,
-// predecessors in the order (+1,-1), (-1,-1), (0,-1), (-1,0)).  See run_band (aggregate.cu).
-template <int K, int GL, int NJ, bool DIAG>
+// Row-per-worker bands.  MODE 0: axis sweeps 0-3 (lag 1; lag 2 with TSGM = 4); MODE 1: sweeps 4-7 with TSGM = 4 (lag 2,
+// predecessors in the order (+1,-1), (-1,-1), (0,-1), (-1,0)); MODE 2: sweeps 8-15 (lag 2, predecessor order by the
+// parity of the scan coordinates, knight_pred_type in common.cuh).  See run_band (aggregate.cu).
+template <int K, int GL, int NJ, int MODE>
 __device__ void run_band_sgm(const AggParams &P, const SweepDesc &D, const int band, unsigned char *smem, int *s_step) {
    constexpr int G = GL;
-   constexpr int SIG = (DIAG || K == 4) ? 2 : 1;
+   constexpr bool DIAG = (MODE == 1), KN = (MODE == 2);
+   constexpr int SIG = (MODE != 0 || K == 4) ? 2 : 1;
    constexpr int R = SIG + 2;
-   constexpr int CLS = DIAG ? CLS_DIAG : CLS_AXIS;
+   constexpr int CLS = KN ? CLS_KNIGHT : (DIAG ? CLS_DIAG : CLS_AXIS);
+   const bool kn_diag = (D.pass & 7) >= 4;
    constexpr int VS = 4 * G * NJ;
    constexpr int V4 = VS / 4;       // float4 per vector
    constexpr int SLOT2 = VS / 2;    // float2 per ring slot
@@ -246,7 +249,7 @@ __device__ void run_band_sgm(const AggParams &P, const SweepDesc &D, const int b
                const float2 *S[K];
 #pragma unroll
                for (int k = 0; k < K; ++k) {
-                  const int pt = pred_type<DIAG>(k);
+                  const int pt = KN ? knight_pred_type(kn_diag, k, xs, ys) : pred_type<DIAG>(k);
                   S[k] = (pt == PRED_SAME) ? same : (pt == PRED_UP) ? up : (pt == PRED_UPL) ? upl : upr;
                }
                m = gather_sgm<K, NJ, G>(cc, S);
@@ -498,9 +501,10 @@ __global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_sgm_kern
          else run_finish_tile(P, s_stage.f, pb.y % P.fin_ntiles, smem);
       } else {
          const SweepDesc &D = s_stage.d;
-         if (D.pass < 4) run_band_sgm<K, GL, NJ, false>(P, D, pb.y, smem, &s_step);
+         if (D.pass >= 8) run_band_sgm<K, GL, NJ, 2>(P, D, pb.y, smem, &s_step);
+         else if (D.pass < 4) run_band_sgm<K, GL, NJ, 0>(P, D, pb.y, smem, &s_step);
          else if constexpr (K <= 3) run_band_shear_sgm<K, GL, NJ>(P, D, pb.y, smem, &s_step);
-         else run_band_sgm<K, GL, NJ, true>(P, D, pb.y, smem, &s_step);
+         else run_band_sgm<K, GL, NJ, 1>(P, D, pb.y, smem, &s_step);
       }
       __syncthreads();
    }

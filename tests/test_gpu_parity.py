@@ -110,7 +110,7 @@ def test_mgm_matches_oracle(ctx, K, felz, weighted):
 @pytest.mark.parametrize("knob", ["MGMB200_GROUPS=2", "MGMB200_GROUPS=3", "MGMB200_NO_SHEAR=1", "MGMB200_NO_CREG=1",
                                   "MGMB200_STATIC_ORDER=1", "MGMB200_NO_FUSED_SGM=1", "MGMB200_LANES4=1",
                                   "MGMB200_NO_FUSED_FINISH=1", "MGMB200_FUSED_FINISH=1", "MGMB200_FIN_TILE=7x3", "MGMB200_FIN_TILE=4096x4096",
-                                  "MGMB200_CC_PF=3", "MGMB200_REG_CHAINS=1", "MGMB200_NO_LEAN_SGM=1"])
+                                  "MGMB200_CC_PF=3", "MGMB200_REG_CHAINS=1", "MGMB200_NO_LEAN_SGM=1", "MGMB200_NO_LEAN_TRUNC=1"])
 def test_mgm_alternative_kernel_layouts(ctx, knob):
     """The aggregation kernel's alternative layouts (row groups on their own named barriers, row-per-worker diagonal
     sweeps, cp.async cost ring, static band order, finish stage as a separate launch or fused with other tile sizes,
@@ -152,6 +152,27 @@ def test_mgm_lean_sgm_kernels(ctx, lanes):
                 ctx.set_option("no_lean_sgm", 0 if lean else 1)
                 r = ctx.mgm(cc, None, -(L - 1), 8, 32, 8, K, 0, 1)
                 tag = (lanes, L, K, rows, pf, lean, mism(r["S"], o["S"]), mism(r["out"], o["out"]))
+                assert same(r["S"], o["S"]) and same(r["out"], o["out"]) and same(r["outcost"], o["outcost"]), tag
+    finally:
+        ctx.set_rows_per_band(0)
+        ctx.set_option("reset")
+
+
+def test_mgm_lean_trunc_kernels(ctx):
+    """The lean unweighted truncated-linear kernels (aggregate_trunc.cu: compile-time label layout, band hand-off off the
+    step barriers) against the oracle for every chunk count per lane they are built for (2, 4, 6, 8), TSGM 1-4, chained
+    bands (16 rows) and default bands; the generic kernel runs the same cases under MGMB200_NO_LEAN_TRUNC=1."""
+    try:
+        for L, K in itertools.product([40, 100, 180, 250], (1, 2, 3, 4)):
+            nx, ny = (75, 44) if L > 150 else (101, 58)
+            cc = synth_volume(nx, ny, L, seed=L + K, real=True)
+            P1, P2 = (2, 20000) if K != 4 else (1.5, 11)
+            o = O.orc_mgm(cc, None, -(L - 1), P1, P2, 8, K, 1, 1)
+            for rows, lean in ((16, 1), (0, 1), (16, 0)):
+                ctx.set_rows_per_band(rows)
+                ctx.set_option("no_lean_trunc", 0 if lean else 1)
+                r = ctx.mgm(cc, None, -(L - 1), P1, P2, 8, K, 1, 1)
+                tag = (L, K, rows, lean, mism(r["S"], o["S"]), mism(r["out"], o["out"]))
                 assert same(r["S"], o["S"]) and same(r["out"], o["out"]) and same(r["outcost"], o["outcost"]), tag
     finally:
         ctx.set_rows_per_band(0)
