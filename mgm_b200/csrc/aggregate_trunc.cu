@@ -19,6 +19,11 @@
 // Arithmetic and its order are those of the generic path (bit-identical; tests/test_gpu_parity.py runs both).
 #include "aggregate_dev.cuh"
 
+#ifndef MGM_TRUNC_LB_T
+#define MGM_TRUNC_LB_T MGM_AGG_MAX_THREADS   // __launch_bounds__ of the kernels: threads per CTA ...
+#define MGM_TRUNC_LB_B 1                     // ... and CTAs per SM the register allocation allows
+#endif
+
 namespace mgm {
 
 namespace {
@@ -491,7 +496,7 @@ __device__ void run_band_shear_trunc(const AggParams &P, const SweepDesc &D, con
 
 // The persistent kernel: same claim loop and finish tiles as mgm_aggregate_kernel (aggregate.cu).
 template <int K, int NJ>
-__global__ void __launch_bounds__(MGM_AGG_MAX_THREADS, 1) mgm_aggregate_trunc_kernel(const AggParams P) {
+__global__ void __launch_bounds__(MGM_TRUNC_LB_T, MGM_TRUNC_LB_B) mgm_aggregate_trunc_kernel(const AggParams P) {
    extern __shared__ __align__(128) unsigned char smem[];
    __shared__ int2 s_ticket;
    __shared__ BandCtl s_ctl;

@@ -25,6 +25,9 @@ if len(sys.argv) > 1:
     cases = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
 optsets = [{}, {"no_lean_sgm": 1}, {"cc_pf": 0}, {"cc_pf": 6}] if not FELZ else [{}, {"no_lean_trunc": 1}]
 P1, P2 = (2.0, 20000.0) if FELZ else (8.0, 32.0)
+if os.environ.get("OPTS"):
+    import json
+    optsets = json.loads(os.environ["OPTS"])
 for (W, H, L, K) in cases:
     VS = ctx.padded_labels(L)
     cc = torch.rand((H, W, VS), device="cuda") * 60
