@@ -1234,9 +1234,9 @@ void agg_sweep_bands(const AggPlan &plan, int pass, int nx, int ny, int *nb, siz
 }
 
 cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st) {
-   if (pot == POT_SGM && !weighted && plan.lean_sgm && P.nslabs == 1 && plan.ng[0] == 1 && plan.ng[1] == 1)
+   if (pot == POT_SGM && !weighted && plan.lean_sgm && plan.ng[0] == 1 && plan.ng[1] == 1)
       return agg_launch_sgm_lean(P, plan, K, st);
-   if (pot == POT_TRUNC && !weighted && plan.lean_trunc && P.nslabs == 1 && plan.ng[0] == 1 && plan.ng[1] == 1)
+   if (pot == POT_TRUNC && !weighted && plan.lean_trunc && plan.ng[0] == 1 && plan.ng[1] == 1)
       return agg_launch_trunc_lean(P, plan, K, st);
    if (pot == POT_SGM)
       return weighted ? launch_k<POT_SGM, true>(K, P, plan, st) : launch_k<POT_SGM, false>(K, P, plan, st);

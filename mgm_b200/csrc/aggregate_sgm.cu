@@ -26,7 +26,7 @@
 //         and the lanes that read the virtual row wait on the slot's mbarrier themselves.
 // Arithmetic and its order are those of the generic path (bit-identical results; tests/test_gpu_parity.py runs every
 // SGM case through both).  Not covered here (the generic kernel runs them): image-dependent weights,
-// row slabs on peer GPUs, label counts whose chunk count per lane is odd, diagonal sweeps without the sheared wavefront.
+// label counts whose chunk count per lane is odd, diagonal sweeps without the sheared wavefront.
 #include "aggregate_dev.cuh"
 
 namespace mgm {
@@ -202,7 +202,9 @@ __device__ void run_band_sgm(const AggParams &P, const SweepDesc &D, const int b
       const long long pix0 = g.base0 + (long long)ys * g.dys;
       const long long inc4 = g.dxs * V4;
       const float4 *cp = reinterpret_cast<const float4 *>(D.cc) + (pix0 + (long long)(xs + 1) * g.dxs) * V4 + gl;   // pixel xs+1
-      float4 *gp = reinterpret_cast<float4 *>(D.ldir[0]) + (pix0 + (long long)xs * g.dxs) * V4 + gl;               // pixel xs
+      long long goff = (pix0 + (long long)xs * g.dxs) * V4 + gl;   // float4 offset of my chunk of pixel xs in a message volume
+      const int nslabs = P.nslabs;                                 // > 1: row slabs of the volume live on peer GPUs (ldir_of_row)
+      int yimg = g.y0 + xs * g.ydxs + ys * g.ydys;                 // image row of pixel xs
       float4 *gb = bline ? reinterpret_cast<float4 *>(D.bnd + (size_t)band * maxii * VS) + (long long)xs * V4 + gl : nullptr;
 
       float4 c0[NJ], c1[NJ];
@@ -254,12 +256,14 @@ __device__ void run_band_sgm(const AggParams &P, const SweepDesc &D, const int b
                }
                m = gather_sgm<K, NJ, G>(cc, S);
             }
+            float4 *gp = reinterpret_cast<float4 *>(nslabs > 1 ? D.ldir[__umulhi((unsigned)yimg, P.slab_magic)] : D.ldir[0]) + goff;
             finish_pixel<K, NJ, G>(cc, m, gp, ownb + so, gb, gl, gmask, p1, p2);
          }
          ++xs;
          ++s;
          cp += inc4;
-         gp += inc4;
+         goff += inc4;
+         yimg += g.ydxs;
          if (bline) gb += V4;
          so = (so == (R - 1) * SLOT2) ? 0 : so + SLOT2;
          compute_barrier(ncomp);
@@ -381,7 +385,9 @@ __device__ void run_band_shear_sgm(const AggParams &P, const SweepDesc &D, const
       const long long dv = g.dys - g.dxs;
       const long long inc4 = dv * V4;
       const float4 *cp = reinterpret_cast<const float4 *>(D.cc) + (pix_u + (long long)(v + 1) * dv) * V4 + gl;   // position v+1
-      float4 *gp = reinterpret_cast<float4 *>(D.ldir[0]) + (pix_u + (long long)v * dv) * V4 + gl;
+      long long goff = (pix_u + (long long)v * dv) * V4 + gl;
+      const int nslabs = P.nslabs;
+      int yimg = g.y0 + (u - v) * g.ydxs + v * g.ydys;   // image row of (xs = u - v, ys = v)
       float4 *gb = bline ? reinterpret_cast<float4 *>(D.bnd + ((size_t)band * 2 + bl) * maxjj * VS) + (long long)v * V4 + gl : nullptr;
 
       float4 c0[NJ], c1[NJ];
@@ -423,11 +429,13 @@ __device__ void run_band_shear_sgm(const AggParams &P, const SweepDesc &D, const
                for (int k = 0; k < K; ++k) S[k] = S3[k];
                m = gather_sgm<K, NJ, G>(cc, S);
             }
+            float4 *gp = reinterpret_cast<float4 *>(nslabs > 1 ? D.ldir[__umulhi((unsigned)yimg, P.slab_magic)] : D.ldir[0]) + goff;
             finish_pixel<K, NJ, G>(cc, m, gp, ownb + (v & 1) * SLOT2, gb, gl, gmask, p1, p2);
          }
          ++v;
          cp += inc4;
-         gp += inc4;
+         goff += inc4;
+         yimg += g.ydys - g.ydxs;
          if (bline) gb += V4;
          compute_barrier(ncomp);
          if (tid == 0) sts_release(s_step, v);

@@ -208,7 +208,9 @@ __device__ void run_band_trunc(const AggParams &P, const SweepDesc &D, const int
       const long long pix0 = g.base0 + (long long)ys * g.dys;
       const long long inc4 = g.dxs * NQ;
       const float4 *cp = reinterpret_cast<const float4 *>(D.cc) + (pix0 + (long long)(xs + 1) * g.dxs) * NQ + gl;   // pixel xs+1
-      float4 *gp = reinterpret_cast<float4 *>(D.ldir[0]) + (pix0 + (long long)xs * g.dxs) * NQ + gl;               // pixel xs
+      long long goff = (pix0 + (long long)xs * g.dxs) * NQ + gl;   // float4 offset of my chunk of pixel xs in a message volume
+      const int nslabs = P.nslabs;                                 // > 1: row slabs of the volume live on peer GPUs (ldir_of_row)
+      int yimg = g.y0 + xs * g.ydxs + ys * g.ydys;                 // image row of pixel xs
 
       // chain lanes: warps [0,ncw) run the upward halves of rows 32w+lane, warps [ncw,2ncw) the downward halves
       const int ncw = (T + 31) >> 5;
@@ -240,6 +242,7 @@ __device__ void run_band_trunc(const AggParams &P, const SweepDesc &D, const int
             if (bline && xs >= R) { while (lds_acquire(&ctl->copied) < s - R + 1) {} }
             const bool border = (xs == 0) | (ys == 0) | (xs == maxii - 1);
             float4 *cur = ownb + si * NQ;
+            float4 *gp = reinterpret_cast<float4 *>(nslabs > 1 ? D.ldir[__umulhi((unsigned)yimg, P.slab_magic)] : D.ldir[0]) + goff;
             float m;
             if (border) m = border_pixel<NJ>(c, cur, gp);
             else {
@@ -267,7 +270,8 @@ __device__ void run_band_trunc(const AggParams &P, const SweepDesc &D, const int
          if (rowok && (unsigned)(xs + 1) < (unsigned)maxii) load_costs<NJ>(c, cp);
          ++xs;
          cp += inc4;
-         gp += inc4;
+         goff += inc4;
+         yimg += g.ydxs;
          si = (si == R - 1) ? 0 : si + 1;
          compute_barrier(ncomp);
 
@@ -413,7 +417,9 @@ __device__ void run_band_shear_trunc(const AggParams &P, const SweepDesc &D, con
       const long long dv = g.dys - g.dxs;
       const long long inc4 = dv * NQ;
       const float4 *cp = reinterpret_cast<const float4 *>(D.cc) + (pix_u + (long long)(sb + 1) * dv) * NQ + gl;   // position v+1
-      float4 *gp = reinterpret_cast<float4 *>(D.ldir[0]) + (pix_u + (long long)sb * dv) * NQ + gl;
+      long long goff = (pix_u + (long long)sb * dv) * NQ + gl;
+      const int nslabs = P.nslabs;
+      int yimg = g.y0 + (u - sb) * g.ydxs + sb * g.ydys;   // image row of (xs = u - v, ys = v)
 
       const int ncw = (T + 31) >> 5;
       const bool chain_warp = warp < 2 * ncw;
@@ -444,6 +450,7 @@ __device__ void run_band_shear_trunc(const AggParams &P, const SweepDesc &D, con
             const int xs = u - v;
             const bool border = (xs == 0) | (v == 0) | (xs == maxii - 1);
             float4 *cur = ownb + (v & 1) * NQ;
+            float4 *gp = reinterpret_cast<float4 *>(nslabs > 1 ? D.ldir[__umulhi((unsigned)yimg, P.slab_magic)] : D.ldir[0]) + goff;
             float m;
             if (border) m = border_pixel<NJ>(c, cur, gp);
             else {
@@ -466,7 +473,8 @@ __device__ void run_band_shear_trunc(const AggParams &P, const SweepDesc &D, con
          }
          if (rowok && v + 1 >= my_lo && v + 1 <= my_hi) load_costs<NJ>(c, cp);
          cp += inc4;
-         gp += inc4;
+         goff += inc4;
+         yimg += g.ydys - g.ydxs;
          compute_barrier(ncomp);
 
          // ---------------- phase 2: min-convolution chains, in place
