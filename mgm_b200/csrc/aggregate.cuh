@@ -10,6 +10,11 @@
 #define MGM_MAX_SLABS 8           // row slabs of a message volume (multi-GPU: one per rank, peer mappings)
 #define MGM_MAX_NDIR 16           // sweeps per stereo pair (8 of the reference + 8 defined here, common.cuh)
 
+#ifndef MGM_TRUNC_LAY
+#define MGM_TRUNC_LAY 1   // shared-memory vector layout of the lean truncated-linear kernels: 1 = 16-byte aligned rows and accesses,
+                         // 0 = 8-byte halves with a row stride of 8 bytes modulo 128 (conflict-free LDS.64 gathers)
+#endif
+
 namespace mgm {
 
 enum PotKind { POT_SGM = 0, POT_TRUNC = 1 };
@@ -100,6 +105,7 @@ struct AggTuning {
    int no_lean_sgm = 0;                // 1: unweighted SGM launches take the generic kernel (aggregate.cu) instead of the lean
                                        // one (aggregate_sgm.cu); parity tests run both
    int no_lean_trunc = 0;              // 1: unweighted truncated-linear launches take the generic kernel instead of aggregate_trunc.cu
+   int full_block = 0;                 // 1: 512 threads per CTA even when the bands hold fewer rows (spare warps serve the finish tiles)
    int lr_sequential = 0;              // 1: mgmb200_stereo_lr runs its two directions in two launches
    int verbose = 0;
    int dbg = 0;                        // 1: print the per-phase clock cycles of the register-chain band steps (axis sweeps)
@@ -121,6 +127,7 @@ void agg_sweep_bands(const AggPlan &plan, int pass, int nx, int ny, int *nb, siz
 void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
               int t_override, bool knight, const AggTuning &tune);
 cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st);
+cudaError_t agg_launch_generic(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st);   // aggregate.cu
 // lean unweighted-SGM kernels (aggregate_sgm.cu): label layouts they are built for, and their launch
 bool agg_sgm_lean_supported(int VS, int lanes);
 cudaError_t agg_launch_sgm_lean(const AggParams &P, const AggPlan &plan, int K, cudaStream_t st);

@@ -203,7 +203,7 @@ __device__ __forceinline__ float4 mask_labels(float4 v, int q, int mlo, int mhi)
    v.w = (o + 3 >= mlo && o + 3 <= mhi) ? v.w : MGM_INF;
    return v;
 }
-template <int DIR, bool MASK = false>
+template <int DIR, bool MASK = false, int LAY = 1>
 __device__ __forceinline__ void minconv_half(bool on, const float2 *src, float2 *dst, int nq, float c, float cap,
                                              float sub, int bar_id, int mlo = 0, int mhi = 0) {
    // D = MGM_CHAIN_PF chunks are loaded ahead of the dependent add/min chain (register ring).  One chunk covers the
@@ -218,7 +218,7 @@ __device__ __forceinline__ void minconv_half(bool on, const float2 *src, float2 
    float4 sb[D];
    auto clampq = [&](int qq) { return DIR ? max(qq, qend) : min(qq, qend); };
    auto ldm = [&](const float2 *p, int qq, bool msk) {
-      float4 v = ld16<true>(p, qq);
+      float4 v = ld16<LAY>(p, qq);
       if (MASK && msk) v = mask_labels(v, qq, mlo, mhi);
       return v;
    };
@@ -233,7 +233,7 @@ __device__ __forceinline__ void minconv_half(bool on, const float2 *src, float2 
                // never beyond this lane's half: in place, the partner is overwriting the other half
                if (i + d + D < h) sb[d] = ldm(src, q + D * dq, true);
                if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
-               st16<true>(dst, q, v);
+               st16<LAY>(dst, q, v);
                q += dq;
             }
          }
@@ -242,16 +242,16 @@ __device__ __forceinline__ void minconv_half(bool on, const float2 *src, float2 
    pair_barrier(bar_id);   // partner's partial values are now in dst
    if (on) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) sb[d] = ld16<true>(dst, clampq(q + d * dq));
+      for (int d = 0; d < D; ++d) sb[d] = ld16<LAY>(dst, clampq(q + d * dq));
       for (int i = h; i < nq; i += D) {
 #pragma unroll
          for (int d = 0; d < D; ++d) {
             if (i + d < nq) {
                float4 v = sb[d];
-               sb[d] = ld16<true>(dst, clampq(q + D * dq));   // beyond the end: a redundant re-load, never used
+               sb[d] = ld16<LAY>(dst, clampq(q + D * dq));   // beyond the end: a redundant re-load, never used
                if (DIR) { chain4(run, v.w, v.z, v.y, v.x, c); } else { chain4(run, v.x, v.y, v.z, v.w, c); }
                v = add4s(make_float4(fminf(v.x, cap), fminf(v.y, cap), fminf(v.z, cap), fminf(v.w, cap)), -sub);
-               st16<true>(dst, q, v);
+               st16<LAY>(dst, q, v);
                q += dq;
             }
          }

@@ -52,13 +52,16 @@ __device__ __forceinline__ void load_costs(float4 (&c)[NJ], const float4 *p) {
 }
 
 // border pixel: the message is the matching cost (mgm_core.cc:538-541)
+constexpr int LAY = MGM_TRUNC_LAY;   // shared-memory vector layout (ld16 / st16 in aggregate_dev.cuh)
+constexpr int F2 = 2;                // float2 per 16-byte chunk
+
 template <int NJ>
-__device__ __forceinline__ float border_pixel(const float4 (&c)[NJ], float4 *cur, float4 *gout) {
+__device__ __forceinline__ float border_pixel(const float4 (&c)[NJ], float2 *cur, float4 *gout) {
    float m = MGM_INF;
 #pragma unroll
    for (int j = 0; j < NJ; ++j) {
       m = hmin4(m, c[j]);
-      cur[G * j] = c[j];
+      st16<LAY>(cur, G * j, c[j]);
       __stcs(gout + G * j, c[j]);
    }
    return m;
@@ -68,8 +71,8 @@ __device__ __forceinline__ float border_pixel(const float4 (&c)[NJ], float4 *cur
 //   TSGM=2  c + (((a0 - m0) + a1) - m1) / 2      (update_cost2_trunclinear, mgm_core.cc:216)
 //   else    c + (a0 + a1 + ...) / K              (update_costW_trunclinear :278; the producers subtracted their minima)
 template <int K, int NJ>
-__device__ __forceinline__ float gather_trunc(const float4 (&c)[NJ], const float4 *const (&S)[K], const float (&mk)[K],
-                                              float4 *cur, float4 *gout) {
+__device__ __forceinline__ float gather_trunc(const float4 (&c)[NJ], const float2 *const (&S)[K], const float (&mk)[K],
+                                              float2 *cur, float4 *gout) {
    float m = MGM_INF;
    constexpr int B = MGM_JB;
    static_assert(NJ % B == 0, "chunk count per lane is a multiple of the gather batch");
@@ -79,7 +82,7 @@ __device__ __forceinline__ float gather_trunc(const float4 (&c)[NJ], const float
 #pragma unroll
       for (int jj = 0; jj < B; ++jj) {
 #pragma unroll
-         for (int k = 0; k < K; ++k) a[k][jj] = S[k][G * (j0 + jj)];
+         for (int k = 0; k < K; ++k) a[k][jj] = ld16<LAY>(S[k], G * (j0 + jj));
       }
 #pragma unroll
       for (int jj = 0; jj < B; ++jj) {
@@ -93,7 +96,7 @@ __device__ __forceinline__ float gather_trunc(const float4 (&c)[NJ], const float
             o = add4(c[j0 + jj], div4_by_k<K>(e));
          }
          m = hmin4(m, o);
-         cur[G * (j0 + jj)] = o;
+         st16<LAY>(cur, G * (j0 + jj), o);
          __stcs(gout + G * (j0 + jj), o);
       }
    }
@@ -193,9 +196,9 @@ __device__ void run_band_trunc(const AggParams &P, const SweepDesc &D, const int
       const bool rowok = r < nrows;
       const int ys = row0 + r;
       float *rowf = thr + (size_t)r * TS;
-      float4 *ownb = reinterpret_cast<float4 *>(rowf) + gl;                 // chunk gl of my row's ring slot 0
+      float2 *ownb = reinterpret_cast<float2 *>(rowf) + F2 * gl;            // chunk gl of my row's ring slot 0
       const bool upvirt = (r == 0);                                         // row -1 = the previous band's last row
-      const float4 *upb = upvirt ? reinterpret_cast<const float4 *>(virt) + gl : reinterpret_cast<const float4 *>(rowf - TS) + gl;
+      const float2 *upb = (upvirt ? reinterpret_cast<const float2 *>(virt) : reinterpret_cast<const float2 *>(rowf - TS)) + F2 * gl;
       const float *upm = upvirt ? vms : msr + (r - 1) * 4;
       const bool waiter = upvirt && has_prev;
       const bool bline = has_next && r == nrows - 1;
@@ -241,7 +244,7 @@ __device__ void run_band_trunc(const AggParams &P, const SweepDesc &D, const int
             // my slot held pixel xs-R: the publisher must have read it out (it does so two steps ahead of this)
             if (bline && xs >= R) { while (lds_acquire(&ctl->copied) < s - R + 1) {} }
             const bool border = (xs == 0) | (ys == 0) | (xs == maxii - 1);
-            float4 *cur = ownb + si * NQ;
+            float2 *cur = ownb + si * (F2 * NQ);
             float4 *gp = reinterpret_cast<float4 *>(nslabs > 1 ? D.ldir[__umulhi((unsigned)yimg, P.slab_magic)] : D.ldir[0]) + goff;
             float m;
             if (border) m = border_pixel<NJ>(c, cur, gp);
@@ -252,12 +255,12 @@ __device__ void run_band_trunc(const AggParams &P, const SweepDesc &D, const int
                const int ui_prev = upvirt ? ((xs - 1) & (RV - 1)) : si_prev;
                const int ui_next = upvirt ? ((xs + 1) & (RV - 1)) : si_next;
                (void)ui_next; (void)ui; (void)ui_prev;
-               const float4 *S[K];
+               const float2 *S[K];
                float mk[K];
 #pragma unroll
                for (int k = 0; k < K; ++k) {
                   const int pt = pred_type<DIAG>(k);
-                  S[k] = (pt == PRED_SAME) ? ownb + si_prev * NQ : upb + ((pt == PRED_UP) ? ui : (pt == PRED_UPL) ? ui_prev : ui_next) * NQ;
+                  S[k] = (pt == PRED_SAME) ? ownb + si_prev * (F2 * NQ) : upb + ((pt == PRED_UP) ? ui : (pt == PRED_UPL) ? ui_prev : ui_next) * (F2 * NQ);
                   mk[k] = 0.f;
                   if (NEEDM) mk[k] = (pt == PRED_SAME) ? msr[r * 4 + si_prev] : upm[(pt == PRED_UP) ? ui : (pt == PRED_UPL) ? ui_prev : ui_next];
                }
@@ -280,8 +283,8 @@ __device__ void run_band_trunc(const AggParams &P, const SweepDesc &D, const int
             const bool on = crow < nrows && (unsigned)cxs < (unsigned)maxii;
             const float cm = on ? msr[crow * 4 + csi] : 0.f;
             float2 *dst = reinterpret_cast<float2 *>(on ? crowf + csi * VS : thr);
-            if (cdir == 0) minconv_half<0>(on, dst, dst, NQ, p1, cm + p2, NEEDM ? 0.0f : cm, 4 + cw);
-            else minconv_half<1>(on, dst, dst, NQ, p1, cm + p2, NEEDM ? 0.0f : cm, 4 + cw);
+            if (cdir == 0) minconv_half<0, false, LAY>(on, dst, dst, NQ, p1, cm + p2, NEEDM ? 0.0f : cm, 4 + cw);
+            else minconv_half<1, false, LAY>(on, dst, dst, NQ, p1, cm + p2, NEEDM ? 0.0f : cm, 4 + cw);
             ++cxs;
             csi = (csi == R - 1) ? 0 : csi + 1;
          }
@@ -400,11 +403,11 @@ __device__ void run_band_shear_trunc(const AggParams &P, const SweepDesc &D, con
       const int u = u0 + r;
       const int my_lo = vlo(u), my_hi = vhi(u);
       float *rowf = thr + (size_t)r * TS;
-      float4 *ownb = reinterpret_cast<float4 *>(rowf) + gl;
+      float2 *ownb = reinterpret_cast<float2 *>(rowf) + F2 * gl;
       // workers r-2 and r-1: real rows, or the virtual workers -1 (line 0) and -2 (line 1) of the previous band
       const bool v1 = r < 2, v2 = r < 1;
-      const float4 *p1b = (v1 ? reinterpret_cast<const float4 *>(virt + (r == 1 ? 0 : RV * VS)) : reinterpret_cast<const float4 *>(rowf - 2 * TS)) + gl;
-      const float4 *p2b = (v2 ? reinterpret_cast<const float4 *>(virt) : reinterpret_cast<const float4 *>(rowf - TS)) + gl;
+      const float2 *p1b = (v1 ? reinterpret_cast<const float2 *>(virt + (r == 1 ? 0 : RV * VS)) : reinterpret_cast<const float2 *>(rowf - 2 * TS)) + F2 * gl;
+      const float2 *p2b = (v2 ? reinterpret_cast<const float2 *>(virt) : reinterpret_cast<const float2 *>(rowf - TS)) + F2 * gl;
       const float *m1b = v1 ? vms + (r == 1 ? 0 : RV) : msr + (r - 2) * 4;
       const float *m2b = v2 ? vms : msr + (r - 1) * 4;
       const bool waiter = v1 && pf_hi >= pf_lo;
@@ -449,15 +452,15 @@ __device__ void run_band_shear_trunc(const AggParams &P, const SweepDesc &D, con
             if (bline && v - 2 >= sb) { while (lds_acquire(&ctl->copied) < v - 1) {} }
             const int xs = u - v;
             const bool border = (xs == 0) | (v == 0) | (xs == maxii - 1);
-            float4 *cur = ownb + (v & 1) * NQ;
+            float2 *cur = ownb + (v & 1) * (F2 * NQ);
             float4 *gp = reinterpret_cast<float4 *>(nslabs > 1 ? D.ldir[__umulhi((unsigned)yimg, P.slab_magic)] : D.ldir[0]) + goff;
             float m;
             if (border) m = border_pixel<NJ>(c, cur, gp);
             else {
                const int po = (v - 1) & 1;            // ring slot of position v-1 in a real row
                const int vo = (v - 1) & (RV - 1);     // ... in the virtual workers' rings
-               const float4 *S3[3] = {ownb + po * NQ, p1b + (v1 ? vo : po) * NQ, p2b + (v2 ? vo : po) * NQ};
-               const float4 *S[K];
+               const float2 *S3[3] = {ownb + po * (F2 * NQ), p1b + (v1 ? vo : po) * (F2 * NQ), p2b + (v2 ? vo : po) * (F2 * NQ)};
+               const float2 *S[K];
                float mk[K];
 #pragma unroll
                for (int k = 0; k < K; ++k) { S[k] = S3[k]; mk[k] = 0.f; }
@@ -482,8 +485,8 @@ __device__ void run_band_shear_trunc(const AggParams &P, const SweepDesc &D, con
             const bool on = crow < nrows && v >= c_lo && v <= c_hi;
             const float cm = on ? msr[crow * 4 + (v & 1)] : 0.f;
             float2 *dst = reinterpret_cast<float2 *>(on ? crowf + (v & 1) * VS : thr);
-            if (cdir == 0) minconv_half<0>(on, dst, dst, NQ, p1, cm + p2, NEEDM ? 0.0f : cm, 4 + cw);
-            else minconv_half<1>(on, dst, dst, NQ, p1, cm + p2, NEEDM ? 0.0f : cm, 4 + cw);
+            if (cdir == 0) minconv_half<0, false, LAY>(on, dst, dst, NQ, p1, cm + p2, NEEDM ? 0.0f : cm, 4 + cw);
+            else minconv_half<1, false, LAY>(on, dst, dst, NQ, p1, cm + p2, NEEDM ? 0.0f : cm, 4 + cw);
          }
          compute_barrier(ncomp);
          if (tid == 0) sts_release(&ctl->step, v + 1);

@@ -166,6 +166,7 @@ static bool apply_option(mgmb200_ctx *c, const char *name, const char *value) {
    if (!strcmp(name, "no_fused_sgm")) { t.no_fused_sgm = iv; return true; }
    if (!strcmp(name, "no_lean_sgm")) { t.no_lean_sgm = iv; return true; }
    if (!strcmp(name, "no_lean_trunc")) { t.no_lean_trunc = iv; return true; }
+   if (!strcmp(name, "full_block")) { t.full_block = iv; return true; }
    if (!strcmp(name, "reg_chains")) { t.reg_chains = iv; return true; }
    if (!strcmp(name, "lanes4")) { t.lanes = iv ? 4 : 0; return true; }
    if (!strcmp(name, "lanes8")) { t.lanes = iv ? 8 : 0; return true; }
@@ -189,7 +190,7 @@ static bool apply_option(mgmb200_ctx *c, const char *name, const char *value) {
 static void tuning_from_env(mgmb200_ctx *c) {
    c->tune = AggTuning();
    c->rows_override = 0;
-   static const char *const names[] = {"rows_per_band", "rows_axis", "rows_diag", "groups", "no_creg", "no_fused_sgm", "no_lean_sgm", "no_lean_trunc", "reg_chains", "lanes4",
+   static const char *const names[] = {"rows_per_band", "rows_axis", "rows_diag", "groups", "no_creg", "no_fused_sgm", "no_lean_sgm", "no_lean_trunc", "full_block", "reg_chains", "lanes4",
                                        "lanes8", "no_shear", "static_order", "no_fused_finish", "fused_finish", "cc_pf", "batch", "lr_sequential", "verbose", "dbg", "fin_tile"};
    for (const char *n : names) {
       char env[64] = "MGMB200_";
