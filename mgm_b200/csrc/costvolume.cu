@@ -445,6 +445,124 @@ __global__ void __launch_bounds__(256) mgm_costvolume_ncc_kernel(const CostArgs 
    }
 }
 
+// Single-channel NCC with windows up to 7x7 and up to MGM_NCC1_MAXL labels: one THREAD per pixel, labels in a loop.
+// The window of the right image slides by one column per label, so it lives in registers as a ring of columns
+// (one new column of 2H+1 shared-memory loads per label instead of (2H+1)^2 loads); the left window and the
+// pixel's statistics stay in registers for all labels; the right image rows and statistics of the block's pixels x
+// labels are staged in shared memory once; costs go to global through a shared-memory transpose (32 labels at a
+// time) so that every store is a full 128-byte line.  Same operations in the same order as the kernel above
+// (products summed dx outer / dy inner, mgm_costvolume.h:137-165): bit-identical, 4096x4096x64 5x5: 28.7 -> see DESIGN.
+#define MGM_NCC1_TP 128     // pixels (threads) per block
+#define MGM_NCC1_MAXL 512   // labels the staged rows are sized for
+template <int H>
+__global__ void __launch_bounds__(MGM_NCC1_TP) mgm_costvolume_ncc1_kernel(const CostArgs A, int dmin, int L, int VS, float cap,
+                                                                          const float *__restrict__ rlo, const float *__restrict__ rhi,
+                                                                          const float *__restrict__ um, const float *__restrict__ ud,
+                                                                          const float *__restrict__ uok, const float *__restrict__ vm,
+                                                                          const float *__restrict__ vd, const float *__restrict__ vok,
+                                                                          float *__restrict__ cc) {
+   constexpr int W = 2 * H + 1, TP = MGM_NCC1_TP;
+   constexpr int NCMAX = TP + MGM_NCC1_MAXL - 1 + 2 * H;
+   __shared__ float s_v[W][NCMAX];                        // right image rows y-H..y+H, columns x0+dmin-H ...
+   __shared__ float s_vm[TP + MGM_NCC1_MAXL], s_vd[TP + MGM_NCC1_MAXL], s_vs[TP + MGM_NCC1_MAXL];   // mean, dev, state of the match pixel
+   __shared__ float s_out[TP][33];                        // 32 labels of every pixel, transposed on the way out
+   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+   const int x0 = blockIdx.x * TP, y = blockIdx.y;
+   const int x = x0 + tid;
+   const bool inimg = x < A.nx;
+   const long long p = (long long)y * A.nx + (inimg ? x : A.nx - 1);
+   const int nc = TP + L - 1 + 2 * H;       // staged columns: vx = x0 + dmin - H + c
+   for (int idx = tid; idx < W * nc; idx += TP) {
+      const int j = idx / nc, c = idx - j * nc;
+      const int vx = x0 + dmin - H + c, vy = y + j - H;
+      s_v[j][c] = (vx >= 0 && vx < A.vnx && vy >= 0 && vy < A.vny) ? __ldg(A.v + vx + (long long)vy * A.vnx) : 0.f;
+   }
+   for (int c = tid; c < TP + L - 1; c += TP) {   // match pixel qx = x0 + dmin + c
+      const int qx = x0 + dmin + c;
+      float st = -1.f, m = 0.f, d = 0.f;          // -1: the match falls outside v (cost = cap, mgm_costvolume.h:398-400)
+      if (qx >= 0 && qx < A.vnx && y < A.vny) {
+         const long long q = qx + (long long)y * A.vnx;
+         st = (__ldg(vok + q) != 0.f) ? 1.f : 0.f;   // 0: a window sample outside the image or NaN (+INF, :150-154)
+         m = __ldg(vm + q); d = __ldg(vd + q);
+      }
+      s_vs[c] = st; s_vm[c] = m; s_vd[c] = d;
+   }
+   const bool pok = inimg && __ldg(uok + p) != 0.f;
+   float uw[W][W];   // left window, [dx][dy]
+#pragma unroll
+   for (int i = 0; i < W; ++i)
+#pragma unroll
+      for (int j = 0; j < W; ++j) uw[i][j] = pok ? __ldg(A.u + (x + i - H) + (long long)(y + j - H) * A.nx) : 0.f;
+   const float mu1 = pok ? __ldg(um + p) : 0.f, dv1 = pok ? __ldg(ud + p) : 0.f;
+   int klo = 0, khi = L - 1;
+   if (rlo && inimg) {
+      klo = max((int)rlo[p] - dmin, 0);
+      khi = min((int)rhi[p] - dmin, L - 1);
+   }
+   const float fn = (float)(W * W);
+   __syncthreads();
+
+   float col[W][W];   // ring of window columns of the right image: column position c sits in slot c % W
+#pragma unroll
+   for (int i = 0; i < W - 1; ++i)
+#pragma unroll
+      for (int j = 0; j < W; ++j) col[i][j] = s_v[j][tid + i];
+   bool anyfinite = false;
+   float *dst0 = cc + ((long long)y * A.nx + x0) * VS;   // the block's first pixel
+   for (int kb = 0; kb < VS; kb += W) {
+#pragma unroll
+      for (int t = 0; t < W; ++t) {
+         const int k = kb + t;
+         if (k < VS) {   // uniform
+            // new column: position k + W - 1 -> slot (t + W - 1) % W
+            if (k < L) {
+#pragma unroll
+               for (int j = 0; j < W; ++j) col[(t + W - 1) % W][j] = s_v[j][tid + k + W - 1];
+            }
+            float e = MGM_INF;   // padding labels, labels outside the pixel's range
+            if (k >= klo && k <= khi) {
+               const float st = s_vs[tid + k];
+               e = cap;
+               if (st >= 0.f) {
+                  e = MGM_INF;
+                  if (pok && st > 0.f) {
+                     float prod = 0.f;
+#pragma unroll
+                     for (int i = 0; i < W; ++i)
+#pragma unroll
+                        for (int j = 0; j < W; ++j) prod += uw[i][j] * col[(t + i) % W][j];
+                     prod = __fdiv_rn(prod, fn);
+                     const float num = prod - mu1 * s_vm[tid + k];
+                     const float var = dv1 * s_vd[tid + k];
+                     const double den = (0.0000001 > (double)var) ? 0.0000001 : (double)var;
+                     const float NCC = (float)((double)0.f + (double)num / sqrt(den));
+                     float t2 = (NCC < 1.f) ? NCC : 1.f;
+                     t2 = (0.f > t2) ? 0.f : t2;
+                     e = (1.f - t2) * 64.f;
+                  }
+               }
+               e = sel_min(e, cap);   // :403
+               anyfinite |= (fabsf(e) < MGM_INF);
+            }
+            s_out[tid][k & 31] = e;
+            if ((k & 31) == 31 || k == VS - 1) {   // flush 32 labels of the block's pixels, one 128-byte line per pixel
+               __syncthreads();
+               const int k0 = k & ~31, nk = (k & 31) + 1;
+               for (int r = 0; r < 32; ++r) {
+                  const int pr = wid * 32 + r;
+                  if (x0 + pr < A.nx && lane < nk) dst0[(long long)pr * VS + k0 + lane] = s_out[pr][lane];
+               }
+               __syncthreads();
+            }
+         }
+      }
+   }
+   if (inimg && !anyfinite) {   // no valid hypothesis: all costs become 0 (:414-421); the staged stores are ordered before
+      float *dst = cc + (size_t)p * VS;
+      for (int k = 0; k < VS; ++k) dst[k] = (k >= klo && k <= khi) ? 0.f : MGM_INF;
+   }
+}
+
 // ------------------------------------------------------------------ layout helpers
 // dense [npix][L] (the flat Dvec layout of mgm_costvolume.h:276-299) <-> padded [npix][VS]
 __global__ void mgm_pad_volume_kernel(const float *__restrict__ src, float *__restrict__ dst, long long npix, int L,
@@ -586,6 +704,14 @@ cudaError_t costvolume_launch(int dist, const float *d_u, const float *d_v, cons
       float *vm = uok + np, *vd = vm + vnp * nch, *vok = vd + vnp * nch;
       mgm_ncc_stats_kernel<<<blocks_for(np, 128), 128, 0, st>>>(d_u, nx, ny, nch, win / 2, um, ud, uok);
       mgm_ncc_stats_kernel<<<blocks_for(vnp, 128), 128, 0, st>>>(d_v, vnx, vny, nch, win / 2, vm, vd, vok);
+      if (nch == 1 && L <= MGM_NCC1_MAXL && ny <= 65535 && (win / 2 >= 1 && win / 2 <= 3)) {
+         // one thread per pixel, the right window as a register ring of columns (mgm_costvolume_ncc1_kernel)
+         const dim3 g1((unsigned)((nx + MGM_NCC1_TP - 1) / MGM_NCC1_TP), (unsigned)ny);
+         if (win / 2 == 1) mgm_costvolume_ncc1_kernel<1><<<g1, MGM_NCC1_TP, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, um, ud, uok, vm, vd, vok, d_cc);
+         else if (win / 2 == 2) mgm_costvolume_ncc1_kernel<2><<<g1, MGM_NCC1_TP, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, um, ud, uok, vm, vd, vok, d_cc);
+         else mgm_costvolume_ncc1_kernel<3><<<g1, MGM_NCC1_TP, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, um, ud, uok, vm, vd, vok, d_cc);
+         return cudaGetLastError();
+      }
       mgm_costvolume_ncc_kernel<<<grid, 256, 0, st>>>(A, dmin, L, VS, cap, d_rlo, d_rhi, um, ud, uok, vm, vd, vok, d_cc);
       return cudaGetLastError();
    }

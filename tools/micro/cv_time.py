@@ -5,7 +5,7 @@ import numpy as np, torch
 import bench
 from mgm_b200 import Context
 ctx = Context(0)
-for (W, H, L, nch, dist, win) in [(2048, 1536, 256, 1, "census", 3), (1920, 1080, 128, 1, "census", 5), (2048, 1536, 256, 3, "ad", 3)]:
+for (W, H, L, nch, dist, win) in [(2048, 1536, 256, 1, "census", 3), (1920, 1080, 128, 1, "census", 5), (2048, 1536, 256, 3, "ad", 3), (4096, 4096, 64, 1, "ncc", 5), (1242, 375, 192, 1, "ad", 3)]:
     u, v = bench.synth_pair(W, H, L, 0)
     u = np.repeat(np.asarray(u, np.float32).reshape(-1, H, W)[:1], nch, 0)
     v = np.repeat(np.asarray(v, np.float32).reshape(-1, H, W)[:1], nch, 0)
