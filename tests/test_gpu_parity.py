@@ -34,7 +34,7 @@ def test_weights(ctx, nch):
 
 
 @pytest.mark.parametrize("dist,win", [("ad", 3), ("sd", 3), ("census", 3), ("census", 5), ("census", 7), ("ncc", 3),
-                                      ("ncc", 5), ("btad", 3), ("btsd", 3)])
+                                      ("ncc", 5), ("ncc", 7), ("btad", 3), ("btsd", 3)])
 @pytest.mark.parametrize("nch", [1, 3])
 def test_costvolume(ctx, dist, win, nch):
     u, v = synth_pair(45, 29, 14, seed=win + nch, nch=nch)
@@ -70,6 +70,26 @@ def test_costvolume_edge_cases(ctx):
                 O.orc_costvolume(u, v, -20, 3, "sobelx", "sd", 90.0, 3))
     assert same(ctx.allocate_and_fill_sgm_costvolume(u, v, -20, 3, "sobel_x", "l1", np.inf, 3),
                 O.orc_costvolume(u, v, -20, 3, "none", "ad", np.inf, 3))
+
+
+def test_costvolume_ncc_thread_per_pixel(ctx):
+    """Single-channel NCC (mgm_costvolume_ncc1_kernel: one thread per pixel, register ring of window columns, staged
+    rows, transposed stores): rows wider than a block of 128 pixels, label counts that are not a multiple of 32, NaN
+    samples, matches outside the right image, truncation, the all-invalid rule, per-pixel ranges."""
+    rng = np.random.default_rng(5)
+    for (nx, ny, L, win) in [(300, 9, 70, 5), (131, 12, 33, 3), (260, 11, 40, 7)]:
+        u, v = synth_pair(nx, ny, L, seed=win, nch=1)
+        u = u + np.float32(0.21)
+        for _ in range(6):
+            u[0, rng.integers(ny), rng.integers(nx)] = np.nan
+            v[0, rng.integers(ny), rng.integers(nx)] = np.nan
+        for dmin, trunc in [(-(L - 10), np.inf), (-5, 30.0), (nx - 20, np.inf)]:
+            a = ctx.allocate_and_fill_sgm_costvolume(u, v, dmin, dmin + L - 1, "none", "ncc", trunc, win)
+            b = O.orc_costvolume(u, v, dmin, dmin + L - 1, "none", "ncc", trunc, win)
+            assert same(a, b), (nx, ny, L, win, dmin, trunc, mism(a, b))
+        lo, hi = _ragged(nx, ny, -(L - 1), 0, 2)
+        assert same(ctx.costvolume_ranges(u, v, lo, hi, -(L - 1), 0, "none", "ncc", np.inf, win),
+                    O.orc_costvolume_ranges(u, v, lo, hi, -(L - 1), 0, "none", "ncc", np.inf, win)), (nx, win)
 
 
 @pytest.mark.parametrize("nch", [1, 3])
