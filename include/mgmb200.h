@@ -58,6 +58,7 @@ int mgmb200_set_rows_per_band(mgmb200_ctx *ctx, int rows);
 /* Tuning / debugging knobs of the aggregation launch (no reference counterpart).  They are read ONCE from the
  * environment by mgmb200_create (MGMB200_<NAME>) and changed afterwards only through this call -- nothing on the
  * per-call path reads the environment.  Names: rows_per_band, rows_axis, rows_diag, groups, no_creg, no_fused_sgm, reg_chains,
+ * no_lean_sgm / no_lean_trunc (run the unweighted potentials through the generic kernel instead of the lean ones), full_block,
  * lanes4, lanes8, no_shear, static_order, no_fused_finish, fused_finish, fin_tile ("WxH"), cc_pf, lr_sequential, batch (pairs per launch of the batch
  * entry points), verbose; "reset" re-reads the
  * environment.  Every layout they select is parity-tested (tests/test_gpu_parity.py). */

@@ -77,6 +77,9 @@ static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, b
    const int tm = max(max(plan->T[0], plan->T[1]), plan->T[2]);
    const int ncomp = (tm * plan->lanes + 31) & ~31;
    plan->block = ncomp + 64;   // + boundary-consumer warp + boundary-publisher warp
+   // the lean truncated-linear kernels run the forward and backward halves of the min-convolution on two COMPUTE warps
+   // (their service warps are off the step barriers): bands of up to 4 rows still get two compute warps
+   if (plan->lean_trunc && ncomp < 64) plan->block = 64 + 64;
    // full_block: keep the largest block although the bands hold fewer rows -- the spare warps idle during the band steps
    // and work in the fused finish tiles (one warp per pixel)
    if (tune.full_block && !plan->regchain && plan->block < MGM_AGG_MAX_THREADS) plan->block = MGM_AGG_MAX_THREADS;

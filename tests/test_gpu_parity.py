@@ -199,6 +199,32 @@ def test_mgm_lean_trunc_kernels(ctx):
         ctx.set_option("reset")
 
 
+def test_mgm_lean_kernels_degenerate_sizes(ctx):
+    """Images with one or two rows / columns, single pixels and thin strips through the lean kernels (label counts they
+    take: 40 labels = 2 chunks per lane), both potentials, TSGM 1-4, 16 sweeps for SGM, chained bands of 2 rows."""
+    try:
+        for nx, ny in [(2, 9), (9, 2), (1, 1), (1, 6), (6, 1), (2, 2), (3, 3), (4, 3), (3, 2), (57, 3), (3, 57), (70, 1), (1, 70)]:
+            cc = synth_volume(nx, ny, 40, seed=nx + 3 * ny, real=True)
+            for felz, K, NDIR, rows in itertools.product((0, 1), (1, 2, 3, 4), (8, 16), (0, 2)):
+                if NDIR == 16 and (felz or K not in (2, 4)):
+                    continue
+                ctx.set_rows_per_band(rows)
+                P1, P2 = (8, 32) if not felz else (2, 20000)
+                r = ctx.mgm(cc, None, -39, P1, P2, NDIR, K, felz, 1)
+                o = O.orc_mgm(cc, None, -39, P1, P2, NDIR, K, felz, 1)
+                assert same(r["S"], o["S"]) and same(r["out"], o["out"]), (nx, ny, felz, K, NDIR, rows, mism(r["S"], o["S"]))
+        # bands of 1, 3 and 5 rows (fewer rows than a warp holds: the chains still need two compute warps)
+        cc = synth_volume(40, 30, 40, seed=1, real=True)
+        for felz, K, rows in itertools.product((0, 1), (1, 2, 3, 4), (1, 3, 5)):
+            ctx.set_rows_per_band(rows)
+            P1, P2 = (8, 32) if not felz else (2, 20000)
+            r = ctx.mgm(cc, None, -39, P1, P2, 8, K, felz, 1)
+            o = O.orc_mgm(cc, None, -39, P1, P2, 8, K, felz, 1)
+            assert same(r["S"], o["S"]) and same(r["out"], o["out"]), (felz, K, rows, mism(r["S"], o["S"]))
+    finally:
+        ctx.set_rows_per_band(0)
+
+
 def test_mgm_overcount_flag_and_small_images(ctx):
     cc = synth_volume(31, 22, 12, seed=8, real=True)
     for fix in [0, 1]:
