@@ -569,7 +569,11 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
    // arguments) and label vectors of at least 128 floats (a warp per pixel is then fully used).  Measured otherwise
    // (profiles/r02_experiments.md): 32 x 1242x375x192 TSGM=4 in launches of 8 pairs 95.7 ms fused vs 74.5 ms with
    // separate finish launches, 4096x4096x64 -O 16 113.2 vs 97.4 ms; 2048x1536x256 20.0 vs 22.2 ms, 1920x1080x128 8.4 vs 9.4.
-   const bool fuse_gain = c->tune.fused_finish > 0 || (c->tune.fused_finish < 0 && R.npairs == 1 && VS >= 128);
+   // ... and, with SGM potentials, frames of a megapixel or more: their band steps are short, a small frame leaves the tiles
+   // to the end of the launch where one CTA of 16 warps per SM is slower than the stand-alone kernel (measured 640x480x100
+   // TSGM=2: 1.80 ms fused vs 1.46 ms, 1242x375x192: 5.4 vs 4.1 ms; 1920x1080x128: 5.68 vs 5.97 ms)
+   const bool fuse_gain = c->tune.fused_finish > 0 || (c->tune.fused_finish < 0 && R.npairs == 1 && VS >= 128 &&
+                                                       (pot == POT_TRUNC || (long long)nx * ny >= 1000000LL));
    const bool fuse = R.fin && !c->tune.no_fused_finish && fuse_gain &&
                      (size_t)(plan.block / 32) * (32 / wta_lanes_per_pixel(VS)) * VS * 4 <= rows_region;
    const int tiles_x = (nx + tw - 1) / tw, tiles_y = (ny + th - 1) / th, ntiles = tiles_x * tiles_y;

@@ -20,8 +20,12 @@ struct WtaParams {
    int refine;              // 0 none, 1 vfit, 2 parabola, 3 cubic, 4 parabolaOCV (mgm_refine.h:14-27)
 };
 
-// lanes of a warp that share one pixel in the finish stage (32, or 16 / 8 for 64 / 32 padded labels)
-__host__ __device__ inline int wta_lanes_per_pixel(int VS) { return VS >= 96 ? 32 : (VS >= 64 ? 16 : 8); }
+// lanes of a warp that share one pixel in the finish stage (32, or 16 / 8 for 64..128 / 32 padded labels)
+#ifndef MGM_WTA_LP32_MIN
+#define MGM_WTA_LP32_MIN 160   // padded labels from which a whole warp takes one pixel (measured: two pixels per warp at 128
+                              // labels make the fused finish tiles of 1920x1080x128 7 % cheaper, the stand-alone kernel is unchanged)
+#endif
+__host__ __device__ inline int wta_lanes_per_pixel(int VS) { return VS >= MGM_WTA_LP32_MIN ? 32 : (VS >= 64 ? 16 : 8); }
 cudaError_t wta_launch(const WtaParams &P, int num_sms, cudaStream_t st);
 // out = ((0 + src[0]) + src[1]) + ...  element-wise over n volumes (partial sums of the all-reduce exchange)
 cudaError_t sum_volumes_launch(const float *const *src, int n, float *out, long long nelem, int num_sms, cudaStream_t st);
