@@ -477,7 +477,19 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
    for (int p = 0; p < NDIR; p++) nsw += (mask >> p) & 1;
    AggPlan plan;
    const bool knight = (mask >> 8) != 0;
-   agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, c->rows_override, knight, c->tune);
+   // The finish stage runs as tile work inside the launch where that is a gain: one pair (its parameters are kernel
+   // arguments) and label vectors of at least 128 floats.  Measured otherwise (profiles/r02_experiments.md): 32 x
+   // 1242x375x192 TSGM=4 in launches of 8 pairs 95.7 ms fused vs 74.5 ms with separate finish launches, 4096x4096x64
+   // -O 16 113.2 vs 97.4 ms; 2048x1536x256 20.0 vs 22.2 ms, 1920x1080x128 8.4 vs 9.4.
+   // ... and, with SGM potentials, frames of a megapixel or more: their band steps are short, a small frame leaves the tiles
+   // to the end of the launch where one CTA of 16 warps per SM is slower than the stand-alone kernel (measured 640x480x100
+   // TSGM=2: 1.80 ms fused vs 1.46 ms, 1242x375x192: 5.4 vs 4.1 ms; 1920x1080x128: 5.68 vs 5.97 ms)
+   const bool fuse_gain = c->tune.fused_finish > 0 || (c->tune.fused_finish < 0 && R.npairs == 1 && VS >= 128 &&
+                                                       (pot == POT_TRUNC || (long long)nx * ny >= 1000000LL));
+   const bool want_fuse = R.fin && !c->tune.no_fused_finish && fuse_gain;
+   AggTuning tune = c->tune;
+   if (want_fuse) tune.full_block = 1;   // bands with fewer rows than the block holds: the spare warps serve the finish tiles
+   agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, c->rows_override, knight, tune);
    if (!c->rows_override && !c->tune.rows_axis && !c->tune.rows_diag && plan.T[0] > 40 && R.npairs == 1 && nsw <= 2) {
       // One or two sweeps on this GPU (sweep-sharded layouts): with fewer bands than SMs the launch is bound by the
       // dependency depth alone, and bands of 40 workers step faster than bands of 56 (measured: one axis sweep of
@@ -490,7 +502,7 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
          agg_sweep_bands(plan, p, nx, ny, &nb, &a, &bq);
          bands += nb;
       }
-      if (bands < c->num_sms) agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 40, knight, c->tune);
+      if (bands < c->num_sms) agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 40, knight, tune);
    } else if (!c->rows_override && !c->tune.rows_axis && !c->tune.rows_diag && pot == POT_SGM && R.npairs == 1) {
       // One small pair with SGM potentials (a KITTI-size frame yields fewer bands than 1.5 x the SMs): the launch is bound
       // by the dependency depth of its sweeps and the step of a band shortens with its rows (no label chain): 40, then
@@ -504,8 +516,13 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
             bands += nb;
          }
          if (2 * bands >= 3L * c->num_sms || plan.T[0] <= t) break;
-         agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, t, knight, c->tune);
+         agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, t, knight, tune);
       }
+      // 128 padded labels, 8 lanes per worker: a step is short enough that bands of 44 rows beat bands of 56 (measured
+      // 1920x1080x128 TSGM=2, full block kept for the finish tiles: 5.55 / 5.39 / 5.11 / 5.05 / 5.24 / 5.47 ms with 56 / 52 /
+      // 48 / 44 / 40 / 36 rows; 256 labels and 64 labels with 4 lanes keep the largest bands)
+      if (!weighted && VS == 128 && plan.lanes == 8 && plan.T[0] > 44)
+         agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 44, knight, tune);
    }
    if (plan.T[0] < 1 || plan.T[1] < 1 || plan.T[2] < 1)
       return fail(MGMB200_EUNSUPPORTED, "%d labels do not fit the shared-memory wavefront (max_smem=%d)", L, c->max_smem);
@@ -565,16 +582,7 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
    // decide: band b of such a sweep is done after about maxii + (b+1)*T steps), pairs interleaved
    const int tw = c->tune.fin_tw, th = c->tune.fin_th;
    const size_t rows_region = plan.smem - plan.off_thr;
-   // The finish stage runs as tile work inside the launch where that is a gain: one pair (its parameters are kernel
-   // arguments) and label vectors of at least 128 floats (a warp per pixel is then fully used).  Measured otherwise
-   // (profiles/r02_experiments.md): 32 x 1242x375x192 TSGM=4 in launches of 8 pairs 95.7 ms fused vs 74.5 ms with
-   // separate finish launches, 4096x4096x64 -O 16 113.2 vs 97.4 ms; 2048x1536x256 20.0 vs 22.2 ms, 1920x1080x128 8.4 vs 9.4.
-   // ... and, with SGM potentials, frames of a megapixel or more: their band steps are short, a small frame leaves the tiles
-   // to the end of the launch where one CTA of 16 warps per SM is slower than the stand-alone kernel (measured 640x480x100
-   // TSGM=2: 1.80 ms fused vs 1.46 ms, 1242x375x192: 5.4 vs 4.1 ms; 1920x1080x128: 5.68 vs 5.97 ms)
-   const bool fuse_gain = c->tune.fused_finish > 0 || (c->tune.fused_finish < 0 && R.npairs == 1 && VS >= 128 &&
-                                                       (pot == POT_TRUNC || (long long)nx * ny >= 1000000LL));
-   const bool fuse = R.fin && !c->tune.no_fused_finish && fuse_gain &&
+   const bool fuse = want_fuse &&
                      (size_t)(plan.block / 32) * (32 / wta_lanes_per_pixel(VS)) * VS * 4 <= rows_region;
    const int tiles_x = (nx + tw - 1) / tw, tiles_y = (ny + th - 1) / th, ntiles = tiles_x * tiles_y;
    if (R.fin)
