@@ -125,7 +125,7 @@ def measured_peaks():
 def kernel_source_sha():
     """Identifies the kernel sources an ncu traffic capture belongs to (profiles/traffic.json is refused when stale)."""
     h = hashlib.sha256()
-    for f in ("aggregate.cu", "aggregate.cuh", "aggregate_dev.cuh", "aggregate_sgm.cu", "aggregate_trunc.cu", "aggregate_plan.cu",
+    for f in ("aggregate.cu", "aggregate.cuh", "aggregate_dev.cuh", "aggregate_sgm.cu", "aggregate_trunc.cu", "aggregate_sgmw.cu", "aggregate_plan.cu",
               "wta_device.cuh", "wta.cuh", "common.cuh"):
         h.update(open(os.path.join(ROOT, "mgm_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]

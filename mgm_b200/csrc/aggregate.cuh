@@ -115,6 +115,7 @@ struct AggPlan {
    int VS, VSP, T[3], TS[3], ncb, shear, ng[3], fused_sgm, regchain, lanes, block, num_sms, verbose;
    int lean_sgm;   // 1: the launch qualifies for the lean unweighted-SGM kernels (aggregate_sgm.cu)
    int lean_trunc; // 1: ... for the lean unweighted truncated-linear kernels (aggregate_trunc.cu)
+   int lean_sgmw;  // 1: ... for the lean SGM kernels with per-edge weights (aggregate_sgmw.cu)
    size_t smem;
    size_t off_phase, off_cbar, off_vbar, off_ms, off_vms, off_virt, off_thr;
 };
@@ -133,5 +134,6 @@ bool agg_sgm_lean_supported(int VS, int lanes);
 cudaError_t agg_launch_sgm_lean(const AggParams &P, const AggPlan &plan, int K, cudaStream_t st);
 bool agg_trunc_lean_supported(int VS);
 cudaError_t agg_launch_trunc_lean(const AggParams &P, const AggPlan &plan, int K, cudaStream_t st);
+cudaError_t agg_launch_sgmw_lean(const AggParams &P, const AggPlan &plan, int K, cudaStream_t st);
 
 }  // namespace mgm

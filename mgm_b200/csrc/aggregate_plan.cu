@@ -46,6 +46,8 @@ static void agg_plan_try(AggPlan *plan, int nx, int ny, int L, int K, int pot, b
    // (TSGM <= 3) or row-per-worker (TSGM = 4), and the label layout is one they are built for
    plan->lean_trunc = (!weighted && pot == POT_TRUNC && plan->ncb == 1 && !plan->regchain && want_groups == 1 && plan->lanes == 8 && !knight &&
                        !tune.no_lean_trunc && (K == 4 || shear) && agg_trunc_lean_supported(VS)) ? 1 : 0;
+   plan->lean_sgmw = (weighted && pot == POT_SGM && plan->ncb == 1 && want_groups == 1 && plan->lanes == 8 && !knight && !tune.no_creg &&
+                      !tune.no_lean_sgm && agg_sgm_lean_supported(VS, 8)) ? 1 : 0;
    plan->lean_sgm = (plan->fused_sgm && !tune.no_lean_sgm && (K == 4 || shear) && agg_sgm_lean_supported(VS, plan->lanes)) ? 1 : 0;
    const int VSP = plan->regchain ? VS + (VS >> 3) : VS;
    plan->VSP = VSP;
@@ -136,6 +138,7 @@ void agg_sweep_bands(const AggPlan &plan, int pass, int nx, int ny, int *nb, siz
 cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st) {
    if (pot == POT_SGM && !weighted && plan.lean_sgm && plan.ng[0] == 1 && plan.ng[1] == 1)
       return agg_launch_sgm_lean(P, plan, K, st);
+   if (pot == POT_SGM && weighted && plan.lean_sgmw && plan.ng[0] == 1 && plan.ng[1] == 1) return agg_launch_sgmw_lean(P, plan, K, st);
    if (pot == POT_TRUNC && !weighted && plan.lean_trunc && plan.ng[0] == 1 && plan.ng[1] == 1)
       return agg_launch_trunc_lean(P, plan, K, st);
    return agg_launch_generic(P, plan, pot, K, weighted, st);

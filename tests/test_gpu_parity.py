@@ -178,6 +178,36 @@ def test_mgm_lean_sgm_kernels(ctx, lanes):
         ctx.set_option("reset")
 
 
+def test_mgm_lean_weighted_sgm_kernels(ctx):
+    """The lean SGM kernels with per-edge weights (aggregate_sgmw.cu: raw messages in the ring, consumer-side transform with
+    the weights of the pixel, every sweep row-per-worker) against the oracle: chunk counts 2, 4, 6, 8 per lane, TSGM 1-4,
+    chained bands (16 rows) and default bands; the generic kernel runs the same cases under MGMB200_NO_LEAN_SGM=1."""
+    try:
+        for L, K in itertools.product([40, 100, 180, 250], (1, 2, 3, 4)):
+            nx, ny = (75, 44) if L > 150 else (101, 58)
+            cc = synth_volume(nx, ny, L, seed=L + K, real=True)
+            w = synth_weights(nx, ny, seed=K)
+            o = O.orc_mgm(cc, w, -(L - 1), 8, 32, 8, K, 0, 1)
+            for rows, lean in ((16, 1), (0, 1), (16, 0)):
+                ctx.set_rows_per_band(rows)
+                ctx.set_option("no_lean_sgm", 0 if lean else 1)
+                r = ctx.mgm(cc, w, -(L - 1), 8, 32, 8, K, 0, 1)
+                tag = (L, K, rows, lean, mism(r["S"], o["S"]), mism(r["out"], o["out"]))
+                assert same(r["S"], o["S"]) and same(r["out"], o["out"]) and same(r["outcost"], o["outcost"]), tag
+        # thin images and tiny bands
+        for nx, ny in [(2, 9), (9, 2), (1, 1), (6, 1), (3, 3), (57, 3), (3, 57)]:
+            cc = synth_volume(nx, ny, 40, seed=nx + ny, real=True)
+            w = synth_weights(nx, ny, seed=nx)
+            for K, rows in itertools.product((2, 4), (0, 1, 2)):
+                ctx.set_rows_per_band(rows)
+                r = ctx.mgm(cc, w, -39, 8, 32, 8, K, 0, 1)
+                o = O.orc_mgm(cc, w, -39, 8, 32, 8, K, 0, 1)
+                assert same(r["S"], o["S"]) and same(r["out"], o["out"]), (nx, ny, K, rows, mism(r["S"], o["S"]))
+    finally:
+        ctx.set_rows_per_band(0)
+        ctx.set_option("reset")
+
+
 def test_mgm_lean_trunc_kernels(ctx):
     """The lean unweighted truncated-linear kernels (aggregate_trunc.cu: compile-time label layout, band hand-off off the
     step barriers) against the oracle for every chunk count per lane they are built for (2, 4, 6, 8), TSGM 1-4, chained
