@@ -503,10 +503,11 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
          bands += nb;
       }
       if (bands < c->num_sms) agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 40, knight, tune);
-   } else if (!c->rows_override && !c->tune.rows_axis && !c->tune.rows_diag && pot == POT_SGM && R.npairs == 1) {
-      // One small pair with SGM potentials (a KITTI-size frame yields fewer bands than 1.5 x the SMs): the launch is bound
-      // by the dependency depth of its sweeps and the step of a band shortens with its rows (no label chain): 40, then
-      // 28 rows per band (measured 1242x375x192 TSGM=4: 7.83 / 6.62 / 6.08 ms with 56 / 40 / 28 rows)
+   } else if (!c->rows_override && !c->tune.rows_axis && !c->tune.rows_diag && R.npairs == 1) {
+      // One small pair (a KITTI-size frame yields fewer bands than 1.5 x the SMs): the launch is bound by the dependency
+      // depth of its sweeps and the step of a band shortens with its rows: 40, then 28 rows per band (measured 1242x375x192
+      // TSGM=4 SGM: 7.83 / 6.62 / 6.08 ms with 56 / 40 / 28 rows; truncated linear TSGM=3: 5.97 / 5.30 / 5.01 ms, 640x480x64:
+      // 1.68 / 1.58 / 1.53 ms)
       for (int t : {40, 28}) {
          long bands = 0;
          for (int p = 0; p < NDIR; p++) {
@@ -521,7 +522,7 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
       // 128 padded labels, 8 lanes per worker: a step is short enough that bands of 44 rows beat bands of 56 (measured
       // 1920x1080x128 TSGM=2, full block kept for the finish tiles: 5.55 / 5.39 / 5.11 / 5.05 / 5.24 / 5.47 ms with 56 / 52 /
       // 48 / 44 / 40 / 36 rows; 256 labels and 64 labels with 4 lanes keep the largest bands)
-      if (!weighted && VS == 128 && plan.lanes == 8 && plan.T[0] > 44)
+      if (pot == POT_SGM && !weighted && VS == 128 && plan.lanes == 8 && plan.T[0] > 44)
          agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 44, knight, tune);
    }
    if (plan.T[0] < 1 || plan.T[1] < 1 || plan.T[2] < 1)
