@@ -519,12 +519,14 @@ static int run_sweeps_multi(mgmb200_ctx *c, const SweepRun &R, int weights_mode,
          if (2 * bands >= 3L * c->num_sms || plan.T[0] <= t) break;
          agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, t, knight, tune);
       }
-      // 128 padded labels, 8 lanes per worker: a step is short enough that bands of 44 rows beat bands of 56 (measured
-      // 1920x1080x128 TSGM=2, full block kept for the finish tiles: 5.55 / 5.39 / 5.11 / 5.05 / 5.24 / 5.47 ms with 56 / 52 /
-      // 48 / 44 / 40 / 36 rows; 256 labels and 64 labels with 4 lanes keep the largest bands)
-      if (pot == POT_SGM && !weighted && VS == 128 && plan.lanes == 8 && plan.T[0] > 44)
-         agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 44, knight, tune);
    }
+   // SGM potentials, 128 padded labels, 8 lanes per worker: a step is short enough that bands of 44 rows beat bands of 56
+   // (measured 1920x1080x128 TSGM=2, full block kept for the finish tiles: 5.55 / 5.39 / 5.11 / 5.05 / 5.24 / 5.47 ms with
+   // 56 / 52 / 48 / 44 / 40 / 36 rows; 256 labels and 64 labels with 4 lanes keep the largest bands; the two directions of a
+   // left-right run in one launch do not gain: 11.6 vs 11.5 ms)
+   if (!c->rows_override && !c->tune.rows_axis && !c->tune.rows_diag && pot == POT_SGM && !weighted && VS == 128 &&
+       plan.lanes == 8 && plan.T[0] > 44 && nsw > 2 && R.npairs == 1)
+      agg_plan(&plan, nx, ny, L, K, pot, weighted, c->max_smem, c->num_sms, 44, knight, tune);
    if (plan.T[0] < 1 || plan.T[1] < 1 || plan.T[2] < 1)
       return fail(MGMB200_EUNSUPPORTED, "%d labels do not fit the shared-memory wavefront (max_smem=%d)", L, c->max_smem);
    c->rows_axis = plan.T[0]; c->rows_diag = plan.T[1]; c->block = plan.block; c->smem = plan.smem;
