@@ -1118,10 +1118,19 @@ static cudaError_t launch_k(int K, const AggParams &P, const AggPlan &plan, cuda
 
 // every variant behind runtime switches (the lean kernels of aggregate_sgm.cu / aggregate_trunc.cu are dispatched by
 // agg_launch in aggregate_plan.cu)
-cudaError_t agg_launch_generic(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st) {
-   if (pot == POT_SGM)
-      return weighted ? launch_k<POT_SGM, true>(K, P, plan, st) : launch_k<POT_SGM, false>(K, P, plan, st);
+// This file is compiled twice, once per potential (aggregate_gsgm.cu / aggregate_gtrunc.cu define MGM_GENERIC_POT and
+// include it): the two halves of the instantiations build in parallel.
+#ifndef MGM_GENERIC_POT
+#error "compile through aggregate_gsgm.cu / aggregate_gtrunc.cu"
+#endif
+#if MGM_GENERIC_POT == 0
+cudaError_t agg_launch_generic_sgm(const AggParams &P, const AggPlan &plan, int K, bool weighted, cudaStream_t st) {
+   return weighted ? launch_k<POT_SGM, true>(K, P, plan, st) : launch_k<POT_SGM, false>(K, P, plan, st);
+}
+#else
+cudaError_t agg_launch_generic_trunc(const AggParams &P, const AggPlan &plan, int K, bool weighted, cudaStream_t st) {
    return weighted ? launch_k<POT_TRUNC, true>(K, P, plan, st) : launch_k<POT_TRUNC, false>(K, P, plan, st);
 }
+#endif
 
 }  // namespace mgm

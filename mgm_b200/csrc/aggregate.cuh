@@ -128,7 +128,8 @@ void agg_sweep_bands(const AggPlan &plan, int pass, int nx, int ny, int *nb, siz
 void agg_plan(AggPlan *plan, int nx, int ny, int L, int K, int pot, bool weighted, int max_smem, int num_sms,
               int t_override, bool knight, const AggTuning &tune);
 cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st);
-cudaError_t agg_launch_generic(const AggParams &P, const AggPlan &plan, int pot, int K, bool weighted, cudaStream_t st);   // aggregate.cu
+cudaError_t agg_launch_generic_sgm(const AggParams &P, const AggPlan &plan, int K, bool weighted, cudaStream_t st);     // aggregate.cu via aggregate_gsgm.cu
+cudaError_t agg_launch_generic_trunc(const AggParams &P, const AggPlan &plan, int K, bool weighted, cudaStream_t st);   // aggregate.cu via aggregate_gtrunc.cu
 // lean unweighted-SGM kernels (aggregate_sgm.cu): label layouts they are built for, and their launch
 bool agg_sgm_lean_supported(int VS, int lanes);
 cudaError_t agg_launch_sgm_lean(const AggParams &P, const AggPlan &plan, int K, cudaStream_t st);

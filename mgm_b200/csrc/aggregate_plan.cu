@@ -141,7 +141,7 @@ cudaError_t agg_launch(const AggParams &P, const AggPlan &plan, int pot, int K, 
    if (pot == POT_SGM && weighted && plan.lean_sgmw && plan.ng[0] == 1 && plan.ng[1] == 1) return agg_launch_sgmw_lean(P, plan, K, st);
    if (pot == POT_TRUNC && !weighted && plan.lean_trunc && plan.ng[0] == 1 && plan.ng[1] == 1)
       return agg_launch_trunc_lean(P, plan, K, st);
-   return agg_launch_generic(P, plan, pot, K, weighted, st);
+   return pot == POT_SGM ? agg_launch_generic_sgm(P, plan, K, weighted, st) : agg_launch_generic_trunc(P, plan, K, weighted, st);
 }
 
 }  // namespace mgm
